@@ -209,11 +209,12 @@ class NeighborCell:
         d = self._dot
         self.d00, self.d11, self.d22 = d(a0, a0), d(a1, a1), d(a2, a2)
         self.d01, self.d02, self.d12 = d(a0, a1), d(a0, a2), d(a1, a2)
-        # NB: the reference calls the C `abs` through <cmath>/<cstdlib>; with
-        # `using std` absent, g++ resolves abs(double) to std::abs(double).
-        self.r01 = abs(self.d01) > 0.5 * self.d00 or abs(self.d01) > 0.5 * self.d11
-        self.r02 = abs(self.d02) > 0.5 * self.d00 or abs(self.d02) > 0.5 * self.d22
-        self.r12 = abs(self.d12) > 0.5 * self.d11 or abs(self.d12) > 0.5 * self.d22
+        # NB: neighbor_cell.cpp:36-38 writes `abs(dot01)` where only ::abs(int) is visible,
+        # so the dot products are truncated to int before the comparison.  Kept on purpose.
+        ia = lambda x: abs(int(x))
+        self.r01 = ia(self.d01) > 0.5 * self.d00 or ia(self.d01) > 0.5 * self.d11
+        self.r02 = ia(self.d02) > 0.5 * self.d00 or ia(self.d02) > 0.5 * self.d22
+        self.r12 = ia(self.d12) > 0.5 * self.d11 or ia(self.d12) > 0.5 * self.d22
         self.ref_sum = int(self.r01) + int(self.r02) + int(self.r12)
 
     def _cart(self, i, j, k):

@@ -1,0 +1,1033 @@
+// pm_capi.cu -- C ABI (include/polymlp_b200.h): host tables, device context, chunked pipeline.
+#include "../../include/polymlp_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "pm_kernels.cuh"
+
+namespace pm {
+void set_features_smem(size_t smem_bytes);
+void set_lrows_kmax(int kmax);
+size_t lrows_mma_smem(const DevModel& m);
+size_t xrows_mma_smem(const DevModel& m);
+double microbench_dgemm(int n, cudaStream_t s);
+}  // namespace pm
+
+using namespace pm;
+
+static thread_local std::string g_err;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));                     \
+    } while (0)
+
+template <typename F> static int guarded(F&& f) {
+    try {
+        f();
+        return PM_OK;
+    } catch (const CudaError& e) {
+        g_err = e.what();
+        return PM_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        g_err = e.what();
+        return PM_ERR_INVALID;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return PM_ERR_RUNTIME;
+    }
+}
+
+struct pm_model {
+    HostModel hm;
+};
+
+enum Stage { ST_H2D = 0, ST_NEIGH, ST_BASIS, ST_ANLM, ST_FEAT, ST_LROWS, ST_XROWS, ST_SYRK, ST_EVAL, ST_D2H, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"h2d", "neighbor", "pair_basis", "anlm", "features_G", "lrows", "xrows",
+                                            "syrk", "eval", "d2h"};
+
+template <typename T> struct DevVec {
+    T* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        size_t want = n + n / 8 + 64;
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostChunk {
+    int n_st = 0, n_atoms = 0, n_rows = 0;
+    std::vector<int> atom_off, st_of_atom, types, trans_off, force, erow, srow, frow;
+    std::vector<double> x, y, z, trans, w, yv;
+    std::vector<long> brow_e, brow_s, brow_f;  // rows in the caller's batch layout
+};
+
+struct pm_context {
+    const pm_model* model = nullptr;
+    int device = 0;
+    int flags = 0;
+    size_t ws_cap = 0;
+    cudaStream_t stream = nullptr;
+    DevModel dm{};
+    std::vector<void*> table_allocs;
+    bool simple_l = false, simple_x = false, simple_s = false;
+    size_t feat_smem = 0;
+    // accumulators
+    double* acc = nullptr;
+    size_t acc_n = 0;
+    int64_t n_data = 0;
+    // chunk device buffers
+    DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
+        d_nbr, d_centre, d_rev, d_err;
+    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_G, d_L, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
+        d_f, d_s;
+    DevVec<double2> d_anc, d_agg;
+    DevVec<unsigned char> d_scan_tmp;
+    DevBatch last_batch{};
+    int last_pairs = 0;
+    // staged batch (bench: inputs resident in HBM)
+    std::vector<HostChunk> staged;
+    std::vector<std::vector<void*>> staged_dev;  // per chunk device copies
+    // stats
+    int64_t launches = 0;
+    bool profile = false;
+    double stage_ms[ST_COUNT] = {0};
+    int64_t stage_launches[ST_COUNT] = {0};
+    cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
+    bool has_coeffs = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> static T* upload(pm_context* c, const std::vector<T>& v) {
+    T* p = nullptr;
+    const size_t n = std::max<size_t>(v.size(), 1);
+    CK(cudaMalloc(&p, n * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    c->table_allocs.push_back(p);
+    return p;
+}
+
+static void build_device_model(pm_context* c) {
+    const HostModel& hm = c->model->hm;
+    DevModel& d = c->dm;
+    if (hm.fp.n_type > MAXT) throw std::invalid_argument("device path supports at most 4 atom types");
+    if (hm.n_lm_half > MAX_NH) throw std::invalid_argument("max_l > 20 is not supported");
+    d.n_type = hm.fp.n_type;
+    d.n_fn = hm.fp.n_fn;
+    d.n_tp = hm.n_tp;
+    d.maxl = hm.fp.maxl;
+    d.nh = hm.n_lm_half;
+    d.n_variables = hm.n_variables;
+    d.n_linear = hm.n_linear;
+    d.fpad = (hm.n_variables + 1 + 127) / 128 * 128;
+    d.cutoff = hm.fp.cutoff;
+    d.pbstride = 4 + 2 * d.n_fn + 8 * d.nh;
+    d.fl = 8;
+    d.hmax = 1;
+    d.gstride = 32;
+    int kmax = 4;
+    for (const auto& T : hm.types) {
+        d.fl = std::max(d.fl, T.n_fpad);
+        d.hmax = std::max(d.hmax, T.n_head);
+        d.gstride = std::max(d.gstride, T.g_size);
+        for (int u = 0; u < d.n_type; ++u)
+            for (int n = 0; n < d.n_fn; ++n) kmax = std::max(kmax, 2 * (T.seg_n_off[u][n + 1] - T.seg_n_off[u][n]));
+    }
+    set_lrows_kmax(kmax);
+    std::vector<double> tpp((size_t)d.n_tp * d.n_fn * 2, 0.0);
+    std::vector<int> tpn(d.n_tp, 0), tpairs((size_t)d.n_type * d.n_type);
+    for (int tp = 0; tp < d.n_tp; ++tp) {
+        tpn[tp] = (int)hm.fp.cond[tp].size();
+        for (size_t k = 0; k < hm.fp.cond[tp].size(); ++k) {
+            tpp[((size_t)tp * d.n_fn + k) * 2] = hm.fp.params[hm.fp.cond[tp][k]][0];
+            tpp[((size_t)tp * d.n_fn + k) * 2 + 1] = hm.fp.params[hm.fp.cond[tp][k]][1];
+        }
+    }
+    for (int i = 0; i < d.n_type; ++i)
+        for (int j = 0; j < d.n_type; ++j) tpairs[(size_t)i * d.n_type + j] = hm.type_pairs[i][j];
+    d.tp_params = upload(c, tpp);
+    d.tp_nfn = upload(c, tpn);
+    d.type_pairs = upload(c, tpairs);
+    d.npv = (int)hm.pv_gid.size();
+    d.npv_pad = std::max(8, (d.npv + 7) / 8 * 8);
+    std::vector<int> pvfp((size_t)d.n_type * d.npv_pad, -1);
+    for (int t = 0; t < d.n_type; ++t)
+        for (int a = 0; a < d.npv; ++a) pvfp[(size_t)t * d.npv_pad + a] = hm.pv_fp[t][a];
+    d.pv_fp = upload(c, pvfp);
+    d.n_pair_terms = (int)hm.pair_terms.size();
+    std::vector<int> pt;
+    for (const auto& x : hm.pair_terms) { pt.push_back(x[0]); pt.push_back(x[1]); pt.push_back(x[2]); }
+    d.pair_terms = upload(c, pt);
+
+    size_t max_full = 1;
+    for (int t = 0; t < d.n_type; ++t) {
+        const TypeTables& T = hm.types[t];
+        DevType& D = d.types[t];
+        D.n_full = T.n_full; D.n_head = T.n_head; D.n_feat = T.n_feat; D.n_fpad = T.n_fpad;
+        D.n_tiles = T.n_fpad / 8; D.max_order = T.max_order; D.n_ent = (int)T.ent_off.size() - 1;
+        D.n_blocks = (int)T.blocks.size(); D.g_size = T.g_size;
+        max_full = std::max<size_t>(max_full, T.n_full);
+        D.full_head = upload(c, T.full_head);
+        std::vector<signed char> fc(T.full_conj.begin(), T.full_conj.end());
+        D.full_conj = upload(c, fc);
+        D.full_cc = upload(c, T.full_cc);
+        D.head_nid = upload(c, T.head_nid);
+        D.head_key = upload(c, T.head_key);
+        std::vector<int> head_seg(T.n_head, 0);
+        for (int h = 0; h < T.n_head; ++h)
+            for (int u = 0; u < d.n_type; ++u)
+                if (T.seg_tp[u] == T.head_tp[h]) { head_seg[h] = u; break; }
+        D.head_seg = upload(c, head_seg);
+        std::vector<int> tile_n_off(d.n_fn + 1, 0);
+        {
+            int tile = 0;
+            for (int n = 0; n < d.n_fn; ++n) {
+                tile_n_off[n] = tile;
+                while (tile < D.n_tiles && T.tile_n[tile] == n) ++tile;
+            }
+            tile_n_off[d.n_fn] = tile;
+            if (tile != D.n_tiles) throw std::runtime_error("feature tiles are not ordered by radial index");
+        }
+        D.tile_n_off = upload(c, tile_n_off);
+        for (int u = 0; u < MAXT; ++u) {
+            D.seg_heads[u] = nullptr; D.seg_len[u] = 0; D.seg_key[u] = nullptr; D.seg_n_off[u] = nullptr;
+            D.seg_nid[u] = nullptr; D.tile_blk_off[u] = nullptr;
+        }
+        for (int u = 0; u < d.n_type; ++u) {
+            D.seg_heads[u] = upload(c, T.seg_heads[u]);
+            D.seg_len[u] = (int)T.seg_heads[u].size();
+            std::vector<int> key(T.seg_heads[u].size(), -1);
+            for (size_t k = 0; k < key.size(); ++k)
+                if (T.seg_heads[u][k] >= 0) key[k] = T.head_key[T.seg_heads[u][k]];
+            D.seg_key[u] = upload(c, key);
+            D.seg_n_off[u] = upload(c, T.seg_n_off[u]);
+            std::vector<int> nid(d.n_fn, -1);
+            for (int n = 0; n < d.n_fn; ++n) nid[n] = hm.tp_nid[T.seg_tp[u]][n];
+            D.seg_nid[u] = upload(c, nid);
+            D.tile_blk_off[u] = upload(c, T.tile_blk_off[u]);
+        }
+        D.term_off = upload(c, T.term_off);
+        D.term_coeff = upload(c, T.term_coeff);
+        D.term_order = upload(c, T.term_order);
+        D.term_ids = upload(c, T.term_ids);
+        D.feat_pad = upload(c, T.feat_pad);
+        D.ent_pos_re = upload(c, T.ent_pos_re);
+        D.ent_pos_im = upload(c, T.ent_pos_im);
+        D.ent_off = upload(c, T.ent_off);
+        std::vector<DevContribution> cb(T.contribs.size());
+        for (size_t k = 0; k < cb.size(); ++k) {
+            cb[k].coeff = T.contribs[k].coeff; cb[k].conj = T.contribs[k].conj; cb[k].n_ids = T.contribs[k].n_ids;
+            for (int q = 0; q < 5; ++q) cb[k].ids[q] = T.contribs[k].ids[q];
+            cb[k].pad = 0;
+        }
+        D.contribs = upload(c, cb);
+        std::vector<int> bk(T.blocks.size());
+        for (size_t k = 0; k < bk.size(); ++k) bk[k] = T.blocks[k].kchunk;
+        D.blk_kchunk = upload(c, bk);
+        D.pad_gid = upload(c, T.pad_gid);
+        std::vector<DevPolyTerm> ct(hm.n_variables);
+        for (int col = 0; col < hm.n_variables; ++col) {
+            const PolyTerm& p = hm.colterm[t][col];
+            ct[col] = {p.order, p.fp[0], p.fp[1], p.fp[2]};
+        }
+        D.colterm = upload(c, ct);
+    }
+    c->feat_smem = max_full * sizeof(double2);
+    if (c->feat_smem > 200 * 1024) throw std::invalid_argument("model too large: a_nlm array exceeds shared memory");
+    if (c->feat_smem > 48 * 1024) set_features_smem(c->feat_smem);
+    const bool force_simple = (c->flags & PM_FLAG_SIMPLE_KERNELS) != 0;
+    c->simple_s = force_simple;
+    c->simple_l = force_simple || lrows_mma_smem(d) > 200 * 1024;
+    c->simple_x = force_simple || hm.has_order3 || xrows_mma_smem(d) > 200 * 1024;
+}
+
+// ------------------------------------------------------------------------------------------------
+static void validate_structures(const pm_context* c, const pm_structures* st) {
+    if (!st || st->n_st < 0) throw std::invalid_argument("invalid structure batch");
+    if (st->n_st > 0 && (!st->axis || !st->positions_c || !st->types || !st->n_atoms))
+        throw std::invalid_argument("null pointer in structure batch");
+    size_t off = 0;
+    for (int s = 0; s < st->n_st; ++s) {
+        if (st->n_atoms[s] < 0) throw std::invalid_argument("negative atom count");
+        for (int a = 0; a < st->n_atoms[s]; ++a) {
+            const int t = st->types[off + a];
+            if (t < 0 || t >= c->dm.n_type) throw std::invalid_argument("atom type out of range");
+        }
+        off += st->n_atoms[s];
+    }
+}
+
+static double est_bytes_per_structure(const pm_context* c, const double* axis, int n_atoms, bool force) {
+    const DevModel& d = c->dm;
+    const double* a = axis;
+    const double vol = std::fabs(a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+                                 a[2] * (a[3] * a[7] - a[4] * a[6]));
+    const double rc = d.cutoff;
+    const double nb = vol > 0 ? n_atoms / vol * 4.18879 * rc * rc * rc * 1.1 + 4 : 64;
+    const double pairs = nb * n_atoms;
+    double bytes = pairs * (d.pbstride * 8.0 + 12.0);
+    bytes += n_atoms * (d.hmax * 16.0 * 10 + d.fl * 8.0 * 10 + 64);
+    if (force) {
+        bytes += pairs * 3.0 * d.fl * 8.0;
+        bytes += (double)n_atoms * d.gstride * 8.0;
+        bytes += (7.0 + 3.0 * n_atoms) * d.fpad * 8.0;
+    } else {
+        bytes += d.fpad * 8.0;
+    }
+    return bytes;
+}
+
+// Prepares structures [s0, s1) of the batch on the host (translations, cell reduction, row maps).
+static void prepare_chunk(const pm_context* c, const pm_structures* st, const std::vector<size_t>& aoff,
+                          const std::vector<long>& be, const std::vector<long>& bs, const std::vector<long>& bf,
+                          int s0, int s1, const double* w, const double* y, HostChunk& h) {
+    h = HostChunk();
+    h.n_st = s1 - s0;
+    h.atom_off.push_back(0);
+    h.trans_off.push_back(0);
+    for (int s = s0; s < s1; ++s) {
+        const int na = st->n_atoms[s];
+        std::vector<double> pos(st->positions_c + 3 * aoff[s], st->positions_c + 3 * aoff[s] + 3 * (size_t)na);
+        CellTranslations ct;
+        find_translations(st->axis + 9 * (size_t)s, pos.data(), na, c->dm.cutoff, ct);
+        for (int a = 0; a < na; ++a) {
+            h.x.push_back(pos[a]); h.y.push_back(pos[na + a]); h.z.push_back(pos[2 * (size_t)na + a]);
+            h.types.push_back(st->types[aoff[s] + a]);
+            h.st_of_atom.push_back(s - s0);
+        }
+        h.trans.insert(h.trans.end(), ct.trans.begin(), ct.trans.end());
+        h.trans_off.push_back((int)(h.trans.size() / 3));
+        h.atom_off.push_back(h.atom_off.back() + na);
+        h.force.push_back(st->force ? (st->force[s] != 0) : 0);
+    }
+    h.n_atoms = h.atom_off.back();
+    // chunk-local PyModel layout
+    int ns_force = 0;
+    for (int f : h.force) ns_force += f;
+    int is = h.n_st, ifo = h.n_st + 6 * ns_force;
+    for (int k = 0; k < h.n_st; ++k) {
+        h.erow.push_back(k);
+        if (h.force[k]) {
+            h.srow.push_back(is); is += 6;
+            h.frow.push_back(ifo); ifo += 3 * (h.atom_off[k + 1] - h.atom_off[k]);
+        } else {
+            h.srow.push_back(-1); h.frow.push_back(-1);
+        }
+        h.brow_e.push_back(be[s0 + k]); h.brow_s.push_back(bs[s0 + k]); h.brow_f.push_back(bf[s0 + k]);
+    }
+    h.n_rows = ifo;
+    h.w.assign(h.n_rows, 1.0);
+    h.yv.assign(h.n_rows, 0.0);
+    if (w && y) {
+        for (int k = 0; k < h.n_st; ++k) {
+            h.w[h.erow[k]] = w[h.brow_e[k]]; h.yv[h.erow[k]] = y[h.brow_e[k]];
+            if (h.force[k]) {
+                for (int r = 0; r < 6; ++r) { h.w[h.srow[k] + r] = w[h.brow_s[k] + r]; h.yv[h.srow[k] + r] = y[h.brow_s[k] + r]; }
+                const int nf = 3 * (h.atom_off[k + 1] - h.atom_off[k]);
+                for (int r = 0; r < nf; ++r) { h.w[h.frow[k] + r] = w[h.brow_f[k] + r]; h.yv[h.frow[k] + r] = y[h.brow_f[k] + r]; }
+            }
+        }
+    }
+}
+
+static void batch_layout(const pm_structures* st, std::vector<size_t>& aoff, std::vector<long>& be,
+                         std::vector<long>& bs, std::vector<long>& bf, long& n_rows) {
+    const int n = st->n_st;
+    aoff.assign(n + 1, 0);
+    for (int s = 0; s < n; ++s) aoff[s + 1] = aoff[s] + st->n_atoms[s];
+    be.assign(n, 0); bs.assign(n, -1); bf.assign(n, -1);
+    long is = n;
+    for (int s = 0; s < n; ++s) { be[s] = s; if (st->force && st->force[s]) { bs[s] = is; is += 6; } }
+    long ifo = is;
+    for (int s = 0; s < n; ++s) if (st->force && st->force[s]) { bf[s] = ifo; ifo += 3L * st->n_atoms[s]; }
+    n_rows = ifo;
+}
+
+static std::vector<std::pair<int, int>> plan_chunks(const pm_context* c, const pm_structures* st) {
+    std::vector<std::pair<int, int>> chunks;
+    int s0 = 0;
+    double bytes = 0.0;
+    for (int s = 0; s < st->n_st; ++s) {
+        const double bs = est_bytes_per_structure(c, st->axis + 9 * (size_t)s, st->n_atoms[s], st->force && st->force[s]);
+        if (s > s0 && bytes + bs > (double)c->ws_cap) {
+            chunks.push_back({s0, s});
+            s0 = s;
+            bytes = 0.0;
+        }
+        bytes += bs;
+    }
+    if (st->n_st > s0) chunks.push_back({s0, st->n_st});
+    return chunks;
+}
+
+template <typename T> static void h2d(DevVec<T>& d, const std::vector<T>& h, cudaStream_t s) {
+    d.ensure(std::max<size_t>(h.size(), 1));
+    if (!h.empty()) CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+struct StageTimer {
+    pm_context* c;
+    int idx = 0;
+    explicit StageTimer(pm_context* c_) : c(c_) {
+        if (c->profile) CK(cudaEventRecord(c->ev[0], c->stream));
+    }
+    void mark(int stage, int launches) {
+        c->launches += launches;
+        c->stage_launches[stage] += launches;
+        if (!c->profile) return;
+        CK(cudaEventRecord(c->ev[idx + 1], c->stream));
+        CK(cudaEventSynchronize(c->ev[idx + 1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev[idx], c->ev[idx + 1]));
+        c->stage_ms[stage] += ms;
+        idx = (idx + 1) % ST_COUNT;
+        if (idx == 0) CK(cudaEventRecord(c->ev[0], c->stream));
+    }
+};
+
+enum Mode { MODE_FIT = 0, MODE_X = 1, MODE_EVAL = 2, MODE_NEIGH = 3 };
+
+// Runs the device pipeline on one prepared chunk.  `upload_inputs` false -> inputs already on the device
+// (staged); dev_in then holds the device pointers in the order of upload below.
+static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_inputs, StageTimer& tm) {
+    cudaStream_t s = c->stream;
+    const DevModel& d = c->dm;
+    const int nt = d.n_type;
+    if (upload_inputs) {
+        h2d(c->d_atom_off, h.atom_off, s); h2d(c->d_st_of_atom, h.st_of_atom, s); h2d(c->d_types, h.types, s);
+        h2d(c->d_trans_off, h.trans_off, s); h2d(c->d_force, h.force, s); h2d(c->d_erow, h.erow, s);
+        h2d(c->d_srow, h.srow, s); h2d(c->d_frow, h.frow, s);
+        h2d(c->d_x, h.x, s); h2d(c->d_y, h.y, s); h2d(c->d_z, h.z, s); h2d(c->d_trans, h.trans, s);
+        h2d(c->d_w, h.w, s); h2d(c->d_yv, h.yv, s);
+    }
+    DevBatch b{};
+    b.n_st = h.n_st; b.n_atoms = h.n_atoms; b.n_pairs = 0; b.n_rows = h.n_rows;
+    b.atom_off = c->d_atom_off.p; b.st_of_atom = c->d_st_of_atom.p; b.types = c->d_types.p;
+    b.x = c->d_x.p; b.y = c->d_y.p; b.z = c->d_z.p; b.trans_off = c->d_trans_off.p; b.trans = c->d_trans.p;
+    b.force = c->d_force.p; b.erow = c->d_erow.p; b.srow = c->d_srow.p; b.frow = c->d_frow.p;
+    b.w = c->d_w.p; b.yv = c->d_yv.p;
+    tm.mark(ST_H2D, 0);
+    if (h.n_atoms == 0) { c->last_batch = b; c->last_pairs = 0; return; }
+
+    // ---- K1 ------------------------------------------------------------------------------------
+    const size_t nseg = (size_t)h.n_atoms * nt;
+    c->d_counts.ensure(nseg + 1);
+    c->d_seg_off.ensure(nseg + 1);
+    c->d_err.ensure(1);
+    CK(cudaMemsetAsync(c->d_counts.p + nseg, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(c->d_err.p, 0, sizeof(int), s));
+    launch_neighbor_count(d, b, c->d_counts.p, s);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
+    c->d_scan_tmp.ensure(tmp_bytes + 16);
+    cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
+    int n_pairs = 0;
+    CK(cudaMemcpyAsync(&n_pairs, c->d_seg_off.p + nseg, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    b.n_pairs = n_pairs;
+    b.seg_off = c->d_seg_off.p;
+    const size_t np1 = std::max<size_t>(n_pairs, 1);
+    c->d_nbr.ensure(np1); c->d_centre.ensure(np1); c->d_rev.ensure(np1);
+    c->d_PB.ensure(np1 * d.pbstride);
+    b.nbr = c->d_nbr.p; b.centre = c->d_centre.p; b.rev = c->d_rev.p;
+    launch_neighbor_fill(d, b, c->d_PB.p, s);
+    launch_neighbor_rev(d, b, c->d_PB.p, c->d_err.p, s);
+    tm.mark(ST_NEIGH, 5);
+    c->last_batch = b;
+    c->last_pairs = n_pairs;
+    if (mode == MODE_NEIGH) return;
+
+    bool any_force = false;
+    for (int f : h.force) any_force = any_force || f;
+    if (mode == MODE_EVAL) any_force = true;
+
+    // ---- K2 ------------------------------------------------------------------------------------
+    launch_pair_basis(d, b, c->d_PB.p, s);
+    tm.mark(ST_BASIS, 1);
+    c->d_anc.ensure((size_t)h.n_atoms * d.hmax);
+    c->d_agg.ensure(any_force ? (size_t)h.n_atoms * d.hmax * 9 : 1);
+    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s);
+    tm.mark(ST_ANLM, 1);
+
+    // ---- K3 ------------------------------------------------------------------------------------
+    c->d_dfeat.ensure((size_t)h.n_atoms * d.fl);
+    c->d_G.ensure(any_force ? (size_t)h.n_atoms * d.gstride : 1);
+    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s);
+    tm.mark(ST_FEAT, 1);
+
+    Workspace ws;
+    ws.PB = c->d_PB.p; ws.anc = c->d_anc.p; ws.agg = c->d_agg.p; ws.dfeat = c->d_dfeat.p; ws.Gbuf = c->d_G.p;
+    c->d_Xown.ensure((size_t)h.n_atoms * 3 * d.fl);
+    c->d_S.ensure((size_t)h.n_atoms * 6 * d.fl);
+    ws.Xown = c->d_Xown.p; ws.Sbuf = c->d_S.p; ws.errflag = c->d_err.p;
+
+    if (mode == MODE_EVAL) {
+        int maxseg = 0;
+        for (int t = 0; t < nt; ++t)
+            for (int u = 0; u < nt; ++u) maxseg = std::max(maxseg, d.types[t].seg_len[u]);
+        c->d_Ah.ensure((size_t)h.n_atoms * nt * 2 * maxseg + 1);
+        ws.Ah = c->d_Ah.p;
+        c->d_e.ensure(h.n_st); c->d_f.ensure((size_t)h.n_atoms * 3 + 1); c->d_s.ensure((size_t)h.n_st * 6);
+        CK(cudaMemsetAsync(c->d_e.p, 0, h.n_st * sizeof(double), s));
+        CK(cudaMemsetAsync(c->d_f.p, 0, ((size_t)h.n_atoms * 3 + 1) * sizeof(double), s));
+        CK(cudaMemsetAsync(c->d_s.p, 0, (size_t)h.n_st * 6 * sizeof(double), s));
+        launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s);
+        tm.mark(ST_EVAL, 5);
+        return;
+    }
+
+    // ---- K4a -------------------------------------------------------------------------------------
+    if (any_force) {
+        c->d_L.ensure(np1 * 3 * d.fl);
+        ws.Lbuf = c->d_L.p;
+        launch_lrows(d, b, ws, c->simple_l, s);
+        tm.mark(ST_LROWS, 1);
+    }
+    // ---- K4b -------------------------------------------------------------------------------------
+    c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
+    ws.X = c->d_X.p;
+    CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
+    const bool fit = mode == MODE_FIT;
+    double* xe_sum = fit ? c->acc + (size_t)d.fpad * d.fpad : nullptr;
+    double* xe_sq = fit ? xe_sum + d.fpad : nullptr;
+    launch_xrows(d, b, ws, xe_sum, xe_sq, c->simple_x, fit, s);
+    tm.mark(ST_XROWS, 3);
+    // ---- K5 --------------------------------------------------------------------------------------
+    if (fit) {
+        launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
+        tm.mark(ST_SYRK, 1);
+        c->n_data += h.n_rows;
+    }
+}
+
+static void check_device_error(pm_context* c) {
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, c->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (err) throw std::runtime_error("neighbour list is not symmetric (reverse pair not found)");
+}
+
+// ================================================================================================
+extern "C" {
+
+const char* pm_last_error(void) { return g_err.c_str(); }
+const char* pm_version(void) { return "pypolymlp_b200 0.1 (sm_100a, fp64)"; }
+
+int pm_gtinv_read(const char* datadir, int order, const int* maxl, int n_maxl, int version, int64_t sizes[4],
+                  int* lcomb_order, int* l_comb, int* n_terms, int* lm_seq, double* lm_coeffs) {
+    return guarded([&] {
+        std::vector<int> ml(maxl, maxl + std::max(0, n_maxl));
+        GtinvTables g = read_gtinv(datadir ? datadir : "", order, ml, version);
+        int64_t s1 = 0, s2 = 0, s3 = 0;
+        for (size_t i = 0; i < g.l_comb.size(); ++i) {
+            if (lcomb_order) lcomb_order[i] = (int)g.l_comb[i].size();
+            if (n_terms) n_terms[i] = (int)g.lm_seq[i].size();
+            for (int v : g.l_comb[i]) { if (l_comb) l_comb[s1] = v; ++s1; }
+            for (size_t t = 0; t < g.lm_seq[i].size(); ++t) {
+                if (lm_coeffs) lm_coeffs[s2] = g.lm_coeffs[i][t];
+                ++s2;
+                for (int v : g.lm_seq[i][t]) { if (lm_seq) lm_seq[s3] = v; ++s3; }
+            }
+        }
+        sizes[0] = (int64_t)g.l_comb.size(); sizes[1] = s1; sizes[2] = s2; sizes[3] = s3;
+    });
+}
+
+int pm_model_create(const pm_feature_params* p, pm_model** out) {
+    return guarded([&] {
+        if (!p || !out) throw std::invalid_argument("null argument");
+        FeatureParams fp;
+        fp.n_type = p->n_type; fp.n_fn = p->n_fn;
+        if (fp.n_type < 1 || fp.n_fn < 1) throw std::invalid_argument("invalid n_type / n_fn");
+        for (int n = 0; n < p->n_fn; ++n) fp.params.push_back({p->pair_params[2 * n], p->pair_params[2 * n + 1]});
+        const int ntp = p->n_type * (p->n_type + 1) / 2;
+        for (int tp = 0; tp < ntp; ++tp)
+            fp.cond.emplace_back(p->cond_values + p->cond_offsets[tp], p->cond_values + p->cond_offsets[tp + 1]);
+        fp.cutoff = p->cutoff; fp.model_type = p->model_type; fp.maxp = p->max_p; fp.maxl = p->max_l;
+        size_t o1 = 0, o2 = 0, o3 = 0;
+        for (int i = 0; i < p->n_lcomb; ++i) {
+            const int o = p->lcomb_order[i], nt_ = p->n_terms[i];
+            fp.l_comb.emplace_back(p->l_comb + o1, p->l_comb + o1 + o);
+            o1 += o;
+            fp.lm_coeffs.emplace_back(p->lm_coeffs + o2, p->lm_coeffs + o2 + nt_);
+            o2 += nt_;
+            std::vector<std::vector<int>> seq(nt_);
+            for (int t = 0; t < nt_; ++t) { seq[t].assign(p->lm_seq + o3, p->lm_seq + o3 + o); o3 += o; }
+            fp.lm_seq.push_back(std::move(seq));
+        }
+        auto m = std::make_unique<pm_model>();
+        m->hm.build(fp);
+        *out = m.release();
+    });
+}
+
+void pm_model_destroy(pm_model* m) { delete m; }
+int pm_model_n_features(const pm_model* m) { return m ? m->hm.n_variables : -1; }
+
+int pm_model_info(const pm_model* m, int64_t info[8]) {
+    return guarded([&] {
+        if (!m) throw std::invalid_argument("null model");
+        info[0] = m->hm.fp.n_type; info[1] = m->hm.n_linear; info[2] = (int64_t)m->hm.comb2.size();
+        info[3] = (int64_t)m->hm.comb3.size(); info[4] = m->hm.n_variables; info[5] = (int64_t)m->hm.pv_gid.size();
+        info[6] = m->hm.n_tp; info[7] = m->hm.n_lm_half;
+    });
+}
+
+int pm_model_type_info(const pm_model* m, int type, int64_t out[12]) {
+    return guarded([&] {
+        if (!m || type < 0 || type >= m->hm.fp.n_type) throw std::invalid_argument("invalid type");
+        const TypeTables& T = m->hm.types[type];
+        out[0] = T.n_full; out[1] = T.n_head; out[2] = T.n_feat; out[3] = T.n_fpad; out[4] = (int64_t)T.term_coeff.size();
+        out[5] = (int64_t)T.ent_off.size() - 1; out[6] = (int64_t)T.contribs.size(); out[7] = (int64_t)T.blocks.size();
+        out[8] = (int64_t)T.poly.size(); out[9] = T.n_deriv_pairs; out[10] = 0; out[11] = 0;
+    });
+}
+
+int pm_model_polynomial(const pm_model* m, int type, int* n, int* col, int* order, int* local_ids3) {
+    return guarded([&] {
+        if (!m || type < 0 || type >= m->hm.fp.n_type) throw std::invalid_argument("invalid type");
+        const TypeTables& T = m->hm.types[type];
+        *n = (int)T.poly.size();
+        if (!col) return;
+        for (size_t i = 0; i < T.poly.size(); ++i) {
+            col[i] = T.poly[i].col; order[i] = T.poly[i].order;
+            for (int k = 0; k < 3; ++k) {
+                const int fp_ = T.poly[i].fp[k];
+                local_ids3[3 * i + k] = fp_ >= 0 ? T.pad_feat[fp_] : -1;
+            }
+        }
+    });
+}
+
+int pm_model_count_flops(const pm_model* m, const int64_t* atoms_t, const int64_t* pairs_tt, int force, double out[5]) {
+    return guarded([&] {
+        if (!m) throw std::invalid_argument("null model");
+        const HostModel& hm = m->hm;
+        const int nt = hm.fp.n_type;
+        double n_atoms = 0, pairs = 0;
+        for (int t = 0; t < nt; ++t) n_atoms += (double)atoms_t[t];
+        for (int k = 0; k < nt * nt; ++k) pairs += (double)pairs_tt[k];
+        const double F = hm.n_variables;
+        const double R = 1.0 + (force ? 3.0 * n_atoms + 6.0 : 0.0);
+        out[0] = R * F * (F + 1.0);
+        out[1] = 2.0 * R * F;
+        double wpoly = 0.0, wderiv = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const TypeTables& T = hm.types[t];
+            double tp_ = 0.0;
+            for (const auto& p : T.poly) tp_ += p.order == 1 ? 1.0 : (p.order == 2 ? 4.0 : 9.0);
+            double pairs_t = 0.0;
+            for (int u = 0; u < nt; ++u) pairs_t += (double)pairs_tt[t * nt + u];
+            // sum_i (r_i + 1) T_p, r_i = 3 (M_i + 1) + 6
+            if (force) wpoly += (3.0 * (pairs_t + atoms_t[t]) + 7.0 * atoms_t[t]) * tp_;
+            else wpoly += atoms_t[t] * tp_;
+            if (force) {
+                // T_d(type, tp): derivative terms whose head belongs to type pair tp
+                std::vector<double> td(nt, 0.0);
+                // count (feature, full head) pairs before conj folding, per segment
+                for (int f = 0; f < T.n_feat; ++f)
+                    for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti)
+                        for (int k = 0; k < T.term_order[ti]; ++k) {
+                            const int h = T.full_head[T.term_ids[(size_t)ti * T.max_order + k]];
+                            for (int u = 0; u < nt; ++u)
+                                if (T.seg_tp[u] == T.head_tp[h]) { td[u] += 1.0; break; }
+                        }
+                for (int u = 0; u < nt; ++u) wderiv += 12.0 * (double)pairs_tt[t * nt + u] * td[u];
+            }
+        }
+        out[2] = wpoly;
+        out[3] = wderiv;
+        out[4] = pairs * hm.fp.n_fn * hm.n_lm_half * (force ? 32.0 : 8.0);
+    });
+}
+
+int pm_device_count(int* n) {
+    return guarded([&] {
+        int k = 0;
+        cudaError_t e = cudaGetDeviceCount(&k);
+        if (e != cudaSuccess) { cudaGetLastError(); k = 0; }
+        *n = k;
+    });
+}
+
+int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int flags, pm_context** out) {
+    return guarded([&] {
+        if (!m || !out) throw std::invalid_argument("null argument");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            throw CudaError("no CUDA device available: pypolymlp_b200 has no CPU fallback");
+        }
+        if (device < 0 || device >= ndev) throw std::invalid_argument("device index out of range");
+        CK(cudaSetDevice(device));
+        auto c = std::make_unique<pm_context>();
+        c->model = m; c->device = device; c->flags = flags;
+        c->ws_cap = workspace_bytes ? workspace_bytes : (size_t)6 << 30;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto& e : c->ev) CK(cudaEventCreate(&e));
+        build_device_model(c.get());
+        const DevModel& d = c->dm;
+        c->acc_n = (size_t)d.fpad * d.fpad + 2 * (size_t)d.fpad + 1;
+        *out = c.release();
+    });
+}
+
+void pm_context_destroy(pm_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->table_allocs) cudaFree(p);
+    if (c->acc) cudaFree(c->acc);
+    c->d_atom_off.release(); c->d_st_of_atom.release(); c->d_types.release(); c->d_trans_off.release();
+    c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
+    c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
+    c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
+    c->d_PB.release(); c->d_dfeat.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
+    c->d_X.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
+    c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int64_t pm_batch_rows(const pm_structures* st) {
+    int64_t r = st->n_st;
+    for (int s = 0; s < st->n_st; ++s)
+        if (st->force && st->force[s]) r += 6 + 3LL * st->n_atoms[s];
+    return r;
+}
+
+static void ensure_acc(pm_context* c) {
+    if (!c->acc) {
+        CK(cudaMalloc(&c->acc, c->acc_n * sizeof(double)));
+        CK(cudaMemsetAsync(c->acc, 0, c->acc_n * sizeof(double), c->stream));
+        c->n_data = 0;
+    }
+}
+
+int pm_fit_reset(pm_context* c) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        ensure_acc(c);
+        CK(cudaMemsetAsync(c->acc, 0, c->acc_n * sizeof(double), c->stream));
+        c->n_data = 0;
+    });
+}
+
+static void process_batch(pm_context* c, const pm_structures* st, const double* w, const double* y, int mode,
+                          double* x_out, double* e_out, double* f_out, double* s_out) {
+    CK(cudaSetDevice(c->device));
+    validate_structures(c, st);
+    std::vector<size_t> aoff;
+    std::vector<long> be, bs, bf;
+    long n_rows = 0;
+    batch_layout(st, aoff, be, bs, bf, n_rows);
+    const DevModel& d = c->dm;
+    const int F = d.n_variables;
+    StageTimer tm(c);
+    for (auto [s0, s1] : plan_chunks(c, st)) {
+        HostChunk h;
+        prepare_chunk(c, st, aoff, be, bs, bf, s0, s1, w, y, h);
+        if (mode == MODE_EVAL)
+            for (auto& f : h.force) f = 1;
+        run_chunk(c, h, mode, true, tm);
+        if (mode == MODE_X) {
+            for (int k = 0; k < h.n_st; ++k) {
+                CK(cudaMemcpy2DAsync(x_out + (size_t)h.brow_e[k] * F, F * sizeof(double), c->d_X.p + (size_t)h.erow[k] * d.fpad,
+                                     d.fpad * sizeof(double), F * sizeof(double), 1, cudaMemcpyDeviceToHost, c->stream));
+                if (h.force[k]) {
+                    CK(cudaMemcpy2DAsync(x_out + (size_t)h.brow_s[k] * F, F * sizeof(double),
+                                         c->d_X.p + (size_t)h.srow[k] * d.fpad, d.fpad * sizeof(double), F * sizeof(double), 6,
+                                         cudaMemcpyDeviceToHost, c->stream));
+                    const int nf = 3 * (h.atom_off[k + 1] - h.atom_off[k]);
+                    if (nf > 0)
+                        CK(cudaMemcpy2DAsync(x_out + (size_t)h.brow_f[k] * F, F * sizeof(double),
+                                             c->d_X.p + (size_t)h.frow[k] * d.fpad, d.fpad * sizeof(double),
+                                             F * sizeof(double), nf, cudaMemcpyDeviceToHost, c->stream));
+                }
+            }
+            tm.mark(ST_D2H, 0);
+        } else if (mode == MODE_EVAL && h.n_atoms > 0) {
+            CK(cudaMemcpyAsync(e_out + s0, c->d_e.p, h.n_st * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(f_out + 3 * aoff[s0], c->d_f.p, (size_t)h.n_atoms * 3 * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(s_out + 6 * (size_t)s0, c->d_s.p, (size_t)h.n_st * 6 * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+            tm.mark(ST_D2H, 0);
+        } else if (mode == MODE_EVAL) {
+            for (int k = 0; k < h.n_st; ++k) { e_out[s0 + k] = 0.0; for (int r = 0; r < 6; ++r) s_out[6 * (size_t)(s0 + k) + r] = 0.0; }
+        }
+        if (h.n_atoms > 0) check_device_error(c);
+        else CK(cudaStreamSynchronize(c->stream));
+    }
+}
+
+int pm_fit_accumulate(pm_context* c, const pm_structures* st, const double* w, const double* y) {
+    return guarded([&] {
+        if (!c || !st || !w || !y) throw std::invalid_argument("null argument");
+        CK(cudaSetDevice(c->device));
+        ensure_acc(c);
+        process_batch(c, st, w, y, MODE_FIT, nullptr, nullptr, nullptr, nullptr);
+    });
+}
+
+int pm_features_x(pm_context* c, const pm_structures* st, double* x) {
+    return guarded([&] {
+        if (!c || !st || !x) throw std::invalid_argument("null argument");
+        process_batch(c, st, nullptr, nullptr, MODE_X, x, nullptr, nullptr, nullptr);
+    });
+}
+
+int pm_fit_stage(pm_context* c, const pm_structures* st, const double* w, const double* y) {
+    return guarded([&] {
+        if (!c || !st || !w || !y) throw std::invalid_argument("null argument");
+        CK(cudaSetDevice(c->device));
+        validate_structures(c, st);
+        ensure_acc(c);
+        std::vector<size_t> aoff;
+        std::vector<long> be, bs, bf;
+        long n_rows = 0;
+        batch_layout(st, aoff, be, bs, bf, n_rows);
+        for (auto& v : c->staged_dev)
+            for (void* p : v) cudaFree(p);
+        c->staged_dev.clear();
+        c->staged.clear();
+        for (auto [s0, s1] : plan_chunks(c, st)) {
+            HostChunk h;
+            prepare_chunk(c, st, aoff, be, bs, bf, s0, s1, w, y, h);
+            std::vector<void*> dev;
+            auto put = [&](const void* src, size_t bytes) {
+                void* p = nullptr;
+                CK(cudaMalloc(&p, std::max<size_t>(bytes, 8)));
+                if (bytes) CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+                dev.push_back(p);
+            };
+            put(h.atom_off.data(), h.atom_off.size() * 4); put(h.st_of_atom.data(), h.st_of_atom.size() * 4);
+            put(h.types.data(), h.types.size() * 4); put(h.trans_off.data(), h.trans_off.size() * 4);
+            put(h.force.data(), h.force.size() * 4); put(h.erow.data(), h.erow.size() * 4);
+            put(h.srow.data(), h.srow.size() * 4); put(h.frow.data(), h.frow.size() * 4);
+            put(h.x.data(), h.x.size() * 8); put(h.y.data(), h.y.size() * 8); put(h.z.data(), h.z.size() * 8);
+            put(h.trans.data(), h.trans.size() * 8); put(h.w.data(), h.w.size() * 8); put(h.yv.data(), h.yv.size() * 8);
+            c->staged_dev.push_back(dev);
+            // keep only the metadata on the host
+            HostChunk meta;
+            meta.n_st = h.n_st; meta.n_atoms = h.n_atoms; meta.n_rows = h.n_rows; meta.force = h.force;
+            c->staged.push_back(std::move(meta));
+        }
+    });
+}
+
+int pm_fit_accumulate_staged(pm_context* c) {
+    return guarded([&] {
+        if (!c) throw std::invalid_argument("null argument");
+        CK(cudaSetDevice(c->device));
+        StageTimer tm(c);
+        for (size_t k = 0; k < c->staged.size(); ++k) {
+            const auto& dev = c->staged_dev[k];
+            // point the chunk buffers at the staged copies (no copy, no ownership change)
+            auto swap_in = [&](auto& vec, void* p) { vec.p = reinterpret_cast<decltype(vec.p)>(p); };
+            struct Saved { void* p; size_t cap; };
+            std::vector<Saved> saved;
+            auto save = [&](auto& vec) { saved.push_back({vec.p, vec.cap}); };
+            save(c->d_atom_off); save(c->d_st_of_atom); save(c->d_types); save(c->d_trans_off); save(c->d_force);
+            save(c->d_erow); save(c->d_srow); save(c->d_frow); save(c->d_x); save(c->d_y); save(c->d_z); save(c->d_trans);
+            save(c->d_w); save(c->d_yv);
+            swap_in(c->d_atom_off, dev[0]); swap_in(c->d_st_of_atom, dev[1]); swap_in(c->d_types, dev[2]);
+            swap_in(c->d_trans_off, dev[3]); swap_in(c->d_force, dev[4]); swap_in(c->d_erow, dev[5]);
+            swap_in(c->d_srow, dev[6]); swap_in(c->d_frow, dev[7]); swap_in(c->d_x, dev[8]); swap_in(c->d_y, dev[9]);
+            swap_in(c->d_z, dev[10]); swap_in(c->d_trans, dev[11]); swap_in(c->d_w, dev[12]); swap_in(c->d_yv, dev[13]);
+            std::exception_ptr ex;
+            try {
+                run_chunk(c, c->staged[k], MODE_FIT, false, tm);
+            } catch (...) { ex = std::current_exception(); }
+            size_t q = 0;
+            auto restore = [&](auto& vec) { vec.p = reinterpret_cast<decltype(vec.p)>(saved[q].p); vec.cap = saved[q].cap; ++q; };
+            restore(c->d_atom_off); restore(c->d_st_of_atom); restore(c->d_types); restore(c->d_trans_off);
+            restore(c->d_force); restore(c->d_erow); restore(c->d_srow); restore(c->d_frow); restore(c->d_x);
+            restore(c->d_y); restore(c->d_z); restore(c->d_trans); restore(c->d_w); restore(c->d_yv);
+            if (ex) std::rethrow_exception(ex);
+        }
+    });
+}
+
+int pm_fit_accumulator(pm_context* c, void** dev_ptr, size_t* n_doubles) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        ensure_acc(c);
+        // n_data travels inside the accumulator so that a cross-GPU sum reduces it too
+        const double nd = (double)c->n_data;
+        CK(cudaMemcpyAsync(c->acc + c->acc_n - 1, &nd, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        *dev_ptr = c->acc;
+        *n_doubles = c->acc_n;
+    });
+}
+
+int pm_fit_fpad(pm_context* c) { return c ? c->dm.fpad : -1; }
+
+int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum, double* y_sq_norm,
+                    int64_t* n_data) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        ensure_acc(c);
+        const DevModel& d = c->dm;
+        const int F = d.n_variables, fp = d.fpad;
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        // rows 0..F of C (the y row is row F); copy the (F+1) x (F+1) corner
+        std::vector<double> corner((size_t)(F + 1) * (F + 1));
+        CK(cudaMemcpy2D(corner.data(), (size_t)(F + 1) * sizeof(double), c->acc, (size_t)fp * sizeof(double),
+                        (size_t)(F + 1) * sizeof(double), F + 1, cudaMemcpyDeviceToHost));
+        const int ld = F + 1;
+        // valid region: 128x128 tiles with tile_row <= tile_col; inside diagonal tiles everything is valid
+        auto get = [&](int i, int j) {
+            const int ti = i / 128, tj = j / 128;
+            return ti <= tj ? corner[(size_t)i * ld + j] : corner[(size_t)j * ld + i];
+        };
+        if (xtx)
+            for (int i = 0; i < F; ++i)
+                for (int j = 0; j < F; ++j) xtx[(size_t)i * F + j] = get(i, j);
+        if (xty)
+            for (int i = 0; i < F; ++i) xty[i] = get(i, F);
+        if (y_sq_norm) *y_sq_norm = get(F, F);
+        std::vector<double> tail(2 * (size_t)fp + 1);
+        CK(cudaMemcpy(tail.data(), c->acc + (size_t)fp * fp, tail.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        if (xe_sum) std::copy(tail.begin(), tail.begin() + F, xe_sum);
+        if (xe_sq_sum) std::copy(tail.begin() + fp, tail.begin() + fp + F, xe_sq_sum);
+        if (n_data) {
+            const double nd = tail[2 * (size_t)fp];
+            *n_data = nd > (double)c->n_data ? (int64_t)llround(nd) : c->n_data;
+        }
+    });
+}
+
+int pm_synchronize(pm_context* c) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+    });
+}
+
+void* pm_stream(pm_context* c) { return c ? (void*)c->stream : nullptr; }
+int64_t pm_launch_count(pm_context* c) { return c ? c->launches : 0; }
+
+int pm_profile_enable(pm_context* c, int on) {
+    c->profile = on != 0;
+    for (int k = 0; k < ST_COUNT; ++k) { c->stage_ms[k] = 0.0; c->stage_launches[k] = 0; }
+    return PM_OK;
+}
+
+int pm_profile_get(pm_context* c, int* n_stages, double* ms, int64_t* launches) {
+    *n_stages = ST_COUNT;
+    for (int k = 0; k < ST_COUNT; ++k) { if (ms) ms[k] = c->stage_ms[k]; if (launches) launches[k] = c->stage_launches[k]; }
+    return PM_OK;
+}
+
+const char* pm_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+
+int pm_neighbor_full(pm_context* c, const double* axis, const double* positions_c, const int* types, int n_atom,
+                     int* offsets, int* neigh, double* dx, double* dy, double* dz) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        pm_structures st{};
+        int na = n_atom, force = 0;
+        st.n_st = 1; st.axis = axis; st.positions_c = positions_c; st.types = types; st.n_atoms = &na; st.force = &force;
+        validate_structures(c, &st);
+        std::vector<size_t> aoff{0, (size_t)n_atom};
+        std::vector<long> be{0}, bs{-1}, bf{-1};
+        HostChunk h;
+        prepare_chunk(c, &st, aoff, be, bs, bf, 0, 1, nullptr, nullptr, h);
+        StageTimer tm(c);
+        run_chunk(c, h, MODE_NEIGH, true, tm);
+        if (n_atom > 0) check_device_error(c);
+        const int nt = c->dm.n_type;
+        std::vector<int> seg((size_t)n_atom * nt + 1, 0);
+        if (n_atom > 0) CK(cudaMemcpy(seg.data(), c->d_seg_off.p, seg.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int i = 0; i <= n_atom; ++i) offsets[i] = seg[(size_t)i * nt];
+        if (neigh && c->last_pairs > 0) {
+            const int P = c->last_pairs;
+            CK(cudaMemcpy(neigh, c->d_nbr.p, P * sizeof(int), cudaMemcpyDeviceToHost));
+            const int stride = c->dm.pbstride;
+            std::vector<double> rec((size_t)P * 3);
+            CK(cudaMemcpy2D(rec.data(), 3 * sizeof(double), c->d_PB.p, (size_t)stride * sizeof(double), 3 * sizeof(double), P,
+                            cudaMemcpyDeviceToHost));
+            for (int p = 0; p < P; ++p) { dx[p] = rec[3 * (size_t)p]; dy[p] = rec[3 * (size_t)p + 1]; dz[p] = rec[3 * (size_t)p + 2]; }
+        }
+    });
+}
+
+int pm_eval_set_coeffs(pm_context* c, const double* coeffs, int n) {
+    return guarded([&] {
+        if (!c || !coeffs) throw std::invalid_argument("null argument");
+        if (n != c->dm.n_variables) throw std::invalid_argument("number of coefficients does not match the model");
+        CK(cudaSetDevice(c->device));
+        c->d_coeffs.ensure(n);
+        CK(cudaMemcpy(c->d_coeffs.p, coeffs, n * sizeof(double), cudaMemcpyHostToDevice));
+        c->has_coeffs = true;
+    });
+}
+
+int pm_eval(pm_context* c, const pm_structures* st, double* energies, double* forces, double* stresses) {
+    return guarded([&] {
+        if (!c || !st || !energies || !forces || !stresses) throw std::invalid_argument("null argument");
+        if (!c->has_coeffs) throw std::runtime_error("coefficients are not set");
+        process_batch(c, st, nullptr, nullptr, MODE_EVAL, nullptr, energies, forces, stresses);
+    });
+}
+
+int pm_debug_fetch(pm_context* c, int what, double* out, size_t cap, size_t* n) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        const DevModel& d = c->dm;
+        const DevBatch& b = c->last_batch;
+        const void* src = nullptr;
+        size_t cnt = 0;
+        if (what == 0) { src = c->d_anc.p; cnt = (size_t)b.n_atoms * d.hmax * 2; }
+        else if (what == 1) { src = c->d_dfeat.p; cnt = (size_t)b.n_atoms * d.fl; }
+        else if (what == 2) { src = c->d_PB.p; cnt = (size_t)c->last_pairs * d.pbstride; }
+        else if (what == 3) { src = c->d_X.p; cnt = (size_t)b.n_rows * d.fpad; }
+        else throw std::invalid_argument("unknown debug buffer");
+        *n = cnt;
+        if (out) {
+            if (cnt > cap) throw std::invalid_argument("debug buffer too small");
+            if (cnt) CK(cudaMemcpy(out, src, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+    });
+}
+
+int pm_microbench(pm_context* c, int which, int n, double* tflops) {
+    return guarded([&] {
+        CK(cudaSetDevice(c->device));
+        if (which == 3) *tflops = microbench_dgemm(n > 0 ? n : 8192, c->stream);
+        else *tflops = microbench_fp64(which, c->stream);
+        CK(cudaGetLastError());
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// pm_device.cuh -- device-side views of the model tables and of one chunk of structures.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pm_tables.hpp"
+
+namespace pm {
+
+constexpr int MAXT = 4;       // max number of atom types on the device path
+constexpr int MAX_NH = 231;   // (L+1)(L+2)/2 for L = 20
+
+struct DevContribution {
+    double coeff;
+    int conj;
+    int n_ids;
+    int ids[5];
+    int pad;
+};
+
+struct DevPolyTerm {
+    int order;  // 0 = column absent for this centre type
+    int fp0, fp1, fp2;
+};
+
+struct DevType {
+    int n_full, n_head, n_feat, n_fpad, n_tiles, max_order, n_ent, n_blocks;
+    long g_size;
+    const int* full_head;
+    const signed char* full_conj;
+    const double* full_cc;
+    const int* head_nid;
+    const int* head_key;
+    const int* head_seg;      // neighbour type u whose pairs feed this head
+    const int* seg_heads[MAXT];
+    int seg_len[MAXT];        // padded number of heads in the segment (even)
+    const int* seg_key[MAXT];   // [seg_len] ylm key of the head at each position (-1 padding)
+    const int* seg_n_off[MAXT]; // [n_fn + 1] head offsets of each radial group inside the segment
+    const int* seg_nid[MAXT];   // [n_fn] radial id inside the pair record for each radial index (-1 inactive)
+    const int* tile_n_off;      // [n_fn + 1] feature tiles of each radial index
+    const int* term_off;
+    const double* term_coeff;
+    const int* term_order;
+    const int* term_ids;
+    const int* feat_pad;
+    const int* ent_pos_re;
+    const int* ent_pos_im;
+    const int* ent_off;
+    const DevContribution* contribs;
+    const int* blk_kchunk;
+    const int* tile_blk_off[MAXT];
+    const int* pad_gid;
+    const DevPolyTerm* colterm;
+};
+
+struct DevModel {
+    int n_type, n_fn, n_tp, maxl, nh, n_variables, n_linear;
+    int fpad;      // padded width of X-tilde = [X | y | 0...], multiple of 128
+    int fl;        // stride of per-centre linear-feature rows (max n_fpad over types)
+    int hmax;      // max n_head over types
+    int pbstride;  // doubles per pair-basis record
+    long gstride;  // doubles per atom in the G buffer
+    double cutoff;
+    const double* tp_params;  // [n_tp][n_fn][2], compacted by radial id of the pair
+    const int* tp_nfn;        // [n_tp]
+    const int* type_pairs;    // [n_type * n_type]
+    int npv;                  // polynomial variables (order-2 terms)
+    int npv_pad;              // padded to a multiple of 8
+    const int* pv_fp;         // [n_type][npv_pad] padded local id or -1
+    int n_pair_terms;
+    const int* pair_terms;    // [n_pair_terms][3] = (col, a, b)
+    DevType types[MAXT];
+};
+
+// pair-basis record layout (doubles): dx dy dz 1/r | fn[n_fn] | fn'[n_fn] | Y (re,im)[nh] | Yx | Yy | Yz
+__host__ __device__ inline int pb_fn(const DevModel& m) { return 4; }
+__host__ __device__ inline int pb_fnd(const DevModel& m) { return 4 + m.n_fn; }
+__host__ __device__ inline int pb_y(const DevModel& m, int comp) { return 4 + 2 * m.n_fn + comp * 2 * m.nh; }
+
+struct DevBatch {
+    int n_st, n_atoms, n_pairs, n_rows;
+    const int* atom_off;    // [n_st + 1]
+    const int* st_of_atom;  // [n_atoms]
+    const int* types;       // [n_atoms]
+    const double* x;        // [n_atoms] Cartesian (possibly wrapped into the refined cell)
+    const double* y;
+    const double* z;
+    const int* trans_off;   // [n_st + 1]
+    const double* trans;    // [n_trans][3]
+    const int* force;       // [n_st]
+    const int* erow;        // [n_st] row of the energy entry in the chunk
+    const int* srow;        // [n_st] first stress row or -1
+    const int* frow;        // [n_st] first force row or -1
+    const double* w;        // [n_rows]
+    const double* yv;       // [n_rows] weighted targets
+    int* seg_off;           // [n_atoms * n_type + 1] pair offsets by (atom, neighbour type)
+    int* nbr;               // [n_pairs] neighbour atom (chunk-global index)
+    int* centre;            // [n_pairs]
+    int* rev;               // [n_pairs] index of the reverse pair
+};
+
+}  // namespace pm

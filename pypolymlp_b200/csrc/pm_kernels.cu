@@ -1,0 +1,709 @@
+// pm_kernels.cu -- hand-written sm_100a kernels of the pypolymlp hot path (fp64 throughout).
+//
+// Pipeline per chunk of structures (all buffers stay in HBM/L2, X is only ever a chunk):
+//   K1  neighbour list            NeighborFull            compute/neighbor_full.cpp:10-76
+//   K2  pair basis + a_nlm        Local::compute_anlmtp_d compute/local.cpp:116-217,
+//                                 get_fn_/get_ylm_        polymlp/polymlp_functions_interface.cpp:41-142
+//   K3  invariants d_f and G      Features::compute_features{,_deriv}  polymlp/polymlp_features.cpp:173-248
+//   K4a L = V.G per centre        (neighbour-sparse replacement of the dense (n_nlmtp x N) arrays)
+//   K4b gather + polynomial       Model::model_order1..3  compute/model.cpp:159-267, apply_weights
+//   K5  C += Xt^T Xt              numpy x.T @ x           src/pypolymlp/mlp_dev/core/utils_sequential.py:94-109
+// This file holds the straightforward kernels (one thread per output); the tensor-core (DMMA)
+// variants of K4a/K4b/K5 live in pm_kernels_mma.cu and are validated against these.
+#include "pm_kernels.cuh"
+
+#include <cstdio>
+
+namespace pm {
+
+// ================================================================================================
+// K1: neighbour list.  One warp per centre atom; lanes sweep the (j, translation) candidates in the
+// reference's order, ballot + popc keeps that order in the output.  The arithmetic uses explicit
+// round-to-nearest intrinsics so that no FMA contraction can change a bit w.r.t. the reference:
+//   dx = (x_j - x_i) + t_x ;  r2 = dx*dx + dy*dy + dz*dz ;  keep if r2 < rc^2 and r2 > 1e-20.
+// ================================================================================================
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_neighbor(DevModel m, DevBatch b, int* __restrict__ counts,
+                                                   double* __restrict__ PB, double cutoff_sq, double tol_sq) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= b.n_atoms) return;
+    const int i = warp;
+    const int s = b.st_of_atom[i];
+    const int a0 = b.atom_off[s];
+    const int N = b.atom_off[s + 1] - a0;
+    const int t0 = b.trans_off[s];
+    const int T = b.trans_off[s + 1] - t0;
+    const double xi = b.x[i], yi = b.y[i], zi = b.z[i];
+    const int nt = m.n_type;
+    const int total = N * T;
+    for (int u = 0; u < nt; ++u) {
+        int cnt = 0;
+        const int base = FILL ? b.seg_off[i * nt + u] : 0;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            const int c = c0 + lane;
+            bool hit = false;
+            double dx = 0.0, dy = 0.0, dz = 0.0;
+            int j = 0;
+            if (c < total) {
+                j = c / T;
+                const int t = c - j * T;
+                if (nt == 1 || b.types[a0 + j] == u) {
+                    const double* tr = b.trans + 3 * (size_t)(t0 + t);
+                    dx = __dadd_rn(__dsub_rn(b.x[a0 + j], xi), tr[0]);
+                    dy = __dadd_rn(__dsub_rn(b.y[a0 + j], yi), tr[1]);
+                    dz = __dadd_rn(__dsub_rn(b.z[a0 + j], zi), tr[2]);
+                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    hit = (r2 < cutoff_sq) && (r2 > tol_sq);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int pos = base + cnt + __popc(mask & ((1u << lane) - 1u));
+                b.nbr[pos] = a0 + j;
+                b.centre[pos] = i;
+                double* rec = PB + (size_t)pos * m.pbstride;
+                rec[0] = dx; rec[1] = dy; rec[2] = dz;
+            }
+            cnt += __popc(mask);
+        }
+        if (!FILL && lane == 0) counts[i * nt + u] = cnt;
+    }
+}
+
+void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s) {
+    const int threads = 256;
+    const int blocks = (b.n_atoms * 32 + threads - 1) / threads;
+    const double tol = 1e-10;
+    k_neighbor<false><<<blocks, threads, 0, s>>>(m, b, counts, nullptr, m.cutoff * m.cutoff, tol * tol);
+}
+
+void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
+    const int threads = 256;
+    const int blocks = (b.n_atoms * 32 + threads - 1) / threads;
+    const double tol = 1e-10;
+    k_neighbor<true><<<blocks, threads, 0, s>>>(m, b, nullptr, PB, m.cutoff * m.cutoff, tol * tol);
+}
+
+// reverse pair: (i -> j, D) <-> (j -> i, -D); exact because negation is exact in every step above.
+__global__ void __launch_bounds__(256) k_neighbor_rev(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                       int* __restrict__ errflag) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n_pairs) return;
+    const int i = b.centre[p], j = b.nbr[p];
+    const double* rec = PB + (size_t)p * m.pbstride;
+    const double dx = -rec[0], dy = -rec[1], dz = -rec[2];
+    const int u = b.types[i];
+    const int q0 = b.seg_off[j * m.n_type + u], q1 = b.seg_off[j * m.n_type + u + 1];
+    int found = -1;
+    for (int q = q0; q < q1; ++q) {
+        if (b.nbr[q] != i) continue;
+        const double* rq = PB + (size_t)q * m.pbstride;
+        if (rq[0] == dx && rq[1] == dy && rq[2] == dz) { found = q; break; }
+    }
+    b.rev[p] = found;
+    if (found < 0) atomicExch(errflag, 1);
+}
+
+void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB, int* errflag, cudaStream_t s) {
+    if (b.n_pairs == 0) return;
+    k_neighbor_rev<<<(b.n_pairs + 255) / 256, 256, 0, s>>>(m, b, PB, errflag);
+}
+
+// ================================================================================================
+// K2a: per-pair basis record: radial functions (Gaussian x cosine cutoff) with d/dr, complex Y_lm
+// (m <= 0) and Cartesian gradients by the normalised associated-Legendre recurrences.
+// ================================================================================================
+__global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n_pairs) return;
+    double* rec = PB + (size_t)p * m.pbstride;
+    const double dx = rec[0], dy = rec[1], dz = rec[2];
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    const double rinv = 1.0 / r;
+    rec[3] = rinv;
+    const int ti = b.types[b.centre[p]], tj = b.types[b.nbr[p]];
+    const int tp = m.type_pairs[ti * m.n_type + tj];
+
+    // radial
+    const double pi = 3.1415926535897932384626433832795;
+    double fc = 0.0, fcd = 0.0;
+    if (r < m.cutoff) {
+        const double v1 = pi / m.cutoff, v2 = v1 * r;
+        double sv, cv;
+        sincos(v2, &sv, &cv);
+        fc = 0.5 * (cv + 1.0);
+        fcd = -0.5 * v1 * sv;
+    }
+    const int nfn = m.tp_nfn[tp];
+    const double* prm = m.tp_params + (size_t)tp * m.n_fn * 2;
+    for (int n = 0; n < m.n_fn; ++n) {
+        double fn = 0.0, fnd = 0.0;
+        if (n < nfn) {
+            const double beta = prm[2 * n], mu = prm[2 * n + 1];
+            const double d = r - mu;
+            const double bf = exp(-beta * d * d);
+            const double bfd = -2.0 * beta * d * bf;
+            fn = bf * fc;
+            fnd = bfd * fc + bf * fcd;
+            if (fn < 1e-20) { fn = 0.0; fnd = 0.0; }  // reference skip rule (local.cpp:164)
+        }
+        rec[4 + n] = fn;
+        rec[4 + m.n_fn + n] = fnd;
+    }
+
+    // angular
+    const int L = m.maxl;
+    const double ct = dz * rinv;
+    const double rho = hypot(dx, dy);
+    double cp = 1.0, sp = 0.0;
+    if (rho > 0.0) { cp = dx / rho; sp = dy / rho; }
+    double pl[MAX_NH], ql[MAX_NH];
+    const double s2pi = 0.39894228040143267794;
+    const double st = sqrt(1.0 - ct * ct);
+#define LM2I(l, mm) ((l) * ((l) + 1) / 2 + (mm))
+    pl[0] = s2pi; ql[0] = 0.0;
+    if (L >= 1) {
+        pl[LM2I(1, 0)] = ct * 1.7320508075688772935 * s2pi; ql[LM2I(1, 0)] = 0.0;
+        pl[LM2I(1, 1)] = -st * 1.2247448713915890491 * s2pi; ql[LM2I(1, 1)] = -1.2247448713915890491 * s2pi;
+        for (int l = 2; l <= L; ++l) {
+            const double c1 = -sqrt(1.0 + 0.5 / l) * st;
+            pl[LM2I(l, l)] = c1 * pl[LM2I(l - 1, l - 1)];
+            ql[LM2I(l, l)] = c1 * ql[LM2I(l - 1, l - 1)];
+            const double c2 = sqrt(2.0 * (l - 1.0) + 3.0) * ct;
+            pl[LM2I(l, l - 1)] = c2 * pl[LM2I(l - 1, l - 1)];
+            ql[LM2I(l, l - 1)] = c2 * ql[LM2I(l - 1, l - 1)];
+        }
+        for (int l = 2; l <= L; ++l) {
+            const double ls = (double)(l * l), lm1s = (double)((l - 1) * (l - 1));
+            for (int mm = 0; mm <= l - 2; ++mm) {
+                const double ms = (double)(mm * mm);
+                const double alm = sqrt((4.0 * ls - 1.0) / (ls - ms));
+                const double blm = -sqrt((lm1s - ms) / (4.0 * lm1s - 1.0));
+                pl[LM2I(l, mm)] = alm * (ct * pl[LM2I(l - 1, mm)] + blm * pl[LM2I(l - 2, mm)]);
+                ql[LM2I(l, mm)] = alm * (ct * ql[LM2I(l - 1, mm)] + blm * ql[LM2I(l - 2, mm)]);
+            }
+        }
+    }
+    double* Y = rec + pb_y(m, 0);
+    double* Yx = rec + pb_y(m, 1);
+    double* Yy = rec + pb_y(m, 2);
+    double* Yz = rec + pb_y(m, 3);
+    const double hs2 = 0.70710678118654752440;
+    for (int l = 0; l <= L; ++l) {
+        const int idx = LM2I(l, 0) + l;
+        Y[2 * idx] = pl[LM2I(l, 0)] * hs2; Y[2 * idx + 1] = 0.0;
+        double common = 0.0;
+        if (l >= 1) common = ql[LM2I(l, 1)] * st * rinv * sqrt(0.5 * l * (l + 1));
+        Yx[2 * idx] = common * ct * cp; Yx[2 * idx + 1] = 0.0;
+        Yy[2 * idx] = common * ct * sp; Yy[2 * idx + 1] = 0.0;
+        Yz[2 * idx] = -common * st; Yz[2 * idx + 1] = 0.0;
+    }
+    double c1 = 1.0, c2 = cp, s1 = 0.0, s2 = -sp;
+    const double tc = 2.0 * c2;
+    double sign = -1.0;
+    for (int mp = 1; mp <= L; ++mp) {
+        const double sn = tc * s1 - s2;
+        const double cs = tc * c1 - c2;
+        c2 = c1; c1 = cs; s2 = s1; s1 = sn;
+        for (int l = mp; l <= L; ++l) {
+            const int idx = LM2I(l, -mp) + l;
+            const double tmp = sign * pl[LM2I(l, mp)] * hs2;
+            Y[2 * idx] = tmp * cs; Y[2 * idx + 1] = -tmp * sn;
+            // common = e^{i m phi} / sqrt(2) / r
+            const double cr = cs * hs2 * rinv, ci = sn * hs2 * rinv;
+            double dth = mp * ct * ql[LM2I(l, mp)];
+            if (mp != l) dth += sqrt((double)((l - mp) * (l + mp + 1))) * ql[LM2I(l, mp + 1)] * st;
+            const double dph = mp * ql[LM2I(l, mp)];  // dphi = i * dph
+            // x: common * (dth*ct*cp - i*dph*sp) ; y: common * (dth*ct*sp + i*dph*cp) ; z: -common*dth*st
+            const double ax = dth * ct * cp, bx = -dph * sp;
+            const double ay = dth * ct * sp, by = dph * cp;
+            const double az = -dth * st;
+            // (cr + i ci)(a + i b) = (cr a - ci b) + i (cr b + ci a); result = sign * conj(.)
+            Yx[2 * idx] = sign * (cr * ax - ci * bx); Yx[2 * idx + 1] = -sign * (cr * bx + ci * ax);
+            Yy[2 * idx] = sign * (cr * ay - ci * by); Yy[2 * idx + 1] = -sign * (cr * by + ci * ay);
+            Yz[2 * idx] = sign * (cr * az); Yz[2 * idx + 1] = -sign * (ci * az);
+        }
+        sign = -sign;
+    }
+#undef LM2I
+}
+
+void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
+    if (b.n_pairs == 0) return;
+    k_pair_basis<<<(b.n_pairs + 127) / 128, 128, 0, s>>>(m, b, PB);
+}
+
+// ================================================================================================
+// K2b: a_nlm(i) = sum_j f_n Y_lm for the m <= 0 heads, plus the aggregated derivative rows
+//   own[alpha]  = sum_j v_alpha(ij)            (row of atom i itself)
+//   str[ab]     = -sum_j v_alpha(ij) D_beta    (six virial rows xx,yy,zz,xy,yz,zx)
+// with v_alpha = f_n' Y D_alpha / r + f_n dY/dalpha (local.cpp:175-196).  One CTA per atom, one
+// thread per head; accumulation is thread-private (deterministic).
+// ================================================================================================
+__global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                               double2* __restrict__ anc, double2* __restrict__ agg) {
+    const int i = blockIdx.x;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const bool force = b.force[b.st_of_atom[i]] != 0;
+    const int nt = m.n_type;
+    const int oy = pb_y(m, 0), oyx = pb_y(m, 1), oyy = pb_y(m, 2), oyz = pb_y(m, 3);
+    for (int h = threadIdx.x; h < T.n_head; h += blockDim.x) {
+        const int u = T.head_seg[h], nid = T.head_nid[h], key = T.head_key[h];
+        const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
+        double ar = 0.0, ai = 0.0;
+        double gr[9], gi[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { gr[k] = 0.0; gi[k] = 0.0; }
+        for (int p = p0; p < p1; ++p) {
+            const double* rec = PB + (size_t)p * m.pbstride;
+            const double fn = rec[4 + nid];
+            if (fn == 0.0) continue;
+            const double yr = rec[oy + 2 * key], yi = rec[oy + 2 * key + 1];
+            ar += fn * yr; ai += fn * yi;
+            if (force) {
+                const double dx = rec[0], dy = rec[1], dz = rec[2];
+                const double d1 = rec[4 + m.n_fn + nid] * rec[3];
+                const double d1r = d1 * yr, d1i = d1 * yi;
+                const double vxr = d1r * dx + fn * rec[oyx + 2 * key], vxi = d1i * dx + fn * rec[oyx + 2 * key + 1];
+                const double vyr = d1r * dy + fn * rec[oyy + 2 * key], vyi = d1i * dy + fn * rec[oyy + 2 * key + 1];
+                const double vzr = d1r * dz + fn * rec[oyz + 2 * key], vzi = d1i * dz + fn * rec[oyz + 2 * key + 1];
+                gr[0] += vxr; gi[0] += vxi; gr[1] += vyr; gi[1] += vyi; gr[2] += vzr; gi[2] += vzi;
+                gr[3] -= vxr * dx; gi[3] -= vxi * dx;
+                gr[4] -= vyr * dy; gi[4] -= vyi * dy;
+                gr[5] -= vzr * dz; gi[5] -= vzi * dz;
+                gr[6] -= vxr * dy; gi[6] -= vxi * dy;
+                gr[7] -= vyr * dz; gi[7] -= vyi * dz;
+                gr[8] -= vzr * dx; gi[8] -= vzi * dx;
+            }
+        }
+        anc[(size_t)i * m.hmax + h] = make_double2(ar, ai);
+        if (force) {
+            double2* g = agg + ((size_t)i * m.hmax + h) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[k] = make_double2(gr[k], gi[k]);
+        }
+    }
+}
+
+void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s) {
+    if (b.n_atoms == 0) return;
+    k_anlm<<<b.n_atoms, 128, 0, s>>>(m, b, PB, anc, agg);
+}
+
+// ================================================================================================
+// K3: linear invariants d_f = sum_t c_t Re(prod a) and G[f, head] = d d_f / d a_head written straight
+// into the block-sparse layout consumed by K4a (one 4x8 block = one DMMA B fragment).
+// ================================================================================================
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void __launch_bounds__(256) k_features(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                   double* __restrict__ dfeat, double* __restrict__ Gbuf) {
+    extern __shared__ double2 afull[];
+    const int i = blockIdx.x;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const bool force = b.force[b.st_of_atom[i]] != 0;
+    for (int k = threadIdx.x; k < T.n_full; k += blockDim.x) {
+        double2 v = anc[(size_t)i * m.hmax + T.full_head[k]];
+        if (T.full_conj[k]) {
+            const double cc = T.full_cc[k];
+            v = make_double2(cc * v.x, -cc * v.y);
+        }
+        afull[k] = v;
+    }
+    double* drow = dfeat + (size_t)i * m.fl;
+    for (int k = threadIdx.x; k < m.fl; k += blockDim.x) drow[k] = 0.0;
+    double* G = Gbuf + (size_t)i * m.gstride;
+    if (force)
+        for (long k = threadIdx.x; k < T.g_size; k += blockDim.x) G[k] = 0.0;
+    __syncthreads();
+    const int mo = T.max_order;
+    for (int f = threadIdx.x; f < T.n_feat; f += blockDim.x) {
+        double sum = 0.0;
+        for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti) {
+            const int o = T.term_order[ti];
+            const int* ids = T.term_ids + (size_t)ti * mo;
+            double2 pr = afull[ids[0]];
+            for (int k = 1; k < o; ++k) pr = cmul(pr, afull[ids[k]]);
+            sum += T.term_coeff[ti] * pr.x;
+        }
+        drow[T.feat_pad[f]] = sum;
+    }
+    if (!force) return;
+    for (int e = threadIdx.x; e < T.n_ent; e += blockDim.x) {
+        double gr = 0.0, gi = 0.0;
+        for (int c = T.ent_off[e]; c < T.ent_off[e + 1]; ++c) {
+            const DevContribution& cb = T.contribs[c];
+            double2 pr = make_double2(1.0, 0.0);
+            for (int q = 0; q < cb.n_ids; ++q) pr = cmul(pr, afull[cb.ids[q]]);
+            if (cb.conj) pr.y = -pr.y;
+            gr += cb.coeff * pr.x;
+            gi += cb.coeff * pr.y;
+        }
+        G[T.ent_pos_re[e]] = gr;
+        G[T.ent_pos_im[e]] = -gi;
+    }
+}
+
+void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
+                     size_t smem_bytes, cudaStream_t s) {
+    if (b.n_atoms == 0) return;
+    k_features<<<b.n_atoms, 256, smem_bytes, s>>>(m, b, anc, dfeat, Gbuf);
+}
+
+void set_features_smem(size_t smem_bytes) {
+    cudaFuncSetAttribute(k_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+// ================================================================================================
+// K4a (straightforward): L[(pair, alpha), f] = sum_heads Re(G[f, head] v_alpha,head(pair)), plus the
+// aggregated own/virial rows from K2b.  One CTA per centre atom, one thread per output element.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_lrows_simple(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                       const double2* __restrict__ agg, const double* __restrict__ Gbuf,
+                                                       double* __restrict__ Lbuf, double* __restrict__ Xown,
+                                                       double* __restrict__ Sbuf) {
+    const int i = blockIdx.x;
+    if (!b.force[b.st_of_atom[i]]) return;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const int nt = m.n_type;
+    const double* G = Gbuf + (size_t)i * m.gstride;
+    const int pb = b.seg_off[i * nt], pe = b.seg_off[i * nt + nt];
+    const int np = pe - pb;
+    const int nrows = 3 * np + 9;
+    const int nf = T.n_fpad;
+    const int oy = pb_y(m, 0);
+    for (int idx = threadIdx.x; idx < nrows * nf; idx += blockDim.x) {
+        const int row = idx / nf, fp = idx - row * nf;
+        const int tile = fp >> 3, nn = fp & 7;
+        double acc = 0.0;
+        if (row < 3 * np) {
+            const int pl = row / 3, al = row - 3 * pl;
+            const int p = pb + pl;
+            const int u = b.types[b.nbr[p]];
+            const double* rec = PB + (size_t)p * m.pbstride;
+            const double dal = rec[al] * rec[3];
+            const int oya = pb_y(m, 1 + al);
+            const int* sh = T.seg_heads[u];
+            for (int bk = T.tile_blk_off[u][tile]; bk < T.tile_blk_off[u][tile + 1]; ++bk) {
+                const int kc = T.blk_kchunk[bk];
+                const double* B = G + 32 * (size_t)bk + nn * 4;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h = sh[2 * kc + hh];
+                    if (h < 0) continue;
+                    const int nid = T.head_nid[h], key = T.head_key[h];
+                    const double fn = rec[4 + nid];
+                    if (fn == 0.0) continue;
+                    const double d1 = rec[4 + m.n_fn + nid] * dal;
+                    const double vr = d1 * rec[oy + 2 * key] + fn * rec[oya + 2 * key];
+                    const double vi = d1 * rec[oy + 2 * key + 1] + fn * rec[oya + 2 * key + 1];
+                    acc += vr * B[2 * hh] + vi * B[2 * hh + 1];
+                }
+            }
+            Lbuf[((size_t)p * 3 + al) * m.fl + fp] = acc;
+        } else {
+            const int r = row - 3 * np;
+            for (int u = 0; u < nt; ++u) {
+                const int* sh = T.seg_heads[u];
+                for (int bk = T.tile_blk_off[u][tile]; bk < T.tile_blk_off[u][tile + 1]; ++bk) {
+                    const int kc = T.blk_kchunk[bk];
+                    const double* B = G + 32 * (size_t)bk + nn * 4;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int h = sh[2 * kc + hh];
+                        if (h < 0) continue;
+                        const double2 v = agg[((size_t)i * m.hmax + h) * 9 + r];
+                        acc += v.x * B[2 * hh] + v.y * B[2 * hh + 1];
+                    }
+                }
+            }
+            if (r < 3) Xown[((size_t)i * 3 + r) * m.fl + fp] = acc;
+            else Sbuf[((size_t)i * 6 + (r - 3)) * m.fl + fp] = acc;
+        }
+    }
+}
+
+// ================================================================================================
+// K4b (straightforward): gather over the centres that touch a row, expand the polynomial, apply the
+// row weight, write X-tilde = [w X | w y | 0].
+//   force row (k, alpha): centres = k itself (Lambda = own row) and every neighbour c of k
+//   (Lambda = -L_c[(c -> k), alpha], found through the reverse-pair index).
+// ================================================================================================
+__device__ __forceinline__ double poly_contrib(const DevPolyTerm& tm, const double* __restrict__ d,
+                                               const double* __restrict__ L) {
+    if (tm.order == 1) return L[tm.fp0];
+    if (tm.order == 2) return d[tm.fp1] * L[tm.fp0] + d[tm.fp0] * L[tm.fp1];
+    const double d0 = d[tm.fp0], d1 = d[tm.fp1], d2 = d[tm.fp2];
+    return d1 * d2 * L[tm.fp0] + d0 * d2 * L[tm.fp1] + d0 * d1 * L[tm.fp2];
+}
+
+__device__ __forceinline__ double poly_value(const DevPolyTerm& tm, const double* __restrict__ d) {
+    if (tm.order == 1) return d[tm.fp0];
+    if (tm.order == 2) return d[tm.fp0] * d[tm.fp1];
+    return d[tm.fp0] * d[tm.fp1] * d[tm.fp2];
+}
+
+__global__ void __launch_bounds__(256) k_xrows_force_simple(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                             const double* __restrict__ Lbuf,
+                                                             const double* __restrict__ Xown, double* __restrict__ X,
+                                                             int apply_w) {
+    const int k = blockIdx.x, al = blockIdx.y;
+    const int s = b.st_of_atom[k];
+    if (!b.force[s]) return;
+    const int row = b.frow[s] + 3 * (k - b.atom_off[s]) + al;
+    const double w = apply_w ? b.w[row] : 1.0;
+    const int nt = m.n_type;
+    const int tk = b.types[k];
+    const int p0 = b.seg_off[k * nt], p1 = b.seg_off[k * nt + nt];
+    double* xr = X + (size_t)row * m.fpad;
+    for (int col = threadIdx.x; col < m.n_variables; col += blockDim.x) {
+        double val = 0.0;
+        {
+            const DevPolyTerm tm = m.types[tk].colterm[col];
+            if (tm.order) val += poly_contrib(tm, dfeat + (size_t)k * m.fl, Xown + ((size_t)k * 3 + al) * m.fl);
+        }
+        for (int p = p0; p < p1; ++p) {
+            const int c = b.nbr[p];
+            const DevPolyTerm tm = m.types[b.types[c]].colterm[col];
+            if (tm.order) val -= poly_contrib(tm, dfeat + (size_t)c * m.fl, Lbuf + ((size_t)b.rev[p] * 3 + al) * m.fl);
+        }
+        xr[col] = w * val;
+    }
+    if (threadIdx.x == 0) xr[m.n_variables] = apply_w ? b.yv[row] : 0.0;
+}
+
+// energy row (r = 0) and the six virial rows (r = 1..6) of each structure
+__global__ void __launch_bounds__(256) k_xrows_struct_simple(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                              const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                              double* __restrict__ xe_sum, double* __restrict__ xe_sq,
+                                                              int apply_w) {
+    const int s = blockIdx.x, r = blockIdx.y;
+    if (r > 0 && !b.force[s]) return;
+    const int row = r == 0 ? b.erow[s] : b.srow[s] + r - 1;
+    const double w = apply_w ? b.w[row] : 1.0;
+    const int a0 = b.atom_off[s], a1 = b.atom_off[s + 1];
+    double* xr = X + (size_t)row * m.fpad;
+    for (int col = threadIdx.x; col < m.n_variables; col += blockDim.x) {
+        double val = 0.0;
+        for (int a = a0; a < a1; ++a) {
+            const DevPolyTerm tm = m.types[b.types[a]].colterm[col];
+            if (!tm.order) continue;
+            if (r == 0) val += poly_value(tm, dfeat + (size_t)a * m.fl);
+            else val += poly_contrib(tm, dfeat + (size_t)a * m.fl, Sbuf + ((size_t)a * 6 + (r - 1)) * m.fl);
+        }
+        if (r == 0 && xe_sum) {
+            atomicAdd(xe_sum + col, val);
+            atomicAdd(xe_sq + col, val * val);
+        }
+        xr[col] = w * val;
+    }
+    if (threadIdx.x == 0) xr[m.n_variables] = apply_w ? b.yv[row] : 0.0;
+}
+
+// ================================================================================================
+// K5 (straightforward): C[i,j] += sum_r Xt[r,i] Xt[r,j] for upper 64x64 tiles, DFMA, 4x4 per thread.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_syrk_simple(const double* __restrict__ X, int n_rows, int fpad,
+                                                      double* __restrict__ C) {
+    const int nt = fpad / 64;
+    // map blockIdx.x -> (ti <= tj)
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+    const int tj = ti + rem;
+    __shared__ double sa[16][64 + 4];
+    __shared__ double sb[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    for (int r0 = 0; r0 < n_rows; r0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int rr = e >> 6, cc = e & 63;
+            const int r = r0 + rr;
+            sa[rr][cc] = r < n_rows ? X[(size_t)r * fpad + ti * 64 + cc] : 0.0;
+            sb[rr][cc] = r < n_rows ? X[(size_t)r * fpad + tj * 64 + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { av[a] = sa[rr][ty * 4 + a]; bv[a] = sb[rr][tx * 4 + a]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] += av[a] * bv[c];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            C[(size_t)(ti * 64 + ty * 4 + a) * fpad + tj * 64 + tx * 4 + c] += acc[a][c];
+}
+
+// ================================================================================================
+// eval: E/F/S with trained coefficients (PolymlpEval::eval_gtinv, compute/polymlp_eval.cpp:182-335).
+// Adjoint form: per atom E_i and w_f = dE_i/dd_f from the polynomial, then the head adjoint
+// Ah[k] = sum_f G[k, f] w_f, then one pass over the pairs: f_alpha(pair) = sum_k V[(pair,alpha),k] Ah[k].
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_eval_atom(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                    const double* __restrict__ Gbuf, const double* __restrict__ coeffs,
+                                                    double* __restrict__ wbuf, double* __restrict__ Ah,
+                                                    int ah_stride, double* __restrict__ energies) {
+    // wbuf: [n_atoms][fl] scratch (reuses Xown); Ah: [n_atoms][ah_stride] with per-segment offsets u * (ah_stride / nt)
+    const int i = blockIdx.x;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const double* d = dfeat + (size_t)i * m.fl;
+    double* w = wbuf + (size_t)i * m.fl;
+    for (int k = threadIdx.x; k < m.fl; k += blockDim.x) w[k] = 0.0;
+    __syncthreads();
+    double e = 0.0;
+    for (int col = threadIdx.x; col < m.n_variables; col += blockDim.x) {
+        const DevPolyTerm tm = T.colterm[col];
+        if (!tm.order) continue;
+        const double c = coeffs[col];
+        if (tm.order == 1) {
+            e += c * d[tm.fp0];
+            atomicAdd(w + tm.fp0, c);
+        } else if (tm.order == 2) {
+            e += c * d[tm.fp0] * d[tm.fp1];
+            atomicAdd(w + tm.fp0, c * d[tm.fp1]);
+            atomicAdd(w + tm.fp1, c * d[tm.fp0]);
+        } else {
+            const double d0 = d[tm.fp0], d1 = d[tm.fp1], d2 = d[tm.fp2];
+            e += c * d0 * d1 * d2;
+            atomicAdd(w + tm.fp0, c * d1 * d2);
+            atomicAdd(w + tm.fp1, c * d0 * d2);
+            atomicAdd(w + tm.fp2, c * d0 * d1);
+        }
+    }
+    // block reduce e
+    __shared__ double red[256];
+    red[threadIdx.x] = e;
+    __syncthreads();
+    for (int sft = 128; sft > 0; sft >>= 1) {
+        if (threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(energies + b.st_of_atom[i], red[0]);
+    // head adjoint
+    const int segstride = ah_stride / m.n_type;
+    double* ah = Ah + (size_t)i * ah_stride;
+    for (int k = threadIdx.x; k < ah_stride; k += blockDim.x) ah[k] = 0.0;
+    __syncthreads();
+    const double* G = Gbuf + (size_t)i * m.gstride;
+    // one thread per (block, k in 0..3)
+    for (int idx = threadIdx.x; idx < T.n_blocks * 4; idx += blockDim.x) {
+        const int bk = idx >> 2, k = idx & 3;
+        // find segment and tile of the block: stored implicitly through tile_blk_off; search segments
+        int u = 0;
+        while (u + 1 < m.n_type && bk >= T.tile_blk_off[u + 1][0]) ++u;
+        // binary search tile
+        int lo = 0, hi = T.n_tiles;
+        const int* off = T.tile_blk_off[u];
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= bk) lo = mid; else hi = mid; }
+        const int tile = lo;
+        double sum = 0.0;
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) sum += G[32 * (size_t)bk + nn * 4 + k] * w[tile * 8 + nn];
+        atomicAdd(ah + u * segstride + 4 * T.blk_kchunk[bk] + k, sum);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_eval_pairs(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                     const double* __restrict__ Ah, int ah_stride,
+                                                     double* __restrict__ forces, double* __restrict__ stresses) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b.n_pairs * 3) return;
+    const int p = idx / 3, al = idx - 3 * p;
+    const int i = b.centre[p], j = b.nbr[p];
+    const DevType& T = m.types[b.types[i]];
+    const int u = b.types[j];
+    const int segstride = ah_stride / m.n_type;
+    const double* ah = Ah + (size_t)i * ah_stride + u * segstride;
+    const double* rec = PB + (size_t)p * m.pbstride;
+    const double dal = rec[al] * rec[3];
+    const int oy = pb_y(m, 0), oya = pb_y(m, 1 + al);
+    const int* sh = T.seg_heads[u];
+    double g = 0.0;
+    for (int q = 0; q < T.seg_len[u]; ++q) {
+        const int h = sh[q];
+        if (h < 0) continue;
+        const int nid = T.head_nid[h], key = T.head_key[h];
+        const double fn = rec[4 + nid];
+        if (fn == 0.0) continue;
+        const double d1 = rec[4 + m.n_fn + nid] * dal;
+        const double vr = d1 * rec[oy + 2 * key] + fn * rec[oya + 2 * key];
+        const double vi = d1 * rec[oy + 2 * key + 1] + fn * rec[oya + 2 * key + 1];
+        g += vr * ah[2 * q] + vi * ah[2 * q + 1];
+    }
+    // X force rows: +g on the centre, -g on the neighbour; virial rows: -g_alpha * D_beta
+    atomicAdd(forces + (size_t)i * 3 + al, g);
+    atomicAdd(forces + (size_t)j * 3 + al, -g);
+    const int s = b.st_of_atom[i];
+    double* S = stresses + (size_t)s * 6;
+    // (alpha,beta) pairs: xx(0) yy(1) zz(2) xy(3) yz(4) zx(5)
+    atomicAdd(S + al, -g * rec[al]);
+    const int be = (al + 1) % 3;
+    atomicAdd(S + 3 + al, -g * rec[be]);
+}
+
+void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
+                         double* energies, double* forces, double* stresses, cudaStream_t s) {
+    if (b.n_atoms == 0) return;
+    int maxseg = 0;
+    for (int t = 0; t < m.n_type; ++t)
+        for (int u = 0; u < m.n_type; ++u) maxseg = max(maxseg, m.types[t].seg_len[u]);
+    const int ah_stride = m.n_type * 2 * maxseg;
+    k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
+    if (b.n_pairs > 0)
+        k_eval_pairs<<<(b.n_pairs * 3 + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
+}
+
+// ================================================================================================
+// launch wrappers with simple / tensor-core dispatch
+// ================================================================================================
+void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s);
+void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
+                      bool apply_weights, cudaStream_t s);
+void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s);
+
+void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, cudaStream_t s) {
+    if (b.n_atoms == 0) return;
+    if (simple) k_lrows_simple<<<b.n_atoms, 256, 0, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
+    else launch_lrows_mma(m, b, ws, s);
+}
+
+void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
+                  bool simple, bool apply_weights, cudaStream_t s) {
+    if (b.n_atoms == 0) return;
+    if (simple) {
+        k_xrows_force_simple<<<dim3(b.n_atoms, 3), 256, 0, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
+        k_xrows_struct_simple<<<dim3(b.n_st, 7), 256, 0, s>>>(m, b, ws.dfeat, ws.Sbuf, ws.X, xe_sum, xe_sq, apply_weights ? 1 : 0);
+    } else {
+        launch_xrows_mma(m, b, ws, xe_sum, xe_sq, apply_weights, s);
+    }
+}
+
+void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s) {
+    if (n_rows == 0) return;
+    if (simple) {
+        const int nt = fpad / 64;
+        k_syrk_simple<<<nt * (nt + 1) / 2, 256, 0, s>>>(X, n_rows, fpad, C);
+    } else {
+        launch_syrk_mma(X, n_rows, fpad, C, s);
+    }
+}
+
+}  // namespace pm

@@ -1,0 +1,47 @@
+// pm_kernels.cuh -- launch wrappers of the sm_100a kernels (definitions in pm_kernels*.cu).
+#pragma once
+#include "pm_device.cuh"
+
+namespace pm {
+
+struct Workspace {
+    // per chunk scratch (device)
+    int* counts = nullptr;      // [n_atoms * n_type]
+    double* PB = nullptr;       // [n_pairs][pbstride]
+    double2* anc = nullptr;     // [n_atoms][hmax]
+    double2* agg = nullptr;     // [n_atoms][hmax][9]
+    double* dfeat = nullptr;    // [n_atoms][fl]
+    double* Gbuf = nullptr;     // [n_atoms][gstride]
+    double* Lbuf = nullptr;     // [n_pairs * 3][fl]
+    double* Xown = nullptr;     // [n_atoms][3][fl]
+    double* Sbuf = nullptr;     // [n_atoms][6][fl]
+    double* X = nullptr;        // [n_rows][fpad]
+    double* Ah = nullptr;       // [n_atoms][ah_stride] head adjoints (eval)
+    int* errflag = nullptr;     // device error flag
+};
+
+// K1: neighbour list
+void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s);
+void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
+void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB, int* errflag, cudaStream_t s);
+// K2: pair basis + order parameters
+void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
+void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s);
+// K3: invariants and G = d feature / d head
+void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
+                     size_t smem_bytes, cudaStream_t s);
+// K4a: per-centre derivative rows L = V . G
+void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, cudaStream_t s);
+// K4b: gather + polynomial expansion -> weighted X-tilde rows
+void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
+                  bool simple, bool apply_weights, cudaStream_t s);
+// K5: C += Xt^T Xt (upper tiles)
+void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s);
+int syrk_launches(int n_rows, int fpad, bool simple);
+// eval: E/F/S through contraction with coefficients
+void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
+                         double* energies, double* forces, double* stresses, cudaStream_t s);
+// micro-benchmarks (TFLOP/s)
+double microbench_fp64(int which, cudaStream_t s);
+
+}  // namespace pm

@@ -1,0 +1,630 @@
+// pm_kernels_mma.cu -- FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) kernels for sm_100a.
+//
+// tcgen05/UMMA has no f64 kind, so on B200 the FP64 matrix path is the legacy warp-level
+// mma.sync.aligned.m8n8k4.row.col.f64 (SASS: DMMA.8x8x4).  Fragment layout (PTX ISA):
+//   a  = A[row = lane>>2][k   = lane&3]          (8 x 4, row-major)
+//   b  = B[k   = lane&3 ][col = lane>>2]         (4 x 8, col-major)
+//   c0,c1 = C[row = lane>>2][col = 2*(lane&3) + {0,1}]
+// Shared-memory operand tiles are stored [k][m] with a row stride == 4 (mod 16) doubles so that the
+// 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.
+//
+//   k_syrk_mma    K5   C += Xt^T Xt, 128x128 upper tiles, cp.async 4-stage pipeline, split-K + RED.F64
+//   k_lrows_mma   K4a  L = V . G : V tile built in shared memory from the pair-basis records,
+//                      G read as ready-made B fragments from the block-sparse buffer (L1/L2)
+//   k_xrows_mma   K4b  gather GEMM C[a,b] = sum_centres d_a Lambda_b, then X = C + C^T per polynomial term
+#include "pm_kernels.cuh"
+
+#include <cstdio>
+#include <cublas_v2.h>
+
+namespace pm {
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ================================================================================================
+// K5: SYRK.  grid = (upper tiles, k-splits).  8 warps as 2 (M) x 4 (N), warp tile 64 x 32.
+// ================================================================================================
+constexpr int SY_BM = 128, SY_BK = 16, SY_STAGES = 4, SY_LD = SY_BM + 4;  // 132 == 4 (mod 16)
+constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LD;
+constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) k_syrk_mma(const double* __restrict__ X, int n_rows, int fpad,
+                                                      double* __restrict__ C, int rows_per_split, int use_atomic) {
+    extern __shared__ __align__(16) double smem[];
+    const int ntile = fpad / SY_BM;
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
+    const int tj = ti + rem;
+    const bool diag = ti == tj;
+    const int r_begin = blockIdx.y * rows_per_split;
+    const int r_end = min(n_rows, r_begin + rows_per_split);
+    if (r_begin >= r_end) return;
+    const int nk = (r_end - r_begin + SY_BK - 1) / SY_BK;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, q = lane & 3;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+    // loader: per stage 2 tiles x 16 rows x 128 cols = 2 x 1024 16-byte chunks; 256 threads -> 4 + 4 each
+    auto load_stage = [&](int kt, int slot) {
+        double* sA = smem + (size_t)slot * SY_STAGE_DOUBLES;
+        double* sB = sA + SY_BK * SY_LD;
+        const int r0 = r_begin + kt * SY_BK;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int e = tid + it * 256;       // 0..1023
+            const int rr = e >> 6, cc = (e & 63) * 2;
+            const int r = r0 + rr;
+            const bool ok = r < r_end;
+            const double* src = X + (size_t)(ok ? r : r_begin) * fpad;
+            cp_async16(sA + rr * SY_LD + cc, src + ti * SY_BM + cc, ok ? 16 : 0);
+            if (!diag) cp_async16(sB + rr * SY_LD + cc, src + tj * SY_BM + cc, ok ? 16 : 0);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < SY_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<SY_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nx = kt + SY_STAGES - 1;
+            if (nx < nk) load_stage(nx, nx % SY_STAGES);
+            cp_async_commit();
+        }
+        const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
+        const double* sB = diag ? sA : sA + SY_BK * SY_LD;
+        const double* pa = sA + q * SY_LD + wm * 64 + g;
+        const double* pb = sB + q * SY_LD + wn * 32 + g;
+#pragma unroll
+        for (int ks = 0; ks < SY_BK / 4; ++ks) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = ti * SY_BM + wm * 64 + a * 8 + g;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int col = tj * SY_BM + wn * 32 + b * 8 + 2 * q;
+            double* dst = C + (size_t)row * fpad + col;
+            if (use_atomic) {
+                atomicAdd(dst, acc[a][b][0]);
+                atomicAdd(dst + 1, acc[a][b][1]);
+            } else {
+                double2 v = *reinterpret_cast<double2*>(dst);
+                v.x += acc[a][b][0];
+                v.y += acc[a][b][1];
+                *reinterpret_cast<double2*>(dst) = v;
+            }
+        }
+    }
+}
+
+static int syrk_splits(int n_rows, int fpad) {
+    const int ntile = fpad / SY_BM;
+    const int tiles = ntile * (ntile + 1) / 2;
+    int ks = (6 * 148 + tiles - 1) / tiles;            // ~6 waves of CTAs
+    const int max_ks = (n_rows + 255) / 256;           // at least 256 rows per split
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    return ks;
+}
+
+void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_syrk_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
+        attr = true;
+    }
+    const int ntile = fpad / SY_BM;
+    const int tiles = ntile * (ntile + 1) / 2;
+    const int ks = syrk_splits(n_rows, fpad);
+    int rps = (n_rows + ks - 1) / ks;
+    rps = (rps + SY_BK - 1) / SY_BK * SY_BK;
+    const int nsplit = (n_rows + rps - 1) / rps;
+    k_syrk_mma<<<dim3(tiles, nsplit), 256, SY_SMEM, s>>>(X, n_rows, fpad, C, rps, nsplit > 1 ? 1 : 0);
+}
+
+int syrk_launches(int n_rows, int fpad, bool simple) { return n_rows > 0 ? 1 : 0; }
+
+// ================================================================================================
+// K4a: L = V . G per centre atom (see pm_tables.hpp for the block-sparse layout of G).
+// One CTA (4 warps) per centre atom.  Rows = (pair, alpha) of one neighbour-type segment, processed in
+// chunks of 32 rows; each warp owns the radial groups n = warp, warp+4, ... : it builds the V tile of
+// that radial group ([2*heads][32 rows]) in its private shared memory and multiplies it with the
+// feature tiles of the same radial index.  The 9 aggregated rows (own x/y/z + 6 virial) are one extra
+// 16-row chunk fed from the K2b sums.
+// ================================================================================================
+constexpr int LR_ROWS = 32;
+constexpr int LR_LD = 36;         // == 4 (mod 16)
+constexpr int LR_MAXPAIR = 12;    // pairs touched by 32 consecutive (pair, alpha) rows
+constexpr int LR_PLD = 13;        // odd stride of the transposed pair-basis tile
+
+__global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                    const double2* __restrict__ agg, const double* __restrict__ Gbuf,
+                                                    double* __restrict__ Lbuf, double* __restrict__ Xown,
+                                                    double* __restrict__ Sbuf, int kmax) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = blockIdx.x;
+    if (!b.force[b.st_of_atom[i]]) return;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const int nt = m.n_type;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* pbs = smem;                                        // [pbstride][LR_PLD]
+    double* Vw = smem + (size_t)m.pbstride * LR_PLD + (size_t)warp * kmax * LR_LD;  // [kmax][LR_LD]
+    const double* G = Gbuf + (size_t)i * m.gstride;
+    const int oy = pb_y(m, 0);
+    // the aggregated rows are accumulated over the neighbour-type segments: start from zero
+    for (int e = tid; e < 3 * m.fl; e += 128) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
+    for (int e = tid; e < 6 * m.fl; e += 128) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
+
+    for (int u = 0; u < nt; ++u) {
+        const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
+        const int nrow = 3 * (p1 - p0);
+        const int* skey = T.seg_key[u];
+        const int* snoff = T.seg_n_off[u];
+        const int* snid = T.seg_nid[u];
+        const int* tboff = T.tile_blk_off[u];
+        for (int row0 = 0; row0 < nrow; row0 += LR_ROWS) {
+            const int pair0 = row0 / 3;
+            const int pair1 = min(p1 - p0, (row0 + LR_ROWS - 1) / 3 + 1);
+            const int npc = pair1 - pair0;
+            __syncthreads();  // previous chunk fully consumed
+            {   // transposed copy of the pair-basis records of this chunk
+                const double* src = PB + (size_t)(p0 + pair0) * m.pbstride;
+                const int tot = npc * m.pbstride;
+                for (int e = tid; e < tot; e += 128) {
+                    const int pp = e / m.pbstride, it = e - pp * m.pbstride;
+                    pbs[it * LR_PLD + pp] = src[e];
+                }
+            }
+            __syncthreads();
+            const int row = row0 + lane;
+            const bool valid = row < nrow;
+            const int pl = valid ? row / 3 - pair0 : 0;
+            const int al = valid ? row % 3 : 0;
+            const double dal = valid ? pbs[al * LR_PLD + pl] * pbs[3 * LR_PLD + pl] : 0.0;
+            const int oya = pb_y(m, 1 + al);
+            for (int n = warp; n < m.n_fn; n += 4) {
+                const int h0 = snoff[n], h1 = snoff[n + 1];
+                if (h1 == h0) {  // radial index inactive for this type pair: rows are exactly zero
+                    for (int tile = T.tile_n_off[n]; tile < T.tile_n_off[n + 1]; ++tile)
+#pragma unroll
+                        for (int rt = 0; rt < 4; ++rt) {
+                            const int r = row0 + rt * 8 + g;
+                            if (r < nrow)
+                                *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q) =
+                                    make_double2(0.0, 0.0);
+                        }
+                    continue;
+                }
+                const int nid = snid[n];
+                const double fn = valid ? pbs[(4 + nid) * LR_PLD + pl] : 0.0;
+                const double c1 = valid ? pbs[(4 + m.n_fn + nid) * LR_PLD + pl] * dal : 0.0;
+                __syncwarp();
+                for (int hq = h0; hq < h1; ++hq) {
+                    const int key = skey[hq];
+                    double vr = 0.0, vi = 0.0;
+                    if (key >= 0) {
+                        vr = c1 * pbs[(oy + 2 * key) * LR_PLD + pl] + fn * pbs[(oya + 2 * key) * LR_PLD + pl];
+                        vi = c1 * pbs[(oy + 2 * key + 1) * LR_PLD + pl] + fn * pbs[(oya + 2 * key + 1) * LR_PLD + pl];
+                    }
+                    Vw[(2 * (hq - h0)) * LR_LD + lane] = vr;
+                    Vw[(2 * (hq - h0) + 1) * LR_LD + lane] = vi;
+                }
+                __syncwarp();
+                const int kc0 = h0 >> 1;
+                for (int tile = T.tile_n_off[n]; tile < T.tile_n_off[n + 1]; ++tile) {
+                    double acc[4][2];
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) { acc[rt][0] = 0.0; acc[rt][1] = 0.0; }
+                    for (int bk = tboff[tile]; bk < tboff[tile + 1]; ++bk) {
+                        const int kcl = T.blk_kchunk[bk] - kc0;
+                        const double bf = G[32 * (size_t)bk + lane];
+                        const double* va = Vw + (4 * kcl + q) * LR_LD + g;
+#pragma unroll
+                        for (int rt = 0; rt < 4; ++rt) dmma(acc[rt][0], acc[rt][1], va[rt * 8], bf);
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) {
+                        const int r = row0 + rt * 8 + g;
+                        if (r < nrow) {
+                            double* dst = Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q;
+                            *reinterpret_cast<double2*>(dst) = make_double2(acc[rt][0], acc[rt][1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // aggregated rows: r = 0..2 own, 3..8 virial (rows 9..15 of the tile are zero)
+    __syncthreads();
+    for (int u = 0; u < nt; ++u) {
+        const int* sh = T.seg_heads[u];
+        const int* snoff = T.seg_n_off[u];
+        const int* tboff = T.tile_blk_off[u];
+        for (int n = warp; n < m.n_fn; n += 4) {
+            const int h0 = snoff[n], h1 = snoff[n + 1];
+            if (h1 == h0) continue;
+            __syncwarp();
+            for (int e = lane; e < (h1 - h0) * 16; e += 32) {
+                const int hq = h0 + (e >> 4), r = e & 15;
+                const int h = sh[hq];
+                double2 v = make_double2(0.0, 0.0);
+                if (h >= 0 && r < 9) v = agg[((size_t)i * m.hmax + h) * 9 + r];
+                Vw[(2 * (hq - h0)) * LR_LD + r] = v.x;
+                Vw[(2 * (hq - h0) + 1) * LR_LD + r] = v.y;
+            }
+            __syncwarp();
+            const int kc0 = h0 >> 1;
+            for (int tile = T.tile_n_off[n]; tile < T.tile_n_off[n + 1]; ++tile) {
+                double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                for (int bk = tboff[tile]; bk < tboff[tile + 1]; ++bk) {
+                    const int kcl = T.blk_kchunk[bk] - kc0;
+                    const double bf = G[32 * (size_t)bk + lane];
+                    const double* va = Vw + (4 * kcl + q) * LR_LD + g;
+                    dmma(acc[0][0], acc[0][1], va[0], bf);
+                    dmma(acc[1][0], acc[1][1], va[8], bf);
+                }
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt) {
+                    const int r = rt * 8 + g;
+                    if (r < 9) {
+                        double* dst = (r < 3 ? Xown + ((size_t)i * 3 + r) * m.fl : Sbuf + ((size_t)i * 6 + (r - 3)) * m.fl) +
+                                      tile * 8 + 2 * q;
+                        double2 v = *reinterpret_cast<double2*>(dst);
+                        v.x += acc[rt][0]; v.y += acc[rt][1];
+                        *reinterpret_cast<double2*>(dst) = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// set by the context at model upload (max over types/segments/radial groups of 2 * padded heads)
+static int g_lrows_kmax = 0;
+void set_lrows_kmax(int kmax) { g_lrows_kmax = kmax; }
+size_t lrows_mma_smem(const DevModel& m) {
+    return ((size_t)m.pbstride * LR_PLD + 4ull * g_lrows_kmax * LR_LD) * sizeof(double);
+}
+
+void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    const size_t smem = lrows_mma_smem(m);
+    static size_t set_for = 0;
+    if (set_for != smem) {
+        cudaFuncSetAttribute(k_lrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set_for = smem;
+    }
+    k_lrows_mma<<<b.n_atoms, 128, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf, g_lrows_kmax);
+}
+
+// ================================================================================================
+// K4b: gather GEMM + polynomial expansion.
+//   mode 0: blockIdx.x = row atom k, three force rows (alpha = 0..2);
+//           centres = k (Lambda = own row) and its neighbours (Lambda = -L[reverse pair]).
+//   mode 1: blockIdx.x = structure, blockIdx.y = r: r = 0 energy row (Lambda = d/2 for the pair terms,
+//           d for the linear ones), r = 1..6 virial rows (Lambda = per-atom virial sums).
+// C[a][b] = sum_c D[a][c] Lambda[c][b] over the polynomial variables (DMMA), then for each order-2 term
+// (col, a, b): X[row][col] = w (C[a][b] + C[b][a]).  Linear columns are plain gathers.
+// 8 warps as 2 (M) x 4 (N) over a 64 x 64 C tile; polynomial variables beyond 64 loop over tiles.
+// ================================================================================================
+constexpr int XR_KC = 64;              // centres per K chunk
+constexpr int XR_LD = 68;              // == 4 (mod 16)
+constexpr int XR_T = 64;               // tile of polynomial variables
+
+__global__ void __launch_bounds__(256) k_xrows_mma(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                    const double* __restrict__ Lbuf, const double* __restrict__ Xown,
+                                                    const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                    double* __restrict__ xe_sum, double* __restrict__ xe_sq,
+                                                    int mode, int apply_w) {
+    extern __shared__ __align__(16) double smem[];
+    double* sD = smem;                            // [XR_KC][XR_LD]  D[c][a]  (a-tile)
+    double* sL = sD + XR_KC * XR_LD;              // [XR_KC][XR_LD]  Lambda[c][b] (b-tile)
+    double* sC = sL + XR_KC * XR_LD;              // [npv_pad][npv_pad + 1]
+    int* sCent = reinterpret_cast<int*>(sC + (size_t)m.npv_pad * (m.npv_pad + 1));  // [XR_KC] centre atom
+    int* sSrc = sCent + XR_KC;                                                      // [XR_KC] Lambda row index
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+    const int nt = m.n_type;
+    const int ldc = m.npv_pad + 1;
+
+    int s, n_cent, n_al, k_atom = 0, r_struct = 0, a0 = 0, p0 = 0;
+    if (mode == 0) {
+        k_atom = blockIdx.x;
+        s = b.st_of_atom[k_atom];
+        if (!b.force[s]) return;
+        p0 = b.seg_off[k_atom * nt];
+        n_cent = 1 + b.seg_off[k_atom * nt + nt] - p0;
+        n_al = 3;
+    } else {
+        s = blockIdx.x;
+        r_struct = blockIdx.y;
+        if (r_struct > 0 && !b.force[s]) return;
+        a0 = b.atom_off[s];
+        n_cent = b.atom_off[s + 1] - a0;
+        n_al = 1;
+    }
+
+    for (int al = 0; al < n_al; ++al) {
+        int row;
+        if (mode == 0) row = b.frow[s] + 3 * (k_atom - b.atom_off[s]) + al;
+        else row = r_struct == 0 ? b.erow[s] : b.srow[s] + r_struct - 1;
+        const double w = apply_w ? b.w[row] : 1.0;
+        double* xr = X + (size_t)row * m.fpad;
+
+        // ---- linear columns: one thread per global linear feature -------------------------------
+        for (int col = tid; col < m.n_linear; col += 256) {
+            double val = 0.0;
+            for (int c = 0; c < n_cent; ++c) {
+                int atom; const double* lam; double sgn = 1.0;
+                if (mode == 0) {
+                    if (c == 0) { atom = k_atom; lam = Xown + ((size_t)k_atom * 3 + al) * m.fl; }
+                    else { const int p = p0 + c - 1; atom = b.nbr[p]; lam = Lbuf + ((size_t)b.rev[p] * 3 + al) * m.fl; sgn = -1.0; }
+                } else {
+                    atom = a0 + c;
+                    lam = r_struct == 0 ? dfeat + (size_t)atom * m.fl : Sbuf + ((size_t)atom * 6 + (r_struct - 1)) * m.fl;
+                }
+                const DevPolyTerm tm = m.types[b.types[atom]].colterm[col];
+                if (tm.order) val += sgn * lam[tm.fp0];
+            }
+            if (mode == 1 && r_struct == 0 && xe_sum) { atomicAdd(xe_sum + col, val); atomicAdd(xe_sq + col, val * val); }
+            xr[col] = w * val;
+        }
+        if (m.n_pair_terms == 0) {
+            if (tid == 0) xr[m.n_variables] = apply_w ? b.yv[row] : 0.0;
+            continue;
+        }
+
+        // ---- C = D . Lambda over tiles of polynomial variables ---------------------------------------
+        for (int ta = 0; ta < m.npv_pad; ta += XR_T)
+            for (int tb = 0; tb < m.npv_pad; tb += XR_T) {
+                double acc[4][2][2];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) { acc[x][y][0] = 0.0; acc[x][y][1] = 0.0; }
+                for (int c0 = 0; c0 < n_cent; c0 += XR_KC) {
+                    __syncthreads();
+                    if (tid < XR_KC) {
+                        const int c = c0 + tid;
+                        int atom = -1, src = -1;
+                        if (c < n_cent) {
+                            if (mode == 0) {
+                                if (c == 0) { atom = k_atom; src = -1; }
+                                else { const int p = p0 + c - 1; atom = b.nbr[p]; src = b.rev[p]; }
+                            } else atom = a0 + c;
+                        }
+                        sCent[tid] = atom;
+                        sSrc[tid] = src;
+                    }
+                    __syncthreads();
+                    for (int e = tid; e < XR_KC * XR_T; e += 256) {
+                        const int cc = e >> 6, a = e & 63;
+                        const int atom = sCent[cc];
+                        double dv = 0.0, lv = 0.0;
+                        if (atom >= 0) {
+                            const int* pvf = m.pv_fp + (size_t)b.types[atom] * m.npv_pad;
+                            const int fa = (ta + a) < m.npv_pad ? pvf[ta + a] : -1;
+                            const int fb = (tb + a) < m.npv_pad ? pvf[tb + a] : -1;
+                            if (fa >= 0) dv = dfeat[(size_t)atom * m.fl + fa];
+                            if (fb >= 0) {
+                                if (mode == 0) {
+                                    if (sSrc[cc] < 0) lv = Xown[((size_t)atom * 3 + al) * m.fl + fb];
+                                    else lv = -Lbuf[((size_t)sSrc[cc] * 3 + al) * m.fl + fb];
+                                } else {
+                                    lv = r_struct == 0 ? 0.5 * dfeat[(size_t)atom * m.fl + fb]
+                                                       : Sbuf[((size_t)atom * 6 + (r_struct - 1)) * m.fl + fb];
+                                }
+                            }
+                        }
+                        sD[cc * XR_LD + a] = dv;
+                        sL[cc * XR_LD + a] = lv;
+                    }
+                    __syncthreads();
+                    const int kend = min(XR_KC, (n_cent - c0 + 3) & ~3);
+                    for (int k0 = 0; k0 < kend; k0 += 4) {
+                        double af[4], bf[2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) af[x] = sD[(k0 + q) * XR_LD + wm * 32 + x * 8 + g];
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) bf[y] = sL[(k0 + q) * XR_LD + wn * 16 + y * 8 + g];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 2; ++y) dmma(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) {
+                        const int ra = ta + wm * 32 + x * 8 + g, cb = tb + wn * 16 + y * 8 + 2 * q;
+                        if (ra < m.npv_pad && cb < m.npv_pad) {
+                            sC[ra * ldc + cb] = acc[x][y][0];
+                            sC[ra * ldc + cb + 1] = acc[x][y][1];
+                        }
+                    }
+            }
+        __syncthreads();
+        // ---- order-2 polynomial columns -----------------------------------------------------------
+        for (int e = tid; e < m.n_pair_terms; e += 256) {
+            const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
+            const double val = sC[a * ldc + bb] + sC[bb * ldc + a];
+            if (mode == 1 && r_struct == 0 && xe_sum) { atomicAdd(xe_sum + col, val); atomicAdd(xe_sq + col, val * val); }
+            xr[col] = w * val;
+        }
+        if (tid == 0) xr[m.n_variables] = apply_w ? b.yv[row] : 0.0;
+        __syncthreads();
+    }
+}
+
+size_t xrows_mma_smem(const DevModel& m) {
+    return (2ull * XR_KC * XR_LD + (size_t)m.npv_pad * (m.npv_pad + 1)) * sizeof(double) + 2 * XR_KC * sizeof(int);
+}
+
+void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
+                      bool apply_weights, cudaStream_t s) {
+    const size_t smem = xrows_mma_smem(m);
+    static size_t set_for = 0;
+    if (set_for != smem) {
+        cudaFuncSetAttribute(k_xrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set_for = smem;
+    }
+    k_xrows_mma<<<b.n_atoms, 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
+                                             apply_weights ? 1 : 0);
+    k_xrows_mma<<<dim3(b.n_st, 7), 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
+                                                   apply_weights ? 1 : 0);
+}
+
+// ================================================================================================
+// micro-benchmarks: register-resident FP64 issue-rate probes (the roofline denominators)
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_bench_dfma(double* out, int iters) {
+    double a[16];
+    const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-12;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_bench_dmma(double* out, int iters) {
+    double c[8][2];
+    const double a = 1.0 + 1e-9 * threadIdx.x, bb = 1e-3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k][0] = k; c[k][1] = -k; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dmma(c[k][0], c[k][1], a, bb);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_bench_mixed(double* out, int iters) {
+    double c[4][2], f[8];
+    const double a = 1.0 + 1e-9 * threadIdx.x, bb = 1e-3, y = 1e-12;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k][0] = k; c[k][1] = -k; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dmma(c[k][0], c[k][1], a, bb);
+            f[2 * k] = fma(f[2 * k], a, y);
+            f[2 * k + 1] = fma(f[2 * k + 1], a, y);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += c[k][0] + c[k][1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k];
+    if (s == 123.456) out[0] = s;
+}
+
+double microbench_fp64(int which, cudaStream_t s) {
+    double* out = nullptr;
+    cudaMalloc(&out, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    double flops = 0.0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, s);
+        if (which == 0) {
+            k_bench_dfma<<<blocks, threads, 0, s>>>(out, iters);
+            flops = (double)blocks * threads * iters * 16 * 2;
+        } else if (which == 1) {
+            k_bench_dmma<<<blocks, threads, 0, s>>>(out, iters);
+            flops = (double)blocks * (threads / 32) * iters * 8 * 512.0;
+        } else {
+            k_bench_mixed<<<blocks, threads, 0, s>>>(out, iters);
+            flops = (double)blocks * (threads / 32) * iters * 4 * 512.0 + (double)blocks * threads * iters * 8 * 2;
+        }
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return flops / (best * 1e-3) * 1e-12;
+}
+
+double microbench_dgemm(int n, cudaStream_t s) {
+    cublasHandle_t h;
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return -1.0;
+    cublasSetStream(h, s);
+    double *A, *B, *C;
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    cudaMalloc(&A, bytes); cudaMalloc(&B, bytes); cudaMalloc(&C, bytes);
+    cudaMemsetAsync(A, 0, bytes, s); cudaMemsetAsync(B, 0, bytes, s); cudaMemsetAsync(C, 0, bytes, s);
+    const double one = 1.0, zero = 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, s);
+        cublasDgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, n, n, n, &one, A, n, B, n, &zero, C, n);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(A); cudaFree(B); cudaFree(C);
+    cublasDestroy(h);
+    return 2.0 * n * n * (double)n / (best * 1e-3) * 1e-12;
+}
+
+}  // namespace pm

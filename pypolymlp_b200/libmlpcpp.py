@@ -1,0 +1,361 @@
+"""Drop-in mirror of the reference's pybind11 module `pypolymlp.cxx.lib.libmlpcpp` for the hot path.
+
+Same class names, constructor arguments, getters and error behaviour as
+src/pypolymlp/cxx/src/python/pybind11_mlp.cpp:10-94 of the reference, implemented on top of the
+C ABI (include/polymlp_b200.h) -> CUDA.  Additive entry point: `PotentialXtX` (fused feature +
+X^T X accumulation, replaces get_x() + apply_weights + x.T @ x of data_sequential.py:97-156).
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import FeatureParamsC, StructureBatch, as_d, as_i, check, lib, pd, pi
+
+
+def default_device():
+    for key in ("POLYMLP_B200_DEVICE", "LOCAL_RANK"):
+        if key in os.environ:
+            return int(os.environ[key])
+    return 0
+
+
+class Readgtinv:
+    """Readgtinv(order, maxl, version) (reference: polymlp_read_gtinv.cpp:10-63)."""
+
+    def __init__(self, gtinv_order, gtinv_maxl, version=1, datadir=None):
+        L = lib()
+        ml = as_i(list(gtinv_maxl) + [0])
+        sizes = (C.c_int64 * 4)()
+        dd = (datadir or _capi.DATA_DIR).encode()
+        n_ml = len(gtinv_maxl)
+        check(L.pm_gtinv_read(dd, gtinv_order, pi(ml), n_ml, version, sizes, None, None, None, None, None))
+        n, s1, s2, s3 = (int(x) for x in sizes)
+        lo, lc, nt = np.zeros(n, np.int32), np.zeros(max(s1, 1), np.int32), np.zeros(n, np.int32)
+        lm, cf = np.zeros(max(s3, 1), np.int32), np.zeros(max(s2, 1), np.float64)
+        check(L.pm_gtinv_read(dd, gtinv_order, pi(ml), n_ml, version, sizes, pi(lo), pi(lc), pi(nt), pi(lm), pd(cf)))
+        self._l_comb, self._lm_seq, self._lm_coeffs = [], [], []
+        p1 = p2 = p3 = 0
+        for i in range(n):
+            o, t = int(lo[i]), int(nt[i])
+            self._l_comb.append([int(x) for x in lc[p1:p1 + o]])
+            self._lm_coeffs.append([float(x) for x in cf[p2:p2 + t]])
+            self._lm_seq.append(lm[p3:p3 + t * o].reshape(t, o).tolist())
+            p1, p2, p3 = p1 + o, p2 + t, p3 + t * o
+
+    def get_lm_seq(self):
+        return self._lm_seq
+
+    def get_l_comb(self):
+        return self._l_comb
+
+    def get_lm_coeffs(self):
+        return self._lm_coeffs
+
+
+class _Model:
+    """Host tables built from `params.as_dict()` (keys read: compute/py_params.cpp:14-43)."""
+
+    def __init__(self, params_dict):
+        model = params_dict["model"]
+        if model["feature_type"] != "gtinv":
+            raise ValueError("pypolymlp_b200 implements feature_type='gtinv' only")
+        if model.get("pair_type", "gaussian") != "gaussian":
+            raise ValueError("pypolymlp_b200 implements pair_type='gaussian' only")
+        n_type = int(params_dict["n_type"])
+        pp = as_d(model["pair_params"]).reshape(-1, 2)
+        cond = model.get("pair_params_conditional")
+        off, val = [0], []
+        for i in range(n_type):
+            for j in range(i, n_type):
+                lst = list(cond[(i, j)]) if cond else list(range(len(pp)))
+                val.extend(lst)
+                off.append(len(val))
+        g = model["gtinv"]
+        l_comb, lm_seq, lm_coeffs = g["l_comb"], g["lm_seq"], g["lm_coeffs"]
+        lo = as_i([len(x) for x in l_comb])
+        lc = as_i([v for x in l_comb for v in x])
+        nt = as_i([len(x) for x in lm_seq])
+        lm = as_i([v for x in lm_seq for term in x for v in term])
+        cf = as_d([v for x in lm_coeffs for v in x])
+        off, val = as_i(off), as_i(val if val else [0])
+        self._keep = (pp, off, val, lo, lc, nt, lm, cf)
+        fp = FeatureParamsC(n_type, len(pp), pd(pp), pi(off), pi(val), float(model["cutoff"]),
+                            int(model["model_type"]), int(model["max_p"]), int(model["max_l"]), len(l_comb),
+                            pi(lo), pi(lc), pi(nt), pi(lm), pd(cf))
+        h = C.c_void_p()
+        check(lib().pm_model_create(C.byref(fp), C.byref(h)))
+        self.handle = h
+        self.n_type = n_type
+        self.n_features = lib().pm_model_n_features(self.handle)
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().pm_model_destroy(self.handle)
+            self.handle = None
+
+    def info(self):
+        out = (C.c_int64 * 8)()
+        check(lib().pm_model_info(self.handle, out))
+        keys = ["n_type", "n_linear", "n_comb2", "n_comb3", "n_variables", "n_polyvars", "n_type_pairs", "n_lm_half"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def type_info(self, t):
+        out = (C.c_int64 * 12)()
+        check(lib().pm_model_type_info(self.handle, t, out))
+        keys = ["n_full", "n_head", "n_feat", "n_fpad", "n_terms", "n_G_entries", "n_contributions", "n_blocks",
+                "n_poly", "n_deriv_pairs"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def polynomial(self, t):
+        n = C.c_int(0)
+        check(lib().pm_model_polynomial(self.handle, t, C.byref(n), None, None, None))
+        col, order, ids = np.zeros(n.value, np.int32), np.zeros(n.value, np.int32), np.zeros((n.value, 3), np.int32)
+        check(lib().pm_model_polynomial(self.handle, t, C.byref(n), pi(col), pi(order), pi(ids)))
+        return col, order, ids
+
+    def count_flops(self, atoms_t, pairs_tt, force=True):
+        a = np.ascontiguousarray(atoms_t, dtype=np.int64)
+        p = np.ascontiguousarray(pairs_tt, dtype=np.int64).reshape(-1)
+        out = (C.c_double * 5)()
+        check(lib().pm_model_count_flops(self.handle, a.ctypes.data_as(_capi._i64p), p.ctypes.data_as(_capi._i64p),
+                                         int(force), out))
+        return dict(zip(["syrk", "xty", "poly", "deriv", "anlm"], (float(x) for x in out)))
+
+
+class FeaturesAttr:
+    """Subset of FeaturesAttr (compute/py_features_attr.cpp) needed by get_num_features."""
+
+    def __init__(self, params_dict):
+        self._model = _Model(params_dict)
+
+    def get_n_features(self):
+        return self._model.n_features
+
+    def get_polynomial_ids(self, t=0):
+        return self._model.polynomial(t)
+
+
+class _Context:
+    def __init__(self, model, device=None, workspace_bytes=0, flags=0):
+        self.model = model
+        self.device = default_device() if device is None else device
+        h = C.c_void_p()
+        check(lib().pm_context_create(model.handle, self.device, workspace_bytes, flags, C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().pm_context_destroy(self.handle)
+            self.handle = None
+
+    def profile(self, on=True):
+        lib().pm_profile_enable(self.handle, int(on))
+
+    def profile_get(self):
+        n = C.c_int(0)
+        ms = (C.c_double * 32)()
+        ln = (C.c_int64 * 32)()
+        lib().pm_profile_get(self.handle, C.byref(n), ms, ln)
+        return {lib().pm_stage_name(i).decode(): (ms[i], int(ln[i])) for i in range(n.value)}
+
+    def launch_count(self):
+        return int(lib().pm_launch_count(self.handle))
+
+    def synchronize(self):
+        check(lib().pm_synchronize(self.handle))
+
+    def microbench(self, which, n=8192):
+        t = C.c_double(0.0)
+        check(lib().pm_microbench(self.handle, which, n, C.byref(t)))
+        return t.value
+
+    def neighbor_full(self, axis, positions_c, types):
+        axis, pos, ty = as_d(axis), as_d(positions_c), as_i(types)
+        n = pos.shape[1]
+        off = np.zeros(n + 1, np.int32)
+        check(lib().pm_neighbor_full(self.handle, pd(axis), pd(pos), pi(ty), n, pi(off), None, None, None, None))
+        P = int(off[-1])
+        nb, dx, dy, dz = np.zeros(max(P, 1), np.int32), np.zeros(max(P, 1)), np.zeros(max(P, 1)), np.zeros(max(P, 1))
+        check(lib().pm_neighbor_full(self.handle, pd(axis), pd(pos), pi(ty), n, pi(off), pi(nb), pd(dx), pd(dy), pd(dz)))
+        return off, nb[:P], dx[:P], dy[:P], dz[:P]
+
+    def debug_fetch(self, what):
+        n = C.c_size_t(0)
+        check(lib().pm_debug_fetch(self.handle, what, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1))
+        check(lib().pm_debug_fetch(self.handle, what, pd(out), out.size, C.byref(n)))
+        return out[: n.value]
+
+
+def _force_per_structure(n_st_dataset, force_dataset):
+    flags = []
+    for n, f in zip(n_st_dataset, force_dataset):
+        flags.extend([bool(f)] * int(n))
+    return flags
+
+
+def _set_index(n_st_dataset, force_dataset, n_atoms_all):
+    """Row bookkeeping of PyModel::set_index (compute/py_model.cpp:58-106)."""
+    n_st = int(sum(n_st_dataset))
+    fbegin, sbegin = [-1] * len(n_st_dataset), [-1] * len(n_st_dataset)
+    n_data = [n_st, 0, 0]
+    ist, k = n_st, 0
+    for i, (n, f) in enumerate(zip(n_st_dataset, force_dataset)):
+        if f:
+            sbegin[i] = ist
+            n_data[2] += 6 * n
+            ist += 6 * n
+        k += n
+    ifo, k = ist, 0
+    for i, (n, f) in enumerate(zip(n_st_dataset, force_dataset)):
+        if f:
+            fbegin[i] = ifo
+        for _ in range(n):
+            if f:
+                ifo += 3 * int(n_atoms_all[k])
+                n_data[1] += 3 * int(n_atoms_all[k])
+            k += 1
+    return fbegin, sbegin, n_data
+
+
+class PotentialModel:
+    """PotentialModel(params_dict, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all)
+    (reference: pybind11_mlp.cpp:12-27, compute/py_model.cpp:10-54).  All work happens in the
+    constructor; get_x() returns the (n_rows, n_features) design matrix."""
+
+    def __init__(self, params_dict, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all,
+                 device=None, flags=0):
+        if len(axis) != sum(n_st_dataset):
+            raise ValueError("n_st_dataset does not match the number of structures")
+        self._model = _Model(params_dict)
+        self._ctx = _Context(self._model, device, flags=flags)
+        batch = StructureBatch(axis, positions_c, types, _force_per_structure(n_st_dataset, force_dataset))
+        self._fbegin, self._sbegin, self._n_data = _set_index(n_st_dataset, force_dataset, n_atoms_all)
+        self._x = np.zeros((batch.n_rows, self._model.n_features))
+        if params_dict.get("print_memory", False):
+            print(" Matrix shape (X):", self._x.shape, flush=True)
+        check(lib().pm_features_x(self._ctx.handle, C.byref(batch.c), pd(self._x)))
+
+    def get_x(self):
+        return self._x
+
+    def get_fbegin(self):
+        return self._fbegin
+
+    def get_sbegin(self):
+        return self._sbegin
+
+    def get_n_data(self):
+        return self._n_data
+
+
+class PotentialXtX:
+    """Fused feature + X^T X / X^T y accumulation on the GPU (additive entry point).
+
+    add(axis, positions_c, types, force_flags, w, y): w and y are the per-row weights and weighted
+    targets of the batch in the PyModel row layout (what apply_weights produces)."""
+
+    def __init__(self, params_dict, device=None, workspace_bytes=0, flags=0):
+        self._model = _Model(params_dict)
+        self._ctx = _Context(self._model, device, workspace_bytes, flags)
+        self.n_features = self._model.n_features
+        check(lib().pm_fit_reset(self._ctx.handle))
+        self._staged = None
+
+    @property
+    def context(self):
+        return self._ctx
+
+    @property
+    def model(self):
+        return self._model
+
+    def reset(self):
+        check(lib().pm_fit_reset(self._ctx.handle))
+
+    def add(self, axis, positions_c, types, force_flags, w, y):
+        batch = StructureBatch(axis, positions_c, types, force_flags)
+        w, y = as_d(w), as_d(y)
+        if len(w) != batch.n_rows or len(y) != batch.n_rows:
+            raise ValueError("w and y must have one entry per row of the batch")
+        check(lib().pm_fit_accumulate(self._ctx.handle, C.byref(batch.c), pd(w), pd(y)))
+        return batch
+
+    def add_batch(self, batch, w, y):
+        check(lib().pm_fit_accumulate(self._ctx.handle, C.byref(batch.c), pd(w), pd(y)))
+
+    def stage(self, axis, positions_c, types, force_flags, w, y):
+        batch = StructureBatch(axis, positions_c, types, force_flags)
+        w, y = as_d(w), as_d(y)
+        check(lib().pm_fit_stage(self._ctx.handle, C.byref(batch.c), pd(w), pd(y)))
+        self._staged = batch
+        return batch
+
+    def add_staged(self):
+        check(lib().pm_fit_accumulate_staged(self._ctx.handle))
+
+    def accumulator(self):
+        """(device pointer, n_doubles) of the packed accumulator, for a cross-GPU reduction."""
+        p, n = C.c_void_p(), C.c_size_t(0)
+        check(lib().pm_fit_accumulator(self._ctx.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def finalize(self, want_xtx=True):
+        F = self.n_features
+        xtx = np.zeros((F, F)) if want_xtx else None
+        xty, xe_sum, xe_sq = np.zeros(F), np.zeros(F), np.zeros(F)
+        ysq, nd = C.c_double(0.0), C.c_int64(0)
+        check(lib().pm_fit_finalize(self._ctx.handle, pd(xtx), pd(xty), pd(xe_sum), pd(xe_sq), C.byref(ysq), C.byref(nd)))
+        return {"xtx": xtx, "xty": xty, "xe_sum": xe_sum, "xe_sq_sum": xe_sq, "y_sq_norm": ysq.value,
+                "total_n_data": int(nd.value)}
+
+
+class PotentialPropertiesFast:
+    """PotentialPropertiesFast(params_dict, coeffs) (reference: pybind11_mlp.cpp:51-67,
+    compute/py_properties_fast.cpp:10-76).  Energies in eV/cell, forces (N, 3) in eV/A,
+    stress as 6 virial components (xx, yy, zz, xy, yz, zx) in eV/cell."""
+
+    def __init__(self, params_dict, coeffs, device=None, flags=0):
+        self._model = _Model(params_dict)
+        self._ctx = _Context(self._model, device, flags=flags)
+        c = as_d(coeffs)
+        check(lib().pm_eval_set_coeffs(self._ctx.handle, pd(c), len(c)))
+        self._e = self._f = self._s = None
+        self._e_array = self._f_array = self._s_array = None
+
+    def _run(self, axis_array, positions_c_array, types_array):
+        batch = StructureBatch(axis_array, positions_c_array, types_array, [True] * len(axis_array))
+        e = np.zeros(batch.n_st)
+        f = np.zeros((int(batch.n_atoms.sum()), 3))
+        s = np.zeros((batch.n_st, 6))
+        check(lib().pm_eval(self._ctx.handle, C.byref(batch.c), pd(e), pd(f), pd(s)))
+        offs = np.concatenate([[0], np.cumsum(batch.n_atoms)])
+        return e, [f[offs[k]:offs[k + 1]] for k in range(batch.n_st)], s
+
+    def eval(self, axis, positions_c, types, use_openmp=True):
+        e, f, s = self._run([axis], [positions_c], [types])
+        self._e, self._f, self._s = float(e[0]), f[0], s[0]
+
+    def eval_multiple(self, axis_array, positions_c_array, types_array):
+        self._e_array, self._f_array, self._s_array = self._run(axis_array, positions_c_array, types_array)
+
+    def get_e(self):
+        return self._e
+
+    def get_f(self):
+        return self._f
+
+    def get_s(self):
+        return self._s
+
+    def get_e_array(self):
+        return self._e_array
+
+    def get_f_array(self):
+        return self._f_array
+
+    def get_s_array(self):
+        return self._s_array

@@ -1,0 +1,179 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol the header
+declares, the host model tables agree with the oracle / reference, and the host logic (weights,
+row bookkeeping, sharding, multi-rank reduction) behaves like the reference's Python."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import polymlp_oracle as po
+from pypolymlp_b200 import _capi, fit
+from pypolymlp_b200.libmlpcpp import Readgtinv, _Model, _set_index
+from pypolymlp_b200.params import make_params_dict, set_gaussian_params
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "polymlp_b200.h")).read()
+    declared = set(re.findall(r"\b(pm_[a-z_0-9]+)\s*\(", header))
+    declared -= {"pm_model", "pm_context"}
+    lib = _capi.lib()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(_capi.EXPORTS) <= declared
+    assert b"sm_100a" in lib.pm_version()
+
+
+def test_no_device_means_error_not_fallback():
+    lib = _capi.lib()
+    n = C.c_int(-1)
+    assert lib.pm_device_count(C.byref(n)) == 0
+    if n.value == 0:
+        m = _Model(make_params_dict(**cases.si_model_kwargs()))
+        h = C.c_void_p()
+        st = lib.pm_context_create(m.handle, 0, 0, 0, C.byref(h))
+        assert st == 3 and b"no CPU fallback" in lib.pm_last_error()
+
+
+def test_readgtinv_matches_oracle_reader_and_reference_shapes():
+    # reference: tests/test_cxx/test_gtinv.py (v1 tables): order-3 maxl [4,4] -> 20 l-combs
+    rg = Readgtinv(3, [4, 4], 1)
+    assert len(rg.get_l_comb()) == 20
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(refdir, "polymlp_gtinv_data_v1_order1.bin")):
+        for order, maxl in ((2, [20]), (3, [12, 12]), (4, [12, 8, 2]), (6, [2, 2, 2, 2, 2])):
+            a = Readgtinv(order, maxl, 1)
+            b = po.readgtinv(order, maxl, refdir, 1)
+            assert a.get_l_comb() == b[0] and a.get_lm_seq() == b[1] and a.get_lm_coeffs() == b[2]
+    with pytest.raises(ValueError):
+        Readgtinv(7, [1] * 6, 1)
+    with pytest.raises(RuntimeError):
+        Readgtinv(3, [4, 4], 2)  # v2 order-3 table is absent from the reference checkout
+
+
+def test_gaussian_params():
+    pp = set_gaussian_params(n_gaussians=10, cutoff=6.0)
+    assert len(pp) == 10 and pp[-1] == [0.0, 0.0] and pp[0] == [1.0, 0.0] and pp[8] == [1.0, 5.0]
+
+
+@pytest.mark.parametrize("kwargs,n_features", [
+    (cases.si_model_kwargs(), 168),            # reference tests/test_mlp_dev/test_core_features.py:18
+    (cases.cfg2_model_kwargs(4), 2030),        # config 1/2/5
+    (cases.cfg2_model_kwargs(3), 255),
+    (dict(n_type=2, cutoff=6.0, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[12, 8, 2], n_gaussians=10), 9385),
+])
+def test_model_sizes(kwargs, n_features):
+    m = _Model(make_params_dict(**kwargs))
+    assert m.n_features == n_features
+
+
+@pytest.mark.parametrize("kwargs", [cases.si_model_kwargs(), cases.binary_model_kwargs(),
+                                    cases.ternary_p3_model_kwargs()])
+def test_tables_match_oracle(kwargs):
+    pd = make_params_dict(**kwargs)
+    m, tab = _Model(pd), po.Tables(pd)
+    info = m.info()
+    assert info["n_variables"] == tab.n_variables and info["n_linear"] == tab.n_linear
+    assert info["n_comb2"] == len(tab.comb2) and info["n_comb3"] == len(tab.comb3)
+    for t in range(tab.n_type):
+        ti = m.type_info(t)
+        assert ti["n_full"] == len(tab.local[t]["gids"]) and ti["n_feat"] == len(tab.features[t])
+        col, order, ids = m.polynomial(t)
+        assert [int(c) for c in col] == [c for c, _ in tab.poly[t]]
+        for k, (_, lids) in enumerate(tab.poly[t]):
+            assert [int(x) for x in ids[k][: len(lids)]] == list(lids)
+
+
+def test_invalid_model_arguments():
+    pd = make_params_dict(**cases.si_model_kwargs())
+    pd["model"]["model_type"] = 5
+    with pytest.raises(ValueError):
+        _Model(pd)
+    pd = make_params_dict(**cases.si_model_kwargs())
+    pd["model"]["feature_type"] = "pair"
+    with pytest.raises(ValueError):
+        _Model(pd)
+
+
+def test_flop_count_config2():
+    # config 2, 256 atoms x 54 neighbours, F = 2030
+    m = _Model(make_params_dict(**cases.cfg2_model_kwargs(4)))
+    w = m.count_flops([256], [[13824]], True)
+    assert w["syrk"] == 775 * 2030 * 2031
+    assert w["anlm"] == 13824 * 10 * 15 * 32
+    assert w["poly"] == 256 * 172 * 7520
+    assert 0.5e9 < w["deriv"] < 2e9
+
+
+def test_set_index_row_layout():
+    # compute/py_model.cpp:58-106: energies | stress | forces
+    fb, sb, nd = _set_index([2, 1, 2], [True, False, True], [4, 4, 3, 2, 5])
+    assert nd == [5, 3 * (4 + 4 + 2 + 5), 24]
+    assert sb == [5, -1, 17] and fb == [29, -1, 53]
+
+
+def test_apply_weights_matches_reference_rules():
+    rng = np.random.default_rng(0)
+    n = 3
+    ds = fit.Dataset([np.eye(3) * 5] * n, [rng.random((3, 2))] * n, [[0, 0]] * n, energies=np.array([-10.0, -7.0, 1.0]),
+                     forces=np.array([0.5, -2.0, 1e-15] * 6), stresses=np.array([1e-3, -20.0, 0.0, 0.3, 5.0, -1e-13] * n),
+                     include_force=True, include_stress=True, weight=2.0)
+    w, y = fit.apply_weights(ds, weight_stress=0.1, min_e=-5.0)
+    we = po.weights_energy(ds.energies, ds.total_n_atoms, -5.0, 2.0)
+    ws = po.weights_stress(ds.stresses, 0.1 * 2.0)
+    wf = po.weights_force(ds.forces, 2.0)
+    np.testing.assert_array_equal(w, np.concatenate([we, ws, wf]))
+    np.testing.assert_array_equal(y, np.concatenate([we * ds.energies, ws * ds.stresses, wf * ds.forces]))
+    ds.include_stress = False
+    w, y = fit.apply_weights(ds, min_e=-5.0)
+    assert np.all(w[n:n + 6 * n] == 0.0) and np.all(y[n:n + 6 * n] == 0.0)
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 10000):
+        for ws in (1, 2, 3, 8):
+            parts = [fit.shard_range(n, r, ws) for r in range(ws)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[k][1] == parts[k + 1][0] for k in range(ws - 1))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(40, 6))
+    y = rng.normal(size=40)
+    b, e = fit.shard_range(40, rank, world)
+    # packed accumulator of this rank's shard, same layout as pm_fit_accumulator: [C | xe_sum | xe_sq | n]
+    Xt = np.hstack([X[b:e], y[b:e, None]])
+    acc = np.concatenate([(Xt.T @ Xt).ravel(), X[b:e].sum(0), np.square(X[b:e]).sum(0), [e - b]])
+    t = torch.from_numpy(acc)
+    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        Xa = np.hstack([X, y[:, None]])
+        ok = np.allclose(t.numpy()[:49], (Xa.T @ Xa).ravel(), rtol=1e-12) and t.numpy()[-1] == 40
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduce_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle / reference golden vectors.
+Run on the B200 box: python -m pytest tests -m gpu.  Tolerances: neighbour lists bit-exact;
+X / XtX / Xty 1e-10 relative (cases.x_rel_err); eval E rel 1e-10, F/S 1e-10 of the largest component."""
+
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import polymlp_oracle as po
+from pypolymlp_b200 import fit
+from pypolymlp_b200._capi import PM_FLAG_SIMPLE_KERNELS
+from pypolymlp_b200.libmlpcpp import (PotentialModel, PotentialPropertiesFast, PotentialXtX, _Context, _Model)
+from pypolymlp_b200.params import make_params_dict
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(cases.GOLDEN, "ref_vectors.npz"))
+FLAVOURS = [pytest.param(PM_FLAG_SIMPLE_KERNELS, id="simple"), pytest.param(0, id="dmma")]
+
+
+def _sort_ref_order(off, nb, dx, dy, dz):
+    """Our lists are grouped by neighbour type inside an atom; a stable sort by j restores the
+    reference's (j, translation) order."""
+    out = [[], [], [], []]
+    for i in range(len(off) - 1):
+        sl = slice(off[i], off[i + 1])
+        order = np.argsort(nb[sl], kind="stable")
+        for k, a in enumerate((nb, dx, dy, dz)):
+            out[k].append(a[sl][order])
+    return [np.concatenate(o) if o else np.zeros(0) for o in out]
+
+
+def test_neighbor_bit_exact():
+    pd = make_params_dict(**cases.binary_model_kwargs())
+    ctx = _Context(_Model(pd))
+    ax, pc, ty = cases.skewed_cell(2)
+    off, nb, dx, dy, dz = ctx.neighbor_full(ax, pc, ty)
+    assert np.array_equal(off, G["bin_nbr_full_off"])
+    nb, dx, dy, dz = _sort_ref_order(off, nb, dx, dy, dz)
+    for a, name in ((nb, "nb"), (dx, "dx"), (dy, "dy"), (dz, "dz")):
+        assert np.array_equal(a, G[f"bin_nbr_full_{name}"]), name
+    # many images + reduced cell
+    kw = dict(cases.si_model_kwargs())
+    kw["cutoff"] = 4.0
+    ctx = _Context(_Model(make_params_dict(**kw)))
+    ax, pc, ty = cases.small_skewed_cell()
+    o = ctx.neighbor_full(ax, pc, ty)
+    for a, name in zip(o, ("off", "nb", "dx", "dy", "dz")):
+        assert np.array_equal(a, G[f"small_nbr_{name}"]), name
+    # empty structure and isolated atom
+    off, nb, *_ = ctx.neighbor_full(np.eye(3) * 50.0, np.zeros((3, 1)), [0])
+    assert list(off) == [0, 0]
+
+
+def test_neighbor_fcc256_checksums():
+    ctx = _Context(_Model(make_params_dict(**cases.cfg2_model_kwargs(4))))
+    ax, pc, ty = cases.fcc_supercell()
+    off, nb, dx, dy, dz = ctx.neighbor_full(ax, pc, ty)
+    assert off[-1] == G["fcc_nbr_count"][0]
+    assert nb.sum() == G["fcc_nbr_checksum"][0]
+    assert np.square(dx).sum() + np.square(dy).sum() + np.square(dz).sum() == pytest.approx(G["fcc_nbr_checksum"][1], rel=1e-14)
+    axo, pco = ax, pc
+    o = po.neighbor_full(axo, pco, 6.0)
+    for a, b in zip((off, nb, dx, dy, dz), o):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_x_si_structure_and_intermediates(flags):
+    axis, positions_c, _, _ = cases.load_si_dataset()
+    pd = make_params_dict(**cases.si_model_kwargs())
+    ty = np.zeros(64, np.int32)
+    pm = PotentialModel(pd, [axis], [positions_c[3]], [ty], [1], [True], [64], flags=flags)
+    x = pm.get_x()
+    assert x.shape == (1 + 6 + 192, 168)
+    assert pm.get_n_data() == [1, 192, 6] and pm.get_sbegin() == [1] and pm.get_fbegin() == [7]
+    # intermediates of the last chunk
+    anc = pm._ctx.debug_fetch(0).view(np.complex128).reshape(64, -1)
+    d = pm._ctx.debug_fetch(1).reshape(64, -1)
+    m = pm._model
+    ti = m.type_info(0)
+    gold_a = G["si3_atom5_anlm"]
+    tab = po.Tables(pd)
+    heads = [k for k, f in enumerate(tab.local[0]["full"]) if not f[5]]
+    assert np.abs(anc[5, : ti["n_head"]] - gold_a[heads]).max() < 1e-12 * np.abs(gold_a).max()
+    dd = d[5][d[5] != 0.0]
+    assert cases.x_rel_err(np.sort(dd), np.sort(G["si3_atom5_d"][G["si3_atom5_d"] != 0.0])) < 1e-11
+    assert cases.x_rel_err(x[0], G["si3_xe"]) < 1e-10
+    assert cases.x_rel_err(x[1:7], G["si3_xs"]) < 1e-10
+    assert cases.x_rel_err(x[7:], G["si3_xf"]) < 1e-10
+    full = np.vstack([G["si3_xe"][None], G["si3_xs"], G["si3_xf"]])
+    assert cases.x_rel_err(x, full) < 1e-10
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_x_binary_conditional(flags):
+    pd = make_params_dict(**cases.binary_model_kwargs())
+    ax, pc, ty = cases.skewed_cell(2)
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [9], flags=flags).get_x()
+    full = np.vstack([G["bin_xe"][None], G["bin_xs"], G["bin_xf"]])
+    assert cases.x_rel_err(x, full) < 1e-10
+
+
+def test_x_ternary_order3_polynomial():
+    pd = make_params_dict(**cases.ternary_p3_model_kwargs())
+    ax, pc, ty = cases.skewed_cell(3, n_atom=7, seed=3)
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [7]).get_x()
+    assert cases.x_rel_err(x[0], G["ter_xe"]) < 1e-10
+    assert cases.x_rel_err(x[1:7], G["ter_xs"]) < 1e-10
+    assert cases.x_rel_err(x[7::3], G["ter_xf"]) < 1e-10
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_x_mixed_batch_layout_energy_only_and_force(flags):
+    """Two datasets (force / energy-only), ragged sizes: PyModel row layout and values vs the oracle."""
+    pd = make_params_dict(**cases.binary_model_kwargs())
+    tab = po.Tables(pd)
+    sts = [cases.skewed_cell(2, n_atom=n, seed=s) for n, s in ((5, 1), (8, 2), (3, 4), (6, 5))]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    pm = PotentialModel(pd, axis, pcs, tys, [2, 2], [True, False], [5, 8, 3, 6], flags=flags)
+    ref_x = po.build_x(tab, axis, pcs, tys, [True, True, False, False])
+    assert pm.get_x().shape == ref_x.shape
+    assert pm.get_fbegin() == [16, -1] and pm.get_sbegin() == [4, -1]
+    assert cases.x_rel_err(pm.get_x(), ref_x) < 1e-10
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_x_fcc256_config2(flags):
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    ax, pc, ty = cases.fcc_supercell()
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [256], flags=flags).get_x()
+    assert x.shape == (775, 2030)
+    assert cases.x_rel_err(x[0], G["fcc_xe"]) < 1e-10
+    assert cases.x_rel_err(x[1:7], G["fcc_xs"]) < 1e-10
+    xf = x[7:]
+    scale = np.abs(xf).max(axis=0)
+    assert (np.abs(xf[G["fcc_rows"]] - G["fcc_xf_rows"]) / np.maximum(scale, 1e-8 * scale.max())).max() < 1e-10
+    assert (np.abs(np.square(xf).sum(axis=0) - G["fcc_xf_colsqsum"]) / G["fcc_xf_colsqsum"].max()).max() < 1e-10
+
+
+def _si_datasets(ids):
+    axis, positions_c, forces, energies = cases.load_si_dataset()
+    return fit.Dataset([axis] * len(ids), [positions_c[i] for i in ids], [np.zeros(64, np.int32)] * len(ids),
+                       energies[ids], forces=forces[ids].reshape(-1), include_force=True, include_stress=False)
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_xtx_xty_vs_oracle_small(flags):
+    pd = make_params_dict(**cases.si_model_kwargs())
+    tab = po.Tables(pd)
+    ds = _si_datasets(np.array([0, 7, 19]))
+    w, y = fit.apply_weights(ds, min_e=-5.737324395625)
+    X = po.build_x(tab, ds.axis, ds.positions_c, ds.types, [True] * 3)
+    xtx, xty, ysq, xe_sum, xe_sq = po.accumulate(X, 3, w, y / np.where(w > 0, w, 1.0))
+    acc = PotentialXtX(pd, flags=flags)
+    acc.add(ds.axis, ds.positions_c, ds.types, [True] * 3, w, y)
+    res = acc.finalize()
+    assert res["total_n_data"] == X.shape[0]
+    assert np.abs(res["xtx"] - xtx).max() < 1e-10 * np.abs(xtx).max()
+    assert np.abs(res["xtx"] - res["xtx"].T).max() == 0.0
+    assert np.abs(res["xty"] - xty).max() < 1e-10 * np.abs(xty).max()
+    assert abs(res["y_sq_norm"] - ysq) < 1e-10 * ysq
+    assert np.abs(res["xe_sum"] - xe_sum).max() < 1e-10 * np.abs(xe_sum).max()
+    assert np.abs(res["xe_sq_sum"] - xe_sq).max() < 1e-10 * np.abs(xe_sq).max()
+    # second accumulate adds on top (linearity) and batching does not matter
+    acc.add(ds.axis[:1], ds.positions_c[:1], ds.types[:1], [True], *_rows_of(w, y, 3, 64, [0]))
+    acc.add(ds.axis[1:], ds.positions_c[1:], ds.types[1:], [True, True], *_rows_of(w, y, 3, 64, [1, 2]))
+    res2 = acc.finalize()
+    assert np.abs(res2["xtx"] - 2 * xtx).max() < 1e-10 * np.abs(xtx).max()
+    assert res2["total_n_data"] == 2 * X.shape[0]
+
+
+def _rows_of(w, y, n_st, n_atom, sel):
+    e = np.array(sel)
+    s = np.concatenate([n_st + 6 * k + np.arange(6) for k in sel])
+    f = np.concatenate([n_st + 6 * n_st + 3 * n_atom * k + np.arange(3 * n_atom) for k in sel])
+    idx = np.concatenate([e, s, f])
+    return w[idx], y[idx]
+
+
+def test_fit_si_reference_goldens():
+    """Config 1: the reference's bundled Si set, 180 training structures.
+    Goldens: tests/test_mlp_dev/test_core_features.py:17-31 and test_core_data.py:39-57 of the reference."""
+    pd = make_params_dict(**cases.si_model_kwargs())
+    train_ids, test_ids = cases.split_ids_train_test(200, 0.9)
+    train = _si_datasets(train_ids)
+    pm = PotentialModel(pd, train.axis, train.positions_c, train.types, [180], [True], [64] * 180)
+    x = pm.get_x()
+    assert x.shape == (35820, 168)
+    assert tuple(pm.get_n_data()) == (180, 34560, 1080) and pm.get_fbegin() == [1260] and pm.get_sbegin() == [180]
+    assert np.sum(x) == pytest.approx(5165294.450079148, rel=1e-6)
+    assert np.sum(x[:, :20]) == pytest.approx(447.7438322711305, rel=1e-6)
+    assert np.sum(x[:, 20:40]) == pytest.approx(15803.28147846774, rel=1e-6)
+    assert np.sum(x[:, 40:60]) == pytest.approx(93568.30539681061, rel=1e-6)
+    assert np.sum(x[:, 60:80]) == pytest.approx(308321.82717270905, rel=1e-6)
+    assert np.sum(x[:, -60:-40]) == pytest.approx(1987480.894857876, rel=1e-6)
+    assert np.sum(x[:, -40:-20]) == pytest.approx(34372.80650408206, rel=1e-6)
+    assert np.sum(x[:, -20:]) == pytest.approx(2008586.8132866116, rel=1e-6)
+    assert np.abs(x.sum(axis=0) - G["si_train_colsum"]).max() < 1e-10 * np.abs(G["si_train_colsum"]).max()
+    assert np.abs(np.square(x).sum(axis=0) - G["si_train_colsqsum"]).max() < 1e-10 * G["si_train_colsqsum"].max()
+
+    for bs in (64, 10, 50):
+        data_xy = fit.calc_xtx_xty(pd, [train], batch_size=bs)
+        assert data_xy.xtx.shape == (168, 168)
+        assert data_xy.xty[56] == pytest.approx(6.899130774433e5, rel=1e-6)
+        assert data_xy.scales[56] == pytest.approx(0.0032488632685359524)
+        assert data_xy.min_energy == pytest.approx(-5.737324395625)
+        assert data_xy.total_n_data == 35820
+    # the same sums from the materialised X (the reference's own route)
+    w, y = fit.apply_weights(train, min_e=data_xy.min_energy)
+    xw = x * w[:, None]
+    xtx_ref = (xw.T @ xw) / data_xy.scales[:, None] / data_xy.scales[None, :]
+    assert np.abs(data_xy.xtx - xtx_ref).max() < 1e-10 * np.abs(xtx_ref).max()
+    # ridge fit: RMSE goldens of tests/test_mlp_dev_api/test_mlp_devel_phono3py.py:22-27 (rel 1e-2)
+    test = _si_datasets(test_ids)
+    alphas = [10.0 ** a for a in np.linspace(-3, 1, 5)]
+    best = fit.fit(pd, [train], [test], alphas)
+    coeffs = best["coeffs"] / best["scales"]
+    prop = PotentialPropertiesFast(pd, coeffs)
+    for ds, e_gold, f_gold in ((train, 1.925e-6, 9.113e-4), (test, 2.067e-6, 9.180e-4)):
+        prop.eval_multiple(ds.axis, ds.positions_c, ds.types)
+        e = np.array(prop.get_e_array())
+        f = np.concatenate([np.asarray(a).reshape(-1) for a in prop.get_f_array()])
+        rmse_e = np.sqrt(np.mean(np.square((e - ds.energies) / 64)))
+        rmse_f = np.sqrt(np.mean(np.square(f - ds.forces)))
+        assert rmse_e == pytest.approx(e_gold, rel=2e-2)
+        assert rmse_f == pytest.approx(f_gold, rel=2e-2)
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_eval_binary_and_fcc(flags):
+    pd = make_params_dict(**cases.binary_model_kwargs())
+    ax, pc, ty = cases.skewed_cell(2)
+    prop = PotentialPropertiesFast(pd, G["bin_coeffs"], flags=flags)
+    prop.eval(ax, pc, ty, True)
+    assert abs(prop.get_e() - G["bin_e"][0]) < 1e-10 * abs(G["bin_e"][0])
+    assert np.abs(prop.get_f() - G["bin_f"]).max() < 1e-10 * np.abs(G["bin_f"]).max()
+    assert np.abs(prop.get_s() - G["bin_s"]).max() < 1e-10 * np.abs(G["bin_s"]).max()
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    ax, pc, ty = cases.fcc_supercell()
+    prop = PotentialPropertiesFast(pd, G["fcc_coeffs"], flags=flags)
+    prop.eval_multiple([ax, ax], [pc, pc], [ty, ty])
+    for k in range(2):
+        assert abs(prop.get_e_array()[k] - G["fcc_e"][0]) < 1e-10 * abs(G["fcc_e"][0])
+        assert np.abs(prop.get_f_array()[k] - G["fcc_f"]).max() < 1e-10 * np.abs(G["fcc_f"]).max()
+        assert np.abs(prop.get_s_array()[k] - G["fcc_s"]).max() < 1e-10 * np.abs(G["fcc_s"]).max()
+    with pytest.raises(ValueError):
+        PotentialPropertiesFast(pd, G["fcc_coeffs"][:-1])
+
+
+def test_config2_full_size_properties():
+    """BASELINE config-2 shapes (256-atom fcc, F = 2030): size-independent properties of the fused path:
+    tensor-core and straightforward kernels agree, accumulation is additive over structures and independent
+    of chunking, C is symmetric, X^T y / y^T y / xe_sum are consistent with the materialised X."""
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    n = 6
+    sts = [cases.fcc_supercell(seed=20240 + s) for s in range(n)]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    rng = np.random.default_rng(5)
+    rows = n * 775
+    w = rng.uniform(0.2, 1.0, rows)
+    y = w * rng.normal(size=rows)
+    a1 = PotentialXtX(pd)
+    a1.add(axis, pcs, tys, [True] * n, w, y)
+    r1 = a1.finalize()
+    a2 = PotentialXtX(pd, flags=PM_FLAG_SIMPLE_KERNELS, workspace_bytes=400 << 20)  # several chunks
+    a2.add(axis, pcs, tys, [True] * n, w, y)
+    r2 = a2.finalize()
+    sc = np.abs(r2["xtx"]).max()
+    assert np.abs(r1["xtx"] - r2["xtx"]).max() < 1e-10 * sc
+    assert np.abs(r1["xty"] - r2["xty"]).max() < 1e-10 * np.abs(r2["xty"]).max()
+    assert np.abs(r1["xtx"] - r1["xtx"].T).max() == 0.0
+    assert r1["total_n_data"] == rows
+    x = PotentialModel(pd, axis, pcs, tys, [n], [True], [256] * n).get_x()
+    xw = x * w[:, None]
+    ref = xw.T @ xw
+    assert np.abs(r1["xtx"] - ref).max() < 1e-10 * np.abs(ref).max()
+    assert np.abs(r1["xty"] - xw.T @ y).max() < 1e-10 * np.abs(xw.T @ y).max()
+    assert abs(r1["y_sq_norm"] - y @ y) < 1e-10 * (y @ y)
+    assert np.abs(r1["xe_sum"] - x[:n].sum(axis=0)).max() < 1e-10 * np.abs(x[:n].sum(axis=0)).max()
+    assert np.abs(r1["xe_sq_sum"] - np.square(x[:n]).sum(axis=0)).max() < 1e-10 * np.square(x[:n]).sum(axis=0).max()
+    # staged (inputs resident in HBM) path gives the same accumulator
+    a3 = PotentialXtX(pd)
+    a3.stage(axis, pcs, tys, [True] * n, w, y)
+    a3.add_staged()
+    r3 = a3.finalize()
+    assert np.abs(r3["xtx"] - r1["xtx"]).max() < 1e-12 * sc
+
+
+def test_error_paths():
+    pd = make_params_dict(**cases.si_model_kwargs())
+    ax, pc, ty = cases.skewed_cell(1)
+    with pytest.raises(ValueError):
+        PotentialModel(pd, [ax], [pc], [np.ones(9, np.int32)], [1], [True], [9])  # type out of range
+    with pytest.raises(ValueError):
+        PotentialXtX(pd).add([ax], [pc], [ty], [True], np.ones(3), np.ones(3))  # wrong row count
+    # empty batch is fine
+    acc = PotentialXtX(pd)
+    acc.add([], [], [], [], np.zeros(0), np.zeros(0))
+    assert acc.finalize()["total_n_data"] == 0

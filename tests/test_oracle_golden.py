@@ -1,0 +1,132 @@
+"""The numpy oracle (oracle/polymlp_oracle.py) against the reference's own known answers and
+against golden vectors produced by the unmodified reference C++ (tests/golden/make_golden.py)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import polymlp_oracle as po
+from pypolymlp_b200.params import make_params_dict
+
+G = np.load(os.path.join(cases.GOLDEN, "ref_vectors.npz"))
+
+
+def test_get_fn_known_answers():
+    # reference: tests/test_cxx/test_functions.py:14-25
+    fn, fnd = po.radial(np.array([1.2]), np.array([[1.0, 0.0], [1.0, 1.0], [1.0, 2.0]]), 6.0)
+    np.testing.assert_allclose(fn[0], [0.21430317094756238, 0.8690422117212636, 0.4769404780495180], rtol=1e-12)
+    np.testing.assert_allclose(fnd[0], [-0.5507864848009192, -0.495464911460655, 0.6819640474131319], rtol=1e-12)
+
+
+def test_ylm_known_answers():
+    # reference: tests/test_cxx/test_functions.py:28-50
+    x, y, z = 0.173723561607389, 0.446843340790007, 0.877582561890373
+    Y, Yx, Yy, Yz = po.ylm_der(np.array([x]), np.array([y]), np.array([z]), 10)
+    assert Y.shape[0] == 66
+    assert Y.sum() == pytest.approx(-3.094632553138235 + 0.09510814961092404j, rel=1e-6)
+    assert Yx.sum() == pytest.approx(-6.916830463136405 - 1.910490992920798j, rel=1e-6)
+    assert Yy.sum() == pytest.approx(12.686387327323297 + 23.645024627283863j, rel=1e-6)
+    assert Yz.sum() == pytest.approx(-5.090360117438893 - 11.661266919165213j, rel=1e-6)
+
+
+ROCKSALT_AXIS = np.eye(3) * 4.0
+ROCKSALT_FRAC = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [0, 0, .5], [0, .5, 0], [.5, 0, 0], [.5, .5, .5]]).T
+
+
+def test_translation_counts_rocksalt():
+    # reference: tests/test_cxx/test_neighbor.py:199-207 (POSCAR-rocksalt, a = 4)
+    pc = ROCKSALT_AXIS @ ROCKSALT_FRAC
+    for cutoff, n in ((6.0, 147), (8.0, 203), (16.0, 751)):
+        assert len(po.NeighborCell(ROCKSALT_AXIS, pc, cutoff).trans) == n
+
+
+def test_neighbor_rocksalt_shells():
+    # reference: tests/test_cxx/test_neighbor.py:14-45
+    pc = ROCKSALT_AXIS @ ROCKSALT_FRAC
+    types = np.array([0, 0, 0, 0, 1, 1, 1, 1])
+    off, nb, dx, dy, dz = po.neighbor_full(ROCKSALT_AXIS, pc, 6.0)
+    sl = slice(off[0], off[1])
+    d = np.sqrt(dx[sl] ** 2 + dy[sl] ** 2 + dz[sl] ** 2)
+    t2 = types[nb[sl]]
+    assert (t2 == 0).sum() == 54 and (t2 == 1).sum() == 38
+    assert np.isclose(d[t2 == 0], 2.8284271247461903).sum() == 12
+    assert np.isclose(d[t2 == 1], 2.0).sum() == 6
+    assert np.sum(dx[sl][t2 == 0] ** 2 + dy[sl][t2 == 0] ** 2 + dz[sl][t2 == 0] ** 2) == pytest.approx(1152)
+    assert nb[sl][t2 == 0].sum() == 72 and nb[sl][t2 == 1].sum() == 206
+
+
+def test_neighbor_bit_exact_vs_reference_vectors():
+    ax, pc, ty = cases.skewed_cell(2)
+    for kind, fn in (("full", po.neighbor_full), ("half", po.neighbor_half)):
+        o = fn(ax, pc, 5.0)
+        for name, arr in zip(("off", "nb", "dx", "dy", "dz"), o):
+            assert np.array_equal(arr, G[f"bin_nbr_{kind}_{name}"]), (kind, name)
+    ax, pc, ty = cases.small_skewed_cell()
+    o = po.neighbor_full(ax, pc, 4.0)
+    for name, arr in zip(("off", "nb", "dx", "dy", "dz"), o):
+        assert np.array_equal(arr, G[f"small_nbr_{name}"]), name
+    nc = po.NeighborCell(ax, pc, 4.0)
+    assert np.array_equal(nc.trans, G["small_trans"])
+    assert np.array_equal(np.array(nc.axis), G["small_axis"])
+
+
+def _rel(a, b):
+    return cases.x_rel_err(a, b)
+
+
+def test_si_structure_x():
+    axis, positions_c, _, _ = cases.load_si_dataset()
+    tab = po.Tables(make_params_dict(**cases.si_model_kwargs()))
+    assert tab.n_variables == 168
+    xe, xf, xs = po.structure_x(tab, axis, positions_c[3], np.zeros(64, int), True)
+    assert _rel(xe, G["si3_xe"]) < 1e-12
+    assert _rel(xf, G["si3_xf"]) < 1e-10
+    assert _rel(xs, G["si3_xs"]) < 1e-10
+
+
+def test_binary_conditional_x_and_eval():
+    tab = po.Tables(make_params_dict(**cases.binary_model_kwargs()))
+    ax, pc, ty = cases.skewed_cell(2)
+    xe, xf, xs = po.structure_x(tab, ax, pc, ty, True)
+    assert _rel(xe, G["bin_xe"]) < 1e-12
+    assert _rel(xf, G["bin_xf"]) < 1e-10
+    assert _rel(xs, G["bin_xs"]) < 1e-10
+    e, f, s = po.eval_structure(tab, G["bin_coeffs"], ax, pc, ty)
+    assert abs(e - G["bin_e"][0]) <= 1e-10 * abs(G["bin_e"][0])
+    assert np.abs(f - G["bin_f"]).max() < 1e-10 * np.abs(G["bin_f"]).max()
+    assert np.abs(s - G["bin_s"]).max() < 1e-10 * np.abs(G["bin_s"]).max()
+
+
+def test_ternary_order3_polynomial():
+    tab = po.Tables(make_params_dict(**cases.ternary_p3_model_kwargs()))
+    ax, pc, ty = cases.skewed_cell(3, n_atom=7, seed=3)
+    xe, xf, xs = po.structure_x(tab, ax, pc, ty, True)
+    assert xe.shape[0] == G["ter_xe"].shape[0]
+    assert _rel(xe, G["ter_xe"]) < 1e-12
+    assert _rel(xf[::3], G["ter_xf"]) < 1e-10
+    assert _rel(xs, G["ter_xs"]) < 1e-10
+
+
+def test_si_train_column_sums_published_goldens():
+    # reference: tests/test_mlp_dev/test_core_features.py:17-31; the golden column sums were produced by
+    # the unmodified reference C++ over the 180 training structures (make_golden.py) and reproduce the
+    # numbers published in the reference's own test.
+    cs = G["si_train_colsum"]
+    assert tuple(G["si_train_shape"]) == (35820, 168)
+    assert cs.sum() == pytest.approx(5165294.450079148, rel=1e-6)
+    assert cs[:20].sum() == pytest.approx(447.7438322711305, rel=1e-6)
+    assert cs[20:40].sum() == pytest.approx(15803.28147846774, rel=1e-6)
+    assert cs[40:60].sum() == pytest.approx(93568.30539681061, rel=1e-6)
+    assert cs[60:80].sum() == pytest.approx(308321.82717270905, rel=1e-6)
+    assert cs[-60:-40].sum() == pytest.approx(1987480.894857876, rel=1e-6)
+    assert cs[-40:-20].sum() == pytest.approx(34372.80650408206, rel=1e-6)
+    assert cs[-20:].sum() == pytest.approx(2008586.8132866116, rel=1e-6)
+    # the oracle on a sample of the training structures agrees with the per-structure golden
+    axis, positions_c, _, _ = cases.load_si_dataset()
+    tab = po.Tables(make_params_dict(**cases.si_model_kwargs()))
+    a, d = po.atom_anlm(tab, np.zeros(64, int), *po.neighbor_full(axis, positions_c[3], 6.0), 5, False)[0], None
+    assert np.abs(a - G["si3_atom5_anlm"]).max() < 1e-12 * np.abs(G["si3_atom5_anlm"]).max()
+    d, _ = po.atom_features(tab, 0, a, False)
+    assert np.abs(d - G["si3_atom5_d"]).max() < 1e-12 * np.abs(G["si3_atom5_d"]).max()

@@ -1,0 +1,54 @@
+"""The numpy oracle against the unmodified reference C++ (oracle/_ref) on seeded random inputs.
+Skipped when oracle/_ref has not been built (it needs /root/reference; it ships to the GPU box)."""
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import polymlp_oracle as po
+from oracle import ref
+from pypolymlp_b200.params import make_params_dict
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("kwargs,n_type", [
+    (dict(n_type=1, cutoff=5.0, model_type=4, max_p=2, gtinv_order=3, gtinv_maxl=[2, 2], n_gaussians=4), 1),
+    (cases.binary_model_kwargs(), 2),
+    (dict(n_type=3, cutoff=4.5, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[2, 2, 1], n_gaussians=3), 3),
+])
+def test_x_and_eval(kwargs, n_type):
+    pd = make_params_dict(**kwargs)
+    tab, rm = po.Tables(pd), ref.RefModel(pd)
+    assert tab.n_variables == rm.n_features
+    for seed in (1, 2):
+        ax, pc, ty = cases.skewed_cell(n_type, n_atom=6, seed=seed)
+        cut = kwargs["cutoff"]
+        for kind, fn in (("full", po.neighbor_full), ("half", po.neighbor_half)):
+            for a, b in zip(fn(ax, pc, cut), ref.neighbor(kind, ax, pc, cut)):
+                assert np.array_equal(a, b)
+        xe, xf, xs = po.structure_x(tab, ax, pc, ty, True)
+        re, rf, rs = rm.run(ax, pc, ty, True)
+        a, b = np.vstack([xe[None], xs, xf]), np.vstack([re[None], rs, rf])
+        assert cases.x_rel_err(a, b) < 1e-10
+        coeffs = np.random.default_rng(seed).normal(size=tab.n_variables)
+        e, f, s = ref.RefEval(pd, coeffs).eval(ax, pc, ty)
+        e2, f2, s2 = po.eval_structure(tab, coeffs, ax, pc, ty)
+        assert abs(e - e2) < 1e-10 * abs(e)
+        assert np.abs(f - f2).max() < 1e-10 * np.abs(f).max()
+        assert np.abs(s - s2).max() < 1e-10 * np.abs(s).max()
+
+
+def test_small_cells_metric_branch():
+    for seed in range(4):
+        ax, pc, ty = cases.small_skewed_cell(seed)
+        for a, b in zip(po.neighbor_full(ax, pc, 3.5), ref.neighbor("full", ax, pc, 3.5)):
+            assert np.array_equal(a, b)
+
+
+def test_readgtinv():
+    import os
+    d = os.path.join(os.path.dirname(ref.__file__), "_ref")
+    for order, maxl in ((2, [6]), (3, [4, 4]), (4, [4, 2, 2])):
+        a, b = po.readgtinv(order, maxl, d), ref.readgtinv(order, maxl)
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
