@@ -646,16 +646,14 @@ int pm_model_count_flops(const pm_model* m, const int64_t* atoms_t, const int64_
             if (force) wpoly += (3.0 * (pairs_t + atoms_t[t]) + 7.0 * atoms_t[t]) * tp_;
             else wpoly += atoms_t[t] * tp_;
             if (force) {
-                // T_d(type, tp): derivative terms whose head belongs to type pair tp
+                // T_d(type, tp): derivative terms (merged by head and product, as the reference's
+                // mapped_features_deriv) whose head belongs to type pair tp = the contributions of our G entries
                 std::vector<double> td(nt, 0.0);
-                // count (feature, full head) pairs before conj folding, per segment
-                for (int f = 0; f < T.n_feat; ++f)
-                    for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti)
-                        for (int k = 0; k < T.term_order[ti]; ++k) {
-                            const int h = T.full_head[T.term_ids[(size_t)ti * T.max_order + k]];
-                            for (int u = 0; u < nt; ++u)
-                                if (T.seg_tp[u] == T.head_tp[h]) { td[u] += 1.0; break; }
-                        }
+                for (size_t e = 0; e + 1 < T.ent_off.size(); ++e) {
+                    // segment of the entry: recover it from the block that holds it
+                    const int blk = T.ent_pos_re[e] / 32;
+                    td[T.blocks[blk].seg] += (double)(T.ent_off[e + 1] - T.ent_off[e]);
+                }
                 for (int u = 0; u < nt; ++u) wderiv += 12.0 * (double)pairs_tt[t * nt + u] * td[u];
             }
         }
@@ -903,11 +901,8 @@ int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, dou
         CK(cudaMemcpy2D(corner.data(), (size_t)(F + 1) * sizeof(double), c->acc, (size_t)fp * sizeof(double),
                         (size_t)(F + 1) * sizeof(double), F + 1, cudaMemcpyDeviceToHost));
         const int ld = F + 1;
-        // valid region: 128x128 tiles with tile_row <= tile_col; inside diagonal tiles everything is valid
-        auto get = [&](int i, int j) {
-            const int ti = i / 128, tj = j / 128;
-            return ti <= tj ? corner[(size_t)i * ld + j] : corner[(size_t)j * ld + i];
-        };
+        // every kernel flavour fills (at least) the upper triangle i <= j
+        auto get = [&](int i, int j) { return i <= j ? corner[(size_t)i * ld + j] : corner[(size_t)j * ld + i]; };
         if (xtx)
             for (int i = 0; i < F; ++i)
                 for (int j = 0; j < F; ++j) xtx[(size_t)i * F + j] = get(i, j);
