@@ -157,6 +157,18 @@ static void build_device_model(pm_context* c) {
             for (int n = 0; n < d.n_fn; ++n) kmax = std::max(kmax, 2 * (T.seg_n_off[u][n + 1] - T.seg_n_off[u][n]));
     }
     set_lrows_kmax(kmax);
+    {   // fast-path template selection for K4a: (tiles per radial index, k-chunks per radial group)
+        int tpn = 1;
+        for (const auto& T : hm.types) {
+            std::vector<int> cnt(d.n_fn, 0);
+            for (int n_ : T.tile_n) cnt[n_]++;
+            for (int v : cnt) tpn = std::max(tpn, v);
+        }
+        const int kc = kmax / 4;
+        d.kpn = kc <= 2 ? 2 : (kc <= 4 ? 4 : (kc <= 8 ? 8 : 0));
+        d.tpn = tpn <= 4 ? tpn : 0;
+        if (d.tpn == 0) d.kpn = 0;
+    }
     std::vector<double> tpp((size_t)d.n_tp * d.n_fn * 2, 0.0);
     std::vector<int> tpn(d.n_tp, 0), tpairs((size_t)d.n_type * d.n_type);
     for (int tp = 0; tp < d.n_tp; ++tp) {
@@ -181,6 +193,15 @@ static void build_device_model(pm_context* c) {
     std::vector<int> pt;
     for (const auto& x : hm.pair_terms) { pt.push_back(x[0]); pt.push_back(x[1]); pt.push_back(x[2]); }
     d.pair_terms = upload(c, pt);
+    {
+        std::vector<int> linfp((size_t)d.n_type * hm.n_linear, -1), pvl(std::max(hm.n_linear, 1), -1);
+        for (int t = 0; t < d.n_type; ++t)
+            for (int f = 0; f < hm.types[t].n_feat; ++f)
+                linfp[(size_t)t * hm.n_linear + hm.types[t].feat_gid[f]] = hm.types[t].feat_pad[f];
+        for (int a = 0; a < d.npv; ++a) pvl[hm.pv_gid[a]] = a;
+        d.lin_fp = upload(c, linfp);
+        d.pv_of_lin = upload(c, pvl);
+    }
 
     size_t max_full = 1;
     for (int t = 0; t < d.n_type; ++t) {
@@ -214,7 +235,7 @@ static void build_device_model(pm_context* c) {
         D.tile_n_off = upload(c, tile_n_off);
         for (int u = 0; u < MAXT; ++u) {
             D.seg_heads[u] = nullptr; D.seg_len[u] = 0; D.seg_key[u] = nullptr; D.seg_n_off[u] = nullptr;
-            D.seg_nid[u] = nullptr; D.tile_blk_off[u] = nullptr;
+            D.seg_nid[u] = nullptr; D.tile_blk_off[u] = nullptr; D.blkmap[u] = nullptr;
         }
         for (int u = 0; u < d.n_type; ++u) {
             D.seg_heads[u] = upload(c, T.seg_heads[u]);
@@ -228,6 +249,16 @@ static void build_device_model(pm_context* c) {
             for (int n = 0; n < d.n_fn; ++n) nid[n] = hm.tp_nid[T.seg_tp[u]][n];
             D.seg_nid[u] = upload(c, nid);
             D.tile_blk_off[u] = upload(c, T.tile_blk_off[u]);
+            D.blkmap[u] = nullptr;
+            if (d.kpn > 0) {
+                std::vector<int> bm((size_t)D.n_tiles * d.kpn, -1);
+                for (int tile = 0; tile < D.n_tiles; ++tile) {
+                    const int kc0 = T.seg_n_off[u][T.tile_n[tile]] / 2;
+                    for (int bk = T.tile_blk_off[u][tile]; bk < T.tile_blk_off[u][tile + 1]; ++bk)
+                        bm[(size_t)tile * d.kpn + (T.blocks[bk].kchunk - kc0)] = bk;
+                }
+                D.blkmap[u] = upload(c, bm);
+            }
         }
         D.term_off = upload(c, T.term_off);
         D.term_coeff = upload(c, T.term_coeff);

@@ -38,6 +38,7 @@ struct DevType {
     const int* seg_n_off[MAXT]; // [n_fn + 1] head offsets of each radial group inside the segment
     const int* seg_nid[MAXT];   // [n_fn] radial id inside the pair record for each radial index (-1 inactive)
     const int* tile_n_off;      // [n_fn + 1] feature tiles of each radial index
+    const int* blkmap[MAXT];    // [n_tiles][kpn] block index of (tile, k-chunk inside the tile's radial group) or -1
     const int* term_off;
     const double* term_coeff;
     const int* term_order;
@@ -59,6 +60,8 @@ struct DevModel {
     int fl;        // stride of per-centre linear-feature rows (max n_fpad over types)
     int hmax;      // max n_head over types
     int pbstride;  // doubles per pair-basis record
+    int kpn;       // k-chunks (2 heads) per radial group, padded to the fast-path template value (0 = no fast path)
+    int tpn;       // max feature tiles per radial index, padded likewise
     long gstride;  // doubles per atom in the G buffer
     double cutoff;
     const double* tp_params;  // [n_tp][n_fn][2], compacted by radial id of the pair
@@ -69,6 +72,8 @@ struct DevModel {
     const int* pv_fp;         // [n_type][npv_pad] padded local id or -1
     int n_pair_terms;
     const int* pair_terms;    // [n_pair_terms][3] = (col, a, b)
+    const int* lin_fp;        // [n_type][n_linear] padded local id of each global linear feature or -1
+    const int* pv_of_lin;     // [n_linear] polynomial-variable index of a linear feature or -1
     DevType types[MAXT];
 };
 

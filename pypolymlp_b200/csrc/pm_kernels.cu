@@ -114,6 +114,7 @@ void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB,
 // K2a: per-pair basis record: radial functions (Gaussian x cosine cutoff) with d/dr, complex Y_lm
 // (m <= 0) and Cartesian gradients by the normalised associated-Legendre recurrences.
 // ================================================================================================
+template <int LT>
 __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n_pairs) return;
@@ -153,12 +154,13 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
     }
 
     // angular
-    const int L = m.maxl;
+    const int L = LT >= 0 ? LT : m.maxl;
+    constexpr int NHT = LT >= 0 ? (LT + 1) * (LT + 2) / 2 : MAX_NH;
     const double ct = dz * rinv;
     const double rho = hypot(dx, dy);
     double cp = 1.0, sp = 0.0;
     if (rho > 0.0) { cp = dx / rho; sp = dy / rho; }
-    double pl[MAX_NH], ql[MAX_NH];
+    double pl[NHT], ql[NHT];
     const double s2pi = 0.39894228040143267794;
     const double st = sqrt(1.0 - ct * ct);
 #define LM2I(l, mm) ((l) * ((l) + 1) / 2 + (mm))
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
     if (L >= 1) {
         pl[LM2I(1, 0)] = ct * 1.7320508075688772935 * s2pi; ql[LM2I(1, 0)] = 0.0;
         pl[LM2I(1, 1)] = -st * 1.2247448713915890491 * s2pi; ql[LM2I(1, 1)] = -1.2247448713915890491 * s2pi;
+#pragma unroll
         for (int l = 2; l <= L; ++l) {
             const double c1 = -sqrt(1.0 + 0.5 / l) * st;
             pl[LM2I(l, l)] = c1 * pl[LM2I(l - 1, l - 1)];
@@ -174,8 +177,10 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             pl[LM2I(l, l - 1)] = c2 * pl[LM2I(l - 1, l - 1)];
             ql[LM2I(l, l - 1)] = c2 * ql[LM2I(l - 1, l - 1)];
         }
+#pragma unroll
         for (int l = 2; l <= L; ++l) {
             const double ls = (double)(l * l), lm1s = (double)((l - 1) * (l - 1));
+#pragma unroll
             for (int mm = 0; mm <= l - 2; ++mm) {
                 const double ms = (double)(mm * mm);
                 const double alm = sqrt((4.0 * ls - 1.0) / (ls - ms));
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
     double* Yy = rec + pb_y(m, 2);
     double* Yz = rec + pb_y(m, 3);
     const double hs2 = 0.70710678118654752440;
+#pragma unroll
     for (int l = 0; l <= L; ++l) {
         const int idx = LM2I(l, 0) + l;
         Y[2 * idx] = pl[LM2I(l, 0)] * hs2; Y[2 * idx + 1] = 0.0;
@@ -202,10 +208,12 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
     double c1 = 1.0, c2 = cp, s1 = 0.0, s2 = -sp;
     const double tc = 2.0 * c2;
     double sign = -1.0;
+#pragma unroll
     for (int mp = 1; mp <= L; ++mp) {
         const double sn = tc * s1 - s2;
         const double cs = tc * c1 - c2;
         c2 = c1; c1 = cs; s2 = s1; s1 = sn;
+#pragma unroll
         for (int l = mp; l <= L; ++l) {
             const int idx = LM2I(l, -mp) + l;
             const double tmp = sign * pl[LM2I(l, mp)] * hs2;
@@ -231,7 +239,17 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
 
 void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
     if (b.n_pairs == 0) return;
-    k_pair_basis<<<(b.n_pairs + 127) / 128, 128, 0, s>>>(m, b, PB);
+    const int blocks = (b.n_pairs + 127) / 128;
+    switch (m.maxl) {
+        case 0: k_pair_basis<0><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 1: k_pair_basis<1><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 2: k_pair_basis<2><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 3: k_pair_basis<3><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 4: k_pair_basis<4><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 5: k_pair_basis<5><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        case 6: k_pair_basis<6><<<blocks, 128, 0, s>>>(m, b, PB); break;
+        default: k_pair_basis<-1><<<blocks, 128, 0, s>>>(m, b, PB); break;
+    }
 }
 
 // ================================================================================================

@@ -316,6 +316,226 @@ __global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4a fast path for models whose radial groups are small (<= TPN feature tiles, <= KPN k-chunks):
+// per (row chunk, radial group) a warp (1) prefetches its B fragments (blocks of G) into registers,
+// (2) builds the V tile in its private shared memory, (3) issues TPN*KPN*4 DMMAs from registers and
+// shared memory only.  The 9 aggregated rows (own x/y/z + 6 virial) ride in the last row chunk of each
+// neighbour-type segment, so no separate pass is needed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+
+constexpr int LR_MAXW = 8;  // max warps per CTA
+
+template <int TPN, int KPN>
+__global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                   const double2* __restrict__ agg, const double* __restrict__ Gbuf,
+                                                   double* __restrict__ Lbuf, double* __restrict__ Xown,
+                                                   double* __restrict__ Sbuf) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = blockIdx.x;
+    if (!b.force[b.st_of_atom[i]]) return;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const int nt = m.n_type;
+    const int nthr = blockDim.x, nwarp = nthr >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    // shared memory: two pair-basis tiles (double buffered, transposed), per-warp V tiles, small tables
+    const int pbs_sz = m.pbstride * LR_PLD;
+    double* pbs0 = smem;
+    double* Vw = smem + 2 * (size_t)pbs_sz + (size_t)warp * (4 * KPN) * LR_LD;   // [4*KPN][LR_LD]
+    int* tab = reinterpret_cast<int*>(smem + 2 * (size_t)pbs_sz + (size_t)nwarp * (4 * KPN) * LR_LD);
+    const int seglen_max = 2 * KPN * m.n_fn;
+    int* s_key = tab;                       // [seglen_max]
+    int* s_head = tab + seglen_max;         // [seglen_max]
+    int* s_noff = s_head + seglen_max;      // [n_fn + 1]
+    int* s_nid = s_noff + m.n_fn + 1;       // [n_fn]
+    int* s_toff = s_nid + m.n_fn;           // [n_fn + 1]
+    int* s_bmap = s_toff + m.n_fn + 1;      // [n_tiles * KPN]
+    const double* G = Gbuf + (size_t)i * m.gstride;
+    const int oy = pb_y(m, 0);
+    for (int e = tid; e < 3 * m.fl; e += nthr) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
+    for (int e = tid; e < 6 * m.fl; e += nthr) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
+    for (int e = tid; e <= m.n_fn; e += nthr) s_toff[e] = T.tile_n_off[e];
+
+    for (int u = 0; u < nt; ++u) {
+        const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
+        const int np = p1 - p0;
+        const int nrow_pair = 3 * np;
+        const int nrow = nrow_pair + 9;
+        __syncthreads();
+        for (int e = tid; e < T.seg_len[u]; e += nthr) { s_key[e] = T.seg_key[u][e]; s_head[e] = T.seg_heads[u][e]; }
+        for (int e = tid; e <= m.n_fn; e += nthr) s_noff[e] = T.seg_n_off[u][e];
+        for (int e = tid; e < m.n_fn; e += nthr) s_nid[e] = T.seg_nid[u][e];
+        for (int e = tid; e < T.n_tiles * KPN; e += nthr) s_bmap[e] = T.blkmap[u][e];
+        // asynchronous transposed copy of the pair-basis records of one row chunk
+        auto issue_copy = [&](int row0, double* dst) {
+            const int pair0 = row0 / 3;
+            const int pair1 = min(np, (row0 + LR_ROWS - 1) / 3 + 1);
+            for (int pp = 0; pp < pair1 - pair0; ++pp) {
+                const double* src = PB + (size_t)(p0 + pair0 + pp) * m.pbstride;
+                for (int it = tid; it < m.pbstride; it += nthr) cp_async8(dst + it * LR_PLD + pp, src + it);
+            }
+            cp_async_commit();
+        };
+        issue_copy(0, pbs0);
+        int buf = 0;
+        for (int row0 = 0; row0 < nrow; row0 += LR_ROWS, buf ^= 1) {
+            const double* pbs = pbs0 + (size_t)buf * pbs_sz;
+            const int pair0 = row0 / 3;
+            __syncthreads();  // everybody is done with the other buffer (chunk row0 - 32)
+            if (row0 + LR_ROWS < nrow) {
+                issue_copy(row0 + LR_ROWS, pbs0 + (size_t)(buf ^ 1) * pbs_sz);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();  // this chunk's tile (and the tables) are visible
+            const int row = row0 + lane;
+            const bool is_pair = row < nrow_pair;
+            const bool is_agg = !is_pair && row < nrow;
+            const int ragg = row - nrow_pair;
+            const int pl = is_pair ? row / 3 - pair0 : 0;
+            const int al = is_pair ? row % 3 : 0;
+            const double dal = is_pair ? pbs[al * LR_PLD + pl] * pbs[3 * LR_PLD + pl] : 0.0;
+            const int oya = pb_y(m, 1 + al);
+            for (int n = warp; n < m.n_fn; n += nwarp) {
+                const int h0 = s_noff[n];
+                const int nhn = s_noff[n + 1] - h0;
+                const int tile0 = s_toff[n];
+                const int ntile = s_toff[n + 1] - tile0;
+                if (nhn == 0) {  // radial index inactive for this type pair: pair rows are exactly zero
+                    for (int tt = 0; tt < ntile; ++tt)
+#pragma unroll
+                        for (int rt = 0; rt < 4; ++rt) {
+                            const int r = row0 + rt * 8 + g;
+                            if (r < nrow_pair)
+                                *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + (tile0 + tt) * 8 + 2 * q) =
+                                    make_double2(0.0, 0.0);
+                        }
+                    continue;
+                }
+                // (1) B fragments of this radial group (L2 -> registers, consumed after the V build)
+                double bf[TPN][KPN];
+#pragma unroll
+                for (int tt = 0; tt < TPN; ++tt)
+#pragma unroll
+                    for (int kc = 0; kc < KPN; ++kc) {
+                        const int bi = tt < ntile ? s_bmap[(tile0 + tt) * KPN + kc] : -1;
+                        bf[tt][kc] = bi >= 0 ? G[32 * (size_t)bi + lane] : 0.0;
+                    }
+                // (2) V tile
+                const int nid = s_nid[n];
+                const double fn = is_pair ? pbs[(4 + nid) * LR_PLD + pl] : 0.0;
+                const double c1 = is_pair ? pbs[(4 + m.n_fn + nid) * LR_PLD + pl] * dal : 0.0;
+                __syncwarp();
+#pragma unroll
+                for (int qh = 0; qh < 2 * KPN; ++qh) {
+                    double vr = 0.0, vi = 0.0;
+                    if (qh < nhn) {
+                        if (is_pair) {
+                            const int key = s_key[h0 + qh];
+                            if (key >= 0) {
+                                vr = c1 * pbs[(oy + 2 * key) * LR_PLD + pl] + fn * pbs[(oya + 2 * key) * LR_PLD + pl];
+                                vi = c1 * pbs[(oy + 2 * key + 1) * LR_PLD + pl] + fn * pbs[(oya + 2 * key + 1) * LR_PLD + pl];
+                            }
+                        } else if (is_agg) {
+                            const int h = s_head[h0 + qh];
+                            if (h >= 0) {
+                                const double2 v = agg[((size_t)i * m.hmax + h) * 9 + ragg];
+                                vr = v.x; vi = v.y;
+                            }
+                        }
+                    }
+                    Vw[(2 * qh) * LR_LD + lane] = vr;
+                    Vw[(2 * qh + 1) * LR_LD + lane] = vi;
+                }
+                __syncwarp();
+                // (3) DMMA
+                double acc[TPN][4][2];
+#pragma unroll
+                for (int tt = 0; tt < TPN; ++tt)
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) { acc[tt][rt][0] = 0.0; acc[tt][rt][1] = 0.0; }
+#pragma unroll
+                for (int kc = 0; kc < KPN; ++kc) {
+                    double af[4];
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) af[rt] = Vw[(4 * kc + q) * LR_LD + rt * 8 + g];
+#pragma unroll
+                    for (int tt = 0; tt < TPN; ++tt)
+#pragma unroll
+                        for (int rt = 0; rt < 4; ++rt) dmma(acc[tt][rt][0], acc[tt][rt][1], af[rt], bf[tt][kc]);
+                }
+                // (4) store
+#pragma unroll
+                for (int tt = 0; tt < TPN; ++tt) {
+                    if (tt >= ntile) break;
+#pragma unroll
+                    for (int rt = 0; rt < 4; ++rt) {
+                        const int r = row0 + rt * 8 + g;
+                        const int col = (tile0 + tt) * 8 + 2 * q;
+                        if (r < nrow_pair) {
+                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + col) =
+                                make_double2(acc[tt][rt][0], acc[tt][rt][1]);
+                        } else if (r < nrow) {
+                            const int ra = r - nrow_pair;
+                            double* dst = (ra < 3 ? Xown + ((size_t)i * 3 + ra) * m.fl : Sbuf + ((size_t)i * 6 + (ra - 3)) * m.fl) + col;
+                            double2 v = *reinterpret_cast<double2*>(dst);
+                            v.x += acc[tt][rt][0]; v.y += acc[tt][rt][1];
+                            *reinterpret_cast<double2*>(dst) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int lrows_v2_warps(const DevModel& m) {
+    // warps per CTA: balance the radial groups over the warps (n_fn = 10 -> 5 warps)
+    int best = 4, waste = 1 << 30;
+    for (int w = 4; w <= LR_MAXW; ++w) {
+        const int ws = (m.n_fn + w - 1) / w * w - m.n_fn;
+        if (ws < waste) { waste = ws; best = w; }
+    }
+    return best;
+}
+
+template <int KPN> static size_t lrows_v2_smem(const DevModel& m, int nwarp, int n_tiles_max) {
+    const size_t ints = 2 * (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN;
+    return (2ull * m.pbstride * LR_PLD + (size_t)nwarp * (4 * KPN) * LR_LD) * sizeof(double) + ints * sizeof(int) + 16;
+}
+
+template <int TPN, int KPN>
+static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    const int nwarp = lrows_v2_warps(m);
+    int ntl = 1;
+    for (int t = 0; t < m.n_type; ++t) ntl = max(ntl, m.types[t].n_tiles);
+    const size_t smem = lrows_v2_smem<KPN>(m, nwarp, ntl);
+    static size_t set_for = 0;
+    if (set_for != smem) {
+        cudaFuncSetAttribute(k_lrows_v2<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set_for = smem;
+    }
+    k_lrows_v2<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
+}
+
+static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    if (m.kpn == 0 || m.tpn == 0) return false;
+    if ((2ull * m.pbstride * LR_PLD + 8ull * (4 * m.kpn) * LR_LD) * sizeof(double) > 150 * 1024) return false;
+#define PM_LR_CASE(TP, KP) if (m.tpn == TP && m.kpn == KP) { launch_lrows_v2_t<TP, KP>(m, b, ws, s); return true; }
+    PM_LR_CASE(1, 2) PM_LR_CASE(2, 2) PM_LR_CASE(3, 2) PM_LR_CASE(4, 2)
+    PM_LR_CASE(1, 4) PM_LR_CASE(2, 4) PM_LR_CASE(3, 4) PM_LR_CASE(4, 4)
+    PM_LR_CASE(1, 8) PM_LR_CASE(2, 8) PM_LR_CASE(3, 8) PM_LR_CASE(4, 8)
+#undef PM_LR_CASE
+    return false;
+}
+
 // set by the context at model upload (max over types/segments/radial groups of 2 * padded heads)
 static int g_lrows_kmax = 0;
 void set_lrows_kmax(int kmax) { g_lrows_kmax = kmax; }
@@ -324,6 +544,7 @@ size_t lrows_mma_smem(const DevModel& m) {
 }
 
 void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    if (launch_lrows_v2(m, b, ws, s)) return;
     const size_t smem = lrows_mma_smem(m);
     static size_t set_for = 0;
     if (set_for != smem) {
@@ -493,12 +714,231 @@ __global__ void __launch_bounds__(256) k_xrows_mma(DevModel m, DevBatch b, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4b fast path (polynomial variables <= 64): up to three X rows that share their centres are built in
+// ONE pass over the derivative rows: every thread owns linear columns, sums them over the centres and,
+// on the way, drops the polynomial-variable entries into the shared Lambda tile of the gather GEMM.
+//   mode 0: blockIdx.x = row atom k; rows = (k, x/y/z); centres = k and its neighbours
+//   mode 1: blockIdx.x = structure, blockIdx.y = row group {E,Sxx,Syy} {Szz,Sxy,Syz} {Szx}; centres = atoms
+// ------------------------------------------------------------------------------------------------
+constexpr int XV_KC = 32;   // centres per K chunk
+constexpr int XV_LD = 68;   // == 4 (mod 16)
+
+__global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                      const double* __restrict__ Lbuf, const double* __restrict__ Xown,
+                                                      const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                      double* __restrict__ xe_sum, double* __restrict__ xe_sq,
+                                                      int mode, int apply_w) {
+    extern __shared__ __align__(16) double smem[];
+    double* sD = smem;                          // [XV_KC][XV_LD]        D[c][a]
+    double* sL = sD + XV_KC * XV_LD;            // [3][XV_KC][XV_LD]     Lambda_r[c][b]
+    double* sC = sL + 3 * XV_KC * XV_LD;        // [64][65]
+    int* sAtom = reinterpret_cast<int*>(sC + 64 * 65);   // [XV_KC] centre atom (-1 = none)
+    int* sSrc = sAtom + XV_KC;                           // [XV_KC] reverse pair (mode 0), -1 = the row atom itself
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+    const int nt = m.n_type;
+
+    int s, n_cent, nrow, k_atom = 0, a0 = 0, p0 = 0, r_first = 0;
+    if (mode == 0) {
+        k_atom = blockIdx.x;
+        s = b.st_of_atom[k_atom];
+        if (!b.force[s]) return;
+        p0 = b.seg_off[k_atom * nt];
+        n_cent = 1 + b.seg_off[k_atom * nt + nt] - p0;
+        nrow = 3;
+    } else {
+        s = blockIdx.x;
+        r_first = 3 * blockIdx.y;               // 0: E,Sxx,Syy  3: Szz,Sxy,Syz  6: Szx
+        nrow = b.force[s] ? min(3, 7 - r_first) : (r_first == 0 ? 1 : 0);
+        if (nrow <= 0) return;
+        a0 = b.atom_off[s];
+        n_cent = b.atom_off[s + 1] - a0;
+    }
+    int rows[3];
+    double wrow[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        int row = 0;
+        if (r < nrow) {
+            if (mode == 0) row = b.frow[s] + 3 * (k_atom - b.atom_off[s]) + r;
+            else row = (r_first + r == 0) ? b.erow[s] : b.srow[s] + r_first + r - 1;
+        }
+        rows[r] = row;
+        wrow[r] = (r < nrow && apply_w) ? b.w[row] : 1.0;
+    }
+
+    // per-thread linear columns: g0 = tid, tid + 256 (at most 2 per thread on this path)
+    double lin[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { lin[j][0] = 0.0; lin[j][1] = 0.0; lin[j][2] = 0.0; }
+    double acc[3][4][2][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) { acc[r][x][y][0] = 0.0; acc[r][x][y][1] = 0.0; }
+
+    for (int c0 = 0; c0 < n_cent; c0 += XV_KC) {
+        __syncthreads();
+        if (tid < XV_KC) {
+            const int c = c0 + tid;
+            int atom = -1, src = -1;
+            if (c < n_cent) {
+                if (mode == 0) {
+                    if (c == 0) atom = k_atom;
+                    else { const int p = p0 + c - 1; atom = b.nbr[p]; src = b.rev[p]; }
+                } else atom = a0 + c;
+            }
+            sAtom[tid] = atom;
+            sSrc[tid] = src;
+        }
+        for (int e = tid; e < 3 * XV_KC * XV_LD; e += 256) sL[e] = 0.0;
+        __syncthreads();
+        const int ncc = min(XV_KC, n_cent - c0);
+        // D tile
+        for (int e = tid; e < XV_KC * 64; e += 256) {
+            const int cc = e >> 6, a = e & 63;
+            double dv = 0.0;
+            const int atom = sAtom[cc];
+            if (atom >= 0 && a < m.npv_pad) {
+                const int fa = m.pv_fp[(size_t)b.types[atom] * m.npv_pad + a];
+                if (fa >= 0) dv = dfeat[(size_t)atom * m.fl + fa];
+            }
+            sD[cc * XV_LD + a] = dv;
+        }
+        // one pass over the derivative rows of the chunk's centres
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gcol = tid + 256 * j;
+            if (gcol >= m.n_linear) break;
+            const int pv = m.pv_of_lin[gcol];
+            int fp1 = nt == 1 ? m.lin_fp[gcol] : -1;
+            for (int cc = 0; cc < ncc; ++cc) {
+                const int atom = sAtom[cc];
+                const int fp_ = nt == 1 ? fp1 : m.lin_fp[(size_t)b.types[atom] * m.n_linear + gcol];
+                if (fp_ < 0) continue;
+                double v[3] = {0.0, 0.0, 0.0};
+                if (mode == 0) {
+                    const int src = sSrc[cc];
+                    if (src < 0) {
+                        const double* base = Xown + (size_t)atom * 3 * m.fl + fp_;
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) v[r] = base[(size_t)r * m.fl];
+                    } else {
+                        const double* base = Lbuf + (size_t)src * 3 * m.fl + fp_;
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) v[r] = -base[(size_t)r * m.fl];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        if (r >= nrow) break;
+                        const int rr = r_first + r;
+                        v[r] = rr == 0 ? dfeat[(size_t)atom * m.fl + fp_] : Sbuf[((size_t)atom * 6 + (rr - 1)) * m.fl + fp_];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) lin[j][r] += v[r];
+                if (pv >= 0) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        // energy row: Lambda = d / 2 so that C + C^T = d_a d_b
+                        const double lv = (mode == 1 && r_first + r == 0) ? 0.5 * v[r] : v[r];
+                        sL[(r * XV_KC + cc) * XV_LD + pv] = lv;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (m.n_pair_terms > 0) {
+            const int kend = (ncc + 3) & ~3;
+            for (int k0 = 0; k0 < kend; k0 += 4) {
+                double af[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) af[x] = sD[(k0 + q) * XV_LD + wm * 32 + x * 8 + g];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double bf[2];
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) bf[y] = sL[(r * XV_KC + k0 + q) * XV_LD + wn * 16 + y * 8 + g];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) dmma(acc[r][x][y][0], acc[r][x][y][1], af[x], bf[y]);
+                }
+            }
+        }
+    }
+    // ---- epilogue: linear columns (thread-owned), then the order-2 terms row by row through sC ----------
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int gcol = tid + 256 * j;
+        if (gcol >= m.n_linear) break;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r >= nrow) break;
+            if (mode == 1 && r_first + r == 0 && xe_sum) {
+                atomicAdd(xe_sum + gcol, lin[j][r]);
+                atomicAdd(xe_sq + gcol, lin[j][r] * lin[j][r]);
+            }
+            X[(size_t)rows[r] * m.fpad + gcol] = wrow[r] * lin[j][r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        if (r >= nrow) break;
+        double* xr = X + (size_t)rows[r] * m.fpad;
+        if (tid == 0) xr[m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+        if (m.n_pair_terms == 0) continue;
+        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) {
+                const int ra = wm * 32 + x * 8 + g, cb = wn * 16 + y * 8 + 2 * q;
+                sC[ra * 65 + cb] = acc[r][x][y][0];
+                sC[ra * 65 + cb + 1] = acc[r][x][y][1];
+            }
+        __syncthreads();
+        const bool erow = mode == 1 && r_first + r == 0 && xe_sum;
+        for (int e = tid; e < m.n_pair_terms; e += 256) {
+            const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
+            const double val = sC[a * 65 + bb] + sC[bb * 65 + a];
+            if (erow) { atomicAdd(xe_sum + col, val); atomicAdd(xe_sq + col, val * val); }
+            xr[col] = wrow[r] * val;
+        }
+    }
+}
+
+static size_t xrows_v2_smem() {
+    return ((size_t)XV_KC * XV_LD * 4 + 64 * 65) * sizeof(double) + 2 * XV_KC * sizeof(int);
+}
+
+static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
+                            bool apply_weights, cudaStream_t s) {
+    if (m.npv_pad > 64 || m.n_linear > 512) return false;
+    const size_t smem = xrows_v2_smem();
+    static bool set = false;
+    if (!set) {
+        cudaFuncSetAttribute(k_xrows_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set = true;
+    }
+    k_xrows_v2<<<b.n_atoms, 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
+                                            apply_weights ? 1 : 0);
+    k_xrows_v2<<<dim3(b.n_st, 3), 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
+                                                  apply_weights ? 1 : 0);
+    return true;
+}
+
 size_t xrows_mma_smem(const DevModel& m) {
     return (2ull * XR_KC * XR_LD + (size_t)m.npv_pad * (m.npv_pad + 1)) * sizeof(double) + 2 * XR_KC * sizeof(int);
 }
 
 void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                       bool apply_weights, cudaStream_t s) {
+    if (launch_xrows_v2(m, b, ws, xe_sum, xe_sq, apply_weights, s)) return;
     const size_t smem = xrows_mma_smem(m);
     static size_t set_for = 0;
     if (set_for != smem) {
