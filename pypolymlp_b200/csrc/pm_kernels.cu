@@ -305,8 +305,102 @@ __global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const doub
     }
 }
 
+// Same sums with the pair records staged through shared memory (coalesced 16-byte copies of 8 records at a
+// time, double buffered with cp.async); one thread per head, so accumulation stays thread-private.
+constexpr int AN_PT = 8;
+
+__global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                  double2* __restrict__ anc, double2* __restrict__ agg) {
+    extern __shared__ __align__(16) double sm_an[];
+    const int i = blockIdx.x;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const bool force = b.force[b.st_of_atom[i]] != 0;
+    const int nt = m.n_type;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int stride = m.pbstride;
+    const int pa = b.seg_off[i * nt], pe = b.seg_off[i * nt + nt];
+    const int oy = pb_y(m, 0), oyx = pb_y(m, 1), oyy = pb_y(m, 2), oyz = pb_y(m, 3);
+    const int h = tid;
+    const bool active = h < T.n_head;
+    int nid = 0, key = 0, ps0 = 0, ps1 = 0;
+    if (active) {
+        const int u = T.head_seg[h];
+        nid = T.head_nid[h];
+        key = T.head_key[h];
+        ps0 = b.seg_off[i * nt + u];
+        ps1 = b.seg_off[i * nt + u + 1];
+    }
+    double ar = 0.0, ai = 0.0, gr[9], gi[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { gr[k] = 0.0; gi[k] = 0.0; }
+    auto issue = [&](int pfirst, double* dst) {
+        const int np = min(AN_PT, pe - pfirst);
+        const double* src = PB + (size_t)pfirst * stride;
+        const int n16 = np * stride / 2;  // stride is even
+        for (int e = tid; e < n16; e += nthr) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + 2 * e));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    if (pe > pa) issue(pa, sm_an);
+    int buf = 0;
+    for (int pf = pa; pf < pe; pf += AN_PT, buf ^= 1) {
+        __syncthreads();
+        if (pf + AN_PT < pe) {
+            issue(pf + AN_PT, sm_an + (size_t)(buf ^ 1) * AN_PT * stride);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
+        __syncthreads();
+        if (!active) continue;
+        const double* tile = sm_an + (size_t)buf * AN_PT * stride;
+        const int q0 = max(pf, ps0), q1 = min(min(pf + AN_PT, pe), ps1);
+        for (int p = q0; p < q1; ++p) {
+            const double* rec = tile + (size_t)(p - pf) * stride;
+            const double fn = rec[4 + nid];
+            if (fn == 0.0) continue;
+            const double2 y = *reinterpret_cast<const double2*>(rec + oy + 2 * key);
+            ar += fn * y.x; ai += fn * y.y;
+            if (force) {
+                const double dx = rec[0], dy = rec[1], dz = rec[2];
+                const double d1 = rec[4 + m.n_fn + nid] * rec[3];
+                const double d1r = d1 * y.x, d1i = d1 * y.y;
+                const double2 yx = *reinterpret_cast<const double2*>(rec + oyx + 2 * key);
+                const double2 yy = *reinterpret_cast<const double2*>(rec + oyy + 2 * key);
+                const double2 yz = *reinterpret_cast<const double2*>(rec + oyz + 2 * key);
+                const double vxr = d1r * dx + fn * yx.x, vxi = d1i * dx + fn * yx.y;
+                const double vyr = d1r * dy + fn * yy.x, vyi = d1i * dy + fn * yy.y;
+                const double vzr = d1r * dz + fn * yz.x, vzi = d1i * dz + fn * yz.y;
+                gr[0] += vxr; gi[0] += vxi; gr[1] += vyr; gi[1] += vyi; gr[2] += vzr; gi[2] += vzi;
+                gr[3] -= vxr * dx; gi[3] -= vxi * dx;
+                gr[4] -= vyr * dy; gi[4] -= vyi * dy;
+                gr[5] -= vzr * dz; gi[5] -= vzi * dz;
+                gr[6] -= vxr * dy; gi[6] -= vxi * dy;
+                gr[7] -= vyr * dz; gi[7] -= vyi * dz;
+                gr[8] -= vzr * dx; gi[8] -= vzi * dx;
+            }
+        }
+    }
+    if (!active) return;
+    anc[(size_t)i * m.hmax + h] = make_double2(ar, ai);
+    if (force) {
+        double2* gp = agg + ((size_t)i * m.hmax + h) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gp[k] = make_double2(gr[k], gi[k]);
+    }
+}
+
 void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s) {
     if (b.n_atoms == 0) return;
+    const int threads = (m.hmax + 31) / 32 * 32;
+    const size_t smem = 2ull * AN_PT * m.pbstride * sizeof(double);
+    if (threads <= 256 && smem <= 48 * 1024 && (m.pbstride % 2) == 0) {
+        k_anlm_v2<<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);
+        return;
+    }
     k_anlm<<<b.n_atoms, 128, 0, s>>>(m, b, PB, anc, agg);
 }
 
@@ -367,9 +461,122 @@ __global__ void __launch_bounds__(256) k_features(DevModel m, DevBatch b, const 
     }
 }
 
+// Several atoms per CTA: every table entry (term / contribution) is read once and applied to all atoms of
+// the group that have the matching centre type, which divides the table traffic by the group size.
+template <int AT>
+__global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                      double* __restrict__ dfeat, double* __restrict__ Gbuf,
+                                                      int nfull_max) {
+    extern __shared__ double2 afull[];   // [AT][nfull_max]
+    const int i0 = blockIdx.x * AT;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int ty[AT];
+    bool fo[AT];
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        const int i = i0 + a;
+        ty[a] = i < b.n_atoms ? b.types[i] : -1;
+        fo[a] = i < b.n_atoms ? b.force[b.st_of_atom[i]] != 0 : false;
+    }
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        if (ty[a] < 0) continue;
+        const int i = i0 + a;
+        const DevType& T = m.types[ty[a]];
+        for (int k = tid; k < T.n_full; k += nthr) {
+            double2 v = anc[(size_t)i * m.hmax + T.full_head[k]];
+            if (T.full_conj[k]) {
+                const double cc = T.full_cc[k];
+                v = make_double2(cc * v.x, -cc * v.y);
+            }
+            afull[(size_t)a * nfull_max + k] = v;
+        }
+        double* drow = dfeat + (size_t)i * m.fl;
+        for (int k = tid; k < m.fl; k += nthr) drow[k] = 0.0;
+        if (fo[a]) {
+            double* G = Gbuf + (size_t)i * m.gstride;
+            for (long k = tid; k < T.g_size; k += nthr) G[k] = 0.0;
+        }
+    }
+    __syncthreads();
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        bool any = false, anyf = false;
+#pragma unroll
+        for (int a = 0; a < AT; ++a) { any = any || ty[a] == tt; anyf = anyf || (ty[a] == tt && fo[a]); }
+        if (!any) continue;
+        const DevType& T = m.types[tt];
+        const int mo = T.max_order;
+        for (int f = tid; f < T.n_feat; f += nthr) {
+            double sum[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) sum[a] = 0.0;
+            for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti) {
+                const int o = T.term_order[ti];
+                const int* ids = T.term_ids + (size_t)ti * mo;
+                const double cf = T.term_coeff[ti];
+                int id[6];
+                for (int k = 0; k < o; ++k) id[k] = ids[k];
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = af[id[0]];
+                    for (int k = 1; k < o; ++k) pr = cmul(pr, af[id[k]]);
+                    sum[a] += cf * pr.x;
+                }
+            }
+            const int fp = T.feat_pad[f];
+#pragma unroll
+            for (int a = 0; a < AT; ++a)
+                if (ty[a] == tt) dfeat[(size_t)(i0 + a) * m.fl + fp] = sum[a];
+        }
+        if (!anyf) continue;
+        for (int e = tid; e < T.n_ent; e += nthr) {
+            double gr[AT], gi[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) { gr[a] = 0.0; gi[a] = 0.0; }
+            for (int c = T.ent_off[e]; c < T.ent_off[e + 1]; ++c) {
+                const DevContribution cb = T.contribs[c];
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt || !fo[a]) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = make_double2(1.0, 0.0);
+                    for (int qq = 0; qq < cb.n_ids; ++qq) pr = cmul(pr, af[cb.ids[qq]]);
+                    if (cb.conj) pr.y = -pr.y;
+                    gr[a] += cb.coeff * pr.x;
+                    gi[a] += cb.coeff * pr.y;
+                }
+            }
+            const int pr_ = T.ent_pos_re[e], pi_ = T.ent_pos_im[e];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                if (ty[a] != tt || !fo[a]) continue;
+                double* G = Gbuf + (size_t)(i0 + a) * m.gstride;
+                G[pr_] = gr[a];
+                G[pi_] = -gi[a];
+            }
+        }
+    }
+}
+
+static size_t g_feat_smem_set = 0;
+
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s) {
     if (b.n_atoms == 0) return;
+    // smem_bytes = bytes of one atom's full a_nlm array
+    const int nfull_max = (int)(smem_bytes / sizeof(double2));
+    constexpr int AT = 4;
+    const size_t smem4 = smem_bytes * AT;
+    if (smem4 <= 96 * 1024) {
+        if (smem4 > 48 * 1024 && g_feat_smem_set != smem4) {
+            cudaFuncSetAttribute(k_features_v2<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            g_feat_smem_set = smem4;
+        }
+        k_features_v2<AT><<<(b.n_atoms + AT - 1) / AT, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);
+        return;
+    }
     k_features<<<b.n_atoms, 256, smem_bytes, s>>>(m, b, anc, dfeat, Gbuf);
 }
 

@@ -330,8 +330,17 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 
 constexpr int LR_MAXW = 8;  // max warps per CTA
 
+// ------------------------------------------------------------------------------------------------
+// K4a, third version: the V tile is never materialised.  With v = f_n' (Y D_alpha / r) + f_n dY/dalpha the
+// lm-dependent factors A1 = Y D_alpha / r and A2 = dY/dalpha do not depend on the radial index, so they are
+// built once per row chunk ([k][row], shared by all warps); a warp forms its A fragments on the fly as
+// cd(row) * A1 + cf(row) * A2 with the two per-row radial scalars of its radial group.  Per (chunk, radial
+// group): 24 coalesced B-fragment loads, 64 LDS + 64 FP64 ops, 96 DMMA, 12 vector stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int LR_LDA = 20;  // row stride of the aggregated-row scratch tile (== 4 mod 16)
+
 template <int TPN, int KPN>
-__global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
+__global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                    const double2* __restrict__ agg, const double* __restrict__ Gbuf,
                                                    double* __restrict__ Lbuf, double* __restrict__ Xown,
                                                    double* __restrict__ Sbuf) {
@@ -344,20 +353,22 @@ __global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const 
     const int nthr = blockDim.x, nwarp = nthr >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    // shared memory: two pair-basis tiles (double buffered, transposed), per-warp V tiles, small tables
+    constexpr int KR = 4 * KPN;  // reals per radial group (padded)
     const int pbs_sz = m.pbstride * LR_PLD;
-    double* pbs0 = smem;
-    double* Vw = smem + 2 * (size_t)pbs_sz + (size_t)warp * (4 * KPN) * LR_LD;   // [4*KPN][LR_LD]
-    int* tab = reinterpret_cast<int*>(smem + 2 * (size_t)pbs_sz + (size_t)nwarp * (4 * KPN) * LR_LD);
-    const int seglen_max = 2 * KPN * m.n_fn;
-    int* s_key = tab;                       // [seglen_max]
-    int* s_head = tab + seglen_max;         // [seglen_max]
-    int* s_noff = s_head + seglen_max;      // [n_fn + 1]
-    int* s_nid = s_noff + m.n_fn + 1;       // [n_fn]
-    int* s_toff = s_nid + m.n_fn;           // [n_fn + 1]
-    int* s_bmap = s_toff + m.n_fn + 1;      // [n_tiles * KPN]
+    double* pbs0 = smem;                                   // [2][pbstride][LR_PLD]
+    double* A1 = smem + 2 * (size_t)pbs_sz;                // [KR][LR_LD]
+    double* A2 = A1 + KR * LR_LD;                          // [KR][LR_LD]
+    double* scD = A2 + KR * LR_LD;                         // [n_fn][32]
+    double* scF = scD + m.n_fn * 32;                       // [n_fn][32]
+    int* tab = reinterpret_cast<int*>(scF + m.n_fn * 32);
+    int* s_head = tab;                                     // [2*KPN*n_fn] head id per segment position
+    int* s_noff = s_head + 2 * KPN * m.n_fn;               // [n_fn + 1]
+    int* s_nid = s_noff + m.n_fn + 1;                      // [n_fn]
+    int* s_toff = s_nid + m.n_fn;                          // [n_fn + 1]
+    int* s_bmap = s_toff + m.n_fn + 1;                     // [n_tiles * KPN]
     const double* G = Gbuf + (size_t)i * m.gstride;
     const int oy = pb_y(m, 0);
+    const int k_real = 2 * m.nh;
     for (int e = tid; e < 3 * m.fl; e += nthr) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
     for (int e = tid; e < 6 * m.fl; e += nthr) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
     for (int e = tid; e <= m.n_fn; e += nthr) s_toff[e] = T.tile_n_off[e];
@@ -365,14 +376,12 @@ __global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const 
     for (int u = 0; u < nt; ++u) {
         const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
         const int np = p1 - p0;
-        const int nrow_pair = 3 * np;
-        const int nrow = nrow_pair + 9;
+        const int nrow = 3 * np;
         __syncthreads();
-        for (int e = tid; e < T.seg_len[u]; e += nthr) { s_key[e] = T.seg_key[u][e]; s_head[e] = T.seg_heads[u][e]; }
+        for (int e = tid; e < T.seg_len[u]; e += nthr) s_head[e] = T.seg_heads[u][e];
         for (int e = tid; e <= m.n_fn; e += nthr) s_noff[e] = T.seg_n_off[u][e];
         for (int e = tid; e < m.n_fn; e += nthr) s_nid[e] = T.seg_nid[u][e];
         for (int e = tid; e < T.n_tiles * KPN; e += nthr) s_bmap[e] = T.blkmap[u][e];
-        // asynchronous transposed copy of the pair-basis records of one row chunk
         auto issue_copy = [&](int row0, double* dst) {
             const int pair0 = row0 / 3;
             const int pair1 = min(np, (row0 + LR_ROWS - 1) / 3 + 1);
@@ -382,44 +391,57 @@ __global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const 
             }
             cp_async_commit();
         };
-        issue_copy(0, pbs0);
+        if (nrow > 0) issue_copy(0, pbs0);
         int buf = 0;
         for (int row0 = 0; row0 < nrow; row0 += LR_ROWS, buf ^= 1) {
             const double* pbs = pbs0 + (size_t)buf * pbs_sz;
             const int pair0 = row0 / 3;
-            __syncthreads();  // everybody is done with the other buffer (chunk row0 - 32)
+            __syncthreads();  // all warps are done with A1/A2/sc and with the other pair tile
             if (row0 + LR_ROWS < nrow) {
                 issue_copy(row0 + LR_ROWS, pbs0 + (size_t)(buf ^ 1) * pbs_sz);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
-            __syncthreads();  // this chunk's tile (and the tables) are visible
-            const int row = row0 + lane;
-            const bool is_pair = row < nrow_pair;
-            const bool is_agg = !is_pair && row < nrow;
-            const int ragg = row - nrow_pair;
-            const int pl = is_pair ? row / 3 - pair0 : 0;
-            const int al = is_pair ? row % 3 : 0;
-            const double dal = is_pair ? pbs[al * LR_PLD + pl] * pbs[3 * LR_PLD + pl] : 0.0;
-            const int oya = pb_y(m, 1 + al);
+            __syncthreads();
+            {   // lm factors and radial scalars of this chunk, lane = row
+                const int row = row0 + lane;
+                const bool valid = row < nrow;
+                const int pl = valid ? row / 3 - pair0 : 0;
+                const int al = valid ? row % 3 : 0;
+                const double dal = valid ? pbs[al * LR_PLD + pl] * pbs[3 * LR_PLD + pl] : 0.0;
+                const int oya = pb_y(m, 1 + al);
+                for (int k = warp; k < KR; k += nwarp) {
+                    double a1 = 0.0, a2 = 0.0;
+                    if (valid && k < k_real) {
+                        a1 = pbs[(oy + k) * LR_PLD + pl] * dal;
+                        a2 = pbs[(oya + k) * LR_PLD + pl];
+                    }
+                    A1[k * LR_LD + lane] = a1;
+                    A2[k * LR_LD + lane] = a2;
+                }
+                for (int n = warp; n < m.n_fn; n += nwarp) {
+                    const int nid = s_nid[n];
+                    const bool on = valid && nid >= 0;
+                    scD[n * 32 + lane] = on ? pbs[(4 + m.n_fn + nid) * LR_PLD + pl] : 0.0;
+                    scF[n * 32 + lane] = on ? pbs[(4 + nid) * LR_PLD + pl] : 0.0;
+                }
+            }
+            __syncthreads();
             for (int n = warp; n < m.n_fn; n += nwarp) {
-                const int h0 = s_noff[n];
-                const int nhn = s_noff[n + 1] - h0;
                 const int tile0 = s_toff[n];
                 const int ntile = s_toff[n + 1] - tile0;
-                if (nhn == 0) {  // radial index inactive for this type pair: pair rows are exactly zero
+                if (s_noff[n + 1] == s_noff[n]) {  // radial index inactive for this type pair: exact zeros
                     for (int tt = 0; tt < ntile; ++tt)
 #pragma unroll
                         for (int rt = 0; rt < 4; ++rt) {
                             const int r = row0 + rt * 8 + g;
-                            if (r < nrow_pair)
+                            if (r < nrow)
                                 *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + (tile0 + tt) * 8 + 2 * q) =
                                     make_double2(0.0, 0.0);
                         }
                     continue;
                 }
-                // (1) B fragments of this radial group (L2 -> registers, consumed after the V build)
                 double bf[TPN][KPN];
 #pragma unroll
                 for (int tt = 0; tt < TPN; ++tt)
@@ -428,34 +450,9 @@ __global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const 
                         const int bi = tt < ntile ? s_bmap[(tile0 + tt) * KPN + kc] : -1;
                         bf[tt][kc] = bi >= 0 ? G[32 * (size_t)bi + lane] : 0.0;
                     }
-                // (2) V tile
-                const int nid = s_nid[n];
-                const double fn = is_pair ? pbs[(4 + nid) * LR_PLD + pl] : 0.0;
-                const double c1 = is_pair ? pbs[(4 + m.n_fn + nid) * LR_PLD + pl] * dal : 0.0;
-                __syncwarp();
+                double cd[4], cf[4];
 #pragma unroll
-                for (int qh = 0; qh < 2 * KPN; ++qh) {
-                    double vr = 0.0, vi = 0.0;
-                    if (qh < nhn) {
-                        if (is_pair) {
-                            const int key = s_key[h0 + qh];
-                            if (key >= 0) {
-                                vr = c1 * pbs[(oy + 2 * key) * LR_PLD + pl] + fn * pbs[(oya + 2 * key) * LR_PLD + pl];
-                                vi = c1 * pbs[(oy + 2 * key + 1) * LR_PLD + pl] + fn * pbs[(oya + 2 * key + 1) * LR_PLD + pl];
-                            }
-                        } else if (is_agg) {
-                            const int h = s_head[h0 + qh];
-                            if (h >= 0) {
-                                const double2 v = agg[((size_t)i * m.hmax + h) * 9 + ragg];
-                                vr = v.x; vi = v.y;
-                            }
-                        }
-                    }
-                    Vw[(2 * qh) * LR_LD + lane] = vr;
-                    Vw[(2 * qh + 1) * LR_LD + lane] = vi;
-                }
-                __syncwarp();
-                // (3) DMMA
+                for (int rt = 0; rt < 4; ++rt) { cd[rt] = scD[n * 32 + rt * 8 + g]; cf[rt] = scF[n * 32 + rt * 8 + g]; }
                 double acc[TPN][4][2];
 #pragma unroll
                 for (int tt = 0; tt < TPN; ++tt)
@@ -465,28 +462,70 @@ __global__ void __launch_bounds__(256) k_lrows_v2(DevModel m, DevBatch b, const 
                 for (int kc = 0; kc < KPN; ++kc) {
                     double af[4];
 #pragma unroll
-                    for (int rt = 0; rt < 4; ++rt) af[rt] = Vw[(4 * kc + q) * LR_LD + rt * 8 + g];
+                    for (int rt = 0; rt < 4; ++rt) {
+                        const int o = (4 * kc + q) * LR_LD + rt * 8 + g;
+                        af[rt] = cd[rt] * A1[o] + cf[rt] * A2[o];
+                    }
 #pragma unroll
                     for (int tt = 0; tt < TPN; ++tt)
 #pragma unroll
                         for (int rt = 0; rt < 4; ++rt) dmma(acc[tt][rt][0], acc[tt][rt][1], af[rt], bf[tt][kc]);
                 }
-                // (4) store
 #pragma unroll
                 for (int tt = 0; tt < TPN; ++tt) {
                     if (tt >= ntile) break;
 #pragma unroll
                     for (int rt = 0; rt < 4; ++rt) {
                         const int r = row0 + rt * 8 + g;
-                        const int col = (tile0 + tt) * 8 + 2 * q;
-                        if (r < nrow_pair) {
-                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + col) =
+                        if (r < nrow)
+                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + (tile0 + tt) * 8 + 2 * q) =
                                 make_double2(acc[tt][rt][0], acc[tt][rt][1]);
-                        } else if (r < nrow) {
-                            const int ra = r - nrow_pair;
-                            double* dst = (ra < 3 ? Xown + ((size_t)i * 3 + ra) * m.fl : Sbuf + ((size_t)i * 6 + (ra - 3)) * m.fl) + col;
+                    }
+                }
+            }
+        }
+        // ---- aggregated rows of this segment: own x/y/z (0..2) and the six virial rows (3..8) -------------
+        __syncthreads();
+        const int nw_agg = min(nwarp, (2 * pbs_sz) / (KR * LR_LDA));
+        if (warp < nw_agg) {
+            double* Vg = pbs0 + (size_t)warp * KR * LR_LDA;  // [KR][LR_LDA], rows 0..15
+            for (int n = warp; n < m.n_fn; n += nw_agg) {
+                const int h0 = s_noff[n];
+                const int nhn = s_noff[n + 1] - h0;
+                if (nhn == 0) continue;
+                const int tile0 = s_toff[n];
+                const int ntile = s_toff[n + 1] - tile0;
+                __syncwarp();
+                for (int e = lane; e < 2 * KPN * 16; e += 32) {
+                    const int hq = e >> 4, r = e & 15;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (hq < nhn && r < 9) {
+                        const int h = s_head[h0 + hq];
+                        if (h >= 0) v = agg[((size_t)i * m.hmax + h) * 9 + r];
+                    }
+                    Vg[(2 * hq) * LR_LDA + r] = v.x;
+                    Vg[(2 * hq + 1) * LR_LDA + r] = v.y;
+                }
+                __syncwarp();
+                for (int tt = 0; tt < ntile; ++tt) {
+                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int kc = 0; kc < KPN; ++kc) {
+                        const int bi = s_bmap[(tile0 + tt) * KPN + kc];
+                        if (bi < 0) continue;
+                        const double bfv = G[32 * (size_t)bi + lane];
+                        const double* va = Vg + (4 * kc + q) * LR_LDA + g;
+                        dmma(acc[0][0], acc[0][1], va[0], bfv);
+                        dmma(acc[1][0], acc[1][1], va[8], bfv);
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < 2; ++rt) {
+                        const int r = rt * 8 + g;
+                        if (r < 9) {
+                            double* dst = (r < 3 ? Xown + ((size_t)i * 3 + r) * m.fl : Sbuf + ((size_t)i * 6 + (r - 3)) * m.fl) +
+                                          (tile0 + tt) * 8 + 2 * q;
                             double2 v = *reinterpret_cast<double2*>(dst);
-                            v.x += acc[tt][rt][0]; v.y += acc[tt][rt][1];
+                            v.x += acc[rt][0]; v.y += acc[rt][1];
                             *reinterpret_cast<double2*>(dst) = v;
                         }
                     }
@@ -507,8 +546,8 @@ static int lrows_v2_warps(const DevModel& m) {
 }
 
 template <int KPN> static size_t lrows_v2_smem(const DevModel& m, int nwarp, int n_tiles_max) {
-    const size_t ints = 2 * (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN;
-    return (2ull * m.pbstride * LR_PLD + (size_t)nwarp * (4 * KPN) * LR_LD) * sizeof(double) + ints * sizeof(int) + 16;
+    const size_t ints = (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN;
+    return (2ull * m.pbstride * LR_PLD + 2ull * (4 * KPN) * LR_LD + 64ull * m.n_fn) * sizeof(double) + ints * sizeof(int) + 16;
 }
 
 template <int TPN, int KPN>
@@ -519,10 +558,10 @@ static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Worksp
     const size_t smem = lrows_v2_smem<KPN>(m, nwarp, ntl);
     static size_t set_for = 0;
     if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_v2<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set_for = smem;
     }
-    k_lrows_v2<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
+    k_lrows_v3<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
 }
 
 static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
@@ -721,22 +760,26 @@ __global__ void __launch_bounds__(256) k_xrows_mma(DevModel m, DevBatch b, const
 //   mode 0: blockIdx.x = row atom k; rows = (k, x/y/z); centres = k and its neighbours
 //   mode 1: blockIdx.x = structure, blockIdx.y = row group {E,Sxx,Syy} {Szz,Sxy,Syz} {Szx}; centres = atoms
 // ------------------------------------------------------------------------------------------------
-constexpr int XV_KC = 32;   // centres per K chunk
+constexpr int XV_KC = 64;   // centres per K chunk
 constexpr int XV_LD = 68;   // == 4 (mod 16)
+constexpr int XV_THREADS = 512;
 
-__global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, const double* __restrict__ dfeat,
-                                                      const double* __restrict__ Lbuf, const double* __restrict__ Xown,
-                                                      const double* __restrict__ Sbuf, double* __restrict__ X,
-                                                      double* __restrict__ xe_sum, double* __restrict__ xe_sq,
-                                                      int mode, int apply_w) {
+__global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                             const double* __restrict__ Lbuf,
+                                                             const double* __restrict__ Xown,
+                                                             const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                             double* __restrict__ xe_sum, double* __restrict__ xe_sq,
+                                                             int mode, int apply_w) {
     extern __shared__ __align__(16) double smem[];
     double* sD = smem;                          // [XV_KC][XV_LD]        D[c][a]
     double* sL = sD + XV_KC * XV_LD;            // [3][XV_KC][XV_LD]     Lambda_r[c][b]
-    double* sC = sL + 3 * XV_KC * XV_LD;        // [64][65]
-    int* sAtom = reinterpret_cast<int*>(sC + 64 * 65);   // [XV_KC] centre atom (-1 = none)
-    int* sSrc = sAtom + XV_KC;                           // [XV_KC] reverse pair (mode 0), -1 = the row atom itself
+    double* sC = sL + 3 * XV_KC * XV_LD;        // [64][65]  (also the cross-group reduction scratch)
+    const double** sPtr = reinterpret_cast<const double**>(sC + 64 * 65);  // [XV_KC][3] Lambda rows of a centre
+    double* sSgn = reinterpret_cast<double*>(sPtr + 3 * XV_KC);           // [XV_KC]
+    int* sAtom = reinterpret_cast<int*>(sSgn + XV_KC);                    // [XV_KC] centre atom (-1 = none)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;   // 16 warps: 4 x 4 over the 64 x 64 C tile
+    const int gsel = tid >> 8, tcol = tid & 255;                            // two thread groups share the centres
     const int nt = m.n_type;
 
     int s, n_cent, nrow, k_atom = 0, a0 = 0, p0 = 0, r_first = 0;
@@ -767,16 +810,16 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
         rows[r] = row;
         wrow[r] = (r < nrow && apply_w) ? b.w[row] : 1.0;
     }
+    const bool half = mode == 1 && r_first == 0;   // energy row: Lambda = d / 2 so that C + C^T = d_a d_b
 
-    // per-thread linear columns: g0 = tid, tid + 256 (at most 2 per thread on this path)
-    double lin[2][3];
+    double lin[2][3];   // linear columns tcol and tcol + 256 (partial over this group's centres)
 #pragma unroll
     for (int j = 0; j < 2; ++j) { lin[j][0] = 0.0; lin[j][1] = 0.0; lin[j][2] = 0.0; }
-    double acc[3][4][2][2];
+    double acc[3][2][2][2];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 2; ++x)
 #pragma unroll
             for (int y = 0; y < 2; ++y) { acc[r][x][y][0] = 0.0; acc[r][x][y][1] = 0.0; }
 
@@ -784,21 +827,36 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
         __syncthreads();
         if (tid < XV_KC) {
             const int c = c0 + tid;
-            int atom = -1, src = -1;
+            int atom = -1;
+            double sgn = 1.0;
+            const double* p3[3] = {dfeat, dfeat, dfeat};
             if (c < n_cent) {
                 if (mode == 0) {
-                    if (c == 0) atom = k_atom;
-                    else { const int p = p0 + c - 1; atom = b.nbr[p]; src = b.rev[p]; }
-                } else atom = a0 + c;
+                    if (c == 0) {
+                        atom = k_atom;
+                        for (int r = 0; r < 3; ++r) p3[r] = Xown + ((size_t)atom * 3 + r) * m.fl;
+                    } else {
+                        const int p = p0 + c - 1;
+                        atom = b.nbr[p];
+                        sgn = -1.0;
+                        for (int r = 0; r < 3; ++r) p3[r] = Lbuf + ((size_t)b.rev[p] * 3 + r) * m.fl;
+                    }
+                } else {
+                    atom = a0 + c;
+                    for (int r = 0; r < 3; ++r) {
+                        const int rr = min(r_first + r, 6);
+                        p3[r] = rr == 0 ? dfeat + (size_t)atom * m.fl : Sbuf + ((size_t)atom * 6 + (rr - 1)) * m.fl;
+                    }
+                }
             }
             sAtom[tid] = atom;
-            sSrc[tid] = src;
+            sSgn[tid] = sgn;
+            for (int r = 0; r < 3; ++r) sPtr[3 * tid + r] = p3[r];
         }
-        for (int e = tid; e < 3 * XV_KC * XV_LD; e += 256) sL[e] = 0.0;
+        for (int e = tid; e < 3 * XV_KC * XV_LD; e += XV_THREADS) sL[e] = 0.0;
         __syncthreads();
         const int ncc = min(XV_KC, n_cent - c0);
-        // D tile
-        for (int e = tid; e < XV_KC * 64; e += 256) {
+        for (int e = tid; e < XV_KC * 64; e += XV_THREADS) {   // D tile
             const int cc = e >> 6, a = e & 63;
             double dv = 0.0;
             const int atom = sAtom[cc];
@@ -808,45 +866,38 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
             }
             sD[cc * XV_LD + a] = dv;
         }
-        // one pass over the derivative rows of the chunk's centres
+        // one pass over the derivative rows of the chunk's centres; group gsel takes centres 4*gsel + 8*i ..+3
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int gcol = tid + 256 * j;
+            const int gcol = tcol + 256 * j;
             if (gcol >= m.n_linear) break;
             const int pv = m.pv_of_lin[gcol];
-            int fp1 = nt == 1 ? m.lin_fp[gcol] : -1;
-            for (int cc = 0; cc < ncc; ++cc) {
-                const int atom = sAtom[cc];
-                const int fp_ = nt == 1 ? fp1 : m.lin_fp[(size_t)b.types[atom] * m.n_linear + gcol];
-                if (fp_ < 0) continue;
-                double v[3] = {0.0, 0.0, 0.0};
-                if (mode == 0) {
-                    const int src = sSrc[cc];
-                    if (src < 0) {
-                        const double* base = Xown + (size_t)atom * 3 * m.fl + fp_;
+            const int fp1 = nt == 1 ? m.lin_fp[gcol] : -1;
+            for (int cc = 4 * gsel; cc < ncc; cc += 8) {
+                double v[4][3];
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) v[r] = base[(size_t)r * m.fl];
-                    } else {
-                        const double* base = Lbuf + (size_t)src * 3 * m.fl + fp_;
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int c = cc + u4;
+                    v[u4][0] = 0.0; v[u4][1] = 0.0; v[u4][2] = 0.0;
+                    if (c < ncc) {
+                        const int fp_ = nt == 1 ? fp1 : m.lin_fp[(size_t)b.types[sAtom[c]] * m.n_linear + gcol];
+                        if (fp_ >= 0) {
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) v[r] = -base[(size_t)r * m.fl];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        if (r >= nrow) break;
-                        const int rr = r_first + r;
-                        v[r] = rr == 0 ? dfeat[(size_t)atom * m.fl + fp_] : Sbuf[((size_t)atom * 6 + (rr - 1)) * m.fl + fp_];
+                            for (int r = 0; r < 3; ++r) v[u4][r] = sPtr[3 * c + r][fp_];
+                        }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 3; ++r) lin[j][r] += v[r];
-                if (pv >= 0) {
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int c = cc + u4;
+                    if (c < ncc) {
+                        const double sg = sSgn[c];
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        // energy row: Lambda = d / 2 so that C + C^T = d_a d_b
-                        const double lv = (mode == 1 && r_first + r == 0) ? 0.5 * v[r] : v[r];
-                        sL[(r * XV_KC + cc) * XV_LD + pv] = lv;
+                        for (int r = 0; r < 3; ++r) {
+                            const double vv = sg * v[u4][r];
+                            lin[j][r] += vv;
+                            if (pv >= 0) sL[(r * XV_KC + c) * XV_LD + pv] = (half && r == 0) ? 0.5 * vv : vv;
+                        }
                     }
                 }
             }
@@ -855,37 +906,49 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
         if (m.n_pair_terms > 0) {
             const int kend = (ncc + 3) & ~3;
             for (int k0 = 0; k0 < kend; k0 += 4) {
-                double af[4];
+                double af[2];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) af[x] = sD[(k0 + q) * XV_LD + wm * 32 + x * 8 + g];
+                for (int x = 0; x < 2; ++x) af[x] = sD[(k0 + q) * XV_LD + wm * 16 + x * 8 + g];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     double bf[2];
 #pragma unroll
                     for (int y = 0; y < 2; ++y) bf[y] = sL[(r * XV_KC + k0 + q) * XV_LD + wn * 16 + y * 8 + g];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x)
+                    for (int x = 0; x < 2; ++x)
 #pragma unroll
                         for (int y = 0; y < 2; ++y) dmma(acc[r][x][y][0], acc[r][x][y][1], af[x], bf[y]);
                 }
             }
         }
     }
-    // ---- epilogue: linear columns (thread-owned), then the order-2 terms row by row through sC ----------
+    // ---- combine the two groups' linear sums -----------------------------------------------------------------
+    __syncthreads();
+    if (gsel == 1) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int gcol = tid + 256 * j;
-        if (gcol >= m.n_linear) break;
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            if (r >= nrow) break;
-            if (mode == 1 && r_first + r == 0 && xe_sum) {
-                atomicAdd(xe_sum + gcol, lin[j][r]);
-                atomicAdd(xe_sq + gcol, lin[j][r] * lin[j][r]);
+            for (int r = 0; r < 3; ++r) sC[(j * 3 + r) * 256 + tcol] = lin[j][r];
+    }
+    __syncthreads();
+    if (gsel == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gcol = tcol + 256 * j;
+            if (gcol >= m.n_linear) break;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (r >= nrow) break;
+                const double val = lin[j][r] + sC[(j * 3 + r) * 256 + tcol];
+                if (half && r == 0 && xe_sum) {
+                    atomicAdd(xe_sum + gcol, val);
+                    atomicAdd(xe_sq + gcol, val * val);
+                }
+                X[(size_t)rows[r] * m.fpad + gcol] = wrow[r] * val;
             }
-            X[(size_t)rows[r] * m.fpad + gcol] = wrow[r] * lin[j][r];
         }
     }
+    // ---- order-2 terms, row by row through sC ------------------------------------------------------------------
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         if (r >= nrow) break;
@@ -894,16 +957,16 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
         if (m.n_pair_terms == 0) continue;
         __syncthreads();
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+        for (int x = 0; x < 2; ++x)
 #pragma unroll
             for (int y = 0; y < 2; ++y) {
-                const int ra = wm * 32 + x * 8 + g, cb = wn * 16 + y * 8 + 2 * q;
+                const int ra = wm * 16 + x * 8 + g, cb = wn * 16 + y * 8 + 2 * q;
                 sC[ra * 65 + cb] = acc[r][x][y][0];
                 sC[ra * 65 + cb + 1] = acc[r][x][y][1];
             }
         __syncthreads();
-        const bool erow = mode == 1 && r_first + r == 0 && xe_sum;
-        for (int e = tid; e < m.n_pair_terms; e += 256) {
+        const bool erow = half && r == 0 && xe_sum;
+        for (int e = tid; e < m.n_pair_terms; e += XV_THREADS) {
             const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
             const double val = sC[a * 65 + bb] + sC[bb * 65 + a];
             if (erow) { atomicAdd(xe_sum + col, val); atomicAdd(xe_sq + col, val * val); }
@@ -913,7 +976,7 @@ __global__ void __launch_bounds__(256, 2) k_xrows_v2(DevModel m, DevBatch b, con
 }
 
 static size_t xrows_v2_smem() {
-    return ((size_t)XV_KC * XV_LD * 4 + 64 * 65) * sizeof(double) + 2 * XV_KC * sizeof(int);
+    return ((size_t)XV_KC * XV_LD * 4 + 64 * 65 + 4 * XV_KC) * sizeof(double) + XV_KC * sizeof(int);
 }
 
 static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
@@ -925,10 +988,10 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         cudaFuncSetAttribute(k_xrows_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set = true;
     }
-    k_xrows_v2<<<b.n_atoms, 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
-                                            apply_weights ? 1 : 0);
-    k_xrows_v2<<<dim3(b.n_st, 3), 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
-                                                  apply_weights ? 1 : 0);
+    k_xrows_v2<<<b.n_atoms, XV_THREADS, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
+                                                   apply_weights ? 1 : 0);
+    k_xrows_v2<<<dim3(b.n_st, 3), XV_THREADS, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
+                                                         apply_weights ? 1 : 0);
     return true;
 }
 
