@@ -114,6 +114,44 @@ void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB,
 // K2a: per-pair basis record: radial functions (Gaussian x cosine cutoff) with d/dr, complex Y_lm
 // (m <= 0) and Cartesian gradients by the normalised associated-Legendre recurrences.
 // ================================================================================================
+// pair-independent coefficients of the Legendre recurrences (filled once on the host with the same
+// IEEE expressions the reference evaluates per pair)
+constexpr int CT_L = 21;                       // l = 0..20
+__constant__ double c_c1[CT_L];                // -sqrt(1 + 0.5 / l)
+__constant__ double c_c2[CT_L];                // sqrt(2 (l - 1) + 3)
+__constant__ double c_alm[CT_L * CT_L];        // sqrt((4 l^2 - 1) / (l^2 - m^2))
+__constant__ double c_blm[CT_L * CT_L];        // -sqrt(((l-1)^2 - m^2) / (4 (l-1)^2 - 1))
+__constant__ double c_sq0[CT_L];               // sqrt(0.5 l (l + 1))
+__constant__ double c_sqd[CT_L * CT_L];        // sqrt((l - m)(l + m + 1))
+
+void init_pair_basis_tables() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return;
+    double c1[CT_L] = {0}, c2[CT_L] = {0}, sq0[CT_L] = {0};
+    static double alm[CT_L * CT_L], blm[CT_L * CT_L], sqd[CT_L * CT_L];
+    for (int l = 0; l < CT_L; ++l) {
+        if (l >= 1) { c1[l] = -sqrt(1.0 + 0.5 / l); c2[l] = sqrt(2.0 * (l - 1.0) + 3.0); }
+        sq0[l] = sqrt(0.5 * l * (l + 1));
+        const double ls = (double)(l * l), lm1s = (double)((l - 1) * (l - 1));
+        for (int mm = 0; mm < CT_L; ++mm) {
+            const double ms = (double)(mm * mm);
+            alm[l * CT_L + mm] = (l >= 2 && mm <= l - 2) ? sqrt((4.0 * ls - 1.0) / (ls - ms)) : 0.0;
+            blm[l * CT_L + mm] = (l >= 2 && mm <= l - 2) ? -sqrt((lm1s - ms) / (4.0 * lm1s - 1.0)) : 0.0;
+            sqd[l * CT_L + mm] = (mm <= l) ? sqrt((double)((l - mm) * (l + mm + 1))) : 0.0;
+        }
+    }
+    cudaMemcpyToSymbol(c_c1, c1, sizeof(c1));
+    cudaMemcpyToSymbol(c_c2, c2, sizeof(c2));
+    cudaMemcpyToSymbol(c_sq0, sq0, sizeof(sq0));
+    cudaMemcpyToSymbol(c_alm, alm, sizeof(alm));
+    cudaMemcpyToSymbol(c_blm, blm, sizeof(blm));
+    cudaMemcpyToSymbol(c_sqd, sqd, sizeof(sqd));
+    done[dev] = true;
+}
+
 template <int LT>
 __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,21 +208,19 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
         pl[LM2I(1, 1)] = -st * 1.2247448713915890491 * s2pi; ql[LM2I(1, 1)] = -1.2247448713915890491 * s2pi;
 #pragma unroll
         for (int l = 2; l <= L; ++l) {
-            const double c1 = -sqrt(1.0 + 0.5 / l) * st;
+            const double c1 = c_c1[l] * st;
             pl[LM2I(l, l)] = c1 * pl[LM2I(l - 1, l - 1)];
             ql[LM2I(l, l)] = c1 * ql[LM2I(l - 1, l - 1)];
-            const double c2 = sqrt(2.0 * (l - 1.0) + 3.0) * ct;
+            const double c2 = c_c2[l] * ct;
             pl[LM2I(l, l - 1)] = c2 * pl[LM2I(l - 1, l - 1)];
             ql[LM2I(l, l - 1)] = c2 * ql[LM2I(l - 1, l - 1)];
         }
 #pragma unroll
         for (int l = 2; l <= L; ++l) {
-            const double ls = (double)(l * l), lm1s = (double)((l - 1) * (l - 1));
 #pragma unroll
             for (int mm = 0; mm <= l - 2; ++mm) {
-                const double ms = (double)(mm * mm);
-                const double alm = sqrt((4.0 * ls - 1.0) / (ls - ms));
-                const double blm = -sqrt((lm1s - ms) / (4.0 * lm1s - 1.0));
+                const double alm = c_alm[l * CT_L + mm];
+                const double blm = c_blm[l * CT_L + mm];
                 pl[LM2I(l, mm)] = alm * (ct * pl[LM2I(l - 1, mm)] + blm * pl[LM2I(l - 2, mm)]);
                 ql[LM2I(l, mm)] = alm * (ct * ql[LM2I(l - 1, mm)] + blm * ql[LM2I(l - 2, mm)]);
             }
@@ -200,7 +236,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
         const int idx = LM2I(l, 0) + l;
         Y[2 * idx] = pl[LM2I(l, 0)] * hs2; Y[2 * idx + 1] = 0.0;
         double common = 0.0;
-        if (l >= 1) common = ql[LM2I(l, 1)] * st * rinv * sqrt(0.5 * l * (l + 1));
+        if (l >= 1) common = ql[LM2I(l, 1)] * st * rinv * c_sq0[l];
         Yx[2 * idx] = common * ct * cp; Yx[2 * idx + 1] = 0.0;
         Yy[2 * idx] = common * ct * sp; Yy[2 * idx + 1] = 0.0;
         Yz[2 * idx] = -common * st; Yz[2 * idx + 1] = 0.0;
@@ -221,7 +257,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             // common = e^{i m phi} / sqrt(2) / r
             const double cr = cs * hs2 * rinv, ci = sn * hs2 * rinv;
             double dth = mp * ct * ql[LM2I(l, mp)];
-            if (mp != l) dth += sqrt((double)((l - mp) * (l + mp + 1))) * ql[LM2I(l, mp + 1)] * st;
+            if (mp != l) dth += c_sqd[l * CT_L + mp] * ql[LM2I(l, mp + 1)] * st;
             const double dph = mp * ql[LM2I(l, mp)];  // dphi = i * dph
             // x: common * (dth*ct*cp - i*dph*sp) ; y: common * (dth*ct*sp + i*dph*cp) ; z: -common*dth*st
             const double ax = dth * ct * cp, bx = -dph * sp;
@@ -239,6 +275,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
 
 void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
     if (b.n_pairs == 0) return;
+    init_pair_basis_tables();
     const int blocks = (b.n_pairs + 127) / 128;
     switch (m.maxl) {
         case 0: k_pair_basis<0><<<blocks, 128, 0, s>>>(m, b, PB); break;

@@ -14,6 +14,7 @@
 //   k_xrows_mma   K4b  gather GEMM C[a,b] = sum_centres d_a Lambda_b, then X = C + C^T per polynomial term
 #include "pm_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cublas_v2.h>
 
@@ -132,29 +133,124 @@ __global__ void __launch_bounds__(256, 1) k_syrk_mma(const double* __restrict__ 
     }
 }
 
-static int syrk_splits(int n_rows, int fpad) {
+// Stream-K variant: one persistent CTA per SM; the (tile, 16-row k-block) work units are cut into equal
+// contiguous ranges, so every SM does the same number of DMMAs (no wave quantisation, no tail).  A CTA that
+// owns only part of a tile's k-range adds its partial tile with RED.F64; a CTA that owns the whole k-range of
+// a tile uses plain vector read-modify-write.
+__global__ void __launch_bounds__(256, 1) k_syrk_sk(const double* __restrict__ X, int n_rows, int fpad,
+                                                     double* __restrict__ C, int nkb, long units_total) {
+    extern __shared__ __align__(16) double smem[];
     const int ntile = fpad / SY_BM;
-    const int tiles = ntile * (ntile + 1) / 2;
-    int ks = (6 * 148 + tiles - 1) / tiles;            // ~6 waves of CTAs
-    const int max_ks = (n_rows + 255) / 256;           // at least 256 rows per split
-    if (ks > max_ks) ks = max_ks;
-    if (ks < 1) ks = 1;
-    return ks;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, q = lane & 3;
+    const long per = (units_total + gridDim.x - 1) / gridDim.x;
+    long u = (long)blockIdx.x * per;
+    const long u_end = min(units_total, u + per);
+
+    while (u < u_end) {
+        const int tile = (int)(u / nkb);
+        const int kb0 = (int)(u - (long)tile * nkb);
+        const int kb1 = (int)min((long)nkb, (long)kb0 + (u_end - u));
+        int ti = 0, rem = tile;
+        while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
+        const int tj = ti + rem;
+        const bool diag = ti == tj;
+        const int r_begin = kb0 * SY_BK;
+        const int r_end = min(n_rows, kb1 * SY_BK);
+        const int nk = kb1 - kb0;
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+        auto load_stage = [&](int kt, int slot) {
+            double* sA = smem + (size_t)slot * SY_STAGE_DOUBLES;
+            double* sB = sA + SY_BK * SY_LD;
+            const int r0 = r_begin + kt * SY_BK;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int e = tid + it * 256;
+                const int rr = e >> 6, cc = (e & 63) * 2;
+                const int r = r0 + rr;
+                const bool ok = r < r_end;
+                const double* src = X + (size_t)(ok ? r : r_begin) * fpad;
+                cp_async16(sA + rr * SY_LD + cc, src + ti * SY_BM + cc, ok ? 16 : 0);
+                if (!diag) cp_async16(sB + rr * SY_LD + cc, src + tj * SY_BM + cc, ok ? 16 : 0);
+            }
+        };
+        __syncthreads();  // previous segment's smem reads are finished
+#pragma unroll
+        for (int s = 0; s < SY_STAGES - 1; ++s) {
+            if (s < nk) load_stage(s, s);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<SY_STAGES - 2>();
+            __syncthreads();
+            {
+                const int nx = kt + SY_STAGES - 1;
+                if (nx < nk) load_stage(nx, nx % SY_STAGES);
+                cp_async_commit();
+            }
+            const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
+            const double* sB = diag ? sA : sA + SY_BK * SY_LD;
+            const double* pa = sA + q * SY_LD + wm * 64 + g;
+            const double* pb = sB + q * SY_LD + wn * 32 + g;
+#pragma unroll
+            for (int ks = 0; ks < SY_BK / 4; ++ks) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+        }
+        cp_async_wait<0>();
+        const bool whole = kb0 == 0 && kb1 == nkb;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int row = ti * SY_BM + wm * 64 + a * 8 + g;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int col = tj * SY_BM + wn * 32 + b * 8 + 2 * q;
+                double* dst = C + (size_t)row * fpad + col;
+                if (!whole) {
+                    atomicAdd(dst, acc[a][b][0]);
+                    atomicAdd(dst + 1, acc[a][b][1]);
+                } else {
+                    double2 v = *reinterpret_cast<double2*>(dst);
+                    v.x += acc[a][b][0];
+                    v.y += acc[a][b][1];
+                    *reinterpret_cast<double2*>(dst) = v;
+                }
+            }
+        }
+        u += nk;
+    }
 }
 
 void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_syrk_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
-        attr = true;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        cudaFuncSetAttribute(k_syrk_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
     }
     const int ntile = fpad / SY_BM;
-    const int tiles = ntile * (ntile + 1) / 2;
-    const int ks = syrk_splits(n_rows, fpad);
-    int rps = (n_rows + ks - 1) / ks;
-    rps = (rps + SY_BK - 1) / SY_BK * SY_BK;
-    const int nsplit = (n_rows + rps - 1) / rps;
-    k_syrk_mma<<<dim3(tiles, nsplit), 256, SY_SMEM, s>>>(X, n_rows, fpad, C, rps, nsplit > 1 ? 1 : 0);
+    const long tiles = (long)ntile * (ntile + 1) / 2;
+    const int nkb = (n_rows + SY_BK - 1) / SY_BK;
+    const long units = tiles * nkb;
+    const int grid = (int)std::min<long>(n_sm, units);
+    k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X, n_rows, fpad, C, nkb, units);
 }
 
 int syrk_launches(int n_rows, int fpad, bool simple) { return n_rows > 0 ? 1 : 0; }
