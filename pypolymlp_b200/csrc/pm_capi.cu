@@ -482,7 +482,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     b.seg_off = c->d_seg_off.p;
     const size_t np1 = std::max<size_t>(n_pairs, 1);
     c->d_nbr.ensure(np1); c->d_centre.ensure(np1); c->d_rev.ensure(np1);
-    c->d_PB.ensure(np1 * d.pbstride);
+    c->d_PB.ensure(pb_doubles(np1, d.pbstride));
     b.nbr = c->d_nbr.p; b.centre = c->d_centre.p; b.rev = c->d_rev.p;
     launch_neighbor_fill(d, b, c->d_PB.p, s);
     launch_neighbor_rev(d, b, c->d_PB.p, c->d_err.p, s);
@@ -999,10 +999,12 @@ int pm_neighbor_full(pm_context* c, const double* axis, const double* positions_
             const int P = c->last_pairs;
             CK(cudaMemcpy(neigh, c->d_nbr.p, P * sizeof(int), cudaMemcpyDeviceToHost));
             const int stride = c->dm.pbstride;
-            std::vector<double> rec((size_t)P * 3);
-            CK(cudaMemcpy2D(rec.data(), 3 * sizeof(double), c->d_PB.p, (size_t)stride * sizeof(double), 3 * sizeof(double), P,
-                            cudaMemcpyDeviceToHost));
-            for (int p = 0; p < P; ++p) { dx[p] = rec[3 * (size_t)p]; dy[p] = rec[3 * (size_t)p + 1]; dz[p] = rec[3 * (size_t)p + 2]; }
+            std::vector<double> raw(pb_doubles(P, stride));
+            CK(cudaMemcpy(raw.data(), c->d_PB.p, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int p = 0; p < P; ++p) {
+                const double* base = raw.data() + (size_t)(p >> 5) * stride * PB_BLK + (p & 31);
+                dx[p] = base[0]; dy[p] = base[PB_BLK]; dz[p] = base[2 * PB_BLK];
+            }
         }
     });
 }
@@ -1036,7 +1038,7 @@ int pm_debug_fetch(pm_context* c, int what, double* out, size_t cap, size_t* n) 
         size_t cnt = 0;
         if (what == 0) { src = c->d_anc.p; cnt = (size_t)b.n_atoms * d.hmax * 2; }
         else if (what == 1) { src = c->d_dfeat.p; cnt = (size_t)b.n_atoms * d.fl; }
-        else if (what == 2) { src = c->d_PB.p; cnt = (size_t)c->last_pairs * d.pbstride; }
+        else if (what == 2) { src = c->d_PB.p; cnt = pb_doubles(c->last_pairs, d.pbstride); }
         else if (what == 3) { src = c->d_X.p; cnt = (size_t)b.n_rows * d.fpad; }
         else throw std::invalid_argument("unknown debug buffer");
         *n = cnt;

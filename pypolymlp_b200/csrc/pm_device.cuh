@@ -77,7 +77,29 @@ struct DevModel {
     DevType types[MAXT];
 };
 
-// pair-basis record layout (doubles): dx dy dz 1/r | fn[n_fn] | fn'[n_fn] | Y (re,im)[nh] | Yx | Yy | Yz
+// pair-basis record items (doubles): dx dy dz 1/r | fn[n_fn] | fn'[n_fn] | Y (re,im)[nh] | Yx | Yy | Yz
+// Storage is blocked: 32 consecutive pairs form a block [item][32], so a warp that writes item k of 32
+// pairs touches 256 contiguous bytes, and the records of consecutive pairs are contiguous per item.
+constexpr int PB_BLK = 32;
+struct PBRec {
+    const double* base;
+    __device__ __forceinline__ double operator[](int item) const { return base[(size_t)item * PB_BLK]; }
+    __device__ __forceinline__ PBRec operator+(int items) const { return PBRec{base + (size_t)items * PB_BLK}; }
+};
+struct PBRecW {
+    double* base;
+    __device__ __forceinline__ double& operator[](int item) const { return base[(size_t)item * PB_BLK]; }
+    __device__ __forceinline__ PBRecW operator+(int items) const { return PBRecW{base + (size_t)items * PB_BLK}; }
+};
+__device__ __forceinline__ PBRec pb_rec(const double* PB, int p, int stride) {
+    return PBRec{PB + (size_t)(p >> 5) * stride * PB_BLK + (p & 31)};
+}
+__device__ __forceinline__ PBRecW pb_rec_w(double* PB, int p, int stride) {
+    return PBRecW{PB + (size_t)(p >> 5) * stride * PB_BLK + (p & 31)};
+}
+__host__ __device__ inline size_t pb_doubles(size_t n_pairs, int stride) {
+    return (n_pairs + PB_BLK - 1) / PB_BLK * PB_BLK * (size_t)stride;
+}
 __host__ __device__ inline int pb_fn(const DevModel& m) { return 4; }
 __host__ __device__ inline int pb_fnd(const DevModel& m) { return 4 + m.n_fn; }
 __host__ __device__ inline int pb_y(const DevModel& m, int comp) { return 4 + 2 * m.n_fn + comp * 2 * m.nh; }

@@ -40,19 +40,20 @@ __global__ void __launch_bounds__(256) k_neighbor(DevModel m, DevBatch b, int* _
     for (int u = 0; u < nt; ++u) {
         int cnt = 0;
         const int base = FILL ? b.seg_off[i * nt + u] : 0;
+        // (j, t) of this lane's candidate, advanced by 32 per iteration without an integer division
+        int j = lane / T, t = lane - (lane / T) * T;
+        const int dj = 32 / T, dt = 32 - (32 / T) * T;
         for (int c0 = 0; c0 < total; c0 += 32) {
             const int c = c0 + lane;
             bool hit = false;
             double dx = 0.0, dy = 0.0, dz = 0.0;
-            int j = 0;
+            const int jc = j;
             if (c < total) {
-                j = c / T;
-                const int t = c - j * T;
-                if (nt == 1 || b.types[a0 + j] == u) {
+                if (nt == 1 || b.types[a0 + jc] == u) {
                     const double* tr = b.trans + 3 * (size_t)(t0 + t);
-                    dx = __dadd_rn(__dsub_rn(b.x[a0 + j], xi), tr[0]);
-                    dy = __dadd_rn(__dsub_rn(b.y[a0 + j], yi), tr[1]);
-                    dz = __dadd_rn(__dsub_rn(b.z[a0 + j], zi), tr[2]);
+                    dx = __dadd_rn(__dsub_rn(b.x[a0 + jc], xi), tr[0]);
+                    dy = __dadd_rn(__dsub_rn(b.y[a0 + jc], yi), tr[1]);
+                    dz = __dadd_rn(__dsub_rn(b.z[a0 + jc], zi), tr[2]);
                     const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                     hit = (r2 < cutoff_sq) && (r2 > tol_sq);
                 }
@@ -60,12 +61,14 @@ __global__ void __launch_bounds__(256) k_neighbor(DevModel m, DevBatch b, int* _
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (FILL && hit) {
                 const int pos = base + cnt + __popc(mask & ((1u << lane) - 1u));
-                b.nbr[pos] = a0 + j;
+                b.nbr[pos] = a0 + jc;
                 b.centre[pos] = i;
-                double* rec = PB + (size_t)pos * m.pbstride;
+                const PBRecW rec = pb_rec_w(PB, pos, m.pbstride);
                 rec[0] = dx; rec[1] = dy; rec[2] = dz;
             }
             cnt += __popc(mask);
+            j += dj; t += dt;
+            if (t >= T) { t -= T; ++j; }
         }
         if (!FILL && lane == 0) counts[i * nt + u] = cnt;
     }
@@ -91,14 +94,14 @@ __global__ void __launch_bounds__(256) k_neighbor_rev(DevModel m, DevBatch b, co
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n_pairs) return;
     const int i = b.centre[p], j = b.nbr[p];
-    const double* rec = PB + (size_t)p * m.pbstride;
+    const PBRec rec = pb_rec(PB, p, m.pbstride);
     const double dx = -rec[0], dy = -rec[1], dz = -rec[2];
     const int u = b.types[i];
     const int q0 = b.seg_off[j * m.n_type + u], q1 = b.seg_off[j * m.n_type + u + 1];
     int found = -1;
     for (int q = q0; q < q1; ++q) {
         if (b.nbr[q] != i) continue;
-        const double* rq = PB + (size_t)q * m.pbstride;
+        const PBRec rq = pb_rec(PB, q, m.pbstride);
         if (rq[0] == dx && rq[1] == dy && rq[2] == dz) { found = q; break; }
     }
     b.rev[p] = found;
@@ -156,7 +159,7 @@ template <int LT>
 __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n_pairs) return;
-    double* rec = PB + (size_t)p * m.pbstride;
+    const PBRecW rec = pb_rec_w(PB, p, m.pbstride);
     const double dx = rec[0], dy = rec[1], dz = rec[2];
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     const double rinv = 1.0 / r;
@@ -226,10 +229,10 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             }
         }
     }
-    double* Y = rec + pb_y(m, 0);
-    double* Yx = rec + pb_y(m, 1);
-    double* Yy = rec + pb_y(m, 2);
-    double* Yz = rec + pb_y(m, 3);
+    const PBRecW Y = rec + pb_y(m, 0);
+    const PBRecW Yx = rec + pb_y(m, 1);
+    const PBRecW Yy = rec + pb_y(m, 2);
+    const PBRecW Yz = rec + pb_y(m, 3);
     const double hs2 = 0.70710678118654752440;
 #pragma unroll
     for (int l = 0; l <= L; ++l) {
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const doub
 #pragma unroll
         for (int k = 0; k < 9; ++k) { gr[k] = 0.0; gi[k] = 0.0; }
         for (int p = p0; p < p1; ++p) {
-            const double* rec = PB + (size_t)p * m.pbstride;
+            const PBRec rec = pb_rec(PB, p, m.pbstride);
             const double fn = rec[4 + nid];
             if (fn == 0.0) continue;
             const double yr = rec[oy + 2 * key], yi = rec[oy + 2 * key + 1];
@@ -373,11 +376,13 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
     for (int k = 0; k < 9; ++k) { gr[k] = 0.0; gi[k] = 0.0; }
     auto issue = [&](int pfirst, double* dst) {
         const int np = min(AN_PT, pe - pfirst);
-        const double* src = PB + (size_t)pfirst * stride;
-        const int n16 = np * stride / 2;  // stride is even
-        for (int e = tid; e < n16; e += nthr) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + 2 * e);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + 2 * e));
+        const int tot = np * stride;
+        for (int e = tid; e < tot; e += nthr) {
+            const int it = e / np, pp = e - it * np;
+            const int p = pfirst + pp;
+            const double* src = PB + ((size_t)(p >> 5) * stride + it) * PB_BLK + (p & 31);
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + it * (AN_PT + 1) + pp);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(src));
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -386,28 +391,29 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
     for (int pf = pa; pf < pe; pf += AN_PT, buf ^= 1) {
         __syncthreads();
         if (pf + AN_PT < pe) {
-            issue(pf + AN_PT, sm_an + (size_t)(buf ^ 1) * AN_PT * stride);
+            issue(pf + AN_PT, sm_an + (size_t)(buf ^ 1) * (AN_PT + 1) * stride);
             asm volatile("cp.async.wait_group 1;\n" ::);
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::);
         }
         __syncthreads();
         if (!active) continue;
-        const double* tile = sm_an + (size_t)buf * AN_PT * stride;
+        const double* tile = sm_an + (size_t)buf * (AN_PT + 1) * stride;
         const int q0 = max(pf, ps0), q1 = min(min(pf + AN_PT, pe), ps1);
         for (int p = q0; p < q1; ++p) {
-            const double* rec = tile + (size_t)(p - pf) * stride;
-            const double fn = rec[4 + nid];
+            const double* rb = tile + (p - pf);
+#define REC(item) rb[(item) * (AN_PT + 1)]
+            const double fn = REC(4 + nid);
             if (fn == 0.0) continue;
-            const double2 y = *reinterpret_cast<const double2*>(rec + oy + 2 * key);
+            const double2 y = make_double2(REC(oy + 2 * key), REC(oy + 2 * key + 1));
             ar += fn * y.x; ai += fn * y.y;
             if (force) {
-                const double dx = rec[0], dy = rec[1], dz = rec[2];
-                const double d1 = rec[4 + m.n_fn + nid] * rec[3];
+                const double dx = REC(0), dy = REC(1), dz = REC(2);
+                const double d1 = REC(4 + m.n_fn + nid) * REC(3);
                 const double d1r = d1 * y.x, d1i = d1 * y.y;
-                const double2 yx = *reinterpret_cast<const double2*>(rec + oyx + 2 * key);
-                const double2 yy = *reinterpret_cast<const double2*>(rec + oyy + 2 * key);
-                const double2 yz = *reinterpret_cast<const double2*>(rec + oyz + 2 * key);
+                const double2 yx = make_double2(REC(oyx + 2 * key), REC(oyx + 2 * key + 1));
+                const double2 yy = make_double2(REC(oyy + 2 * key), REC(oyy + 2 * key + 1));
+                const double2 yz = make_double2(REC(oyz + 2 * key), REC(oyz + 2 * key + 1));
                 const double vxr = d1r * dx + fn * yx.x, vxi = d1i * dx + fn * yx.y;
                 const double vyr = d1r * dy + fn * yy.x, vyi = d1i * dy + fn * yy.y;
                 const double vzr = d1r * dz + fn * yz.x, vzi = d1i * dz + fn * yz.y;
@@ -419,6 +425,7 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
                 gr[7] -= vyr * dz; gi[7] -= vyi * dz;
                 gr[8] -= vzr * dx; gi[8] -= vzi * dx;
             }
+#undef REC
         }
     }
     if (!active) return;
@@ -433,8 +440,8 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
 void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s) {
     if (b.n_atoms == 0) return;
     const int threads = (m.hmax + 31) / 32 * 32;
-    const size_t smem = 2ull * AN_PT * m.pbstride * sizeof(double);
-    if (threads <= 256 && smem <= 48 * 1024 && (m.pbstride % 2) == 0) {
+    const size_t smem = 2ull * (AN_PT + 1) * m.pbstride * sizeof(double);
+    if (threads <= 256 && smem <= 48 * 1024) {
         k_anlm_v2<<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);
         return;
     }
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(256) k_features(DevModel m, DevBatch b, const 
 
 // Several atoms per CTA: every table entry (term / contribution) is read once and applied to all atoms of
 // the group that have the matching centre type, which divides the table traffic by the group size.
-template <int AT>
+template <int AT, int MO>
 __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                       double* __restrict__ dfeat, double* __restrict__ Gbuf,
                                                       int nfull_max) {
@@ -551,14 +558,17 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
                 const int o = T.term_order[ti];
                 const int* ids = T.term_ids + (size_t)ti * mo;
                 const double cf = T.term_coeff[ti];
-                int id[6];
-                for (int k = 0; k < o; ++k) id[k] = ids[k];
+                int id[MO];
+#pragma unroll
+                for (int k = 0; k < MO; ++k) id[k] = k < o ? ids[k] : 0;
 #pragma unroll
                 for (int a = 0; a < AT; ++a) {
                     if (ty[a] != tt) continue;
                     const double2* af = afull + (size_t)a * nfull_max;
                     double2 pr = af[id[0]];
-                    for (int k = 1; k < o; ++k) pr = cmul(pr, af[id[k]]);
+#pragma unroll
+                    for (int k = 1; k < MO; ++k)
+                        if (k < o) pr = cmul(pr, af[id[k]]);
                     sum[a] += cf * pr.x;
                 }
             }
@@ -573,16 +583,24 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
 #pragma unroll
             for (int a = 0; a < AT; ++a) { gr[a] = 0.0; gi[a] = 0.0; }
             for (int c = T.ent_off[e]; c < T.ent_off[e + 1]; ++c) {
-                const DevContribution cb = T.contribs[c];
+                const DevContribution* cbp = T.contribs + c;
+                const double ccf = cbp->coeff;
+                const int cconj = cbp->conj, cn = cbp->n_ids;
+                int cid[MO > 1 ? MO - 1 : 1];
+#pragma unroll
+                for (int qq = 0; qq < MO - 1; ++qq) cid[qq] = qq < cn ? cbp->ids[qq] : 0;
 #pragma unroll
                 for (int a = 0; a < AT; ++a) {
                     if (ty[a] != tt || !fo[a]) continue;
                     const double2* af = afull + (size_t)a * nfull_max;
                     double2 pr = make_double2(1.0, 0.0);
-                    for (int qq = 0; qq < cb.n_ids; ++qq) pr = cmul(pr, af[cb.ids[qq]]);
-                    if (cb.conj) pr.y = -pr.y;
-                    gr[a] += cb.coeff * pr.x;
-                    gi[a] += cb.coeff * pr.y;
+                    if (MO > 1 && cn > 0) pr = af[cid[0]];
+#pragma unroll
+                    for (int qq = 1; qq < MO - 1; ++qq)
+                        if (qq < cn) pr = cmul(pr, af[cid[qq]]);
+                    if (cconj) pr.y = -pr.y;
+                    gr[a] += ccf * pr.x;
+                    gi[a] += ccf * pr.y;
                 }
             }
             const int pr_ = T.ent_pos_re[e], pi_ = T.ent_pos_im[e];
@@ -606,12 +624,21 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     const int nfull_max = (int)(smem_bytes / sizeof(double2));
     constexpr int AT = 4;
     const size_t smem4 = smem_bytes * AT;
-    if (smem4 <= 96 * 1024) {
-        if (smem4 > 48 * 1024 && g_feat_smem_set != smem4) {
-            cudaFuncSetAttribute(k_features_v2<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-            g_feat_smem_set = smem4;
+    int mo = 1;
+    for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
+    if (smem4 <= 96 * 1024 && mo <= 6) {
+        const int grid = (b.n_atoms + AT - 1) / AT;
+#define PM_FEAT_CASE(MO_)                                                                                        \
+    case MO_:                                                                                                    \
+        if (smem4 > 48 * 1024 && g_feat_smem_set != smem4)                                                       \
+            cudaFuncSetAttribute(k_features_v2<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
+        k_features_v2<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);                      \
+        break;
+        switch (mo) {
+            PM_FEAT_CASE(1) PM_FEAT_CASE(2) PM_FEAT_CASE(3) PM_FEAT_CASE(4) PM_FEAT_CASE(5) PM_FEAT_CASE(6)
         }
-        k_features_v2<AT><<<(b.n_atoms + AT - 1) / AT, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);
+#undef PM_FEAT_CASE
+        if (smem4 > 48 * 1024) g_feat_smem_set = smem4;
         return;
     }
     k_features<<<b.n_atoms, 256, smem_bytes, s>>>(m, b, anc, dfeat, Gbuf);
@@ -648,7 +675,7 @@ __global__ void __launch_bounds__(256) k_lrows_simple(DevModel m, DevBatch b, co
             const int pl = row / 3, al = row - 3 * pl;
             const int p = pb + pl;
             const int u = b.types[b.nbr[p]];
-            const double* rec = PB + (size_t)p * m.pbstride;
+            const PBRec rec = pb_rec(PB, p, m.pbstride);
             const double dal = rec[al] * rec[3];
             const int oya = pb_y(m, 1 + al);
             const int* sh = T.seg_heads[u];
@@ -894,7 +921,7 @@ __global__ void __launch_bounds__(128) k_eval_pairs(DevModel m, DevBatch b, cons
     const int u = b.types[j];
     const int segstride = ah_stride / m.n_type;
     const double* ah = Ah + (size_t)i * ah_stride + u * segstride;
-    const double* rec = PB + (size_t)p * m.pbstride;
+    const PBRec rec = pb_rec(PB, p, m.pbstride);
     const double dal = rec[al] * rec[3];
     const int oy = pb_y(m, 0), oya = pb_y(m, 1 + al);
     const int* sh = T.seg_heads[u];

@@ -300,12 +300,11 @@ __global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const
             const int pair1 = min(p1 - p0, (row0 + LR_ROWS - 1) / 3 + 1);
             const int npc = pair1 - pair0;
             __syncthreads();  // previous chunk fully consumed
-            {   // transposed copy of the pair-basis records of this chunk
-                const double* src = PB + (size_t)(p0 + pair0) * m.pbstride;
+            {   // copy of the pair-basis records of this chunk, [item][pair]
                 const int tot = npc * m.pbstride;
                 for (int e = tid; e < tot; e += 128) {
-                    const int pp = e / m.pbstride, it = e - pp * m.pbstride;
-                    pbs[it * LR_PLD + pp] = src[e];
+                    const int it = e / npc, pp = e - it * npc;
+                    pbs[it * LR_PLD + pp] = pb_rec(PB, p0 + pair0 + pp, m.pbstride)[it];
                 }
             }
             __syncthreads();
@@ -481,9 +480,12 @@ __global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const 
         auto issue_copy = [&](int row0, double* dst) {
             const int pair0 = row0 / 3;
             const int pair1 = min(np, (row0 + LR_ROWS - 1) / 3 + 1);
-            for (int pp = 0; pp < pair1 - pair0; ++pp) {
-                const double* src = PB + (size_t)(p0 + pair0 + pp) * m.pbstride;
-                for (int it = tid; it < m.pbstride; it += nthr) cp_async8(dst + it * LR_PLD + pp, src + it);
+            const int npc = pair1 - pair0;
+            const int tot = npc * m.pbstride;
+            for (int e = tid; e < tot; e += nthr) {   // pair index fastest: contiguous in the blocked layout
+                const int it = e / npc, pp = e - it * npc;
+                const int p = p0 + pair0 + pp;
+                cp_async8(dst + it * LR_PLD + pp, PB + ((size_t)(p >> 5) * m.pbstride + it) * PB_BLK + (p & 31));
             }
             cp_async_commit();
         };
