@@ -168,6 +168,8 @@ static void build_device_model(pm_context* c) {
         d.kpn = kc <= 2 ? 2 : (kc <= 4 ? 4 : (kc <= 8 ? 8 : 0));
         d.tpn = tpn <= 4 ? tpn : 0;
         if (d.tpn == 0) d.kpn = 0;
+        d.dense = 1;
+        for (const auto& T : hm.types) d.dense = d.dense && T.dense_blocks;
     }
     std::vector<double> tpp((size_t)d.n_tp * d.n_fn * 2, 0.0);
     std::vector<int> tpn(d.n_tp, 0), tpairs((size_t)d.n_type * d.n_type);

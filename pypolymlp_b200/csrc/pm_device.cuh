@@ -60,6 +60,7 @@ struct DevModel {
     int fl;        // stride of per-centre linear-feature rows (max n_fpad over types)
     int hmax;      // max n_head over types
     int pbstride;  // doubles per pair-basis record
+    int dense;     // 1 if every type stores dense blocks (B fragments addressed as base + (tile*kc_n + kc)*32)
     int kpn;       // k-chunks (2 heads) per radial group, padded to the fast-path template value (0 = no fast path)
     int tpn;       // max feature tiles per radial index, padded likewise
     long gstride;  // doubles per atom in the G buffer

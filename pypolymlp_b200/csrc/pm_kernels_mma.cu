@@ -435,7 +435,7 @@ constexpr int LR_MAXW = 8;  // max warps per CTA
 constexpr int LR_LDA = 20;  // row stride of the aggregated-row scratch tile (== 4 mod 16)
 
 template <int TPN, int KPN>
-__global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const double* __restrict__ PB,
+__global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                    const double2* __restrict__ agg, const double* __restrict__ Gbuf,
                                                    double* __restrict__ Lbuf, double* __restrict__ Xown,
                                                    double* __restrict__ Sbuf) {
@@ -526,28 +526,40 @@ __global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const 
                 }
             }
             __syncthreads();
+            // per-lane row pointers of this chunk (row = row0 + rt*8 + g), nullptr for rows past the end
+            double* rowp[4];
+#pragma unroll
+            for (int rt = 0; rt < 4; ++rt) {
+                const int r = row0 + rt * 8 + g;
+                rowp[rt] = r < nrow ? Lbuf + ((size_t)p0 * 3 + r) * m.fl + 2 * q : nullptr;
+            }
             for (int n = warp; n < m.n_fn; n += nwarp) {
                 const int tile0 = s_toff[n];
                 const int ntile = s_toff[n + 1] - tile0;
-                if (s_noff[n + 1] == s_noff[n]) {  // radial index inactive for this type pair: exact zeros
+                const int kcn = (s_noff[n + 1] - s_noff[n]) >> 1;
+                if (kcn == 0) {  // radial index inactive for this type pair: exact zeros
                     for (int tt = 0; tt < ntile; ++tt)
 #pragma unroll
-                        for (int rt = 0; rt < 4; ++rt) {
-                            const int r = row0 + rt * 8 + g;
-                            if (r < nrow)
-                                *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + (tile0 + tt) * 8 + 2 * q) =
-                                    make_double2(0.0, 0.0);
-                        }
+                        for (int rt = 0; rt < 4; ++rt)
+                            if (rowp[rt]) *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(0.0, 0.0);
                     continue;
                 }
                 double bf[TPN][KPN];
+                if (m.dense && kcn == KPN && ntile == TPN) {
+                    const double* Gt = G + 32 * (size_t)s_bmap[tile0 * KPN] + lane;
 #pragma unroll
-                for (int tt = 0; tt < TPN; ++tt)
+                    for (int tt = 0; tt < TPN; ++tt)
 #pragma unroll
-                    for (int kc = 0; kc < KPN; ++kc) {
-                        const int bi = tt < ntile ? s_bmap[(tile0 + tt) * KPN + kc] : -1;
-                        bf[tt][kc] = bi >= 0 ? G[32 * (size_t)bi + lane] : 0.0;
-                    }
+                        for (int kc = 0; kc < KPN; ++kc) bf[tt][kc] = Gt[(tt * KPN + kc) * 32];
+                } else {
+#pragma unroll
+                    for (int tt = 0; tt < TPN; ++tt)
+#pragma unroll
+                        for (int kc = 0; kc < KPN; ++kc) {
+                            const int bi = tt < ntile ? s_bmap[(tile0 + tt) * KPN + kc] : -1;
+                            bf[tt][kc] = bi >= 0 ? G[32 * (size_t)bi + lane] : 0.0;
+                        }
+                }
                 double cd[4], cf[4];
 #pragma unroll
                 for (int rt = 0; rt < 4; ++rt) { cd[rt] = scD[n * 32 + rt * 8 + g]; cf[rt] = scF[n * 32 + rt * 8 + g]; }
@@ -556,14 +568,14 @@ __global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const 
                 for (int tt = 0; tt < TPN; ++tt)
 #pragma unroll
                     for (int rt = 0; rt < 4; ++rt) { acc[tt][rt][0] = 0.0; acc[tt][rt][1] = 0.0; }
+                const double* a1p = A1 + q * LR_LD + g;
+                const double* a2p = A2 + q * LR_LD + g;
 #pragma unroll
                 for (int kc = 0; kc < KPN; ++kc) {
                     double af[4];
 #pragma unroll
-                    for (int rt = 0; rt < 4; ++rt) {
-                        const int o = (4 * kc + q) * LR_LD + rt * 8 + g;
-                        af[rt] = cd[rt] * A1[o] + cf[rt] * A2[o];
-                    }
+                    for (int rt = 0; rt < 4; ++rt)
+                        af[rt] = cd[rt] * a1p[4 * kc * LR_LD + rt * 8] + cf[rt] * a2p[4 * kc * LR_LD + rt * 8];
 #pragma unroll
                     for (int tt = 0; tt < TPN; ++tt)
 #pragma unroll
@@ -573,12 +585,9 @@ __global__ void __launch_bounds__(256) k_lrows_v3(DevModel m, DevBatch b, const 
                 for (int tt = 0; tt < TPN; ++tt) {
                     if (tt >= ntile) break;
 #pragma unroll
-                    for (int rt = 0; rt < 4; ++rt) {
-                        const int r = row0 + rt * 8 + g;
-                        if (r < nrow)
-                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + (tile0 + tt) * 8 + 2 * q) =
-                                make_double2(acc[tt][rt][0], acc[tt][rt][1]);
-                    }
+                    for (int rt = 0; rt < 4; ++rt)
+                        if (rowp[rt])
+                            *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(acc[tt][rt][0], acc[tt][rt][1]);
                 }
             }
         }

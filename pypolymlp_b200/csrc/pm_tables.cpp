@@ -288,6 +288,25 @@ void HostModel::build(const FeatureParams& fp_in) {
             const int fp_ = T.feat_pad[e.first.f];
             blkset.insert({head_seg[e.first.h], fp_ / 8, head_pos[e.first.h] / 2});
         }
+        {   // small radial groups (<= 8 k-chunks, <= 4 feature tiles): store EVERY block of a (segment, tile) so
+            // that the K4a fast path addresses B fragments as base + constant offset
+            const int n_tiles_ = T.n_fpad / 8;
+            int max_kc = 0, max_tpn = 0;
+            std::vector<int> cnt(fp.n_fn, 0);
+            for (int n_ : T.tile_n) cnt[n_]++;
+            for (int v : cnt) max_tpn = std::max(max_tpn, v);
+            for (int u = 0; u < nt; ++u)
+                for (int n = 0; n < n_fn; ++n) max_kc = std::max(max_kc, (T.seg_n_off[u][n + 1] - T.seg_n_off[u][n]) / 2);
+            T.dense_blocks = max_kc <= 8 && max_tpn <= 4;
+            if (T.dense_blocks)
+                for (int u = 0; u < nt; ++u) {
+                    if (u > 0 && T.seg_tp[u] == T.seg_tp[u - 1]) continue;
+                    for (int tile = 0; tile < n_tiles_; ++tile) {
+                        const int n = T.tile_n[tile];
+                        for (int kc = T.seg_n_off[u][n] / 2; kc < T.seg_n_off[u][n + 1] / 2; ++kc) blkset.insert({u, tile, kc});
+                    }
+                }
+        }
         std::map<std::array<int, 3>, int> blkid;
         const int n_tiles = T.n_fpad / 8;
         T.tile_blk_off.assign(nt, std::vector<int>(n_tiles + 1, 0));

@@ -93,6 +93,7 @@ struct TypeTables {
     std::vector<int> ent_off;                    // [n_ent+1] -> contributions
     std::vector<Contribution> contribs;
     long g_size = 0;                             // doubles per atom (= 32 * n_blocks)
+    bool dense_blocks = false;                   // every (segment, tile, k-chunk of the tile's radial group) block exists
     // ---- polynomial ----------------------------------------------------------
     std::vector<PolyTerm> poly;
     long n_deriv_pairs = 0;  // (f, full head) pairs before folding, for reporting
