@@ -36,7 +36,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // ================================================================================================
 // K5: SYRK.  grid = (upper tiles, k-splits).  8 warps as 2 (M) x 4 (N), warp tile 64 x 32.
 // ================================================================================================
-constexpr int SY_BM = 128, SY_BK = 16, SY_STAGES = 4, SY_LD = SY_BM + 4;  // 132 == 4 (mod 16)
+constexpr int SY_BM = 128, SY_BK = 32, SY_STAGES = 3, SY_LD = SY_BM + 4;  // 132 == 4 (mod 16)
 constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LD;
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * sizeof(double);
 
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256, 1) k_syrk_mma(const double* __restrict__ 
         double* sB = sA + SY_BK * SY_LD;
         const int r0 = r_begin + kt * SY_BK;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int e = tid + it * 256;       // 0..1023
+        for (int it = 0; it < SY_BK / 4; ++it) {
+            const int e = tid + it * 256;
             const int rr = e >> 6, cc = (e & 63) * 2;
             const int r = r0 + rr;
             const bool ok = r < r_end;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) k_syrk_sk(const double* __restrict__ X
             double* sB = sA + SY_BK * SY_LD;
             const int r0 = r_begin + kt * SY_BK;
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
+            for (int it = 0; it < SY_BK / 4; ++it) {
                 const int e = tid + it * 256;
                 const int rr = e >> 6, cc = (e & 63) * 2;
                 const int r = r0 + rr;
