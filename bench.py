@@ -147,10 +147,14 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
     from pypolymlp_b200 import fit
+    from pypolymlp_b200._capi import StructureBatch, check, lib
+    from pypolymlp_b200._capi import pd as pd_
     from pypolymlp_b200.libmlpcpp import PotentialXtX
     from pypolymlp_b200.params import make_params_dict
 
@@ -232,6 +236,30 @@ def main():
     h2d = batch_host.h2d_bytes + w_h.nbytes + y_h.nbytes
     d2h = ((F + 1) * (F + 1) + 2 * F + 1) * 8
 
+    # ---- secondary metric: atoms/s of E/F/S evaluation (BASELINE config 5), sharded by structure -----------
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+
+    n_ev = 32
+    ev_sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + rank * n_ev + k) for k in range(n_ev)]
+    ev_axis, ev_pcs, ev_tys = [x[0] for x in ev_sts], [x[1] for x in ev_sts], [x[2] for x in ev_sts]
+    prop = PotentialPropertiesFast(pd, np.random.default_rng(12).normal(size=F) * 1e-3, device=local_rank)
+    ev_batch = StructureBatch(ev_axis, ev_pcs, ev_tys, [True] * n_ev)
+    ev_out = (np.zeros(n_ev), np.zeros((n_ev * 512, 3)), np.zeros((n_ev, 6)))
+
+    def step_eval():
+        check(lib().pm_eval(prop._ctx.handle, ctypes.byref(ev_batch.c), pd_(ev_out[0]), pd_(ev_out[1]), pd_(ev_out[2])))
+
+    step_eval()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_eval()
+    barrier()
+    tev = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tev, op=dist.ReduceOp.MAX)
+    eval_atoms_s = world * n_ev * 512 * 3 / float(tev.item())
+
     if rank == 0:
         # ---- roofline of the dominant kernel (SYRK, DMMA): one profiled step, CUDA events per stage -------
         acc.reset()
@@ -283,6 +311,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "note": "pm_fit_reset + pm_fit_accumulate(host buffers) + pm_fit_finalize (X^T X, X^T y to host) per step"},
             "roofline": roofline, "cpu_baseline": cpu,
+            "eval": {"metric": "atoms/sec, E/F/S evaluation (config 5: F=2030 model, 512-atom fcc, sigma 0.03 A)",
+                     "value": eval_atoms_s, "unit": "atoms/s", "structures_per_step_per_gpu": n_ev,
+                     "note": "pm_eval through the C ABI: host arrays in, E/F/S back on the host (end to end)"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

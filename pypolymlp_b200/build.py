@@ -63,7 +63,31 @@ def build_library(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_pybind_module()
     return LIB
+
+
+def pybind_module_path():
+    import sysconfig
+
+    return os.path.join(LIBDIR, "libmlpcpp" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_pybind_module():
+    """pybind11 module `libmlpcpp` (host C++ above the C ABI), the drop-in for pypolymlp.cxx.lib.libmlpcpp."""
+    import sysconfig
+
+    import pybind11
+
+    out = pybind_module_path()
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+           os.path.join(CSRC, "pybind_module.cpp"), "-L", LIBDIR, "-lpolymlp_b200",
+           "-Wl,-rpath,$ORIGIN", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"pybind11 module build failed:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

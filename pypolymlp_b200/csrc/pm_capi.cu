@@ -118,6 +118,8 @@ struct pm_context {
     int64_t stage_launches[ST_COUNT] = {0};
     cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
     bool has_coeffs = false;
+    double* pinned = nullptr;   // host staging for pm_fit_finalize
+    size_t pinned_n = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -741,6 +743,9 @@ void pm_context_destroy(pm_context* c) {
     c->d_X.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto& v : c->staged_dev)
+        for (void* p : v) cudaFree(p);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -929,19 +934,32 @@ int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, dou
         const int F = d.n_variables, fp = d.fpad;
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
-        // rows 0..F of C (the y row is row F); copy the (F+1) x (F+1) corner
-        std::vector<double> corner((size_t)(F + 1) * (F + 1));
-        CK(cudaMemcpy2D(corner.data(), (size_t)(F + 1) * sizeof(double), c->acc, (size_t)fp * sizeof(double),
-                        (size_t)(F + 1) * sizeof(double), F + 1, cudaMemcpyDeviceToHost));
+        // rows 0..F of C (the y row is row F); copy the (F+1) x (F+1) corner through a pinned staging buffer
         const int ld = F + 1;
+        const size_t corner_n = (size_t)ld * ld;
+        if (c->pinned_n < corner_n) {
+            if (c->pinned) cudaFreeHost(c->pinned);
+            c->pinned = nullptr;
+            CK(cudaHostAlloc(&c->pinned, corner_n * sizeof(double), cudaHostAllocDefault));
+            c->pinned_n = corner_n;
+        }
+        double* corner = c->pinned;
+        CK(cudaMemcpy2DAsync(corner, (size_t)ld * sizeof(double), c->acc, (size_t)fp * sizeof(double),
+                             (size_t)ld * sizeof(double), ld, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         // every kernel flavour fills (at least) the upper triangle i <= j
-        auto get = [&](int i, int j) { return i <= j ? corner[(size_t)i * ld + j] : corner[(size_t)j * ld + i]; };
-        if (xtx)
+        if (xtx) {
             for (int i = 0; i < F; ++i)
-                for (int j = 0; j < F; ++j) xtx[(size_t)i * F + j] = get(i, j);
+                std::memcpy(xtx + (size_t)i * F + i, corner + (size_t)i * ld + i, (size_t)(F - i) * sizeof(double));
+            constexpr int TB = 64;  // mirror the strict upper triangle, blocked for cache reuse
+            for (int ib = 0; ib < F; ib += TB)
+                for (int jb = 0; jb <= ib; jb += TB)
+                    for (int i = ib; i < std::min(F, ib + TB); ++i)
+                        for (int j = jb; j < std::min(i, jb + TB); ++j) xtx[(size_t)i * F + j] = xtx[(size_t)j * F + i];
+        }
         if (xty)
-            for (int i = 0; i < F; ++i) xty[i] = get(i, F);
-        if (y_sq_norm) *y_sq_norm = get(F, F);
+            for (int i = 0; i < F; ++i) xty[i] = corner[(size_t)i * ld + F];
+        if (y_sq_norm) *y_sq_norm = corner[(size_t)F * ld + F];
         std::vector<double> tail(2 * (size_t)fp + 1);
         CK(cudaMemcpy(tail.data(), c->acc + (size_t)fp * fp, tail.size() * sizeof(double), cudaMemcpyDeviceToHost));
         if (xe_sum) std::copy(tail.begin(), tail.begin() + F, xe_sum);

@@ -177,3 +177,38 @@ def test_two_rank_reduce_gloo():
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+def _pybind_module():
+    import importlib.util
+
+    from pypolymlp_b200.build import pybind_module_path
+
+    spec = importlib.util.spec_from_file_location("libmlpcpp", pybind_module_path())
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_pybind_dropin_module_host_side():
+    """The pybind11 `libmlpcpp` drop-in exposes the reference's class names and getters
+    (python/pybind11_mlp.cpp:10-94) and maps C-ABI errors to ValueError / RuntimeError."""
+    m = _pybind_module()
+    for cls, methods in (("PotentialModel", ("get_x", "get_fbegin", "get_sbegin", "get_n_data")),
+                         ("PotentialPropertiesFast", ("eval", "eval_multiple", "get_e", "get_f", "get_s",
+                                                      "get_e_array", "get_f_array", "get_s_array")),
+                         ("Readgtinv", ("get_lm_seq", "get_l_comb", "get_lm_coeffs")),
+                         ("FeaturesAttr", ("get_n_features",)), ("PotentialXtX", ("add", "finalize"))):
+        assert all(hasattr(getattr(m, cls), k) for k in methods), cls
+    rg = m.Readgtinv(3, [4, 4], 1)
+    ours = Readgtinv(3, [4, 4], 1)
+    assert rg.get_l_comb() == ours.get_l_comb() and rg.get_lm_seq() == ours.get_lm_seq()
+    assert rg.get_lm_coeffs() == ours.get_lm_coeffs()
+    pd = make_params_dict(**cases.si_model_kwargs())
+    assert m.FeaturesAttr(pd).get_n_features() == 168
+    with pytest.raises(ValueError):
+        m.Readgtinv(9, [1], 1)
+    bad = make_params_dict(**cases.si_model_kwargs())
+    bad["model"]["max_p"] = 7
+    with pytest.raises(ValueError):
+        m.FeaturesAttr(bad)

@@ -299,3 +299,28 @@ def test_error_paths():
     acc = PotentialXtX(pd)
     acc.add([], [], [], [], np.zeros(0), np.zeros(0))
     assert acc.finalize()["total_n_data"] == 0
+
+
+def test_pybind_dropin_module_gpu():
+    """Same calls a reference user makes on `pypolymlp.cxx.lib.libmlpcpp`, through the pybind11 drop-in."""
+    import importlib.util
+
+    from pypolymlp_b200.build import pybind_module_path
+
+    spec = importlib.util.spec_from_file_location("libmlpcpp", pybind_module_path())
+    libmlpcpp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(libmlpcpp)
+    pd = make_params_dict(**cases.binary_model_kwargs())
+    ax, pc, ty = cases.skewed_cell(2)
+    obj = libmlpcpp.PotentialModel(pd, [ax.tolist()], [pc.tolist()], [ty.tolist()], [1], [True], [9])
+    full = np.vstack([G["bin_xe"][None], G["bin_xs"], G["bin_xf"]])
+    assert cases.x_rel_err(np.asarray(obj.get_x()), full) < 1e-10
+    assert obj.get_n_data() == [1, 27, 6] and obj.get_fbegin() == [7] and obj.get_sbegin() == [1]
+    prop = libmlpcpp.PotentialPropertiesFast(pd, G["bin_coeffs"].tolist())
+    prop.eval(ax.tolist(), pc.tolist(), ty.tolist(), True)
+    assert abs(prop.get_e() - G["bin_e"][0]) < 1e-10 * abs(G["bin_e"][0])
+    assert np.abs(np.array(prop.get_f()) - G["bin_f"]).max() < 1e-10 * np.abs(G["bin_f"]).max()
+    prop.eval_multiple([ax.tolist()] * 2, [pc.tolist()] * 2, [ty.tolist()] * 2)
+    assert np.abs(np.array(prop.get_s_array())[1] - G["bin_s"]).max() < 1e-10 * np.abs(G["bin_s"]).max()
+    with pytest.raises(ValueError):
+        libmlpcpp.PotentialPropertiesFast(pd, [0.0, 1.0])
