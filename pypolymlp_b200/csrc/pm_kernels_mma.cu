@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
     for (int u = 0; u < nt; ++u) {
         const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
         const int np = p1 - p0;
-        const int nrow = 3 * np;
+        const int nrow = 3 * np;          // pair rows
+        const int nrow_all = nrow + 9;    // + own x/y/z and six virial rows, fed from the K2b sums
         __syncthreads();
         for (int e = tid; e < T.seg_len[u]; e += nthr) s_head[e] = T.seg_heads[u][e];
         for (int e = tid; e <= m.n_fn; e += nthr) s_noff[e] = T.seg_n_off[u][e];
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
         auto issue_copy = [&](int row0, double* dst) {
             const int pair0 = row0 / 3;
             const int pair1 = min(np, (row0 + LR_ROWS - 1) / 3 + 1);
-            const int npc = pair1 - pair0;
+            const int npc = max(0, pair1 - pair0);
             const int tot = npc * m.pbstride;
             for (int e = tid; e < tot; e += nthr) {   // pair index fastest: contiguous in the blocked layout
                 const int it = e / npc, pp = e - it * npc;
@@ -489,13 +490,13 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
             }
             cp_async_commit();
         };
-        if (nrow > 0) issue_copy(0, pbs0);
+        issue_copy(0, pbs0);
         int buf = 0;
-        for (int row0 = 0; row0 < nrow; row0 += LR_ROWS, buf ^= 1) {
+        for (int row0 = 0; row0 < nrow_all; row0 += LR_ROWS, buf ^= 1) {
             const double* pbs = pbs0 + (size_t)buf * pbs_sz;
             const int pair0 = row0 / 3;
             __syncthreads();  // all warps are done with A1/A2/sc and with the other pair tile
-            if (row0 + LR_ROWS < nrow) {
+            if (row0 + LR_ROWS < nrow_all) {
                 issue_copy(row0 + LR_ROWS, pbs0 + (size_t)(buf ^ 1) * pbs_sz);
                 cp_async_wait<1>();
             } else {
@@ -528,11 +529,16 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
             __syncthreads();
             // per-lane row pointers of this chunk (row = row0 + rt*8 + g), nullptr for rows past the end
             double* rowp[4];
+            int ragg[4];   // >= 0: this lane's row of the tile is aggregated row ragg (accumulated over segments)
 #pragma unroll
             for (int rt = 0; rt < 4; ++rt) {
                 const int r = row0 + rt * 8 + g;
-                rowp[rt] = r < nrow ? Lbuf + ((size_t)p0 * 3 + r) * m.fl + 2 * q : nullptr;
+                ragg[rt] = (r >= nrow && r < nrow_all) ? r - nrow : -1;
+                rowp[rt] = r < nrow ? Lbuf + ((size_t)p0 * 3 + r) * m.fl + 2 * q
+                         : (ragg[rt] < 0 ? nullptr
+                         : (ragg[rt] < 3 ? Xown + ((size_t)i * 3 + ragg[rt]) * m.fl : Sbuf + ((size_t)i * 6 + (ragg[rt] - 3)) * m.fl) + 2 * q);
             }
+            const bool chunk_has_agg = row0 + LR_ROWS > nrow;
             for (int n = warp; n < m.n_fn; n += nwarp) {
                 const int tile0 = s_toff[n];
                 const int ntile = s_toff[n + 1] - tile0;
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                     for (int tt = 0; tt < ntile; ++tt)
 #pragma unroll
                         for (int rt = 0; rt < 4; ++rt)
-                            if (rowp[rt]) *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(0.0, 0.0);
+                            if (rowp[rt] && ragg[rt] < 0) *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(0.0, 0.0);
                     continue;
                 }
                 double bf[TPN][KPN];
@@ -560,79 +566,62 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                             bf[tt][kc] = bi >= 0 ? G[32 * (size_t)bi + lane] : 0.0;
                         }
                 }
-                double cd[4], cf[4];
-#pragma unroll
-                for (int rt = 0; rt < 4; ++rt) { cd[rt] = scD[n * 32 + rt * 8 + g]; cf[rt] = scF[n * 32 + rt * 8 + g]; }
-                double acc[TPN][4][2];
-#pragma unroll
-                for (int tt = 0; tt < TPN; ++tt)
-#pragma unroll
-                    for (int rt = 0; rt < 4; ++rt) { acc[tt][rt][0] = 0.0; acc[tt][rt][1] = 0.0; }
+                // two row tiles at a time: accumulators stay at TPN*2*2 doubles (registers decide the occupancy)
                 const double* a1p = A1 + q * LR_LD + g;
                 const double* a2p = A2 + q * LR_LD + g;
 #pragma unroll
-                for (int kc = 0; kc < KPN; ++kc) {
-                    double af[4];
+                for (int rh = 0; rh < 2; ++rh) {
+                    double cd[2], cf[2];
 #pragma unroll
-                    for (int rt = 0; rt < 4; ++rt)
-                        af[rt] = cd[rt] * a1p[4 * kc * LR_LD + rt * 8] + cf[rt] * a2p[4 * kc * LR_LD + rt * 8];
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        cd[r2] = scD[n * 32 + (2 * rh + r2) * 8 + g];
+                        cf[r2] = scF[n * 32 + (2 * rh + r2) * 8 + g];
+                    }
+                    double acc[TPN][2][2];
 #pragma unroll
                     for (int tt = 0; tt < TPN; ++tt)
 #pragma unroll
-                        for (int rt = 0; rt < 4; ++rt) dmma(acc[tt][rt][0], acc[tt][rt][1], af[rt], bf[tt][kc]);
-                }
-#pragma unroll
-                for (int tt = 0; tt < TPN; ++tt) {
-                    if (tt >= ntile) break;
-#pragma unroll
-                    for (int rt = 0; rt < 4; ++rt)
-                        if (rowp[rt])
-                            *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(acc[tt][rt][0], acc[tt][rt][1]);
-                }
-            }
-        }
-        // ---- aggregated rows of this segment: own x/y/z (0..2) and the six virial rows (3..8) -------------
-        __syncthreads();
-        const int nw_agg = min(nwarp, (2 * pbs_sz) / (KR * LR_LDA));
-        if (warp < nw_agg) {
-            double* Vg = pbs0 + (size_t)warp * KR * LR_LDA;  // [KR][LR_LDA], rows 0..15
-            for (int n = warp; n < m.n_fn; n += nw_agg) {
-                const int h0 = s_noff[n];
-                const int nhn = s_noff[n + 1] - h0;
-                if (nhn == 0) continue;
-                const int tile0 = s_toff[n];
-                const int ntile = s_toff[n + 1] - tile0;
-                __syncwarp();
-                for (int e = lane; e < 2 * KPN * 16; e += 32) {
-                    const int hq = e >> 4, r = e & 15;
-                    double2 v = make_double2(0.0, 0.0);
-                    if (hq < nhn && r < 9) {
-                        const int h = s_head[h0 + hq];
-                        if (h >= 0) v = agg[((size_t)i * m.hmax + h) * 9 + r];
-                    }
-                    Vg[(2 * hq) * LR_LDA + r] = v.x;
-                    Vg[(2 * hq + 1) * LR_LDA + r] = v.y;
-                }
-                __syncwarp();
-                for (int tt = 0; tt < ntile; ++tt) {
-                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                        for (int r2 = 0; r2 < 2; ++r2) { acc[tt][r2][0] = 0.0; acc[tt][r2][1] = 0.0; }
 #pragma unroll
                     for (int kc = 0; kc < KPN; ++kc) {
-                        const int bi = s_bmap[(tile0 + tt) * KPN + kc];
-                        if (bi < 0) continue;
-                        const double bfv = G[32 * (size_t)bi + lane];
-                        const double* va = Vg + (4 * kc + q) * LR_LDA + g;
-                        dmma(acc[0][0], acc[0][1], va[0], bfv);
-                        dmma(acc[1][0], acc[1][1], va[8], bfv);
+                        double af[2];
+#pragma unroll
+                        for (int r2 = 0; r2 < 2; ++r2)
+                            af[r2] = cd[r2] * a1p[4 * kc * LR_LD + (2 * rh + r2) * 8] + cf[r2] * a2p[4 * kc * LR_LD + (2 * rh + r2) * 8];
+                        if (chunk_has_agg) {
+#pragma unroll
+                            for (int r2 = 0; r2 < 2; ++r2) {
+                                const int ra = ragg[2 * rh + r2];
+                                if (ra >= 0) {
+                                    const int hq = 2 * kc + (q >> 1);
+                                    const int h = hq < 2 * kcn ? s_head[s_noff[n] + hq] : -1;
+                                    double v = 0.0;
+                                    if (h >= 0) {
+                                        const double2 a2 = agg[((size_t)i * m.hmax + h) * 9 + ra];
+                                        v = (q & 1) ? a2.y : a2.x;
+                                    }
+                                    af[r2] = v;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int tt = 0; tt < TPN; ++tt)
+#pragma unroll
+                            for (int r2 = 0; r2 < 2; ++r2) dmma(acc[tt][r2][0], acc[tt][r2][1], af[r2], bf[tt][kc]);
                     }
 #pragma unroll
-                    for (int rt = 0; rt < 2; ++rt) {
-                        const int r = rt * 8 + g;
-                        if (r < 9) {
-                            double* dst = (r < 3 ? Xown + ((size_t)i * 3 + r) * m.fl : Sbuf + ((size_t)i * 6 + (r - 3)) * m.fl) +
-                                          (tile0 + tt) * 8 + 2 * q;
-                            double2 v = *reinterpret_cast<double2*>(dst);
-                            v.x += acc[rt][0]; v.y += acc[rt][1];
+                    for (int tt = 0; tt < TPN; ++tt) {
+                        if (tt >= ntile) break;
+#pragma unroll
+                        for (int r2 = 0; r2 < 2; ++r2) {
+                            double* dst = rowp[2 * rh + r2];
+                            if (!dst) continue;
+                            dst += (tile0 + tt) * 8;
+                            double2 v = make_double2(acc[tt][r2][0], acc[tt][r2][1]);
+                            if (ragg[2 * rh + r2] >= 0) {
+                                const double2 o = *reinterpret_cast<double2*>(dst);
+                                v.x += o.x; v.y += o.y;
+                            }
                             *reinterpret_cast<double2*>(dst) = v;
                         }
                     }
