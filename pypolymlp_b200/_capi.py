@@ -18,6 +18,7 @@ _ip = C.POINTER(C.c_int)
 _i64p = C.POINTER(C.c_int64)
 
 PM_FLAG_SIMPLE_KERNELS = 1
+PM_FLAG_SCATTER = 2
 
 
 class FeatureParamsC(C.Structure):

@@ -19,6 +19,7 @@ void set_lrows_kmax(int kmax);
 size_t lrows_mma_smem(const DevModel& m);
 size_t xrows_mma_smem(const DevModel& m);
 double microbench_dgemm(int n, cudaStream_t s);
+double microbench_red(int n_rows, cudaStream_t s);
 }  // namespace pm
 
 using namespace pm;
@@ -93,7 +94,7 @@ struct pm_context {
     cudaStream_t stream = nullptr;
     DevModel dm{};
     std::vector<void*> table_allocs;
-    bool simple_l = false, simple_x = false, simple_s = false;
+    bool simple_l = false, simple_x = false, simple_s = false, scatter = false;
     size_t feat_smem = 0;
     // accumulators
     double* acc = nullptr;
@@ -102,7 +103,7 @@ struct pm_context {
     // chunk device buffers
     DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
         d_nbr, d_centre, d_rev, d_err;
-    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_G, d_L, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
+    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
         d_f, d_s;
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
@@ -283,6 +284,13 @@ static void build_device_model(pm_context* c) {
         for (size_t k = 0; k < bk.size(); ++k) bk[k] = T.blocks[k].kchunk;
         D.blk_kchunk = upload(c, bk);
         D.pad_gid = upload(c, T.pad_gid);
+        {
+            std::vector<int> gid2pv(std::max(hm.n_linear, 1), -1), padpv(T.n_fpad, -1);
+            for (int a = 0; a < (int)hm.pv_gid.size(); ++a) gid2pv[hm.pv_gid[a]] = a;
+            for (int fp_ = 0; fp_ < T.n_fpad; ++fp_)
+                if (T.pad_gid[fp_] >= 0) padpv[fp_] = gid2pv[T.pad_gid[fp_]];
+            D.pad_pv = upload(c, padpv);
+        }
         std::vector<DevPolyTerm> ct(hm.n_variables);
         for (int col = 0; col < hm.n_variables; ++col) {
             const PolyTerm& p = hm.colterm[t][col];
@@ -297,6 +305,7 @@ static void build_device_model(pm_context* c) {
     c->simple_s = force_simple;
     c->simple_l = force_simple || lrows_mma_smem(d) > 200 * 1024;
     c->simple_x = force_simple || hm.has_order3 || xrows_mma_smem(d) > 200 * 1024;
+    c->scatter = !c->simple_l && !c->simple_x && scatter_mode_supported(d) && (c->flags & PM_FLAG_SCATTER);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,7 +335,7 @@ static double est_bytes_per_structure(const pm_context* c, const double* axis, i
     double bytes = pairs * (d.pbstride * 8.0 + 12.0);
     bytes += n_atoms * (d.hmax * 16.0 * 10 + d.fl * 8.0 * 10 + 64);
     if (force) {
-        bytes += pairs * 3.0 * d.fl * 8.0;
+        bytes += pairs * 3.0 * (c->scatter ? d.npv_pad : d.fl) * 8.0;
         bytes += (double)n_atoms * d.gstride * 8.0;
         bytes += (7.0 + 3.0 * n_atoms) * d.fpad * 8.0;
     } else {
@@ -534,18 +543,25 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         return;
     }
 
-    // ---- K4a -------------------------------------------------------------------------------------
-    if (any_force) {
-        c->d_L.ensure(np1 * 3 * d.fl);
-        ws.Lbuf = c->d_L.p;
-        launch_lrows(d, b, ws, c->simple_l, s);
-        tm.mark(ST_LROWS, 1);
-    }
-    // ---- K4b -------------------------------------------------------------------------------------
+    // X-tilde chunk first: in scatter mode K4a adds into it with RED.F64
     c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
     ws.X = c->d_X.p;
     CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
     const bool fit = mode == MODE_FIT;
+    ws.scatter = c->scatter;
+    // ---- K4a -------------------------------------------------------------------------------------
+    if (any_force) {
+        if (ws.scatter) {
+            c->d_Lpv.ensure(np1 * 3 * d.npv_pad);
+            ws.Lpv = c->d_Lpv.p;
+        } else {
+            c->d_L.ensure(np1 * 3 * d.fl);
+            ws.Lbuf = c->d_L.p;
+        }
+        launch_lrows(d, b, ws, c->simple_l, fit, s);
+        tm.mark(ST_LROWS, 1);
+    }
+    // ---- K4b -------------------------------------------------------------------------------------
     double* xe_sum = fit ? c->acc + (size_t)d.fpad * d.fpad : nullptr;
     double* xe_sq = fit ? xe_sum + d.fpad : nullptr;
     launch_xrows(d, b, ws, xe_sum, xe_sq, c->simple_x, fit, s);
@@ -740,7 +756,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
     c->d_PB.release(); c->d_dfeat.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
-    c->d_X.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
+    c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1073,6 +1089,7 @@ int pm_microbench(pm_context* c, int which, int n, double* tflops) {
     return guarded([&] {
         CK(cudaSetDevice(c->device));
         if (which == 3) *tflops = microbench_dgemm(n > 0 ? n : 8192, c->stream);
+        else if (which == 4) *tflops = microbench_red(n > 16 ? n : 768, c->stream);  // giga fp64 atomics / s
         else *tflops = microbench_fp64(which, c->stream);
         CK(cudaGetLastError());
     });

@@ -50,7 +50,8 @@ struct DevType {
     const DevContribution* contribs;
     const int* blk_kchunk;
     const int* tile_blk_off[MAXT];
-    const int* pad_gid;
+    const int* pad_gid;     // [n_fpad] global linear column of a padded feature id or -1
+    const int* pad_pv;      // [n_fpad] polynomial-variable index of a padded feature id or -1
     const DevPolyTerm* colterm;
 };
 

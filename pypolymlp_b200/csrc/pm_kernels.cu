@@ -963,15 +963,15 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
 // ================================================================================================
 // launch wrappers with simple / tensor-core dispatch
 // ================================================================================================
-void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s);
+void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_weights, cudaStream_t s);
 void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                       bool apply_weights, cudaStream_t s);
 void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s);
 
-void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, cudaStream_t s) {
+void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s) {
     if (b.n_atoms == 0) return;
     if (simple) k_lrows_simple<<<b.n_atoms, 256, 0, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
-    else launch_lrows_mma(m, b, ws, s);
+    else launch_lrows_mma(m, b, ws, apply_weights, s);
 }
 
 void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,

@@ -12,7 +12,9 @@ struct Workspace {
     double2* agg = nullptr;     // [n_atoms][hmax][9]
     double* dfeat = nullptr;    // [n_atoms][fl]
     double* Gbuf = nullptr;     // [n_atoms][gstride]
-    double* Lbuf = nullptr;     // [n_pairs * 3][fl]
+    double* Lbuf = nullptr;     // [n_pairs * 3][fl]   (not used in scatter mode)
+    double* Lpv = nullptr;      // [n_pairs * 3][npv_pad] derivative rows of the polynomial variables (scatter mode)
+    bool scatter = false;       // K4a adds the linear columns straight into X with RED.F64, K4b only does the GEMM part
     double* Xown = nullptr;     // [n_atoms][3][fl]
     double* Sbuf = nullptr;     // [n_atoms][6][fl]
     double* X = nullptr;        // [n_rows][fpad]
@@ -31,7 +33,8 @@ void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s);
 // K4a: per-centre derivative rows L = V . G
-void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, cudaStream_t s);
+void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s);
+bool scatter_mode_supported(const DevModel& m);
 // K4b: gather + polynomial expansion -> weighted X-tilde rows
 void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                   bool simple, bool apply_weights, cudaStream_t s);

@@ -438,7 +438,8 @@ template <int TPN, int KPN>
 __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                    const double2* __restrict__ agg, const double* __restrict__ Gbuf,
                                                    double* __restrict__ Lbuf, double* __restrict__ Xown,
-                                                   double* __restrict__ Sbuf) {
+                                                   double* __restrict__ Sbuf, double* __restrict__ X,
+                                                   double* __restrict__ Lpv, int apply_w) {
     extern __shared__ __align__(16) double smem[];
     const int i = blockIdx.x;
     if (!b.force[b.st_of_atom[i]]) return;
@@ -455,18 +456,26 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
     double* A2 = A1 + KR * LR_LD;                          // [KR][LR_LD]
     double* scD = A2 + KR * LR_LD;                         // [n_fn][32]
     double* scF = scD + m.n_fn * 32;                       // [n_fn][32]
-    int* tab = reinterpret_cast<int*>(scF + m.n_fn * 32);
+    double* s_w = scF + m.n_fn * 32;                       // [32] signed weight of the target X row (scatter mode)
+    int* tab = reinterpret_cast<int*>(s_w + 32);
     int* s_head = tab;                                     // [2*KPN*n_fn] head id per segment position
     int* s_noff = s_head + 2 * KPN * m.n_fn;               // [n_fn + 1]
     int* s_nid = s_noff + m.n_fn + 1;                      // [n_fn]
     int* s_toff = s_nid + m.n_fn;                          // [n_fn + 1]
     int* s_bmap = s_toff + m.n_fn + 1;                     // [n_tiles * KPN]
+    int* s_gid = s_bmap + T.n_tiles * KPN;                 // [n_fpad] global linear column (scatter mode)
+    int* s_pv = s_gid + T.n_fpad;                          // [n_fpad] polynomial-variable index
+    int* s_trow = s_pv + T.n_fpad;                         // [32] target X row of each chunk row (scatter mode)
+    const bool scatter = X != nullptr;
+    const int st_i = b.st_of_atom[i];
     const double* G = Gbuf + (size_t)i * m.gstride;
     const int oy = pb_y(m, 0);
     const int k_real = 2 * m.nh;
     for (int e = tid; e < 3 * m.fl; e += nthr) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
     for (int e = tid; e < 6 * m.fl; e += nthr) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
     for (int e = tid; e <= m.n_fn; e += nthr) s_toff[e] = T.tile_n_off[e];
+    if (scatter)
+        for (int e = tid; e < T.n_fpad; e += nthr) { s_gid[e] = T.pad_gid[e]; s_pv[e] = T.pad_pv[e]; }
 
     for (int u = 0; u < nt; ++u) {
         const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
@@ -519,6 +528,22 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                     A1[k * LR_LD + lane] = a1;
                     A2[k * LR_LD + lane] = a2;
                 }
+                if (scatter && warp == 0) {
+                    // force on atom k is -d/dr_k: the pair row (i -> j, alpha) lands, negated, in X row (j, alpha);
+                    // the aggregated own rows land in X row (i, alpha)
+                    int trow = -1;
+                    double wv = 0.0;
+                    if (valid) {
+                        const int j = b.nbr[p0 + row / 3];
+                        trow = b.frow[st_i] + 3 * (j - b.atom_off[st_i]) + al;
+                        wv = -(apply_w ? b.w[trow] : 1.0);
+                    } else if (row < nrow_all && row - nrow < 3) {
+                        trow = b.frow[st_i] + 3 * (i - b.atom_off[st_i]) + (row - nrow);
+                        wv = apply_w ? b.w[trow] : 1.0;
+                    }
+                    s_trow[lane] = trow;
+                    s_w[lane] = wv;
+                }
                 for (int n = warp; n < m.n_fn; n += nwarp) {
                     const int nid = s_nid[n];
                     const bool on = valid && nid >= 0;
@@ -534,7 +559,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
             for (int rt = 0; rt < 4; ++rt) {
                 const int r = row0 + rt * 8 + g;
                 ragg[rt] = (r >= nrow && r < nrow_all) ? r - nrow : -1;
-                rowp[rt] = r < nrow ? Lbuf + ((size_t)p0 * 3 + r) * m.fl + 2 * q
+                rowp[rt] = r < nrow ? (scatter ? Lpv + ((size_t)p0 * 3 + r) * m.npv_pad : Lbuf + ((size_t)p0 * 3 + r) * m.fl + 2 * q)
                          : (ragg[rt] < 0 ? nullptr
                          : (ragg[rt] < 3 ? Xown + ((size_t)i * 3 + ragg[rt]) * m.fl : Sbuf + ((size_t)i * 6 + (ragg[rt] - 3)) * m.fl) + 2 * q);
             }
@@ -546,8 +571,18 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                 if (kcn == 0) {  // radial index inactive for this type pair: exact zeros
                     for (int tt = 0; tt < ntile; ++tt)
 #pragma unroll
-                        for (int rt = 0; rt < 4; ++rt)
-                            if (rowp[rt] && ragg[rt] < 0) *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(0.0, 0.0);
+                        for (int rt = 0; rt < 4; ++rt) {
+                            if (!rowp[rt] || ragg[rt] >= 0) continue;
+                            if (!scatter) {
+                                *reinterpret_cast<double2*>(rowp[rt] + (tile0 + tt) * 8) = make_double2(0.0, 0.0);
+                            } else {
+#pragma unroll
+                                for (int e2 = 0; e2 < 2; ++e2) {
+                                    const int pv = s_pv[(tile0 + tt) * 8 + 2 * q + e2];
+                                    if (pv >= 0) rowp[rt][pv] = 0.0;
+                                }
+                            }
+                        }
                     continue;
                 }
                 double bf[TPN][KPN];
@@ -614,11 +649,31 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                         if (tt >= ntile) break;
 #pragma unroll
                         for (int r2 = 0; r2 < 2; ++r2) {
-                            double* dst = rowp[2 * rh + r2];
+                            const int rt = 2 * rh + r2;
+                            double* dst = rowp[rt];
                             if (!dst) continue;
+                            const int ra = ragg[rt];
+                            if (scatter && ra < 3) {
+                                // linear columns: RED.F64 into the target X row; polynomial variables of pair rows
+                                // are kept (unweighted) for the gather GEMM of K4b
+                                const int lrow = rt * 8 + g;
+                                double* xr = X + (size_t)s_trow[lrow] * m.fpad;
+                                const double wv = s_w[lrow];
+#pragma unroll
+                                for (int e2 = 0; e2 < 2; ++e2) {
+                                    const int fp_ = (tile0 + tt) * 8 + 2 * q + e2;
+                                    const int gc = s_gid[fp_];
+                                    if (gc >= 0) atomicAdd(xr + gc, wv * acc[tt][r2][e2]);
+                                    if (ra < 0) {
+                                        const int pv = s_pv[fp_];
+                                        if (pv >= 0) dst[pv] = acc[tt][r2][e2];
+                                    }
+                                }
+                                if (ra < 0) continue;
+                            }
                             dst += (tile0 + tt) * 8;
                             double2 v = make_double2(acc[tt][r2][0], acc[tt][r2][1]);
-                            if (ragg[2 * rh + r2] >= 0) {
+                            if (ra >= 0) {
                                 const double2 o = *reinterpret_cast<double2*>(dst);
                                 v.x += o.x; v.y += o.y;
                             }
@@ -642,12 +697,12 @@ static int lrows_v2_warps(const DevModel& m) {
 }
 
 template <int KPN> static size_t lrows_v2_smem(const DevModel& m, int nwarp, int n_tiles_max) {
-    const size_t ints = (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN;
-    return (2ull * m.pbstride * LR_PLD + 2ull * (4 * KPN) * LR_LD + 64ull * m.n_fn) * sizeof(double) + ints * sizeof(int) + 16;
+    const size_t ints = (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN + 16ull * n_tiles_max + 34;
+    return (2ull * m.pbstride * LR_PLD + 2ull * (4 * KPN) * LR_LD + 64ull * m.n_fn + 32) * sizeof(double) + ints * sizeof(int) + 32;
 }
 
 template <int TPN, int KPN>
-static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
     const int nwarp = lrows_v2_warps(m);
     int ntl = 1;
     for (int t = 0; t < m.n_type; ++t) ntl = max(ntl, m.types[t].n_tiles);
@@ -657,13 +712,14 @@ static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Worksp
         cudaFuncSetAttribute(k_lrows_v3<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set_for = smem;
     }
-    k_lrows_v3<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf);
+    k_lrows_v3<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
+                                                             ws.scatter ? ws.X : nullptr, ws.Lpv, apply_w ? 1 : 0);
 }
 
-static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
     if (m.kpn == 0 || m.tpn == 0) return false;
     if ((2ull * m.pbstride * LR_PLD + 8ull * (4 * m.kpn) * LR_LD) * sizeof(double) > 150 * 1024) return false;
-#define PM_LR_CASE(TP, KP) if (m.tpn == TP && m.kpn == KP) { launch_lrows_v2_t<TP, KP>(m, b, ws, s); return true; }
+#define PM_LR_CASE(TP, KP) if (m.tpn == TP && m.kpn == KP) { launch_lrows_v2_t<TP, KP>(m, b, ws, apply_w, s); return true; }
     PM_LR_CASE(1, 2) PM_LR_CASE(2, 2) PM_LR_CASE(3, 2) PM_LR_CASE(4, 2)
     PM_LR_CASE(1, 4) PM_LR_CASE(2, 4) PM_LR_CASE(3, 4) PM_LR_CASE(4, 4)
     PM_LR_CASE(1, 8) PM_LR_CASE(2, 8) PM_LR_CASE(3, 8) PM_LR_CASE(4, 8)
@@ -678,8 +734,8 @@ size_t lrows_mma_smem(const DevModel& m) {
     return ((size_t)m.pbstride * LR_PLD + 4ull * g_lrows_kmax * LR_LD) * sizeof(double);
 }
 
-void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
-    if (launch_lrows_v2(m, b, ws, s)) return;
+void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
+    if (launch_lrows_v2(m, b, ws, apply_w, s)) return;
     const size_t smem = lrows_mma_smem(m);
     static size_t set_for = 0;
     if (set_for != smem) {
@@ -1071,6 +1127,124 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4b in scatter mode: the linear columns were already added by K4a (RED.F64), so a row atom only needs the
+// gather GEMM over the polynomial variables.  Lambda rows come from the compact Lpv buffer (512 contiguous
+// bytes per (pair, alpha)), the own row from Xown; all three force rows at once, 512 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(XV_THREADS, 1) k_xpoly(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                          const double* __restrict__ Lpv, const double* __restrict__ Xown,
+                                                          double* __restrict__ X, int apply_w) {
+    extern __shared__ __align__(16) double smem[];
+    double* sD = smem;                          // [XV_KC][XV_LD]
+    double* sL = sD + XV_KC * XV_LD;            // [3][XV_KC][XV_LD]
+    double* sC = sL + 3 * XV_KC * XV_LD;        // [64][65]
+    int* sAtom = reinterpret_cast<int*>(sC + 64 * 65);   // [XV_KC]
+    int* sSrc = sAtom + XV_KC;                           // [XV_KC] reverse pair, -1 = the row atom itself
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+    const int nt = m.n_type;
+    const int k_atom = blockIdx.x;
+    const int s = b.st_of_atom[k_atom];
+    if (!b.force[s]) return;
+    const int p0 = b.seg_off[k_atom * nt];
+    const int n_cent = 1 + b.seg_off[k_atom * nt + nt] - p0;
+    const int row_base = b.frow[s] + 3 * (k_atom - b.atom_off[s]);
+    if (m.n_pair_terms == 0) {
+        if (tid < 3) X[(size_t)(row_base + tid) * m.fpad + m.n_variables] = apply_w ? b.yv[row_base + tid] : 0.0;
+        return;
+    }
+    double acc[3][2][2][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) { acc[r][x][y][0] = 0.0; acc[r][x][y][1] = 0.0; }
+    const int npv = m.npv_pad;
+    for (int c0 = 0; c0 < n_cent; c0 += XV_KC) {
+        __syncthreads();
+        if (tid < XV_KC) {
+            const int c = c0 + tid;
+            int atom = -1, src = -1;
+            if (c < n_cent) {
+                if (c == 0) atom = k_atom;
+                else { const int p = p0 + c - 1; atom = b.nbr[p]; src = b.rev[p]; }
+            }
+            sAtom[tid] = atom;
+            sSrc[tid] = src;
+        }
+        __syncthreads();
+        const int ncc = min(XV_KC, n_cent - c0);
+        for (int e = tid; e < XV_KC * 64; e += XV_THREADS) {
+            const int cc = e >> 6, a = e & 63;
+            const int atom = sAtom[cc];
+            double dv = 0.0, l0 = 0.0, l1 = 0.0, l2 = 0.0;
+            if (atom >= 0 && a < npv) {
+                const int fa = m.pv_fp[(size_t)b.types[atom] * npv + a];
+                if (fa >= 0) {
+                    dv = dfeat[(size_t)atom * m.fl + fa];
+                    const int src = sSrc[cc];
+                    if (src < 0) {
+                        const double* o = Xown + (size_t)atom * 3 * m.fl + fa;
+                        l0 = o[0]; l1 = o[m.fl]; l2 = o[2 * (size_t)m.fl];
+                    } else {
+                        const double* o = Lpv + (size_t)src * 3 * npv + a;
+                        l0 = -o[0]; l1 = -o[npv]; l2 = -o[2 * npv];
+                    }
+                }
+            }
+            sD[cc * XV_LD + a] = dv;
+            sL[(0 * XV_KC + cc) * XV_LD + a] = l0;
+            sL[(1 * XV_KC + cc) * XV_LD + a] = l1;
+            sL[(2 * XV_KC + cc) * XV_LD + a] = l2;
+        }
+        __syncthreads();
+        const int kend = (ncc + 3) & ~3;
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            double af[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) af[x] = sD[(k0 + q) * XV_LD + wm * 16 + x * 8 + g];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double bf[2];
+#pragma unroll
+                for (int y = 0; y < 2; ++y) bf[y] = sL[(r * XV_KC + k0 + q) * XV_LD + wn * 16 + y * 8 + g];
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+#pragma unroll
+                    for (int y = 0; y < 2; ++y) dmma(acc[r][x][y][0], acc[r][x][y][1], af[x], bf[y]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int row = row_base + r;
+        const double wrow = apply_w ? b.w[row] : 1.0;
+        double* xr = X + (size_t)row * m.fpad;
+        if (tid == 0) xr[m.n_variables] = apply_w ? b.yv[row] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) {
+                const int ra = wm * 16 + x * 8 + g, cb = wn * 16 + y * 8 + 2 * q;
+                sC[ra * 65 + cb] = acc[r][x][y][0];
+                sC[ra * 65 + cb + 1] = acc[r][x][y][1];
+            }
+        __syncthreads();
+        for (int e = tid; e < m.n_pair_terms; e += XV_THREADS) {
+            const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
+            xr[col] = wrow * (sC[a * 65 + bb] + sC[bb * 65 + a]);
+        }
+    }
+}
+
+bool scatter_mode_supported(const DevModel& m) {
+    return m.kpn > 0 && m.tpn > 0 && m.npv_pad <= 64 && m.n_linear <= 512 &&
+           (2ull * m.pbstride * LR_PLD + 8ull * (4 * m.kpn) * LR_LD) * sizeof(double) <= 150 * 1024;
+}
+
 static size_t xrows_v2_smem() {
     return ((size_t)XV_KC * XV_LD * 4 + 64 * 65 + 4 * XV_KC) * sizeof(double) + XV_KC * sizeof(int);
 }
@@ -1078,6 +1252,19 @@ static size_t xrows_v2_smem() {
 static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                             bool apply_weights, cudaStream_t s) {
     if (m.npv_pad > 64 || m.n_linear > 512) return false;
+    if (ws.scatter) {
+        const size_t smem2 = xrows_v2_smem();
+        static bool set2 = false;
+        if (!set2) {
+            cudaFuncSetAttribute(k_xpoly, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            cudaFuncSetAttribute(k_xrows_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            set2 = true;
+        }
+        k_xpoly<<<b.n_atoms, XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lpv, ws.Xown, ws.X, apply_weights ? 1 : 0);
+        k_xrows_v2<<<dim3(b.n_st, 3), XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq,
+                                                             1, apply_weights ? 1 : 0);
+        return true;
+    }
     const size_t smem = xrows_v2_smem();
     static bool set = false;
     if (!set) {
@@ -1164,6 +1351,46 @@ __global__ void __launch_bounds__(256) k_bench_mixed(double* out, int iters) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += f[k];
     if (s == 123.456) out[0] = s;
+}
+
+// RED.F64 throughput probe: every warp adds 8 row segments of 64 B (the C-fragment store shape of K4a) into
+// pseudo-random rows of a [n_rows][ld] fp64 matrix.  Returns giga-atomics per second.
+__global__ void __launch_bounds__(256) k_bench_red(double* __restrict__ X, int n_rows, int ld, int tiles, int iters) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    unsigned state = (blockIdx.x * 256 + threadIdx.x) / 32 * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        state = state * 1664525u + 1013904223u;
+        const unsigned base = __shfl_sync(0xffffffffu, state, 0);
+        const int row = (int)((base >> 8) % (unsigned)(n_rows - 8)) + g;
+        const int tile = (int)((base >> 3) % (unsigned)tiles);
+        double* dst = X + (size_t)row * ld + tile * 8 + 2 * q;
+        atomicAdd(dst, 1.0);
+        atomicAdd(dst + 1, 1.0);
+    }
+}
+
+double microbench_red(int n_rows, cudaStream_t s) {
+    const int ld = 2048, tiles = 25;
+    double* X = nullptr;
+    cudaMalloc(&X, (size_t)n_rows * ld * sizeof(double));
+    cudaMemsetAsync(X, 0, (size_t)n_rows * ld * sizeof(double), s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = 148 * 8, iters = 2048;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, s);
+        k_bench_red<<<blocks, 256, 0, s>>>(X, n_rows, ld, tiles, iters);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(X);
+    const double n_atomics = (double)blocks * 256 * iters * 2;
+    return n_atomics / (best * 1e-3) * 1e-9;
 }
 
 double microbench_fp64(int which, cudaStream_t s) {

@@ -10,13 +10,14 @@ import pytest
 import cases
 from oracle import polymlp_oracle as po
 from pypolymlp_b200 import fit
-from pypolymlp_b200._capi import PM_FLAG_SIMPLE_KERNELS
+from pypolymlp_b200._capi import PM_FLAG_SCATTER, PM_FLAG_SIMPLE_KERNELS
 from pypolymlp_b200.libmlpcpp import (PotentialModel, PotentialPropertiesFast, PotentialXtX, _Context, _Model)
 from pypolymlp_b200.params import make_params_dict
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(cases.GOLDEN, "ref_vectors.npz"))
-FLAVOURS = [pytest.param(PM_FLAG_SIMPLE_KERNELS, id="simple"), pytest.param(0, id="dmma")]
+FLAVOURS = [pytest.param(PM_FLAG_SIMPLE_KERNELS, id="simple"), pytest.param(0, id="dmma"),
+            pytest.param(PM_FLAG_SCATTER, id="dmma-scatter")]
 
 
 def _sort_ref_order(off, nb, dx, dy, dz):
@@ -285,7 +286,7 @@ def test_config2_full_size_properties():
     a3.stage(axis, pcs, tys, [True] * n, w, y)
     a3.add_staged()
     r3 = a3.finalize()
-    assert np.abs(r3["xtx"] - r1["xtx"]).max() < 1e-12 * sc
+    assert np.abs(r3["xtx"] - r1["xtx"]).max() < 1e-11 * sc  # RED.F64 summation order varies run to run
 
 
 def test_error_paths():
