@@ -80,7 +80,7 @@ template <typename T> struct DevVec {
 };
 
 struct HostChunk {
-    int n_st = 0, n_atoms = 0, n_rows = 0;
+    int n_st = 0, n_atoms = 0, n_rows = 0, max_trans = 0;
     std::vector<int> atom_off, st_of_atom, types, trans_off, force, erow, srow, frow;
     std::vector<double> x, y, z, trans, w, yv;
     std::vector<long> brow_e, brow_s, brow_f;  // rows in the caller's batch layout
@@ -364,6 +364,7 @@ static void prepare_chunk(const pm_context* c, const pm_structures* st, const st
         }
         h.trans.insert(h.trans.end(), ct.trans.begin(), ct.trans.end());
         h.trans_off.push_back((int)(h.trans.size() / 3));
+        h.max_trans = std::max(h.max_trans, (int)(ct.trans.size() / 3));
         h.atom_off.push_back(h.atom_off.back() + na);
         h.force.push_back(st->force ? (st->force[s] != 0) : 0);
     }
@@ -468,7 +469,8 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         h2d(c->d_w, h.w, s); h2d(c->d_yv, h.yv, s);
     }
     DevBatch b{};
-    b.n_st = h.n_st; b.n_atoms = h.n_atoms; b.n_pairs = 0; b.n_rows = h.n_rows;
+    b.n_st = h.n_st; b.n_atoms = h.n_atoms; b.n_pairs = 0; b.n_rows = h.n_rows; b.max_trans = h.max_trans;
+    b.need_agg = mode == MODE_EVAL ? 0 : 1;
     b.atom_off = c->d_atom_off.p; b.st_of_atom = c->d_st_of_atom.p; b.types = c->d_types.p;
     b.x = c->d_x.p; b.y = c->d_y.p; b.z = c->d_z.p; b.trans_off = c->d_trans_off.p; b.trans = c->d_trans.p;
     b.force = c->d_force.p; b.erow = c->d_erow.p; b.srow = c->d_srow.p; b.frow = c->d_frow.p;
@@ -888,6 +890,7 @@ int pm_fit_stage(pm_context* c, const pm_structures* st, const double* w, const 
             // keep only the metadata on the host
             HostChunk meta;
             meta.n_st = h.n_st; meta.n_atoms = h.n_atoms; meta.n_rows = h.n_rows; meta.force = h.force;
+            meta.max_trans = h.max_trans;
             c->staged.push_back(std::move(meta));
         }
     });

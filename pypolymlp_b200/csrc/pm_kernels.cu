@@ -74,10 +74,86 @@ __global__ void __launch_bounds__(256) k_neighbor(DevModel m, DevBatch b, int* _
     }
 }
 
+// Faster sweep for the common case (<= 128 lattice translations): lane = neighbour atom j (32 at a time), the
+// translation loop is sequential per lane and records hits in a bit mask, so there is no per-candidate ballot and
+// no integer division; a warp prefix sum over the lanes' hit counts restores the reference's (j, translation)
+// output order.  Same exact arithmetic as k_neighbor.
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_neighbor_mask(DevModel m, DevBatch b, int* __restrict__ counts,
+                                                        double* __restrict__ PB, double cutoff_sq, double tol_sq) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= b.n_atoms) return;
+    const int i = warp;
+    const int s = b.st_of_atom[i];
+    const int a0 = b.atom_off[s];
+    const int N = b.atom_off[s + 1] - a0;
+    const int t0 = b.trans_off[s];
+    const int T = b.trans_off[s + 1] - t0;
+    const double xi = b.x[i], yi = b.y[i], zi = b.z[i];
+    const int nt = m.n_type;
+    const double* __restrict__ tr = b.trans + 3 * (size_t)t0;
+    for (int u = 0; u < nt; ++u) {
+        int cnt = 0;
+        const int base = FILL ? b.seg_off[i * nt + u] : 0;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned long long m0 = 0ull, m1 = 0ull;
+            double dxij = 0.0, dyij = 0.0, dzij = 0.0;
+            const bool act = j < N && (nt == 1 || b.types[a0 + j] == u);
+            if (act) {
+                dxij = __dsub_rn(b.x[a0 + j], xi);
+                dyij = __dsub_rn(b.y[a0 + j], yi);
+                dzij = __dsub_rn(b.z[a0 + j], zi);
+                for (int t = 0; t < T; ++t) {
+                    const double dx = __dadd_rn(dxij, tr[3 * t]);
+                    const double dy = __dadd_rn(dyij, tr[3 * t + 1]);
+                    const double dz = __dadd_rn(dzij, tr[3 * t + 2]);
+                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (r2 < cutoff_sq && r2 > tol_sq) {
+                        if (t < 64) m0 |= 1ull << t; else m1 |= 1ull << (t - 64);
+                    }
+                }
+            }
+            const int mine = __popcll(m0) + __popcll(m1);
+            int incl = mine;   // inclusive warp scan
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (FILL && mine) {
+                int pos = base + cnt + incl - mine;
+                for (int w = 0; w < 2; ++w) {
+                    unsigned long long mm = w == 0 ? m0 : m1;
+                    while (mm) {
+                        const int t = __ffsll((long long)mm) - 1 + 64 * w;
+                        mm &= mm - 1;
+                        b.nbr[pos] = a0 + j;
+                        b.centre[pos] = i;
+                        const PBRecW rec = pb_rec_w(PB, pos, m.pbstride);
+                        rec[0] = __dadd_rn(dxij, tr[3 * t]);
+                        rec[1] = __dadd_rn(dyij, tr[3 * t + 1]);
+                        rec[2] = __dadd_rn(dzij, tr[3 * t + 2]);
+                        ++pos;
+                    }
+                }
+            }
+            cnt += total;
+        }
+        if (!FILL && lane == 0) counts[i * nt + u] = cnt;
+    }
+}
+
 void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s) {
     const int threads = 256;
     const int blocks = (b.n_atoms * 32 + threads - 1) / threads;
     const double tol = 1e-10;
+    if (b.max_trans <= 128) {
+        k_neighbor_mask<false><<<blocks, threads, 0, s>>>(m, b, counts, nullptr, m.cutoff * m.cutoff, tol * tol);
+        return;
+    }
     k_neighbor<false><<<blocks, threads, 0, s>>>(m, b, counts, nullptr, m.cutoff * m.cutoff, tol * tol);
 }
 
@@ -85,6 +161,10 @@ void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cuda
     const int threads = 256;
     const int blocks = (b.n_atoms * 32 + threads - 1) / threads;
     const double tol = 1e-10;
+    if (b.max_trans <= 128) {
+        k_neighbor_mask<true><<<blocks, threads, 0, s>>>(m, b, nullptr, PB, m.cutoff * m.cutoff, tol * tol);
+        return;
+    }
     k_neighbor<true><<<blocks, threads, 0, s>>>(m, b, nullptr, PB, m.cutoff * m.cutoff, tol * tol);
 }
 
@@ -304,7 +384,7 @@ __global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const doub
     const int i = blockIdx.x;
     const int t = b.types[i];
     const DevType& T = m.types[t];
-    const bool force = b.force[b.st_of_atom[i]] != 0;
+    const bool force = b.force[b.st_of_atom[i]] != 0 && b.need_agg != 0;
     const int nt = m.n_type;
     const int oy = pb_y(m, 0), oyx = pb_y(m, 1), oyy = pb_y(m, 2), oyz = pb_y(m, 3);
     for (int h = threadIdx.x; h < T.n_head; h += blockDim.x) {
@@ -347,7 +427,7 @@ __global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const doub
 
 // Same sums with the pair records staged through shared memory (coalesced 16-byte copies of 8 records at a
 // time, double buffered with cp.async); one thread per head, so accumulation stays thread-private.
-constexpr int AN_PT = 8;
+constexpr int AN_PT = 16;
 
 __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                   double2* __restrict__ anc, double2* __restrict__ agg) {
@@ -355,7 +435,7 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
     const int i = blockIdx.x;
     const int t = b.types[i];
     const DevType& T = m.types[t];
-    const bool force = b.force[b.st_of_atom[i]] != 0;
+    const bool force = b.force[b.st_of_atom[i]] != 0 && b.need_agg != 0;
     const int nt = m.n_type;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int stride = m.pbstride;

@@ -434,7 +434,7 @@ constexpr int LR_MAXW = 8;  // max warps per CTA
 // ------------------------------------------------------------------------------------------------
 constexpr int LR_LDA = 20;  // row stride of the aggregated-row scratch tile (== 4 mod 16)
 
-template <int TPN, int KPN>
+template <int TPN, int KPN, bool SCATTER>
 __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                    const double2* __restrict__ agg, const double* __restrict__ Gbuf,
                                                    double* __restrict__ Lbuf, double* __restrict__ Xown,
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
     int* s_gid = s_bmap + T.n_tiles * KPN;                 // [n_fpad] global linear column (scatter mode)
     int* s_pv = s_gid + T.n_fpad;                          // [n_fpad] polynomial-variable index
     int* s_trow = s_pv + T.n_fpad;                         // [32] target X row of each chunk row (scatter mode)
-    const bool scatter = X != nullptr;
+    constexpr bool scatter = SCATTER;
     const int st_i = b.st_of_atom[i];
     const double* G = Gbuf + (size_t)i * m.gstride;
     const int oy = pb_y(m, 0);
@@ -709,11 +709,16 @@ static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Worksp
     const size_t smem = lrows_v2_smem<KPN>(m, nwarp, ntl);
     static size_t set_for = 0;
     if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set_for = smem;
     }
-    k_lrows_v3<TPN, KPN><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
-                                                             ws.scatter ? ws.X : nullptr, ws.Lpv, apply_w ? 1 : 0);
+    if (ws.scatter)
+        k_lrows_v3<TPN, KPN, true><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
+                                                                       ws.X, ws.Lpv, apply_w ? 1 : 0);
+    else
+        k_lrows_v3<TPN, KPN, false><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown,
+                                                                        ws.Sbuf, nullptr, nullptr, 0);
 }
 
 static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
