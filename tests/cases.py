@@ -25,6 +25,16 @@ def binary_model_kwargs():
                 pair_params_conditional={(0, 0): [0, 1, 2, 5], (0, 1): [1, 2, 3, 4, 5], (1, 1): [0, 2, 4, 5]})
 
 
+def cfg3_model_kwargs():
+    # BASELINE config 3: binary, order 4, maxl [12,8,2], 10 radial functions, model_type 3 (F = 9385)
+    return dict(n_type=2, cutoff=6.0, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[12, 8, 2], n_gaussians=10)
+
+
+def cfg4_model_kwargs():
+    # BASELINE config 4: ternary, same gtinv settings (F = 45090)
+    return dict(n_type=3, cutoff=6.0, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[12, 8, 2], n_gaussians=10)
+
+
 def ternary_p3_model_kwargs():
     # small on purpose: max_p = 3 models grow as n_linear^3 / 6
     return dict(n_type=3, cutoff=4.5, model_type=2, max_p=3, gtinv_order=2, gtinv_maxl=[0],

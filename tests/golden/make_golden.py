@@ -93,6 +93,15 @@ coeffs = np.random.default_rng(12).normal(size=rm.n_features) * 1e-3
 e, f, s = ref.RefEval(pd, coeffs).eval(ax, pc, ty)
 out["fcc_coeffs"], out["fcc_e"], out["fcc_f"], out["fcc_s"] = coeffs, np.array([e]), f, s
 
+# ---- config-3 model (binary, order 4, maxl [12,8,2], F = 9385) on a 16-atom bcc cell: summaries -----------
+pd = make_params_dict(**cases.cfg3_model_kwargs())
+rm = ref.RefModel(pd)
+ax, pc, ty = cases.bcc_supercell(rep=(2, 2, 2), a=3.2, n_type=2, seed=5)
+xe, xf, xs = rm.run(ax, pc, ty, True)
+out["cfg3_xe"], out["cfg3_xs"] = xe, xs
+out["cfg3_xf_rows"] = xf[::6]
+out["cfg3_xf_colsum"], out["cfg3_xf_colsqsum"] = xf.sum(axis=0), np.square(xf).sum(axis=0)
+
 np.savez_compressed(os.path.join(cases.GOLDEN, "ref_vectors.npz"), **out)
 for k, v in out.items():
     print(k, v.shape)

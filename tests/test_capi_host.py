@@ -65,7 +65,8 @@ def test_gaussian_params():
     (cases.si_model_kwargs(), 168),            # reference tests/test_mlp_dev/test_core_features.py:18
     (cases.cfg2_model_kwargs(4), 2030),        # config 1/2/5
     (cases.cfg2_model_kwargs(3), 255),
-    (dict(n_type=2, cutoff=6.0, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[12, 8, 2], n_gaussians=10), 9385),
+    (cases.cfg3_model_kwargs(), 9385),         # config 3
+    (cases.cfg4_model_kwargs(), 45090),        # config 4
 ])
 def test_model_sizes(kwargs, n_features):
     m = _Model(make_params_dict(**kwargs))

@@ -140,6 +140,32 @@ def test_x_fcc256_config2(flags):
     assert (np.abs(np.square(xf).sum(axis=0) - G["fcc_xf_colsqsum"]) / G["fcc_xf_colsqsum"].max()).max() < 1e-10
 
 
+def test_x_config3_binary_order4_maxl12():
+    """BASELINE config 3 model (F = 9385, L = 12: generic kernels) on a 16-atom bcc cell vs the reference."""
+    pd = make_params_dict(**cases.cfg3_model_kwargs())
+    ax, pc, ty = cases.bcc_supercell(rep=(2, 2, 2), a=3.2, n_type=2, seed=5)
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [16]).get_x()
+    assert x.shape == (1 + 6 + 48, 9385)
+    assert cases.x_rel_err(x[0], G["cfg3_xe"]) < 1e-10
+    assert cases.x_rel_err(x[1:7], G["cfg3_xs"]) < 1e-10
+    xf = x[7:]
+    scale = np.maximum(np.abs(xf).max(axis=0), 1e-8 * np.abs(xf).max())
+    assert (np.abs(xf[::6] - G["cfg3_xf_rows"]) / scale).max() < 1e-10
+    assert (np.abs(np.square(xf).sum(axis=0) - G["cfg3_xf_colsqsum"]) / G["cfg3_xf_colsqsum"].max()).max() < 1e-10
+    # fused accumulation on the same structure: X^T X against the materialised X
+    rows = x.shape[0]
+    rng = np.random.default_rng(3)
+    w = rng.uniform(0.2, 1.0, rows)
+    y = w * rng.normal(size=rows)
+    acc = PotentialXtX(pd)
+    acc.add([ax], [pc], [ty], [True], w, y)
+    res = acc.finalize()
+    xw = x * w[:, None]
+    ref_xtx = xw.T @ xw
+    assert np.abs(res["xtx"] - ref_xtx).max() < 1e-10 * np.abs(ref_xtx).max()
+    assert np.abs(res["xty"] - xw.T @ y).max() < 1e-10 * np.abs(xw.T @ y).max()
+
+
 def _si_datasets(ids):
     axis, positions_c, forces, energies = cases.load_si_dataset()
     return fit.Dataset([axis] * len(ids), [positions_c[i] for i in ids], [np.zeros(64, np.int32)] * len(ids),
