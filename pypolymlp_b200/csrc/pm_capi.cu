@@ -803,11 +803,18 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
     const DevModel& d = c->dm;
     const int F = d.n_variables;
     StageTimer tm(c);
-    for (auto [s0, s1] : plan_chunks(c, st)) {
-        HostChunk h;
-        prepare_chunk(c, st, aoff, be, bs, bf, s0, s1, w, y, h);
+    // The host prepares chunk k+1 (translations, row maps) while the GPU still works on chunk k.
+    const auto chunks = plan_chunks(c, st);
+    HostChunk h_next;
+    auto prepare = [&](size_t k, HostChunk& out) {
+        prepare_chunk(c, st, aoff, be, bs, bf, chunks[k].first, chunks[k].second, w, y, out);
         if (mode == MODE_EVAL)
-            for (auto& f : h.force) f = 1;
+            for (auto& f : out.force) f = 1;
+    };
+    if (!chunks.empty()) prepare(0, h_next);
+    for (size_t ck = 0; ck < chunks.size(); ++ck) {
+        const int s0 = chunks[ck].first;
+        HostChunk h = std::move(h_next);
         run_chunk(c, h, mode, true, tm);
         if (mode == MODE_X) {
             for (int k = 0; k < h.n_st; ++k) {
@@ -835,6 +842,7 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
         } else if (mode == MODE_EVAL) {
             for (int k = 0; k < h.n_st; ++k) { e_out[s0 + k] = 0.0; for (int r = 0; r < 6; ++r) s_out[6 * (size_t)(s0 + k) + r] = 0.0; }
         }
+        if (ck + 1 < chunks.size()) prepare(ck + 1, h_next);
         if (h.n_atoms > 0) check_device_error(c);
         else CK(cudaStreamSynchronize(c->stream));
     }
