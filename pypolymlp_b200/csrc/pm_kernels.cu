@@ -1028,6 +1028,91 @@ __global__ void __launch_bounds__(128) k_eval_pairs(DevModel m, DevBatch b, cons
     atomicAdd(S + 3 + al, -g * rec[be]);
 }
 
+// One thread per pair (consecutive pairs are contiguous per item in the blocked pair-basis layout, so every
+// load is coalesced); Y_lm and its gradient are read once per lm and reused for all radial indices; the three
+// Cartesian components are accumulated together.  Virial sums are reduced over the warp before the atomics.
+constexpr int EV_MAXFN = 16;
+
+__global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                        const double* __restrict__ Ah, int ah_stride,
+                                                        double* __restrict__ forces, double* __restrict__ stresses) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = p < b.n_pairs;
+    double g[3] = {0.0, 0.0, 0.0};
+    double dl[3] = {0.0, 0.0, 0.0};
+    int i = 0, j = 0, s = -1;
+    if (act) {
+        i = b.centre[p];
+        j = b.nbr[p];
+        s = b.st_of_atom[i];
+        const DevType& T = m.types[b.types[i]];
+        const int u = b.types[j];
+        const int segstride = ah_stride / m.n_type;
+        const double* ah = Ah + (size_t)i * ah_stride + u * segstride;
+        const PBRec rec = pb_rec(PB, p, m.pbstride);
+        const double rinv = rec[3];
+        dl[0] = rec[0]; dl[1] = rec[1]; dl[2] = rec[2];
+        const int* snid = T.seg_nid[u];
+        const int* snoff = T.seg_n_off[u];
+        double fn[EV_MAXFN], fd[EV_MAXFN];
+#pragma unroll
+        for (int n = 0; n < EV_MAXFN; ++n) {
+            fn[n] = 0.0; fd[n] = 0.0;
+            if (n < m.n_fn) {
+                const int nid = snid[n];
+                if (nid >= 0) { fn[n] = rec[4 + nid]; fd[n] = rec[4 + m.n_fn + nid] * rinv; }
+            }
+        }
+        const int oy = pb_y(m, 0), oyx = pb_y(m, 1), oyy = pb_y(m, 2), oyz = pb_y(m, 3);
+        for (int key = 0; key < m.nh; ++key) {
+            const double yr = rec[oy + 2 * key], yi = rec[oy + 2 * key + 1];
+            const double xr = rec[oyx + 2 * key], xi = rec[oyx + 2 * key + 1];
+            const double wr = rec[oyy + 2 * key], wi = rec[oyy + 2 * key + 1];
+            const double zr = rec[oyz + 2 * key], zi = rec[oyz + 2 * key + 1];
+            // sum over radial indices of Ah[(n, lm)] weighted by f_n'/r and f_n
+            double s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
+#pragma unroll
+            for (int n = 0; n < EV_MAXFN; ++n) {
+                if (n < m.n_fn && snoff[n + 1] > snoff[n]) {
+                    const int q = snoff[n] + key;   // every radial group lists all lm keys in order
+                    const double ar = ah[2 * q], ai = ah[2 * q + 1];
+                    s1r += fd[n] * ar; s1i += fd[n] * ai;
+                    s2r += fn[n] * ar; s2i += fn[n] * ai;
+                }
+            }
+            // g_alpha += Re-part contraction: (f' Y D_alpha / r + f dY_alpha) . Ah
+            const double t1 = yr * s1r + yi * s1i;
+            g[0] += t1 * dl[0] + xr * s2r + xi * s2i;
+            g[1] += t1 * dl[1] + wr * s2r + wi * s2i;
+            g[2] += t1 * dl[2] + zr * s2r + zi * s2i;
+        }
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+            atomicAdd(forces + (size_t)i * 3 + al, g[al]);
+            atomicAdd(forces + (size_t)j * 3 + al, -g[al]);
+        }
+    }
+    // virial: xx yy zz xy yz zx = -g_alpha * D_beta, reduced over the warp when all lanes share the structure
+    double sv[6] = {-g[0] * dl[0], -g[1] * dl[1], -g[2] * dl[2], -g[0] * dl[1], -g[1] * dl[2], -g[2] * dl[0]};
+    const int s0 = __shfl_sync(0xffffffffu, s, 0);
+    const bool uniform = __all_sync(0xffffffffu, s == s0 || s < 0);
+    if (uniform) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], d);
+        }
+        const int sl = __reduce_max_sync(0xffffffffu, s);
+        if ((threadIdx.x & 31) == 0 && sl >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(stresses + (size_t)sl * 6 + k, sv[k]);
+        }
+    } else if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(stresses + (size_t)s * 6 + k, sv[k]);
+    }
+}
+
 void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
                          double* energies, double* forces, double* stresses, cudaStream_t s) {
     if (b.n_atoms == 0) return;
@@ -1036,8 +1121,12 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
         for (int u = 0; u < m.n_type; ++u) maxseg = max(maxseg, m.types[t].seg_len[u]);
     const int ah_stride = m.n_type * 2 * maxseg;
     k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
-    if (b.n_pairs > 0)
-        k_eval_pairs<<<(b.n_pairs * 3 + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
+    if (b.n_pairs > 0) {
+        if (m.n_fn <= EV_MAXFN)
+            k_eval_pairs_v2<<<(b.n_pairs + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
+        else
+            k_eval_pairs<<<(b.n_pairs * 3 + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
+    }
 }
 
 // ================================================================================================
