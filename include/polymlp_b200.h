@@ -135,6 +135,17 @@ int pm_fit_fpad(pm_context* c);
 /* Copies results to HOST: xtx (F x F, symmetric, row-major), xty (F), xe_sum (F), xe_sq_sum (F). */
 int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum,
                     double* y_sq_norm, int64_t* n_data);
+/* ---- ridge solve on the device (reported separately from the hot path) ---------------------------------
+ * Replaces the tail of calc_xtx_xty (scales, zeroing, normalisation; data_sequential.py:72-92), solver_ridge
+ * (Cholesky per alpha with incremental diagonal update; src/pypolymlp/mlp_dev/standard/solvers.py:48-84) and
+ * compute_rmse from X^T X (utils_model_selection.py:37-72) on the accumulator that is already resident:
+ * cuSOLVER potrf/potrs + cuBLAS symv.  scales_in may be NULL (then they are computed from xe_sum / xe_sq_sum
+ * with n_energy = number of energy rows accumulated, as compute_scales does).  Outputs (host): scales_out[F],
+ * coefs[n_alpha][F] (in the scaled basis, like the reference's coefs_array columns), rmse[n_alpha].
+ * A failed factorisation yields coefficients 1e30 for that alpha (solvers.py:40-45). */
+int pm_fit_solve_ridge(pm_context* c, const double* alphas, int n_alpha, const double* scales_in, int64_t n_energy,
+                       int include_force, double scale_threshold, double* scales_out, double* coefs, double* rmse);
+
 /* Blocks until all queued device work of the context is finished. */
 int pm_synchronize(pm_context* c);
 /* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpolymlp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["pm_tables.cpp", "pm_kernels.cu", "pm_kernels_mma.cu", "pm_capi.cu"]
+SOURCES = ["pm_tables.cpp", "pm_kernels.cu", "pm_kernels_mma.cu", "pm_solver.cu", "pm_capi.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",
@@ -58,7 +58,7 @@ def build_library(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcublas", "-lcudart", "-ldl",
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcublas", "-lcusolver", "-lcudart", "-ldl",
                                                  "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -20,6 +20,10 @@ size_t lrows_mma_smem(const DevModel& m);
 size_t xrows_mma_smem(const DevModel& m);
 double microbench_dgemm(int n, cudaStream_t s);
 double microbench_red(int n_rows, cudaStream_t s);
+void solve_ridge_device(const double* C, int fpad, int F, const double* xe_sum_h, const double* xe_sq_h,
+                        double y_sq_norm, long n_data, const double* alphas, int n_alpha, const double* scales_in,
+                        long n_energy, bool include_force, double threshold, double* scales_out, double* coefs,
+                        double* rmse, cudaStream_t stream);
 }  // namespace pm
 
 using namespace pm;
@@ -995,6 +999,28 @@ int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, dou
             const double nd = tail[2 * (size_t)fp];
             *n_data = nd > (double)c->n_data ? (int64_t)llround(nd) : c->n_data;
         }
+    });
+}
+
+int pm_fit_solve_ridge(pm_context* c, const double* alphas, int n_alpha, const double* scales_in, int64_t n_energy,
+                       int include_force, double scale_threshold, double* scales_out, double* coefs, double* rmse) {
+    return guarded([&] {
+        if (!c || !alphas || n_alpha < 1 || !coefs || !rmse) throw std::invalid_argument("null argument");
+        CK(cudaSetDevice(c->device));
+        ensure_acc(c);
+        const DevModel& d = c->dm;
+        const int F = d.n_variables, fp = d.fpad;
+        CK(cudaStreamSynchronize(c->stream));
+        std::vector<double> tail(2 * (size_t)fp + 1);
+        CK(cudaMemcpy(tail.data(), c->acc + (size_t)fp * fp, tail.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        double ysq = 0.0;
+        CK(cudaMemcpy(&ysq, c->acc + (size_t)F * fp + F, sizeof(double), cudaMemcpyDeviceToHost));
+        const double nd_acc = tail[2 * (size_t)fp];
+        const long n_data = nd_acc > (double)c->n_data ? (long)llround(nd_acc) : (long)c->n_data;
+        if (!scales_in && n_energy <= 0) throw std::invalid_argument("n_energy is required when scales are not given");
+        if (n_data <= 0) throw std::runtime_error("no data accumulated");
+        solve_ridge_device(c->acc, fp, F, tail.data(), tail.data() + fp, ysq, n_data, alphas, n_alpha, scales_in,
+                           (long)n_energy, include_force != 0, scale_threshold, scales_out, coefs, rmse, c->stream);
     });
 }
 

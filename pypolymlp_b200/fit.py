@@ -226,6 +226,24 @@ def fit(params_dict, train, test, alphas, weight_stress=0.1, batch_size=64, devi
             "rmse_train_array": rmse_train, "rmse_test_array": rmse_test}
 
 
+def fit_device(params_dict, train, test, alphas, weight_stress=0.1, batch_size=64, device=None):
+    """Same as fit(), with the ridge solve of the training set on the GPU (cuSOLVER Cholesky on the
+    device-resident accumulator; pm_fit_solve_ridge).  The O(F^2) test-set RMSE stays on the host."""
+    min_energy = get_min_energy(train)
+    acc = PotentialXtX(params_dict, device=device)
+    accumulate_datasets(acc, train, min_energy, weight_stress, batch_size)
+    n_energy = sum(len(d.energies) for d in train)
+    include_force = any(d.include_force for d in train)
+    scales, coefs, rmse_train = acc.solve_ridge(alphas, n_energy, include_force=include_force)
+    test_xy = calc_xtx_xty(params_dict, test, scales=scales, min_energy=min_energy, weight_stress=weight_stress,
+                           batch_size=batch_size, device=device)
+    rmse_test = compute_rmse(coefs, test_xy)
+    idx = int(np.argmin(rmse_test))
+    return {"coeffs": coefs[:, idx], "scales": scales, "alpha": alphas[idx], "rmse_train": rmse_train[idx],
+            "rmse_test": rmse_test[idx], "coefs_array": coefs, "rmse_train_array": rmse_train,
+            "rmse_test_array": rmse_test}
+
+
 # ---- multi-GPU: structures shard across ranks, one NCCL reduce of the packed accumulator ----------
 class _DevicePtr:
     def __init__(self, ptr, n):

@@ -313,6 +313,19 @@ class PotentialXtX:
                 "total_n_data": int(nd.value)}
 
 
+    def solve_ridge(self, alphas, n_energy, scales=None, include_force=True, scale_threshold=1e-10):
+        """Ridge solve on the device-resident accumulator (cuSOLVER Cholesky per alpha).
+        Returns scales (F,), coefs_array (F, n_alpha) in the scaled basis, rmse (n_alpha,)."""
+        F = self.n_features
+        al = as_d(alphas)
+        sc_in = as_d(scales) if scales is not None else None
+        sc_out, coefs, rmse = np.zeros(F), np.zeros((len(al), F)), np.zeros(len(al))
+        check(lib().pm_fit_solve_ridge(self._ctx.handle, pd(al), len(al), pd(sc_in), C.c_int64(int(n_energy)),
+                                       int(bool(include_force)), C.c_double(scale_threshold), pd(sc_out), pd(coefs),
+                                       pd(rmse)))
+        return sc_out, coefs.T.copy(), rmse
+
+
 class PotentialPropertiesFast:
     """PotentialPropertiesFast(params_dict, coeffs) (reference: pybind11_mlp.cpp:51-67,
     compute/py_properties_fast.cpp:10-76).  Energies in eV/cell, forces (N, 3) in eV/A,
