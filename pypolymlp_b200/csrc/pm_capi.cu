@@ -284,6 +284,131 @@ static void build_device_model(pm_context* c) {
             cb[k].pad = 0;
         }
         D.contribs = upload(c, cb);
+        {   // sliced tables (k_features_v3)
+            const int mo = std::max(T.max_order, 1);
+            const int nw = (mo + 1) / 2;
+            std::vector<double> scoef;
+            std::vector<std::vector<unsigned>> sw(nw);
+            auto grow = [&](size_t n) {
+                scoef.resize(n, 0.0);
+                for (auto& w : sw) w.resize(n, 0u);
+            };
+            std::vector<int4> fmeta, emeta;
+            std::vector<int> fout;
+            std::vector<int2> eout;
+            bool ids_fit = T.n_full < 32768;
+            // features: rows of 8, 4 k-lanes
+            {
+                std::vector<int> order_of(T.n_feat, 1), idx(T.n_feat);
+                for (int f = 0; f < T.n_feat; ++f) {
+                    idx[f] = f;
+                    int o = 1;
+                    for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti) o = std::max(o, T.term_order[ti]);
+                    order_of[f] = o;
+                }
+                std::sort(idx.begin(), idx.end(), [&](int a, int b2) {
+                    if (order_of[a] != order_of[b2]) return order_of[a] < order_of[b2];
+                    const int na = T.term_off[a + 1] - T.term_off[a], nb = T.term_off[b2 + 1] - T.term_off[b2];
+                    if (na != nb) return na > nb;
+                    return a < b2;
+                });
+                for (int p0 = 0; p0 < T.n_feat;) {
+                    int p1 = p0;
+                    while (p1 < T.n_feat && p1 - p0 < 8 && order_of[idx[p1]] == order_of[idx[p0]]) ++p1;
+                    int mx = 0;
+                    for (int p = p0; p < p1; ++p) mx = std::max(mx, T.term_off[idx[p] + 1] - T.term_off[idx[p]]);
+                    const int iters = (mx + 3) / 4;
+                    const size_t base = scoef.size();
+                    grow(base + (size_t)iters * 32);
+                    fmeta.push_back(make_int4((int)base, iters, order_of[idx[p0]], 0));
+                    for (int r = 0; r < 8; ++r) fout.push_back(p0 + r < p1 ? T.feat_pad[idx[p0 + r]] : -1);
+                    for (int p = p0; p < p1; ++p) {
+                        const int f = idx[p], row = p - p0;
+                        for (int ti = T.term_off[f], k = 0; ti < T.term_off[f + 1]; ++ti, ++k) {
+                            // slot of k-th term: iteration k / 4, k-lane k % 4 -> lane = (k % 4) * 8 + row
+                            const size_t slot = base + (size_t)(k / 4) * 32 + (k % 4) * 8 + row;
+                            scoef[slot] = T.term_coeff[ti];
+                            const int o = T.term_order[ti];
+                            if (o != order_of[f]) ids_fit = false;   // mixed orders inside a feature: keep v2
+                            for (int q = 0; q < o && q < mo; ++q)
+                                sw[q / 2][slot] |= (unsigned)T.term_ids[(size_t)ti * mo + q] << (16 * (q & 1));
+                        }
+                    }
+                    p0 = p1;
+                }
+            }
+            // G entries: 32 per slice
+            {
+                std::vector<int> idx(T.ent_pos_re.size()), cn_of(idx.size(), 0);
+                for (size_t e = 0; e < idx.size(); ++e) {
+                    idx[e] = (int)e;
+                    int cn = 0;
+                    for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) {
+                        if (q > T.ent_off[e] && T.contribs[q].n_ids != cn) ids_fit = false;
+                        cn = T.contribs[q].n_ids;
+                    }
+                    cn_of[e] = cn;
+                }
+                std::sort(idx.begin(), idx.end(), [&](int a, int b2) {
+                    if (cn_of[a] != cn_of[b2]) return cn_of[a] < cn_of[b2];
+                    const int na = T.ent_off[a + 1] - T.ent_off[a], nb = T.ent_off[b2 + 1] - T.ent_off[b2];
+                    if (na != nb) return na > nb;
+                    return a < b2;
+                });
+                const int ne = (int)idx.size();
+                for (int p0 = 0; p0 < ne;) {
+                    int p1 = p0;
+                    while (p1 < ne && p1 - p0 < 32 && cn_of[idx[p1]] == cn_of[idx[p0]]) ++p1;
+                    int mx = 0;
+                    for (int p = p0; p < p1; ++p) mx = std::max(mx, T.ent_off[idx[p] + 1] - T.ent_off[idx[p]]);
+                    const size_t base = scoef.size();
+                    grow(base + (size_t)mx * 32);
+                    emeta.push_back(make_int4((int)base, mx, cn_of[idx[p0]], 0));
+                    for (int r = 0; r < 32; ++r)
+                        eout.push_back(p0 + r < p1 ? make_int2(T.ent_pos_re[idx[p0 + r]], T.ent_pos_im[idx[p0 + r]])
+                                                   : make_int2(-1, -1));
+                    for (int p = p0; p < p1; ++p) {
+                        const int e = idx[p], row = p - p0;
+                        for (int q = T.ent_off[e], k = 0; q < T.ent_off[e + 1]; ++q, ++k) {
+                            const size_t slot = base + (size_t)k * 32 + row;
+                            scoef[slot] = T.contribs[q].coeff;
+                            for (int z = 0; z < T.contribs[q].n_ids && z < 2 * nw; ++z)
+                                sw[z / 2][slot] |= (unsigned)T.contribs[q].ids[z] << (16 * (z & 1));
+                            if (T.contribs[q].conj) sw[0][slot] |= 0x80000000u;
+                        }
+                    }
+                    p0 = p1;
+                }
+            }
+            // slice order: longest first so that the round-robin over warps is balanced
+            auto by_len = [](const int4& a, const int4& b2) { return a.y > b2.y; };
+            {
+                std::vector<int> perm(fmeta.size());
+                for (size_t k = 0; k < perm.size(); ++k) perm[k] = (int)k;
+                std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return by_len(fmeta[a], fmeta[b2]); });
+                std::vector<int4> fm2; std::vector<int> fo2;
+                for (int k : perm) { fm2.push_back(fmeta[k]); fo2.insert(fo2.end(), fout.begin() + 8 * k, fout.begin() + 8 * k + 8); }
+                fmeta.swap(fm2); fout.swap(fo2);
+                perm.resize(emeta.size());
+                for (size_t k = 0; k < perm.size(); ++k) perm[k] = (int)k;
+                std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return by_len(emeta[a], emeta[b2]); });
+                std::vector<int4> em2; std::vector<int2> eo2;
+                for (int k : perm) { em2.push_back(emeta[k]); eo2.insert(eo2.end(), eout.begin() + 32 * k, eout.begin() + 32 * k + 32); }
+                emeta.swap(em2); eout.swap(eo2);
+            }
+            D.n_fsl = ids_fit ? (int)fmeta.size() : 0;
+            D.n_esl = ids_fit ? (int)emeta.size() : 0;
+            D.sl_words = nw;
+            D.n_slots = (long)scoef.size();
+            std::vector<unsigned> flat;
+            for (auto& w : sw) flat.insert(flat.end(), w.begin(), w.end());
+            D.fsl_meta = upload(c, fmeta); D.fsl_out = upload(c, fout);
+            D.esl_meta = upload(c, emeta); D.esl_out = upload(c, eout);
+            D.sl_coeff = upload(c, scoef); D.sl_ids = upload(c, flat);
+            if (getenv("PM_DEBUG_TABLES"))
+                fprintf(stderr, "[pm] type %d: %d feature slices, %d entry slices, %ld slots (terms %zu, contribs %zu)\n",
+                        t, D.n_fsl, D.n_esl, D.n_slots, T.term_coeff.size(), T.contribs.size());
+        }
         std::vector<int> bk(T.blocks.size());
         for (size_t k = 0; k < bk.size(); ++k) bk[k] = T.blocks[k].kchunk;
         D.blk_kchunk = upload(c, bk);

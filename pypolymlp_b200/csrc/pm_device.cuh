@@ -48,6 +48,17 @@ struct DevType {
     const int* ent_pos_im;
     const int* ent_off;
     const DevContribution* contribs;
+    // sliced (ELL-like) copies of the term / contribution tables for k_features_v3: a slice is a group of rows
+    // (8 features x 4 k-lanes, or 32 G entries) whose slots are stored slot-major so that a warp reads 32
+    // consecutive slots per iteration; padded slots carry coefficient 0.  Slices have a uniform product order.
+    int n_fsl, n_esl, sl_words;   // sl_words = 32-bit id words per slot (two 16-bit full ids each)
+    long n_slots;
+    const int4* fsl_meta;         // [n_fsl] (first slot, iterations, order, 0)
+    const int* fsl_out;           // [n_fsl][8] padded feature id or -1
+    const int4* esl_meta;         // [n_esl] (first slot, iterations, number of ids, 0)
+    const int2* esl_out;          // [n_esl][32] (pos_re, pos_im) in the atom's G buffer, or (-1, -1)
+    const double* sl_coeff;       // [n_slots]
+    const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;
     const int* tile_blk_off[MAXT];
     const int* pad_gid;     // [n_fpad] global linear column of a padded feature id or -1

@@ -695,7 +695,147 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
     }
 }
 
-static size_t g_feat_smem_set = 0;
+// v3: same work split as v2 (AT atoms per CTA share every table read) but the term / contribution tables are
+// read through the sliced copies (DevType::fsl_* / esl_*): every warp iteration loads 32 consecutive slots
+// (coefficient + packed 16-bit ids), so table reads are coalesced and independent of the accumulation chain.
+template <int AT, int MO>
+__global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                      double* __restrict__ dfeat, double* __restrict__ Gbuf,
+                                                      int nfull_max) {
+    extern __shared__ double2 afull[];   // [AT][nfull_max]
+    constexpr int NW = (MO + 1) / 2;
+    const int i0 = blockIdx.x * AT;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    int ty[AT];
+    bool fo[AT];
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        const int i = i0 + a;
+        ty[a] = i < b.n_atoms ? b.types[i] : -1;
+        fo[a] = i < b.n_atoms ? b.force[b.st_of_atom[i]] != 0 : false;
+    }
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        if (ty[a] < 0) continue;
+        const int i = i0 + a;
+        const DevType& T = m.types[ty[a]];
+        for (int k = tid; k < T.n_full; k += nthr) {
+            double2 v = anc[(size_t)i * m.hmax + T.full_head[k]];
+            if (T.full_conj[k]) {
+                const double cc = T.full_cc[k];
+                v = make_double2(cc * v.x, -cc * v.y);
+            }
+            afull[(size_t)a * nfull_max + k] = v;
+        }
+        double* drow = dfeat + (size_t)i * m.fl;
+        for (int k = tid; k < m.fl; k += nthr) drow[k] = 0.0;
+        if (fo[a]) {
+            double2* G = reinterpret_cast<double2*>(Gbuf + (size_t)i * m.gstride);
+            for (long k = tid; k < T.g_size / 2; k += nthr) G[k] = make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        bool any = false, anyf = false;
+#pragma unroll
+        for (int a = 0; a < AT; ++a) { any = any || ty[a] == tt; anyf = anyf || (ty[a] == tt && fo[a]); }
+        if (!any) continue;
+        const DevType& T = m.types[tt];
+        const double* __restrict__ coef = T.sl_coeff;
+        const unsigned* __restrict__ ids = T.sl_ids;
+        const long ns = T.n_slots;
+        for (int s = warp; s < T.n_fsl; s += nwarp) {
+            const int4 meta = T.fsl_meta[s];
+            const int o = meta.z;
+            double sum[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) sum[a] = 0.0;
+#pragma unroll 2
+            for (int it = 0; it < meta.y; ++it) {
+                const long slot = meta.x + it * 32 + lane;
+                const double cf = coef[slot];
+                int id[2 * NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned v = ids[w * ns + slot];
+                    id[2 * w] = v & 0xffffu;
+                    id[2 * w + 1] = v >> 16;
+                }
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = af[id[0]];
+#pragma unroll
+                    for (int k = 1; k < MO; ++k)
+                        if (k < o) pr = cmul(pr, af[id[k]]);
+                    sum[a] += cf * pr.x;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], 8);
+                sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], 16);
+            }
+            if (lane < 8) {
+                const int fp = T.fsl_out[s * 8 + lane];
+                if (fp >= 0) {
+#pragma unroll
+                    for (int a = 0; a < AT; ++a)
+                        if (ty[a] == tt) dfeat[(size_t)(i0 + a) * m.fl + fp] = sum[a];
+                }
+            }
+        }
+        if (!anyf) continue;
+        for (int s = warp; s < T.n_esl; s += nwarp) {
+            const int4 meta = T.esl_meta[s];
+            const int cn = meta.z;
+            double gr[AT], gi[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) { gr[a] = 0.0; gi[a] = 0.0; }
+#pragma unroll 2
+            for (int it = 0; it < meta.y; ++it) {
+                const long slot = meta.x + it * 32 + lane;
+                const double cf = coef[slot];
+                int id[2 * NW];
+                unsigned w0 = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned v = ids[w * ns + slot];
+                    if (w == 0) w0 = v;
+                    id[2 * w] = v & 0xffffu;
+                    id[2 * w + 1] = (v >> 16) & 0x7fffu;
+                }
+                const double cfi = (w0 & 0x80000000u) ? -cf : cf;
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt || !fo[a]) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = make_double2(1.0, 0.0);
+                    if (MO > 1 && cn > 0) pr = af[id[0]];
+#pragma unroll
+                    for (int qq = 1; qq < MO - 1; ++qq)
+                        if (qq < cn) pr = cmul(pr, af[id[qq]]);
+                    gr[a] += cf * pr.x;
+                    gi[a] += cfi * pr.y;
+                }
+            }
+            const int2 pos = T.esl_out[s * 32 + lane];
+            if (pos.x >= 0) {
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt || !fo[a]) continue;
+                    double* G = Gbuf + (size_t)(i0 + a) * m.gstride;
+                    G[pos.x] = gr[a];
+                    G[pos.y] = -gi[a];
+                }
+            }
+        }
+    }
+}
+
+static size_t g_feat_smem_set = 0, g_feat3_smem_set = 0;
 
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s) {
@@ -706,6 +846,23 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     const size_t smem4 = smem_bytes * AT;
     int mo = 1;
     for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
+    bool sliced = mo <= 6 && smem4 <= 96 * 1024;
+    for (int t = 0; t < m.n_type; ++t) sliced = sliced && m.types[t].n_fsl > 0;
+    if (sliced) {
+        const int grid = (b.n_atoms + AT - 1) / AT;
+#define PM_FEAT3_CASE(MO_)                                                                                       \
+    case MO_:                                                                                                    \
+        if (smem4 > 48 * 1024 && g_feat3_smem_set != smem4)                                                      \
+            cudaFuncSetAttribute(k_features_v3<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
+        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);                      \
+        break;
+        switch (mo) {
+            PM_FEAT3_CASE(1) PM_FEAT3_CASE(2) PM_FEAT3_CASE(3) PM_FEAT3_CASE(4) PM_FEAT3_CASE(5) PM_FEAT3_CASE(6)
+        }
+#undef PM_FEAT3_CASE
+        if (smem4 > 48 * 1024) g_feat3_smem_set = smem4;
+        return;
+    }
     if (smem4 <= 96 * 1024 && mo <= 6) {
         const int grid = (b.n_atoms + AT - 1) / AT;
 #define PM_FEAT_CASE(MO_)                                                                                        \
