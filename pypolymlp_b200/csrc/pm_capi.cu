@@ -203,6 +203,17 @@ static void build_device_model(pm_context* c) {
     for (const auto& x : hm.pair_terms) { pt.push_back(x[0]); pt.push_back(x[1]); pt.push_back(x[2]); }
     d.pair_terms = upload(c, pt);
     {
+        std::vector<int> colof(64 * 64, -1);
+        bool ok = hm.pv_gid.size() <= 64;
+        for (const auto& x : hm.pair_terms) {
+            if (!ok) break;
+            const int a = std::min(x[1], x[2]), b2 = std::max(x[1], x[2]);
+            if (colof[a * 64 + b2] >= 0) ok = false;   // two columns for one pair: not expected
+            colof[a * 64 + b2] = x[0];
+        }
+        d.pair_colof = ok ? upload(c, colof) : nullptr;
+    }
+    {
         std::vector<int> linfp((size_t)d.n_type * hm.n_linear, -1), pvl(std::max(hm.n_linear, 1), -1);
         for (int t = 0; t < d.n_type; ++t)
             for (int f = 0; f < hm.types[t].n_feat; ++f)

@@ -85,6 +85,7 @@ struct DevModel {
     const int* pv_fp;         // [n_type][npv_pad] padded local id or -1
     int n_pair_terms;
     const int* pair_terms;    // [n_pair_terms][3] = (col, a, b)
+    const int* pair_colof;    // [64][64] column of the unordered PV pair (min, max), -1 elsewhere (npv_pad <= 64 only)
     const int* lin_fp;        // [n_type][n_linear] padded local id of each global linear feature or -1
     const int* pv_of_lin;     // [n_linear] polynomial-variable index of a linear feature or -1
     DevType types[MAXT];

@@ -969,6 +969,16 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
     }
     const bool half = mode == 1 && r_first == 0;   // energy row: Lambda = d / 2 so that C + C^T = d_a d_b
 
+    // padded gather (single type): thread -> (group of centres, double2 of the padded row)
+    const int npr = m.fl >> 1;
+    const int ngrp = min(4, XV_THREADS / max(npr, 1));
+    const bool padg = nt == 1 && ngrp >= 1 && 12 * m.fl <= 64 * 65 && (m.fl & 1) == 0;
+    const int pgrp = padg ? tid / npr : 0, ppr = padg ? tid - pgrp * npr : 0;
+    int ppv0 = -1, ppv1 = -1;
+    if (padg && pgrp < ngrp) {
+        ppv0 = m.types[0].pad_pv[2 * ppr];
+        ppv1 = m.types[0].pad_pv[2 * ppr + 1];
+    }
     double lin[2][3];   // linear columns tcol and tcol + 256 (partial over this group's centres)
 #pragma unroll
     for (int j = 0; j < 2; ++j) { lin[j][0] = 0.0; lin[j][1] = 0.0; lin[j][2] = 0.0; }
@@ -1010,9 +1020,16 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
             sSgn[tid] = sgn;
             for (int r = 0; r < 3; ++r) sPtr[3 * tid + r] = p3[r];
         }
-        for (int e = tid; e < 3 * XV_KC * XV_LD; e += XV_THREADS) sL[e] = 0.0;
-        __syncthreads();
         const int ncc = min(XV_KC, n_cent - c0);
+        {   // Lambda rows beyond the chunk's centres (up to the next multiple of 4) must be finite zeros; the
+            // columns >= npv of valid rows are never read by a pair term and may hold anything
+            const int ntail = ((ncc + 3) & ~3) - ncc;
+            for (int e = tid; e < 3 * ntail * XV_LD; e += XV_THREADS) {
+                const int r = e / (ntail * XV_LD), rem = e - r * ntail * XV_LD;
+                sL[(r * XV_KC + ncc) * XV_LD + rem] = 0.0;
+            }
+        }
+        __syncthreads();
         for (int e = tid; e < XV_KC * 64; e += XV_THREADS) {   // D tile
             const int cc = e >> 6, a = e & 63;
             double dv = 0.0;
@@ -1023,6 +1040,37 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
             }
             sD[cc * XV_LD + a] = dv;
         }
+        if (padg) {
+            // single-type fast path: rows are read in the padded local layout as double2, npr threads per row and
+            // ngrp groups of centres; 4 centres x 3 rows (12 x 16 B) in flight per thread
+            if (pgrp < ngrp) {
+                for (int cc = 4 * pgrp; cc < ncc; cc += 4 * ngrp) {
+                    double2 v[4][3];
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        const int c = min(cc + u4, ncc - 1);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) v[u4][r] = reinterpret_cast<const double2*>(sPtr[3 * c + r])[ppr];
+                    }
+#pragma unroll
+                    for (int u4 = 0; u4 < 4; ++u4) {
+                        const int c = cc + u4;
+                        if (c < ncc) {
+                            const double sg = sSgn[c];
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) {
+                                const double v0 = sg * v[u4][r].x, v1 = sg * v[u4][r].y;
+                                lin[0][r] += v0;
+                                lin[1][r] += v1;
+                                const double hf = (half && r == 0) ? 0.5 : 1.0;
+                                if (ppv0 >= 0) sL[(r * XV_KC + c) * XV_LD + ppv0] = hf * v0;
+                                if (ppv1 >= 0) sL[(r * XV_KC + c) * XV_LD + ppv1] = hf * v1;
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
         // one pass over the derivative rows of the chunk's centres; group gsel takes centres 4*gsel + 8*i ..+3
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -1059,6 +1107,7 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
                 }
             }
         }
+        }
         __syncthreads();
         if (m.n_pair_terms > 0) {
             const int kend = (ncc + 3) & ~3;
@@ -1079,8 +1128,31 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
             }
         }
     }
-    // ---- combine the two groups' linear sums -----------------------------------------------------------------
+    // ---- combine the groups' linear sums ------------------------------------------------------------------------
     __syncthreads();
+    if (padg) {
+        if (pgrp < ngrp) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                sC[(pgrp * 3 + r) * m.fl + 2 * ppr] = lin[0][r];
+                sC[(pgrp * 3 + r) * m.fl + 2 * ppr + 1] = lin[1][r];
+            }
+        }
+        __syncthreads();
+        const int* pad_gid = m.types[0].pad_gid;
+        for (int idx = tid; idx < nrow * m.fl; idx += XV_THREADS) {
+            const int r = idx / m.fl, fp = idx - r * m.fl;
+            const int gcol = pad_gid[fp];
+            if (gcol < 0) continue;
+            double val = 0.0;
+            for (int gq = 0; gq < ngrp; ++gq) val += sC[(gq * 3 + r) * m.fl + fp];
+            if (half && r == 0 && xe_sum) {
+                atomicAdd(xe_sum + gcol, val);
+                atomicAdd(xe_sq + gcol, val * val);
+            }
+            X[(size_t)rows[r] * m.fpad + gcol] = wrow[r] * val;
+        }
+    } else {
     if (gsel == 1) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -1105,38 +1177,40 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xrows_v2(DevModel m, DevBatch
             }
         }
     }
-    // ---- order-2 terms, row by row through sC ------------------------------------------------------------------
+    }
+    // ---- order-2 terms: the three C tiles go to shared memory (over the dead Lambda tiles), one pass over the terms ---
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        if (r >= nrow) break;
-        double* xr = X + (size_t)rows[r] * m.fpad;
-        if (tid == 0) xr[m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
-        if (m.n_pair_terms == 0) continue;
-        __syncthreads();
+    for (int r = 0; r < 3; ++r)
+        if (tid == r && r < nrow) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+    if (m.n_pair_terms == 0) return;
+    __syncthreads();
+    double* sC3 = sL;   // [3][64][65]
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int x = 0; x < 2; ++x)
 #pragma unroll
             for (int y = 0; y < 2; ++y) {
                 const int ra = wm * 16 + x * 8 + g, cb = wn * 16 + y * 8 + 2 * q;
-                sC[ra * 65 + cb] = acc[r][x][y][0];
-                sC[ra * 65 + cb + 1] = acc[r][x][y][1];
+                sC3[(r * 64 + ra) * 65 + cb] = acc[r][x][y][0];
+                sC3[(r * 64 + ra) * 65 + cb + 1] = acc[r][x][y][1];
             }
-        __syncthreads();
-        const bool erow = half && r == 0 && xe_sum;
-        for (int e = tid; e < m.n_pair_terms; e += XV_THREADS) {
-            const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
-            const double val = sC[a * 65 + bb] + sC[bb * 65 + a];
-            if (erow) { atomicAdd(xe_sum + col, val); atomicAdd(xe_sq + col, val * val); }
-            xr[col] = wrow[r] * val;
-        }
+    __syncthreads();
+    const bool erow = half && xe_sum;
+    double* xr0 = X + (size_t)rows[0] * m.fpad;
+    double* xr1 = X + (size_t)rows[1] * m.fpad;
+    double* xr2 = X + (size_t)rows[2] * m.fpad;
+    for (int e = tid; e < m.n_pair_terms; e += XV_THREADS) {
+        const int col = m.pair_terms[3 * e], a = m.pair_terms[3 * e + 1], bb = m.pair_terms[3 * e + 2];
+        const int i1 = a * 65 + bb, i2 = bb * 65 + a;
+        const double v0 = sC3[i1] + sC3[i2];
+        if (erow) { atomicAdd(xe_sum + col, v0); atomicAdd(xe_sq + col, v0 * v0); }
+        xr0[col] = wrow[0] * v0;
+        if (nrow > 1) xr1[col] = wrow[1] * (sC3[64 * 65 + i1] + sC3[64 * 65 + i2]);
+        if (nrow > 2) xr2[col] = wrow[2] * (sC3[2 * 64 * 65 + i1] + sC3[2 * 64 * 65 + i2]);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K4b in scatter mode: the linear columns were already added by K4a (RED.F64), so a row atom only needs the
-// gather GEMM over the polynomial variables.  Lambda rows come from the compact Lpv buffer (512 contiguous
-// bytes per (pair, alpha)), the own row from Xown; all three force rows at once, 512 threads.
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(XV_THREADS, 1) k_xpoly(DevModel m, DevBatch b, const double* __restrict__ dfeat,
                                                           const double* __restrict__ Lpv, const double* __restrict__ Xown,
                                                           double* __restrict__ X, int apply_w) {
@@ -1245,6 +1319,237 @@ __global__ void __launch_bounds__(XV_THREADS, 1) k_xpoly(DevModel m, DevBatch b,
     }
 }
 
+
+// ================================================================================================
+// K4b v4 (single-type models): 2 CTAs of 256 threads per SM so that one CTA's gather overlaps the other's MMA
+// and epilogue.  The order-2 block is accumulated directly in its symmetric form
+//   X2[a][b] = sum_c D[c][a] Lambda[c][b] + Lambda[c][a] D[c][b]          (a <= b, 8 x 8 tiles ta <= tb)
+// (two DMMAs with swapped operand roles into ONE accumulator), which needs 36 instead of 64 tiles per row and
+// lets the epilogue write X straight from the accumulator fragments through the (a, b) -> column table.
+// ================================================================================================
+constexpr int X4_KC = 32;
+constexpr int X4_LD = 68;
+constexpr int X4_THREADS = 256;
+constexpr int X4_SLOTS = 5;
+// upper-triangle tiles of the 8 x 8 tile grid dealt to 8 warps (rows w and 7 - w hold 9 tiles together)
+__constant__ signed char c_x4_tiles[8][X4_SLOTS][2] = {
+    {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}},   {{0, 5}, {0, 6}, {0, 7}, {7, 7}, {-1, -1}},
+    {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}},   {{1, 6}, {1, 7}, {6, 6}, {6, 7}, {-1, -1}},
+    {{2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6}},   {{2, 7}, {5, 5}, {5, 6}, {5, 7}, {-1, -1}},
+    {{3, 3}, {3, 4}, {3, 5}, {3, 6}, {3, 7}},   {{4, 4}, {4, 5}, {4, 6}, {4, 7}, {-1, -1}}};
+
+template <int X4_U>   // centres per gather step and thread
+__global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v4(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                             const double* __restrict__ Lbuf,
+                                                             const double* __restrict__ Xown,
+                                                             const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                             double* __restrict__ xe_sum, double* __restrict__ xe_sq,
+                                                             int mode, int apply_w) {
+    extern __shared__ __align__(16) double smem[];
+    double* sD = smem;                          // [X4_KC][X4_LD]        D[c][a]
+    double* sL = sD + X4_KC * X4_LD;            // [3][X4_KC][X4_LD]     Lambda_r[c][b]; later the lin scratch
+    const double** sPtr = reinterpret_cast<const double**>(sL + 3 * X4_KC * X4_LD);   // [X4_KC][3]
+    double* sSgn = reinterpret_cast<double*>(sPtr + 3 * X4_KC);                       // [X4_KC]
+    int* sAtom = reinterpret_cast<int*>(sSgn + X4_KC);                                // [X4_KC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+
+    int s, n_cent, nrow, k_atom = 0, a0 = 0, p0 = 0, r_first = 0;
+    if (mode == 0) {
+        k_atom = blockIdx.x;
+        s = b.st_of_atom[k_atom];
+        if (!b.force[s]) return;
+        p0 = b.seg_off[k_atom];
+        n_cent = 1 + b.seg_off[k_atom + 1] - p0;
+        nrow = 3;
+    } else {
+        s = blockIdx.x;
+        r_first = 3 * blockIdx.y;               // 0: E,Sxx,Syy  3: Szz,Sxy,Syz  6: Szx
+        nrow = b.force[s] ? min(3, 7 - r_first) : (r_first == 0 ? 1 : 0);
+        if (nrow <= 0) return;
+        a0 = b.atom_off[s];
+        n_cent = b.atom_off[s + 1] - a0;
+    }
+    int rows[3];
+    double wrow[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        int row = 0;
+        if (r < nrow) {
+            if (mode == 0) row = b.frow[s] + 3 * (k_atom - b.atom_off[s]) + r;
+            else row = (r_first + r == 0) ? b.erow[s] : b.srow[s] + r_first + r - 1;
+        }
+        rows[r] = row;
+        wrow[r] = (r < nrow && apply_w) ? b.w[row] : 1.0;
+    }
+    const bool half = mode == 1 && r_first == 0;   // energy row: Lambda = d / 2 so that the symmetric sum is d_a d_b
+
+    const int npr = m.fl >> 1;
+    const int ngrp = X4_THREADS / npr >= 4 ? 4 : (X4_THREADS / npr >= 2 ? 2 : 1);   // X4_U * ngrp divides X4_KC
+    const int pgrp = tid / npr, ppr = tid - pgrp * npr;
+    int ppv0 = -1, ppv1 = -1;
+    if (pgrp < ngrp) {
+        ppv0 = m.types[0].pad_pv[2 * ppr];
+        ppv1 = m.types[0].pad_pv[2 * ppr + 1];
+    }
+    int ta[X4_SLOTS], tb[X4_SLOTS];
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i) { ta[i] = c_x4_tiles[warp][i][0]; tb[i] = c_x4_tiles[warp][i][1]; }
+    double lin[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { lin[j][0] = 0.0; lin[j][1] = 0.0; lin[j][2] = 0.0; }
+    double acc[X4_SLOTS][3][2];
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc[i][r][0] = 0.0; acc[i][r][1] = 0.0; }
+
+    for (int c0 = 0; c0 < n_cent; c0 += X4_KC) {
+        __syncthreads();
+        const int ncc = min(X4_KC, n_cent - c0);
+        if (tid < X4_KC) {
+            const int c = c0 + tid;
+            int atom = -1;
+            double sgn = 0.0;   // padding centres read a valid row (dfeat) with weight 0: no branches in the gather
+            const double* p3[3] = {dfeat, dfeat, dfeat};
+            if (c < n_cent) {
+                sgn = 1.0;
+                if (mode == 0) {
+                    if (c == 0) {
+                        atom = k_atom;
+                        for (int r = 0; r < 3; ++r) p3[r] = Xown + ((size_t)atom * 3 + r) * m.fl;
+                    } else {
+                        const int p = p0 + c - 1;
+                        atom = b.nbr[p];
+                        sgn = -1.0;
+                        for (int r = 0; r < 3; ++r) p3[r] = Lbuf + ((size_t)b.rev[p] * 3 + r) * m.fl;
+                    }
+                } else {
+                    atom = a0 + c;
+                    for (int r = 0; r < 3; ++r) {
+                        const int rr = min(r_first + r, 6);
+                        p3[r] = rr == 0 ? dfeat + (size_t)atom * m.fl : Sbuf + ((size_t)atom * 6 + (rr - 1)) * m.fl;
+                    }
+                }
+            }
+            sAtom[tid] = atom;
+            sSgn[tid] = sgn;
+            for (int r = 0; r < 3; ++r) sPtr[3 * tid + r] = p3[r];
+        }
+        __syncthreads();
+        for (int e = tid; e < X4_KC * 64; e += X4_THREADS) {   // D tile
+            const int cc = e >> 6, a = e & 63;
+            double dv = 0.0;
+            const int atom = sAtom[cc];
+            if (atom >= 0 && a < m.npv_pad) {
+                const int fa = m.pv_fp[a];
+                if (fa >= 0) dv = dfeat[(size_t)atom * m.fl + fa];
+            }
+            sD[cc * X4_LD + a] = dv;
+        }
+        if (pgrp < ngrp) {
+            // X4_U centres x 3 rows (16 B each) in flight per thread; the chunk is processed up to the next multiple
+            // of X4_U * ngrp centres (<= X4_KC), the padding centres have weight 0 and so zero their Lambda rows
+            const double hf0 = half ? 0.5 : 1.0;
+            const int cend = (ncc + 3) & ~3;
+            for (int cc = X4_U * pgrp; cc < cend; cc += X4_U * ngrp) {
+                double2 v[X4_U][3];
+#pragma unroll
+                for (int u4 = 0; u4 < X4_U; ++u4)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        v[u4][r] = __ldg(reinterpret_cast<const double2*>(sPtr[3 * (cc + u4) + r]) + ppr);
+#pragma unroll
+                for (int u4 = 0; u4 < X4_U; ++u4) {
+                    const int c = cc + u4;
+                    const double sg = sSgn[c];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double v0 = sg * v[u4][r].x, v1 = sg * v[u4][r].y;
+                        lin[0][r] += v0;
+                        lin[1][r] += v1;
+                        const double hf = r == 0 ? hf0 : 1.0;
+                        if (ppv0 >= 0) sL[(r * X4_KC + c) * X4_LD + ppv0] = hf * v0;
+                        if (ppv1 >= 0) sL[(r * X4_KC + c) * X4_LD + ppv1] = hf * v1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (m.n_pair_terms > 0) {
+            const int kend = (ncc + 3) & ~3;
+            for (int k0 = 0; k0 < kend; k0 += 4) {
+                const double* dk = sD + (k0 + q) * X4_LD + g;
+                const double* lk = sL + (k0 + q) * X4_LD + g;
+#pragma unroll
+                for (int i = 0; i < X4_SLOTS; ++i) {
+                    if (ta[i] < 0) continue;
+                    const double fDa = dk[ta[i] * 8], fDb = dk[tb[i] * 8];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double fLa = lk[r * X4_KC * X4_LD + ta[i] * 8], fLb = lk[r * X4_KC * X4_LD + tb[i] * 8];
+                        dmma(acc[i][r][0], acc[i][r][1], fDa, fLb);
+                        dmma(acc[i][r][0], acc[i][r][1], fLa, fDb);
+                    }
+                }
+            }
+        }
+    }
+    // ---- linear columns: combine the groups' partial sums (scratch over the dead Lambda tiles) ---------------------
+    __syncthreads();
+    double* sS = sL;   // [ngrp][3][fl]
+    if (pgrp < ngrp) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            sS[(pgrp * 3 + r) * m.fl + 2 * ppr] = lin[0][r];
+            sS[(pgrp * 3 + r) * m.fl + 2 * ppr + 1] = lin[1][r];
+        }
+    }
+    __syncthreads();
+    {
+        const int* pad_gid = m.types[0].pad_gid;
+        for (int idx = tid; idx < nrow * m.fl; idx += X4_THREADS) {
+            const int r = idx / m.fl, fp = idx - r * m.fl;
+            const int gcol = pad_gid[fp];
+            if (gcol < 0) continue;
+            double val = 0.0;
+            for (int gq = 0; gq < ngrp; ++gq) val += sS[(gq * 3 + r) * m.fl + fp];
+            const int row = r == 0 ? rows[0] : (r == 1 ? rows[1] : rows[2]);
+            const double wv = r == 0 ? wrow[0] : (r == 1 ? wrow[1] : wrow[2]);
+            if (half && r == 0 && xe_sum) {
+                atomicAdd(xe_sum + gcol, val);
+                atomicAdd(xe_sq + gcol, val * val);
+            }
+            X[(size_t)row * m.fpad + gcol] = wv * val;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        if (tid == r && r < nrow) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+    if (m.n_pair_terms == 0) return;
+    // ---- order-2 columns straight from the accumulator fragments -----------------------------------------------------
+    const bool erow = half && xe_sum;
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i) {
+        if (ta[i] < 0) continue;
+        const int a = ta[i] * 8 + g, bq = tb[i] * 8 + 2 * q;
+        const int col0 = m.pair_colof[a * 64 + bq], col1 = m.pair_colof[a * 64 + bq + 1];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r >= nrow) break;
+            double* xr = X + (size_t)rows[r] * m.fpad;
+            if (col0 >= 0) {
+                xr[col0] = wrow[r] * acc[i][r][0];
+                if (erow && r == 0) { atomicAdd(xe_sum + col0, acc[i][r][0]); atomicAdd(xe_sq + col0, acc[i][r][0] * acc[i][r][0]); }
+            }
+            if (col1 >= 0) {
+                xr[col1] = wrow[r] * acc[i][r][1];
+                if (erow && r == 0) { atomicAdd(xe_sum + col1, acc[i][r][1]); atomicAdd(xe_sq + col1, acc[i][r][1] * acc[i][r][1]); }
+            }
+        }
+    }
+}
+
 bool scatter_mode_supported(const DevModel& m) {
     return m.kpn > 0 && m.tpn > 0 && m.npv_pad <= 64 && m.n_linear <= 512 &&
            (2ull * m.pbstride * LR_PLD + 8ull * (4 * m.kpn) * LR_LD) * sizeof(double) <= 150 * 1024;
@@ -1268,6 +1573,22 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         k_xpoly<<<b.n_atoms, XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lpv, ws.Xown, ws.X, apply_weights ? 1 : 0);
         k_xrows_v2<<<dim3(b.n_st, 3), XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq,
                                                              1, apply_weights ? 1 : 0);
+        return true;
+    }
+    if (m.n_type == 1 && m.pair_colof != nullptr && (m.fl & 1) == 0 && m.fl / 2 <= X4_THREADS &&
+        4 * 3 * m.fl <= 3 * X4_KC * X4_LD && !getenv("PM_XROWS_V2")) {
+        const size_t smem4 = ((size_t)4 * X4_KC * X4_LD + 4 * X4_KC) * sizeof(double) + X4_KC * sizeof(int);
+        static int u4 = 0;
+        if (!u4) {
+            cudaFuncSetAttribute(k_xrows_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            cudaFuncSetAttribute(k_xrows_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            u4 = getenv("PM_X4_U") ? atoi(getenv("PM_X4_U")) : 2;   // 2 measured faster than 4 (register pressure)
+        }
+        auto kern = u4 == 2 ? k_xrows_v4<2> : k_xrows_v4<4>;
+        kern<<<b.n_atoms, X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
+                                                  apply_weights ? 1 : 0);
+        kern<<<dim3(b.n_st, 3), X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
+                                                        apply_weights ? 1 : 0);
         return true;
     }
     const size_t smem = xrows_v2_smem();
