@@ -451,8 +451,8 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
     const int g = lane >> 2, q = lane & 3;
     constexpr int KR = 4 * KPN;  // reals per radial group (padded)
     const int pbs_sz = m.pbstride * LR_PLD;
-    double* pbs0 = smem;                                   // [2][pbstride][LR_PLD]
-    double* A1 = smem + 2 * (size_t)pbs_sz;                // [KR][LR_LD]
+    double* pbs0 = smem;                                   // [2][pbstride][LR_PLD]; also sAgg [n_fn][KR][9]
+    double* A1 = smem + max(2 * (size_t)pbs_sz, (size_t)m.n_fn * KR * 9);   // [KR][LR_LD]
     double* A2 = A1 + KR * LR_LD;                          // [KR][LR_LD]
     double* scD = A2 + KR * LR_LD;                         // [n_fn][32]
     double* scF = scD + m.n_fn * 32;                       // [n_fn][32]
@@ -552,6 +552,25 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                 }
             }
             __syncthreads();
+            const bool chunk_has_agg = row0 + LR_ROWS > nrow;
+            // The aggregated rows sit in the last chunk, whose pair tiles (both buffers: nothing is in flight any
+            // more) are dead after the lm-factor pass: stage the K2b sums there as sAgg[(n * KR + k) * 9 + r], so
+            // that the DMMA loop reads its A operand of those rows from shared memory (one global latency in total)
+            double* sAgg = pbs0;
+            if (chunk_has_agg) {
+                const int per_n = 2 * KPN * 9;
+                for (int e = tid; e < m.n_fn * per_n; e += nthr) {
+                    const int n = e / per_n, rem = e - n * per_n;
+                    const int hq = rem / 9, ra = rem - hq * 9;
+                    const int kcn2 = s_noff[n + 1] - s_noff[n];
+                    const int h = hq < kcn2 ? s_head[s_noff[n] + hq] : -1;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (h >= 0) v = agg[((size_t)i * m.hmax + h) * 9 + ra];
+                    sAgg[(n * KR + 2 * hq) * 9 + ra] = v.x;
+                    sAgg[(n * KR + 2 * hq + 1) * 9 + ra] = v.y;
+                }
+                __syncthreads();
+            }
             // per-lane row pointers of this chunk (row = row0 + rt*8 + g), nullptr for rows past the end
             double* rowp[4];
             int ragg[4];   // >= 0: this lane's row of the tile is aggregated row ragg (accumulated over segments)
@@ -563,7 +582,6 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                          : (ragg[rt] < 0 ? nullptr
                          : (ragg[rt] < 3 ? Xown + ((size_t)i * 3 + ragg[rt]) * m.fl : Sbuf + ((size_t)i * 6 + (ragg[rt] - 3)) * m.fl) + 2 * q);
             }
-            const bool chunk_has_agg = row0 + LR_ROWS > nrow;
             for (int n = warp; n < m.n_fn; n += nwarp) {
                 const int tile0 = s_toff[n];
                 const int ntile = s_toff[n + 1] - tile0;
@@ -627,16 +645,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
 #pragma unroll
                             for (int r2 = 0; r2 < 2; ++r2) {
                                 const int ra = ragg[2 * rh + r2];
-                                if (ra >= 0) {
-                                    const int hq = 2 * kc + (q >> 1);
-                                    const int h = hq < 2 * kcn ? s_head[s_noff[n] + hq] : -1;
-                                    double v = 0.0;
-                                    if (h >= 0) {
-                                        const double2 a2 = agg[((size_t)i * m.hmax + h) * 9 + ra];
-                                        v = (q & 1) ? a2.y : a2.x;
-                                    }
-                                    af[r2] = v;
-                                }
+                                if (ra >= 0) af[r2] = sAgg[(n * KR + 4 * kc + q) * 9 + ra];
                             }
                         }
 #pragma unroll
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(256, 2) k_lrows_v3(DevModel m, DevBatch b, con
                             }
                             dst += (tile0 + tt) * 8;
                             double2 v = make_double2(acc[tt][r2][0], acc[tt][r2][1]);
-                            if (ra >= 0) {
+                            if (ra >= 0 && u > 0) {   // aggregated rows accumulate over the neighbour-type segments
                                 const double2 o = *reinterpret_cast<double2*>(dst);
                                 v.x += o.x; v.y += o.y;
                             }
@@ -698,7 +707,8 @@ static int lrows_v2_warps(const DevModel& m) {
 
 template <int KPN> static size_t lrows_v2_smem(const DevModel& m, int nwarp, int n_tiles_max) {
     const size_t ints = (size_t)(2 * KPN * m.n_fn) + 3 * (size_t)m.n_fn + 2 + (size_t)n_tiles_max * KPN + 16ull * n_tiles_max + 34;
-    return (2ull * m.pbstride * LR_PLD + 2ull * (4 * KPN) * LR_LD + 64ull * m.n_fn + 32) * sizeof(double) + ints * sizeof(int) + 32;
+    const size_t tiles = std::max<size_t>(2ull * m.pbstride * LR_PLD, 36ull * KPN * m.n_fn);
+    return (tiles + 2ull * (4 * KPN) * LR_LD + 64ull * m.n_fn + 32) * sizeof(double) + ints * sizeof(int) + 32;
 }
 
 template <int TPN, int KPN>
