@@ -219,7 +219,7 @@ def main():
         if world > 1:
             fit.reduce_accumulator(acc, dst=0)
         if rank == 0:
-            acc.finalize()
+            acc.finalize(copy=False)   # X^T X, X^T y ... in (pinned) host memory
 
     e2e_steps = max(2, min(args.steps, 4))
     step_e2e()
@@ -234,7 +234,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * e2e_steps / float(t.item())
     h2d = batch_host.h2d_bytes + w_h.nbytes + y_h.nbytes
-    d2h = ((F + 1) * (F + 1) + 2 * F + 1) * 8
+    d2h = (F * F + 3 * F + 2) * 8
 
     # ---- secondary metric: atoms/s of E/F/S evaluation (BASELINE config 5), sharded by structure -----------
     from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
@@ -309,7 +309,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": "pm_fit_reset + pm_fit_accumulate(host buffers) + pm_fit_finalize (X^T X, X^T y to host) per step"},
+                    "note": "pm_fit_reset + pm_fit_accumulate(host buffers) + pm_fit_finalize_view (X^T X, X^T y to pinned host memory) per step"},
             "roofline": roofline, "cpu_baseline": cpu,
             "eval": {"metric": "atoms/sec, E/F/S evaluation (config 5: F=2030 model, 512-atom fcc, sigma 0.03 A)",
                      "value": eval_atoms_s, "unit": "atoms/s", "structures_per_step_per_gpu": n_ev,

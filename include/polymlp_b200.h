@@ -135,6 +135,10 @@ int pm_fit_fpad(pm_context* c);
 /* Copies results to HOST: xtx (F x F, symmetric, row-major), xty (F), xe_sum (F), xe_sq_sum (F). */
 int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum,
                     double* y_sq_norm, int64_t* n_data);
+/* Same result without the final host copy: *packed points at the context's pinned host buffer
+ *   [ xtx (F*F, symmetric, row-major) | xty (F) | xe_sum (F) | xe_sq_sum (F) | y_sq_norm | n_data ]
+ * valid until the next pm_fit_finalize* call on this context or pm_context_destroy. */
+int pm_fit_finalize_view(pm_context* c, const double** packed, size_t* n_doubles);
 /* ---- ridge solve on the device (reported separately from the hot path) ---------------------------------
  * Replaces the tail of calc_xtx_xty (scales, zeroing, normalisation; data_sequential.py:72-92), solver_ridge
  * (Cholesky per alpha with incremental diagonal update; src/pypolymlp/mlp_dev/standard/solvers.py:48-84) and

@@ -45,7 +45,7 @@ EXPORTS = [
     "pm_model_count_flops", "pm_device_count", "pm_context_create", "pm_context_destroy",
     "pm_batch_rows", "pm_neighbor_full", "pm_features_x", "pm_fit_reset", "pm_fit_accumulate",
     "pm_fit_stage", "pm_fit_accumulate_staged", "pm_fit_accumulator", "pm_fit_fpad",
-    "pm_fit_finalize", "pm_fit_solve_ridge", "pm_synchronize", "pm_stream", "pm_launch_count", "pm_profile_enable",
+    "pm_fit_finalize", "pm_fit_finalize_view", "pm_fit_solve_ridge", "pm_synchronize", "pm_stream", "pm_launch_count", "pm_profile_enable",
     "pm_profile_get", "pm_stage_name", "pm_eval_set_coeffs", "pm_eval", "pm_debug_fetch",
     "pm_microbench",
 ]

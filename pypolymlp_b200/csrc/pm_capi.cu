@@ -7,6 +7,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -123,8 +124,9 @@ struct pm_context {
     int64_t stage_launches[ST_COUNT] = {0};
     cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
     bool has_coeffs = false;
-    double* pinned = nullptr;   // host staging for pm_fit_finalize
+    double* pinned = nullptr;   // host (pinned) copy of the packed result of pm_fit_finalize
     size_t pinned_n = 0;
+    double* packed = nullptr;   // device: [xtx F*F | xty F | xe_sum F | xe_sq F | y_sq_norm | n_data]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -902,6 +904,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->packed) cudaFree(c->packed);
     for (auto& v : c->staged_dev)
         for (void* p : v) cudaFree(p);
     cudaStreamDestroy(c->stream);
@@ -1092,49 +1095,107 @@ int pm_fit_accumulator(pm_context* c, void** dev_ptr, size_t* n_doubles) {
 
 int pm_fit_fpad(pm_context* c) { return c ? c->dm.fpad : -1; }
 
+// Packs the accumulator for the host: symmetric dense X^T X (the kernels fill the upper triangle of the padded,
+// tiled C), X^T y (the y column), the energy-row sums and y^T y.  One 32 x 32 tile per CTA; the lower triangle is
+// written from the transposed upper tile through shared memory so that reads and writes stay coalesced.
+__global__ void __launch_bounds__(256) k_pack_result(const double* __restrict__ acc, int fp, int F, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int si = min(bi, bj), sj = max(bi, bj);   // source tile (upper)
+    for (int r = ty; r < 32; r += 8) {
+        const int i = si * 32 + r, j = sj * 32 + tx;
+        tile[r][tx] = (i < F && j < F) ? acc[(size_t)i * fp + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i >= F || j >= F) continue;
+        double v;
+        if (bi < bj) v = tile[r][tx];
+        else if (bi > bj) v = tile[tx][r];
+        else v = r <= tx ? tile[r][tx] : tile[tx][r];
+        out[(size_t)i * F + j] = v;
+    }
+    if (bi == 0 && bj == 0) {
+        double* tail = out + (size_t)F * F;
+        for (int i = threadIdx.x; i < F; i += blockDim.x) {
+            tail[i] = acc[(size_t)i * fp + F];
+            tail[F + i] = acc[(size_t)fp * fp + i];
+            tail[2 * F + i] = acc[(size_t)fp * fp + fp + i];
+        }
+        if (threadIdx.x == 0) {
+            tail[3 * F] = acc[(size_t)F * fp + F];
+            tail[3 * F + 1] = acc[(size_t)fp * fp + 2 * (size_t)fp];
+        }
+    }
+}
+
+// pack on the device, one D2H copy into the context's pinned buffer; returns the host pointer
+static const double* finalize_packed(pm_context* c, size_t* n_out) {
+    CK(cudaSetDevice(c->device));
+    ensure_acc(c);
+    const DevModel& d = c->dm;
+    const int F = d.n_variables, fp = d.fpad;
+    const size_t n = (size_t)F * F + 3 * (size_t)F + 2;
+    if (c->pinned_n < n) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        if (c->packed) cudaFree(c->packed);
+        c->pinned = nullptr; c->packed = nullptr; c->pinned_n = 0;
+        CK(cudaHostAlloc(&c->pinned, n * sizeof(double), cudaHostAllocDefault));
+        CK(cudaMalloc(&c->packed, n * sizeof(double)));
+        c->pinned_n = n;
+    }
+    const int nb = (F + 31) / 32;
+    k_pack_result<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc, fp, F, c->packed);
+    c->launches += 1;
+    CK(cudaMemcpyAsync(c->pinned, c->packed, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    double* tail = c->pinned + (size_t)F * F;
+    const double nd = tail[3 * (size_t)F + 1];
+    tail[3 * (size_t)F + 1] = nd > (double)c->n_data ? (double)llround(nd) : (double)c->n_data;
+    if (n_out) *n_out = n;
+    return c->pinned;
+}
+
+// large host copies (the 33 MB X^T X into a caller buffer whose pages are usually untouched): a few threads
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t MIN_PER_THREAD = 4u << 20;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthr = std::min<size_t>({(size_t)8, (size_t)hw, bytes / MIN_PER_THREAD});
+    if (nthr < 2) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nthr) + 4095) & ~(size_t)4095;
+    for (size_t k = 0; k < nthr; ++k) {
+        const size_t o = k * per;
+        if (o >= bytes) break;
+        const size_t len = std::min(per, bytes - o);
+        th.emplace_back([=] { std::memcpy((char*)dst + o, (const char*)src + o, len); });
+    }
+    for (auto& t : th) t.join();
+}
+
+int pm_fit_finalize_view(pm_context* c, const double** packed, size_t* n_doubles) {
+    return guarded([&] {
+        if (!c || !packed) throw std::invalid_argument("null argument");
+        *packed = finalize_packed(c, n_doubles);
+    });
+}
+
 int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum, double* y_sq_norm,
                     int64_t* n_data) {
     return guarded([&] {
-        CK(cudaSetDevice(c->device));
-        ensure_acc(c);
-        const DevModel& d = c->dm;
-        const int F = d.n_variables, fp = d.fpad;
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaGetLastError());
-        // rows 0..F of C (the y row is row F); copy the (F+1) x (F+1) corner through a pinned staging buffer
-        const int ld = F + 1;
-        const size_t corner_n = (size_t)ld * ld;
-        if (c->pinned_n < corner_n) {
-            if (c->pinned) cudaFreeHost(c->pinned);
-            c->pinned = nullptr;
-            CK(cudaHostAlloc(&c->pinned, corner_n * sizeof(double), cudaHostAllocDefault));
-            c->pinned_n = corner_n;
-        }
-        double* corner = c->pinned;
-        CK(cudaMemcpy2DAsync(corner, (size_t)ld * sizeof(double), c->acc, (size_t)fp * sizeof(double),
-                             (size_t)ld * sizeof(double), ld, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        // every kernel flavour fills (at least) the upper triangle i <= j
-        if (xtx) {
-            for (int i = 0; i < F; ++i)
-                std::memcpy(xtx + (size_t)i * F + i, corner + (size_t)i * ld + i, (size_t)(F - i) * sizeof(double));
-            constexpr int TB = 64;  // mirror the strict upper triangle, blocked for cache reuse
-            for (int ib = 0; ib < F; ib += TB)
-                for (int jb = 0; jb <= ib; jb += TB)
-                    for (int i = ib; i < std::min(F, ib + TB); ++i)
-                        for (int j = jb; j < std::min(i, jb + TB); ++j) xtx[(size_t)i * F + j] = xtx[(size_t)j * F + i];
-        }
-        if (xty)
-            for (int i = 0; i < F; ++i) xty[i] = corner[(size_t)i * ld + F];
-        if (y_sq_norm) *y_sq_norm = corner[(size_t)F * ld + F];
-        std::vector<double> tail(2 * (size_t)fp + 1);
-        CK(cudaMemcpy(tail.data(), c->acc + (size_t)fp * fp, tail.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        if (xe_sum) std::copy(tail.begin(), tail.begin() + F, xe_sum);
-        if (xe_sq_sum) std::copy(tail.begin() + fp, tail.begin() + fp + F, xe_sq_sum);
-        if (n_data) {
-            const double nd = tail[2 * (size_t)fp];
-            *n_data = nd > (double)c->n_data ? (int64_t)llround(nd) : c->n_data;
-        }
+        if (!c) throw std::invalid_argument("null argument");
+        const double* pk = finalize_packed(c, nullptr);
+        const size_t F = (size_t)c->dm.n_variables;
+        const double* tail = pk + F * F;
+        if (xtx) parallel_memcpy(xtx, pk, F * F * sizeof(double));
+        if (xty) std::memcpy(xty, tail, F * sizeof(double));
+        if (xe_sum) std::memcpy(xe_sum, tail + F, F * sizeof(double));
+        if (xe_sq_sum) std::memcpy(xe_sq_sum, tail + 2 * F, F * sizeof(double));
+        if (y_sq_norm) *y_sq_norm = tail[3 * F];
+        if (n_data) *n_data = (int64_t)tail[3 * F + 1];
     });
 }
 

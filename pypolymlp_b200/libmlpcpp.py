@@ -303,15 +303,26 @@ class PotentialXtX:
         check(lib().pm_fit_accumulator(self._ctx.handle, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def finalize(self, want_xtx=True):
+    def finalize(self, want_xtx=True, copy=True):
+        """X^T X (F, F), X^T y, energy-row sums, y^T y and the row count on the host.
+
+        copy=False returns read-only views of the context's pinned result buffer (no extra host copy of the
+        33 MB matrix); they are overwritten by the next finalize() of this accumulator."""
         F = self.n_features
-        xtx = np.zeros((F, F)) if want_xtx else None
+        if not copy:
+            p, n = C.POINTER(C.c_double)(), C.c_size_t(0)
+            check(lib().pm_fit_finalize_view(self._ctx.handle, C.byref(p), C.byref(n)))
+            flat = np.ctypeslib.as_array(p, shape=(n.value,))
+            flat.flags.writeable = False
+            tail = flat[F * F:]
+            return {"xtx": flat[:F * F].reshape(F, F) if want_xtx else None, "xty": tail[:F], "xe_sum": tail[F:2 * F],
+                    "xe_sq_sum": tail[2 * F:3 * F], "y_sq_norm": float(tail[3 * F]), "total_n_data": int(tail[3 * F + 1])}
+        xtx = np.empty((F, F)) if want_xtx else None
         xty, xe_sum, xe_sq = np.zeros(F), np.zeros(F), np.zeros(F)
         ysq, nd = C.c_double(0.0), C.c_int64(0)
         check(lib().pm_fit_finalize(self._ctx.handle, pd(xtx), pd(xty), pd(xe_sum), pd(xe_sq), C.byref(ysq), C.byref(nd)))
         return {"xtx": xtx, "xty": xty, "xe_sum": xe_sum, "xe_sq_sum": xe_sq, "y_sq_norm": ysq.value,
                 "total_n_data": int(nd.value)}
-
 
     def solve_ridge(self, alphas, n_energy, scales=None, include_force=True, scale_threshold=1e-10):
         """Ridge solve on the device-resident accumulator (cuSOLVER Cholesky per alpha).

@@ -328,6 +328,21 @@ def test_error_paths():
     assert acc.finalize()["total_n_data"] == 0
 
 
+def test_finalize_view_matches_copy():
+    """pm_fit_finalize_view (pinned, no host copy) returns the same packed result as pm_fit_finalize."""
+    pd = make_params_dict(**cases.si_model_kwargs())
+    ds = _si_datasets(list(range(6)))
+    acc = PotentialXtX(pd)
+    fit.accumulate_datasets(acc, [ds], fit.get_min_energy([ds]))
+    a = acc.finalize()
+    b = acc.finalize(copy=False)
+    assert not b["xtx"].flags.writeable
+    for k in ("xtx", "xty", "xe_sum", "xe_sq_sum"):
+        assert np.array_equal(a[k], b[k])
+    assert a["y_sq_norm"] == b["y_sq_norm"] and a["total_n_data"] == b["total_n_data"] > 0
+    assert np.array_equal(a["xtx"], a["xtx"].T)
+
+
 def test_pybind_dropin_module_gpu():
     """Same calls a reference user makes on `pypolymlp.cxx.lib.libmlpcpp`, through the pybind11 drop-in."""
     import importlib.util
