@@ -124,6 +124,11 @@ struct pm_context {
     int64_t stage_launches[ST_COUNT] = {0};
     cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
     bool has_coeffs = false;
+    // K5 runs on its own stream: the front end of the next chunk (neighbour list .. features, small CTAs that fit
+    // next to the persistent SYRK CTA on an SM) overlaps the SYRK of the previous chunk
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_s = nullptr;
+    bool two_stream = true, syrk_pending = false;
     double* pinned = nullptr;   // host (pinned) copy of the packed result of pm_fit_finalize
     size_t pinned_n = 0;
     double* packed = nullptr;   // device: [xtx F*F | xty F | xe_sum F | xe_sq F | y_sq_norm | n_data]
@@ -597,6 +602,13 @@ struct StageTimer {
 
 enum Mode { MODE_FIT = 0, MODE_X = 1, MODE_EVAL = 2, MODE_NEIGH = 3 };
 
+// makes the main stream wait for the SYRK that is still running on stream2 (no host sync)
+static void join_syrk(pm_context* c) {
+    if (!c->syrk_pending) return;
+    CK(cudaStreamWaitEvent(c->stream, c->ev_s, 0));
+    c->syrk_pending = false;
+}
+
 // Runs the device pipeline on one prepared chunk.  `upload_inputs` false -> inputs already on the device
 // (staged); dev_in then holds the device pointers in the order of upload below.
 static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_inputs, StageTimer& tm) {
@@ -657,7 +669,8 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     tm.mark(ST_BASIS, 1);
     c->d_anc.ensure((size_t)h.n_atoms * d.hmax);
     c->d_agg.ensure(any_force ? (size_t)h.n_atoms * d.hmax * 9 : 1);
-    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s);
+    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s,
+                (mode == MODE_FIT && c->two_stream && !c->profile) || getenv("PM_ANLM_SMALL") != nullptr);
     tm.mark(ST_ANLM, 1);
 
     // ---- K3 ------------------------------------------------------------------------------------
@@ -687,12 +700,17 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         return;
     }
 
-    // X-tilde chunk first: in scatter mode K4a adds into it with RED.F64
-    c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
-    ws.X = c->d_X.p;
-    CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
+    // X-tilde chunk: zeroed before K4a in scatter mode (K4a adds into it with RED.F64), else right before K4b so
+    // that K4a of this chunk does not have to wait for the previous chunk's SYRK (which still reads X)
     const bool fit = mode == MODE_FIT;
     ws.scatter = c->scatter;
+    auto prep_X = [&] {
+        join_syrk(c);
+        c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
+        ws.X = c->d_X.p;
+        CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
+    };
+    if (ws.scatter) prep_X();
     // ---- K4a -------------------------------------------------------------------------------------
     if (any_force) {
         if (ws.scatter) {
@@ -706,13 +724,22 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         tm.mark(ST_LROWS, 1);
     }
     // ---- K4b -------------------------------------------------------------------------------------
+    if (!ws.scatter) prep_X();
     double* xe_sum = fit ? c->acc + (size_t)d.fpad * d.fpad : nullptr;
     double* xe_sq = fit ? xe_sum + d.fpad : nullptr;
     launch_xrows(d, b, ws, xe_sum, xe_sq, c->simple_x, fit, s);
     tm.mark(ST_XROWS, 3);
     // ---- K5 --------------------------------------------------------------------------------------
     if (fit) {
-        launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
+        if (c->two_stream && !c->profile) {
+            CK(cudaEventRecord(c->ev_x, s));
+            CK(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
+            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, c->stream2);
+            CK(cudaEventRecord(c->ev_s, c->stream2));
+            c->syrk_pending = true;
+        } else {
+            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
+        }
         tm.mark(ST_SYRK, 1);
         c->n_data += h.n_rows;
     }
@@ -882,6 +909,10 @@ int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int
         c->ws_cap = workspace_bytes ? workspace_bytes : (size_t)6 << 30;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
+        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_s, cudaEventDisableTiming));
+        c->two_stream = getenv("PM_ONE_STREAM") == nullptr;
         build_device_model(c.get());
         const DevModel& d = c->dm;
         c->acc_n = (size_t)d.fpad * d.fpad + 2 * (size_t)d.fpad + 1;
@@ -893,6 +924,9 @@ void pm_context_destroy(pm_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_x) cudaEventDestroy(c->ev_x);
+    if (c->ev_s) cudaEventDestroy(c->ev_s);
     for (void* p : c->table_allocs) cudaFree(p);
     if (c->acc) cudaFree(c->acc);
     c->d_atom_off.release(); c->d_st_of_atom.release(); c->d_types.release(); c->d_trans_off.release();
@@ -989,6 +1023,7 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
         if (h.n_atoms > 0) check_device_error(c);
         else CK(cudaStreamSynchronize(c->stream));
     }
+    join_syrk(c);   // later work on the main stream (reset, finalize, the caller's events) is ordered after K5
 }
 
 int pm_fit_accumulate(pm_context* c, const pm_structures* st, const double* w, const double* y) {
@@ -1077,6 +1112,7 @@ int pm_fit_accumulate_staged(pm_context* c) {
             restore(c->d_y); restore(c->d_z); restore(c->d_trans); restore(c->d_w); restore(c->d_yv);
             if (ex) std::rethrow_exception(ex);
         }
+        join_syrk(c);
     });
 }
 

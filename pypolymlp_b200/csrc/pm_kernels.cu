@@ -427,8 +427,9 @@ __global__ void __launch_bounds__(128) k_anlm(DevModel m, DevBatch b, const doub
 
 // Same sums with the pair records staged through shared memory (coalesced 16-byte copies of 8 records at a
 // time, double buffered with cp.async); one thread per head, so accumulation stays thread-private.
-constexpr int AN_PT = 16;
-
+// AN_PT = pairs per staged tile: 16 standalone; 8 keeps the CTA under 24 KB of shared memory so that it fits on an SM
+// next to the persistent SYRK CTA when K5 of the previous chunk runs concurrently (pm_capi.cu, stream2).
+template <int AN_PT>
 __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                   double2* __restrict__ anc, double2* __restrict__ agg) {
     extern __shared__ __align__(16) double sm_an[];
@@ -517,12 +518,18 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
     }
 }
 
-void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s) {
+void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s,
+                 bool small_footprint) {
     if (b.n_atoms == 0) return;
     const int threads = (m.hmax + 31) / 32 * 32;
-    const size_t smem = 2ull * (AN_PT + 1) * m.pbstride * sizeof(double);
-    if (threads <= 256 && smem <= 48 * 1024) {
-        k_anlm_v2<<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);
+    const size_t smem16 = 2ull * (16 + 1) * m.pbstride * sizeof(double);
+    const size_t smem8 = 2ull * (8 + 1) * m.pbstride * sizeof(double);
+    if (threads <= 256 && small_footprint && smem8 <= 23 * 1024) {
+        k_anlm_v2<8><<<b.n_atoms, threads, smem8, s>>>(m, b, PB, anc, agg);
+        return;
+    }
+    if (threads <= 256 && smem16 <= 48 * 1024) {
+        k_anlm_v2<16><<<b.n_atoms, threads, smem16, s>>>(m, b, PB, anc, agg);
         return;
     }
     k_anlm<<<b.n_atoms, 128, 0, s>>>(m, b, PB, anc, agg);

@@ -28,7 +28,8 @@ void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cuda
 void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB, int* errflag, cudaStream_t s);
 // K2: pair basis + order parameters
 void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
-void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s);
+void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s,
+                 bool small_footprint = false);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s);
