@@ -2,6 +2,7 @@
 #include "../../include/polymlp_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -124,8 +125,9 @@ struct pm_context {
     int64_t stage_launches[ST_COUNT] = {0};
     cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
     bool has_coeffs = false;
-    // K5 runs on its own stream: the front end of the next chunk (neighbour list .. features, small CTAs that fit
-    // next to the persistent SYRK CTA on an SM) overlaps the SYRK of the previous chunk
+    // K5 runs on its own stream: the host-side work and the first kernels of the next chunk overlap the SYRK of the
+    // previous chunk.  (Measured: the FP64-heavy small kernels make little progress next to the DMMA-saturating SYRK
+    // CTA -- the FP64 pipe is the shared resource -- so the gain is ~1 % on the device and ~2 % end to end.)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_x = nullptr, ev_s = nullptr;
     bool two_stream = true, syrk_pending = false;
@@ -640,10 +642,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     CK(cudaMemsetAsync(c->d_counts.p + nseg, 0, sizeof(int), s));
     CK(cudaMemsetAsync(c->d_err.p, 0, sizeof(int), s));
     launch_neighbor_count(d, b, c->d_counts.p, s);
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
-    c->d_scan_tmp.ensure(tmp_bytes + 16);
-    cub::DeviceScan::ExclusiveSum(c->d_scan_tmp.p, tmp_bytes, c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
+    launch_scan_exclusive(c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
     int n_pairs = 0;
     CK(cudaMemcpyAsync(&n_pairs, c->d_seg_off.p + nseg, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -669,8 +668,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     tm.mark(ST_BASIS, 1);
     c->d_anc.ensure((size_t)h.n_atoms * d.hmax);
     c->d_agg.ensure(any_force ? (size_t)h.n_atoms * d.hmax * 9 : 1);
-    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s,
-                (mode == MODE_FIT && c->two_stream && !c->profile) || getenv("PM_ANLM_SMALL") != nullptr);
+    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s);
     tm.mark(ST_ANLM, 1);
 
     // ---- K3 ------------------------------------------------------------------------------------

@@ -146,7 +146,33 @@ __global__ void __launch_bounds__(256) k_neighbor_mask(DevModel m, DevBatch b, i
     }
 }
 
+// Exclusive prefix sum of the per-(atom, neighbour type) counts: one CTA, 256 threads, each thread owns a
+// contiguous slice (n is ~12k per chunk).
+__global__ void __launch_bounds__(256) k_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, int n) {
+    __shared__ int part[256];
+    const int tid = threadIdx.x;
+    const int per = (n + 255) / 256;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int k = lo; k < hi; ++k) sum += in[k];
+    part[tid] = sum;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const int v = tid >= d ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = part[tid] - sum;
+    for (int k = lo; k < hi; ++k) { const int v = in[k]; out[k] = run; run += v; }
+}
+
+void launch_scan_exclusive(const int* in, int* out, int n, cudaStream_t s) {
+    k_scan_exclusive<<<1, 256, 0, s>>>(in, out, n);
+}
+
 void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s) {
+
     const int threads = 256;
     const int blocks = (b.n_atoms * 32 + threads - 1) / threads;
     const double tol = 1e-10;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256, 1) k_syrk_mma(const double* __restrict__ 
 // owns only part of a tile's k-range adds its partial tile with RED.F64; a CTA that owns the whole k-range of
 // a tile uses plain vector read-modify-write.
 __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_rows, int fpad,
-                                                     double* __restrict__ C, int nkb, long units_total) {
+                                            double* __restrict__ C, int nkb, long units_total) {
     extern __shared__ __align__(16) double smem[];
     const int ntile = fpad / SY_BM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
