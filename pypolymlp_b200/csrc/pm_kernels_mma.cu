@@ -147,11 +147,26 @@ __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_r
     const long per = (units_total + gridDim.x - 1) / gridDim.x;
     long u = (long)blockIdx.x * per;
     const long u_end = min(units_total, u + per);
+    // Order of this CTA's runs: a CTA usually owns the tail [a, nkb) of one tile and the head [0, b) of the next
+    // (b < a).  Doing the head first and the tail last makes every CTA sweep the k-blocks upwards in step
+    // (k-block ~ time + at most nkb - per), so at any instant all CTAs read X rows from the same narrow window,
+    // which then comes from L2 instead of HBM once per tile pair.
+    long first_u = -1;
+    if (u < u_end && u % nkb != 0) {
+        first_u = u;
+        u = min(u_end, (u / nkb + 1) * (long)nkb);
+    }
 
-    while (u < u_end) {
-        const int tile = (int)(u / nkb);
-        const int kb0 = (int)(u - (long)tile * nkb);
-        const int kb1 = (int)min((long)nkb, (long)kb0 + (u_end - u));
+    while (u < u_end || first_u >= 0) {
+        long cur = u, cur_end = u_end;
+        if (u >= u_end) {   // the deferred tail run
+            cur = first_u;
+            cur_end = min(u_end, (first_u / nkb + 1) * (long)nkb);
+            first_u = -1;
+        }
+        const int tile = (int)(cur / nkb);
+        const int kb0 = (int)(cur - (long)tile * nkb);
+        const int kb1 = (int)min((long)nkb, (long)kb0 + (cur_end - cur));
         int ti = 0, rem = tile;
         while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
         const int tj = ti + rem;
@@ -232,7 +247,7 @@ __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_r
                 }
             }
         }
-        u += nk;
+        if (cur == u) u += nk;
     }
 }
 
