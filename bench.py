@@ -113,11 +113,12 @@ def run_reference(args, rank, world):
 
     pd = make_params_dict(**cases.cfg2_model_kwargs(4))
     cores = os.cpu_count() or 1
-    n_st = max(4, min(64, cores // 2))
-    rate, threads, step_s = cpu_reference_rate(pd, n_st, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    n_st = max(8, min(64, 2 * cores))   # two structures per OpenMP thread: every core busy, ~5-10 s per step
+    k_steps, k_warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    rate, threads, step_s = cpu_reference_rate(pd, n_st, steps=k_steps, warmup=k_warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "structures/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "steps": k_steps, "warmup": k_warm, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "structures_per_step": n_st,
                    "note": "reference C++ (oracle/_ref, OpenMP over structures) + numpy x.T@x on host cores; "
@@ -276,9 +277,23 @@ def main():
         stage_ms = {k: round(v[0], 3) for k, v in prof.items() if v[0] > 0}
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        # DRAM traffic of one SYRK launch from the committed ncu --set full capture (profiles/r01_ncu_kernels.json):
+        # dram__bytes_read.sum + dram__bytes_write.sum of the 46-structure chunk launch (bench chunks are 46 structures)
+        traffic, traffic_alg = None, None
+        try:
+            met = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]["metrics"]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic = sum(float(met[k]["value"]) * scale[met[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            fpad = (F + 1 + 127) // 128 * 128
+            traffic_alg = 46 * 775 * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde chunk once + upper C tiles RMW
+        except Exception:
+            pass
         roofline = {
-            "bound": "tensor", "kernel": "k_syrk_mma (fp64 DMMA m8n8k4)", "achieved": syrk_tflops, "peak": peak,
-            "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": None,
+            "bound": "tensor", "kernel": "k_syrk_sk (fp64 DMMA m8n8k4, stream-K SYRK)", "achieved": syrk_tflops, "peak": peak,
+            "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
+            "traffic_note": "DRAM bytes of one 46-structure launch (ncu --set full, profiles/r01_ncu_kernels.json); "
+                            "algorithmic bytes of that launch in traffic_algorithmic",
+            "traffic_algorithmic": traffic_alg,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
                            "tcgen05 has no f64 kind, DMMA peak == DFMA peak on B200)",
             "algorithmic_flops_per_structure": w_alg, "stage_ms_one_step": stage_ms,
@@ -291,7 +306,7 @@ def main():
             from oracle import ref
 
             if ref.available():
-                n_cpu = max(4, min(32, (os.cpu_count() or 1) // 4))
+                n_cpu = max(8, min(64, 2 * (os.cpu_count() or 1)))   # ~5-15 s of CPU work, every core busy
                 rate, threads, _ = cpu_reference_rate(pd, n_cpu)
                 cpu = {"value": rate, "unit": "structures/s", "cores": threads, "kind": "reference",
                        "sample": f"{n_cpu} structures of the same workload through oracle/_ref + numpy x.T@x"}
@@ -303,8 +318,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "structures_per_step_per_gpu": S, "n_features": F,
-                       "l2": "no flush: each step streams ~100 MB of intermediates per structure through HBM, "
-                             "far above the 126 MB L2; staged inputs are ~6 KB/structure",
+                       "l2": "no flush: each step streams ~200 MB of intermediates per structure through HBM "
+                             "(51 GB per 256-structure step), far above the 126 MB L2; staged inputs are ~6 KB/structure",
                        "parallelism": f"structures sharded over {world} GPU(s), one NCCL reduce per step"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": int(h2d),
