@@ -86,6 +86,13 @@ def cpu_reference_rate(pd, n_st, steps=1, warmup=0):
     PyModel semantics) + weights + numpy x.T @ x, exactly as _compute_products_single_batch."""
     from oracle import ref
 
+    cores = os.cpu_count() or 1
+    ref.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: use every host core, as the reference would
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)  # numpy's BLAS for x.T @ x
+    except Exception:
+        pass
     rm = ref.RefModel(pd)
     axis, pcs, tys, w, y = make_batch(n_st, 0)
     times = []

@@ -68,6 +68,13 @@ def num_threads() -> int:
     return lib().ref_num_threads()
 
 
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the reference library (torchrun exports OMP_NUM_THREADS=1)."""
+    L = lib()
+    if hasattr(L, "ref_set_num_threads"):
+        L.ref_set_num_threads(int(n))
+
+
 def _cond_arrays(params_dict):
     n_type = params_dict["n_type"]
     model = params_dict["model"]

@@ -94,6 +94,15 @@ extern "C" {
 
 const char* ref_last_error() { return g_err.c_str(); }
 
+// torchrun exports OMP_NUM_THREADS=1; the reference arm of bench.py asks for all host cores explicitly
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
