@@ -131,6 +131,7 @@ struct pm_context {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_x = nullptr, ev_s = nullptr;
     bool two_stream = true, syrk_pending = false;
+    size_t g_zero_cap = 0;              // capacity of d_G for which the buffer has been cleared (single-type models)
     double* pinned = nullptr;   // host (pinned) copy of the packed result of pm_fit_finalize
     size_t pinned_n = 0;
     double* packed = nullptr;   // device: [xtx F*F | xty F | xe_sum F | xe_sq F | y_sq_norm | n_data]
@@ -674,7 +675,17 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     // ---- K3 ------------------------------------------------------------------------------------
     c->d_dfeat.ensure((size_t)h.n_atoms * d.fl);
     c->d_G.ensure(any_force ? (size_t)h.n_atoms * d.gstride : 1);
-    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s);
+    // single-type models: every atom slot of G has the same zero pattern, so the buffer is cleared once per
+    // allocation and the kernel only writes the non-zero entries afterwards
+    bool zero_g = true;
+    if (d.n_type == 1 && any_force) {
+        if (c->g_zero_cap != c->d_G.cap) {
+            CK(cudaMemsetAsync(c->d_G.p, 0, c->d_G.cap * sizeof(double), s));
+            c->g_zero_cap = c->d_G.cap;
+        }
+        zero_g = false;
+    }
+    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s, zero_g);
     tm.mark(ST_FEAT, 1);
 
     Workspace ws;

@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
 template <int AT, int MO>
 __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                       double* __restrict__ dfeat, double* __restrict__ Gbuf,
-                                                      int nfull_max) {
+                                                      int nfull_max, int zero_g) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
     constexpr int NW = (MO + 1) / 2;
     const int i0 = blockIdx.x * AT;
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, con
         }
         double* drow = dfeat + (size_t)i * m.fl;
         for (int k = tid; k < m.fl; k += nthr) drow[k] = 0.0;
-        if (fo[a]) {
+        if (fo[a] && zero_g) {   // single-type models: the structural zeros of G are written once per allocation (host)
             double2* G = reinterpret_cast<double2*>(Gbuf + (size_t)i * m.gstride);
             for (long k = tid; k < T.g_size / 2; k += nthr) G[k] = make_double2(0.0, 0.0);
         }
@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, con
 static size_t g_feat_smem_set = 0, g_feat3_smem_set = 0;
 
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
-                     size_t smem_bytes, cudaStream_t s) {
+                     size_t smem_bytes, cudaStream_t s, bool zero_g) {
     if (b.n_atoms == 0) return;
     // smem_bytes = bytes of one atom's full a_nlm array
     const int nfull_max = (int)(smem_bytes / sizeof(double2));
@@ -887,7 +887,7 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     case MO_:                                                                                                    \
         if (smem4 > 48 * 1024 && g_feat3_smem_set != smem4)                                                      \
             cudaFuncSetAttribute(k_features_v3<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
-        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);                      \
+        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0);               \
         break;
         switch (mo) {
             PM_FEAT3_CASE(1) PM_FEAT3_CASE(2) PM_FEAT3_CASE(3) PM_FEAT3_CASE(4) PM_FEAT3_CASE(5) PM_FEAT3_CASE(6)

@@ -32,7 +32,7 @@ void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2
                  bool small_footprint = false);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
-                     size_t smem_bytes, cudaStream_t s);
+                     size_t smem_bytes, cudaStream_t s, bool zero_g = true);
 // K4a: per-centre derivative rows L = V . G
 void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s);
 bool scatter_mode_supported(const DevModel& m);

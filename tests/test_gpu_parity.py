@@ -127,6 +127,22 @@ def test_x_mixed_batch_layout_energy_only_and_force(flags):
 
 
 @pytest.mark.parametrize("flags", FLAVOURS)
+def test_x_single_type_ragged_batches(flags):
+    """Single-type model (the k_xrows_v4 / zero-once G fast paths): ragged cells, an energy-only structure in the
+    middle, and a second call on the same context with different structures (buffers are reused)."""
+    pd = make_params_dict(**cases.si_model_kwargs())
+    tab = po.Tables(pd)
+    for seeds in (((7, 1), (3, 2), (12, 3), (5, 4)), ((4, 9), (9, 8), (6, 7), (2, 6))):
+        sts = [cases.skewed_cell(1, n_atom=n, seed=s) for n, s in seeds]
+        axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+        n_atoms = [len(t) for t in tys]
+        pm = PotentialModel(pd, axis, pcs, tys, [1, 1, 2], [True, False, True], n_atoms, flags=flags)
+        ref_x = po.build_x(tab, axis, pcs, tys, [True, False, True, True])
+        assert pm.get_x().shape == ref_x.shape
+        assert cases.x_rel_err(pm.get_x(), ref_x) < 1e-10
+
+
+@pytest.mark.parametrize("flags", FLAVOURS)
 def test_x_fcc256_config2(flags):
     pd = make_params_dict(**cases.cfg2_model_kwargs(4))
     ax, pc, ty = cases.fcc_supercell()
