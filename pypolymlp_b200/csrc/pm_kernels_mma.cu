@@ -1575,6 +1575,229 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v4(DevModel m, DevBatch
     }
 }
 
+
+// ================================================================================================
+// K4b v5 (force rows, single-type models): same math as v4, but the neighbours' derivative rows (3 contiguous rows =
+// 24 * fl bytes per centre) are brought in by the TMA unit: one `cp.async.bulk` per centre into a small shared-memory
+// ring, completion on an mbarrier.  No registers are tied up by loads in flight, the ring keeps 3 centres per thread
+// group in flight continuously, and it keeps filling while the CTA is in its DMMA phase.
+// The two thread groups (4 warps each) own the even / odd centres and their own ring; a group leader re-arms a slot
+// after the group's named barrier.
+// ================================================================================================
+constexpr int X5_R = 3;        // ring slots per group
+constexpr int X5_MAXC = 128;   // centres per pointer-table pass
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                             const double* __restrict__ Lbuf,
+                                                             const double* __restrict__ Xown, double* __restrict__ X,
+                                                             int apply_w) {
+    extern __shared__ __align__(128) double smem[];
+    double* sD = smem;                          // [X4_KC][X4_LD]        D[c][a]
+    double* sL = sD + X4_KC * X4_LD;            // [3][X4_KC][X4_LD]     Lambda_r[c][b]; later the lin scratch
+    double* ring = sL + 3 * X4_KC * X4_LD;      // [2 groups][X5_R][3 * fl]
+    const int slot_d = 3 * m.fl;
+    const double** sSrc = reinterpret_cast<const double**>(ring + 2 * X5_R * slot_d);   // [X5_MAXC]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sSrc + X5_MAXC);   // [2][X5_R]
+    int* sAtom = reinterpret_cast<int*>(bars + 2 * X5_R);                               // [X5_MAXC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int grp = tid >> 7, gt = tid & 127;
+
+    const int k_atom = blockIdx.x;
+    const int s = b.st_of_atom[k_atom];
+    if (!b.force[s]) return;
+    const int p0 = b.seg_off[k_atom];
+    const int n_cent = 1 + b.seg_off[k_atom + 1] - p0;
+    int rows[3];
+    double wrow[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        rows[r] = b.frow[s] + 3 * (k_atom - b.atom_off[s]) + r;
+        wrow[r] = apply_w ? b.w[rows[r]] : 1.0;
+    }
+    const int npr = m.fl >> 1;
+    const bool act = gt < npr;
+    int ppv0 = -1, ppv1 = -1;
+    if (act) {
+        ppv0 = m.types[0].pad_pv[2 * gt];
+        ppv1 = m.types[0].pad_pv[2 * gt + 1];
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 2 * X5_R; ++k) mbar_init(smem_u32(bars + k), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int ta[X4_SLOTS], tb[X4_SLOTS];
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i) { ta[i] = c_x4_tiles[warp][i][0]; tb[i] = c_x4_tiles[warp][i][1]; }
+    double lin[2][3];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { lin[j][0] = 0.0; lin[j][1] = 0.0; lin[j][2] = 0.0; }
+    double acc[X4_SLOTS][3][2];
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { acc[i][r][0] = 0.0; acc[i][r][1] = 0.0; }
+
+    const unsigned bytes = (unsigned)(slot_d * sizeof(double));
+    double* myring = ring + (size_t)grp * X5_R * slot_d;
+    const unsigned bar0 = smem_u32(bars + grp * X5_R);
+    int jbase = 0;   // copies this group has consumed in earlier table passes (slot / phase bookkeeping)
+
+    for (int sc0 = 0; sc0 < n_cent; sc0 += X5_MAXC) {
+        const int nsc = min(X5_MAXC, n_cent - sc0);
+        __syncthreads();   // ring drained, tables and barriers free / initialised
+        for (int c = tid; c < nsc; c += X4_THREADS) {
+            const int cc = sc0 + c;
+            int atom;
+            const double* src;
+            if (cc == 0) {
+                atom = k_atom;
+                src = Xown + (size_t)k_atom * 3 * m.fl;
+            } else {
+                const int p = p0 + cc - 1;
+                atom = b.nbr[p];
+                src = Lbuf + (size_t)b.rev[p] * 3 * m.fl;
+            }
+            sAtom[c] = atom;
+            sSrc[c] = src;
+        }
+        __syncthreads();
+        const int ng = (nsc - grp + 1) >> 1;   // centres of this group in this pass: c = 2 j + grp
+        auto issue = [&](int j) {
+            const int slot = (jbase + j) % X5_R;
+            const unsigned bar = bar0 + 8 * slot;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(myring + (size_t)slot * slot_d), sSrc[2 * j + grp], bytes, bar);
+        };
+        if (gt == 0)
+            for (int j = 0; j < min(X5_R, ng); ++j) issue(j);
+
+        for (int c0 = 0; c0 < nsc; c0 += X4_KC) {
+            if (c0 > 0) __syncthreads();   // the previous chunk's DMMAs are done with sD / sL
+            const int ncc = min(X4_KC, nsc - c0);
+            for (int e = tid; e < X4_KC * 64; e += X4_THREADS) {   // D tile
+                const int cc = e >> 6, a = e & 63;
+                double dv = 0.0;
+                if (cc < ncc && a < m.npv_pad) {
+                    const int fa = m.pv_fp[a];
+                    if (fa >= 0) dv = dfeat[(size_t)sAtom[c0 + cc] * m.fl + fa];
+                }
+                sD[cc * X4_LD + a] = dv;
+            }
+            {   // Lambda rows between ncc and the next multiple of 4 must be finite zeros
+                const int ntail = ((ncc + 3) & ~3) - ncc;
+                for (int e = tid; e < 3 * ntail * X4_LD; e += X4_THREADS) {
+                    const int r = e / (ntail * X4_LD), rem = e - r * ntail * X4_LD;
+                    sL[(r * X4_KC + ncc) * X4_LD + rem] = 0.0;
+                }
+            }
+            for (int cl = grp; cl < ncc; cl += 2) {   // c0 is even, so the group's centres are cl = grp, grp + 2, ..
+                const int j = (c0 + cl) >> 1;
+                const int use = jbase + j;
+                const int slot = use % X5_R;
+                const unsigned parity = (unsigned)(use / X5_R) & 1u;
+                while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+                if (act) {
+                    const double2* src = reinterpret_cast<const double2*>(myring + (size_t)slot * slot_d) + gt;
+                    const double sg = (sc0 + c0 + cl == 0) ? 1.0 : -1.0;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double2 v = src[r * npr];
+                        const double v0 = sg * v.x, v1 = sg * v.y;
+                        lin[0][r] += v0;
+                        lin[1][r] += v1;
+                        if (ppv0 >= 0) sL[(r * X4_KC + cl) * X4_LD + ppv0] = v0;
+                        if (ppv1 >= 0) sL[(r * X4_KC + cl) * X4_LD + ppv1] = v1;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group is done with the slot
+                if (gt == 0 && j + X5_R < ng) issue(j + X5_R);
+            }
+            __syncthreads();
+            if (m.n_pair_terms > 0) {
+                const int kend = (ncc + 3) & ~3;
+                for (int k0 = 0; k0 < kend; k0 += 4) {
+                    const double* dk = sD + (k0 + q) * X4_LD + g;
+                    const double* lk = sL + (k0 + q) * X4_LD + g;
+#pragma unroll
+                    for (int i = 0; i < X4_SLOTS; ++i) {
+                        if (ta[i] < 0) continue;
+                        const double fDa = dk[ta[i] * 8], fDb = dk[tb[i] * 8];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const double fLa = lk[r * X4_KC * X4_LD + ta[i] * 8], fLb = lk[r * X4_KC * X4_LD + tb[i] * 8];
+                            dmma(acc[i][r][0], acc[i][r][1], fDa, fLb);
+                            dmma(acc[i][r][0], acc[i][r][1], fLa, fDb);
+                        }
+                    }
+                }
+            }
+        }
+        jbase += ng;
+    }
+    // ---- linear columns: combine the two groups' partial sums (scratch over the dead Lambda tiles) -----------------
+    __syncthreads();
+    double* sS = sL;   // [2][3][fl]
+    if (act) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            sS[(grp * 3 + r) * m.fl + 2 * gt] = lin[0][r];
+            sS[(grp * 3 + r) * m.fl + 2 * gt + 1] = lin[1][r];
+        }
+    }
+    __syncthreads();
+    {
+        const int* pad_gid = m.types[0].pad_gid;
+        for (int idx = tid; idx < 3 * m.fl; idx += X4_THREADS) {
+            const int r = idx / m.fl, fp = idx - r * m.fl;
+            const int gcol = pad_gid[fp];
+            if (gcol < 0) continue;
+            const double val = sS[r * m.fl + fp] + sS[(3 + r) * m.fl + fp];
+            const int row = r == 0 ? rows[0] : (r == 1 ? rows[1] : rows[2]);
+            const double wv = r == 0 ? wrow[0] : (r == 1 ? wrow[1] : wrow[2]);
+            X[(size_t)row * m.fpad + gcol] = wv * val;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        if (tid == r) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+    if (m.n_pair_terms == 0) return;
+#pragma unroll
+    for (int i = 0; i < X4_SLOTS; ++i) {
+        if (ta[i] < 0) continue;
+        const int a = ta[i] * 8 + g, bq = tb[i] * 8 + 2 * q;
+        const int col0 = m.pair_colof[a * 64 + bq], col1 = m.pair_colof[a * 64 + bq + 1];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double* xr = X + (size_t)rows[r] * m.fpad;
+            if (col0 >= 0) xr[col0] = wrow[r] * acc[i][r][0];
+            if (col1 >= 0) xr[col1] = wrow[r] * acc[i][r][1];
+        }
+    }
+}
+
 bool scatter_mode_supported(const DevModel& m) {
     return m.kpn > 0 && m.tpn > 0 && m.npv_pad <= 64 && m.n_linear <= 512 &&
            (2ull * m.pbstride * LR_PLD + 8ull * (4 * m.kpn) * LR_LD) * sizeof(double) <= 150 * 1024;
@@ -1610,8 +1833,20 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
             u4 = getenv("PM_X4_U") ? atoi(getenv("PM_X4_U")) : 2;   // 2 measured faster than 4 (register pressure)
         }
         auto kern = u4 == 2 ? k_xrows_v4<2> : k_xrows_v4<4>;
-        kern<<<b.n_atoms, X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
-                                                  apply_weights ? 1 : 0);
+        static const bool use_v5 = getenv("PM_XROWS_V4") == nullptr;
+        const size_t smem5 = ((size_t)4 * X4_KC * X4_LD + 2 * X5_R * 3 * (size_t)m.fl + X5_MAXC + 2 * X5_R) * sizeof(double) +
+                             X5_MAXC * sizeof(int) + 128;
+        if (use_v5 && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
+            static size_t set5_for = 0;   // the ring size depends on the model (fl)
+            if (set5_for < smem5) {
+                cudaFuncSetAttribute(k_xrows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
+                set5_for = smem5;
+            }
+            k_xrows_v5<<<b.n_atoms, X4_THREADS, smem5, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
+        } else {
+            kern<<<b.n_atoms, X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
+                                                      apply_weights ? 1 : 0);
+        }
         kern<<<dim3(b.n_st, 3), X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
                                                         apply_weights ? 1 : 0);
         return true;
