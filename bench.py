@@ -277,7 +277,14 @@ def main():
         prof = ctx.profile_get()
         ctx.profile(False)
         w_alg = acc.model.count_flops([256], [[13824]], True)
-        syrk_ms = prof["syrk"][0]
+        # the dominant kernel timed live: event pairs around every SYRK launch of K unperturbed steps, on its stream
+        ctx.profile(2)
+        for _ in range(args.steps):
+            acc.add_staged()
+        ctx.synchronize()
+        syrk_total_ms, syrk_launches = ctx.profile_get()["syrk"]
+        ctx.profile(False)
+        syrk_ms = syrk_total_ms / args.steps
         syrk_tflops = S * w_alg["syrk"] / (syrk_ms * 1e-3) * 1e-12
         peak = ctx.microbench(3, 8192)
         total_alg = S * sum(w_alg.values())
@@ -285,25 +292,29 @@ def main():
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         # DRAM traffic of one SYRK launch from the committed ncu --set full capture (profiles/r01_ncu_kernels.json):
-        # dram__bytes_read.sum + dram__bytes_write.sum of the 46-structure chunk launch (bench chunks are 46 structures)
+        # dram__bytes_read.sum + dram__bytes_write.sum of a full-chunk launch (42 structures, as in the bench steps)
         traffic, traffic_alg = None, None
         try:
-            met = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]["metrics"]
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]
+            met, n_cap = cap["metrics"], cap.get("structures_in_launch", 42)
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             traffic = sum(float(met[k]["value"]) * scale[met[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             fpad = (F + 1 + 127) // 128 * 128
-            traffic_alg = 46 * 775 * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde chunk once + upper C tiles RMW
+            traffic_alg = n_cap * 775 * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde chunk once + upper C tiles RMW
         except Exception:
             pass
         roofline = {
             "bound": "tensor", "kernel": "k_syrk_sk (fp64 DMMA m8n8k4, stream-K SYRK)", "achieved": syrk_tflops, "peak": peak,
             "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
-            "traffic_note": "DRAM bytes of one 46-structure launch (ncu --set full, profiles/r01_ncu_kernels.json); "
-                            "algorithmic bytes of that launch in traffic_algorithmic",
+            "traffic_note": "DRAM bytes of one full-chunk launch (42 structures; ncu --set full, "
+                            "profiles/r01_ncu_kernels.json); algorithmic bytes of that launch in traffic_algorithmic",
             "traffic_algorithmic": traffic_alg,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
                            "tcgen05 has no f64 kind, DMMA peak == DFMA peak on B200)",
+            "syrk_ms_per_step_live": syrk_ms, "syrk_launches_per_step": syrk_launches / args.steps,
             "algorithmic_flops_per_structure": w_alg, "stage_ms_one_step": stage_ms,
+            "stage_note": "stage_ms_one_step comes from one extra step with a host sync after every stage (idle gaps "
+                          "inflate it by ~8 %); achieved/frac use syrk_ms_per_step_live",
             "whole_step_tflops": total_alg / (ms / args.steps * 1e-3) * 1e-12,
             "whole_step_frac_of_peak": total_alg / (ms / args.steps * 1e-3) * 1e-12 / peak,
             "hbm_gbs_measured": hbm,

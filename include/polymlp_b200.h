@@ -157,7 +157,9 @@ void* pm_stream(pm_context* c);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 int64_t pm_launch_count(pm_context* c);
 /* Accumulated device time (ms, CUDA events) per pipeline stage since the last reset; names are
- * returned through a static table: pm_stage_name(i).  Only collected when enabled. */
+ * returned through a static table: pm_stage_name(i).  on = 1: every stage, with a host synchronisation after each
+ * (single stream; the idle gaps inflate the stage times by a few percent).  on = 2: only the SYRK launches, bracketed
+ * by event pairs on the stream they run on, no synchronisation (the live figure bench.py's roofline uses). */
 int pm_profile_enable(pm_context* c, int on);
 int pm_profile_get(pm_context* c, int* n_stages, double* ms, int64_t* launches);
 const char* pm_stage_name(int i);

@@ -131,6 +131,10 @@ struct pm_context {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_x = nullptr, ev_s = nullptr;
     bool two_stream = true, syrk_pending = false;
+    // pm_profile_enable(c, 2): only K5 is timed, with event pairs on its own stream and no host synchronisation
+    bool time_syrk = false;
+    std::vector<cudaEvent_t> syrk_ev;   // pairs (before, after), created lazily
+    size_t syrk_ev_used = 0;
     size_t g_zero_cap = 0;              // capacity of d_G for which the buffer has been cleared (single-type models)
     double* pinned = nullptr;   // host (pinned) copy of the packed result of pm_fit_finalize
     size_t pinned_n = 0;
@@ -740,14 +744,28 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     tm.mark(ST_XROWS, 3);
     // ---- K5 --------------------------------------------------------------------------------------
     if (fit) {
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (c->time_syrk) {
+            if (c->syrk_ev.size() < 2 * (c->syrk_ev_used + 1)) {
+                cudaEvent_t a, bq;
+                CK(cudaEventCreate(&a)); CK(cudaEventCreate(&bq));
+                c->syrk_ev.push_back(a); c->syrk_ev.push_back(bq);
+            }
+            t0 = c->syrk_ev[2 * c->syrk_ev_used]; t1 = c->syrk_ev[2 * c->syrk_ev_used + 1];
+            ++c->syrk_ev_used;
+        }
         if (c->two_stream && !c->profile) {
             CK(cudaEventRecord(c->ev_x, s));
             CK(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
+            if (t0) CK(cudaEventRecord(t0, c->stream2));
             launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, c->stream2);
+            if (t1) CK(cudaEventRecord(t1, c->stream2));
             CK(cudaEventRecord(c->ev_s, c->stream2));
             c->syrk_pending = true;
         } else {
+            if (t0) CK(cudaEventRecord(t0, s));
             launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
+            if (t1) CK(cudaEventRecord(t1, s));
         }
         tm.mark(ST_SYRK, 1);
         c->n_data += h.n_rows;
@@ -935,6 +953,7 @@ void pm_context_destroy(pm_context* c) {
     cudaStreamSynchronize(c->stream);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->ev_x) cudaEventDestroy(c->ev_x);
+    for (auto e : c->syrk_ev) cudaEventDestroy(e);
     if (c->ev_s) cudaEventDestroy(c->ev_s);
     for (void* p : c->table_allocs) cudaFree(p);
     if (c->acc) cudaFree(c->acc);
@@ -1278,13 +1297,28 @@ void* pm_stream(pm_context* c) { return c ? (void*)c->stream : nullptr; }
 int64_t pm_launch_count(pm_context* c) { return c ? c->launches : 0; }
 
 int pm_profile_enable(pm_context* c, int on) {
-    c->profile = on != 0;
+    c->profile = on == 1;
+    c->time_syrk = on == 2;
+    c->syrk_ev_used = 0;
     for (int k = 0; k < ST_COUNT; ++k) { c->stage_ms[k] = 0.0; c->stage_launches[k] = 0; }
     return PM_OK;
 }
 
 int pm_profile_get(pm_context* c, int* n_stages, double* ms, int64_t* launches) {
     *n_stages = ST_COUNT;
+    if (c->time_syrk && c->syrk_ev_used > 0) {   // mode 2: sum the K5 launches recorded since pm_profile_enable
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (c->stream2) cudaStreamSynchronize(c->stream2);
+        double tot = 0.0;
+        for (size_t k = 0; k < c->syrk_ev_used; ++k) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->syrk_ev[2 * k], c->syrk_ev[2 * k + 1]) == cudaSuccess) tot += t;
+        }
+        c->stage_ms[ST_SYRK] = tot;
+        c->stage_launches[ST_SYRK] = (int64_t)c->syrk_ev_used;
+        c->syrk_ev_used = 0;
+    }
     for (int k = 0; k < ST_COUNT; ++k) { if (ms) ms[k] = c->stage_ms[k]; if (launches) launches[k] = c->stage_launches[k]; }
     return PM_OK;
 }
