@@ -84,7 +84,7 @@ int pm_model_count_flops(const pm_model* m, const int64_t* atoms_t, const int64_
 
 /* ---- device context --------------------------------------------------------------------------- */
 int pm_device_count(int* n);
-/* workspace_bytes: cap for per-chunk scratch (0 -> default 6 GiB). flags: PM_FLAG_* */
+/* workspace_bytes: cap for per-chunk scratch (0 -> default 12 GiB). flags: PM_FLAG_* */
 #define PM_FLAG_SIMPLE_KERNELS 1 /* use the straightforward (non tensor-core) kernels: debug/parity */
 #define PM_FLAG_SCATTER 2        /* K4a adds the linear columns into X with RED.F64 and keeps only the polynomial-variable
                                     derivative rows (4x less scratch per structure, same speed, run-to-run summation order) */

@@ -721,7 +721,8 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         join_syrk(c);
         c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
         ws.X = c->d_X.p;
-        CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
+        if (c->simple_x || !xrows_fills_rows(d, ws.scatter))
+            CK(cudaMemsetAsync(ws.X, 0, (size_t)h.n_rows * d.fpad * sizeof(double), s));
     };
     if (ws.scatter) prep_X();
     // ---- K4a -------------------------------------------------------------------------------------
@@ -933,7 +934,8 @@ int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int
         CK(cudaSetDevice(device));
         auto c = std::make_unique<pm_context>();
         c->model = m; c->device = device; c->flags = flags;
-        c->ws_cap = workspace_bytes ? workspace_bytes : (size_t)6 << 30;
+        c->ws_cap = workspace_bytes ? workspace_bytes : (size_t)12 << 30;   // measured sweet spot on B200 (bigger chunks: less SYRK fix-up; smaller: more host/device overlap)
+        if (!workspace_bytes && getenv("PM_WORKSPACE_GB")) c->ws_cap = (size_t)atol(getenv("PM_WORKSPACE_GB")) << 30;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto& e : c->ev) CK(cudaEventCreate(&e));
         CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));

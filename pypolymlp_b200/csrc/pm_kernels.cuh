@@ -39,6 +39,8 @@ bool scatter_mode_supported(const DevModel& m);
 // K4b: gather + polynomial expansion -> weighted X-tilde rows
 void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                   bool simple, bool apply_weights, cudaStream_t s);
+// K4b (tensor-core flavour) writes every column of every row for this model: no memset of the X chunk needed
+bool xrows_fills_rows(const DevModel& m, bool scatter);
 // exclusive prefix sum (segment offsets of the neighbour list)
 void launch_scan_exclusive(const int* in, int* out, int n, cudaStream_t s);
 // K5: C += Xt^T Xt (upper tiles)

@@ -1549,8 +1549,12 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v4(DevModel m, DevBatch
         }
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-        if (tid == r && r < nrow) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+    for (int r = 0; r < 3; ++r) {
+        if (r >= nrow) break;
+        if (tid == r) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+        // the padding columns behind y: this kernel writes every column of its rows, so X is not cleared beforehand
+        for (int cz = m.n_variables + 1 + tid; cz < m.fpad; cz += X4_THREADS) X[(size_t)rows[r] * m.fpad + cz] = 0.0;
+    }
     if (m.n_pair_terms == 0) return;
     // ---- order-2 columns straight from the accumulator fragments -----------------------------------------------------
     const bool erow = half && xe_sum;
@@ -1781,8 +1785,10 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
         }
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r) {
         if (tid == r) X[(size_t)rows[r] * m.fpad + m.n_variables] = apply_w ? b.yv[rows[r]] : 0.0;
+        for (int cz = m.n_variables + 1 + tid; cz < m.fpad; cz += X4_THREADS) X[(size_t)rows[r] * m.fpad + cz] = 0.0;
+    }
     if (m.n_pair_terms == 0) return;
 #pragma unroll
     for (int i = 0; i < X4_SLOTS; ++i) {
@@ -1796,6 +1802,14 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
             if (col1 >= 0) xr[col1] = wrow[r] * acc[i][r][1];
         }
     }
+}
+
+// true when K4b runs on the single-type kernels (v4 / v5), which write every column of every X row (so the caller
+// does not have to clear the X chunk first)
+bool xrows_fills_rows(const DevModel& m, bool scatter) {
+    static const bool off = getenv("PM_XROWS_V2") != nullptr;
+    return !scatter && !off && m.npv_pad <= 64 && m.n_linear <= 512 && m.n_type == 1 && m.pair_colof != nullptr &&
+           (m.fl & 1) == 0 && m.fl / 2 <= X4_THREADS && 4 * 3 * m.fl <= 3 * X4_KC * X4_LD;
 }
 
 bool scatter_mode_supported(const DevModel& m) {
@@ -1823,8 +1837,7 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
                                                              1, apply_weights ? 1 : 0);
         return true;
     }
-    if (m.n_type == 1 && m.pair_colof != nullptr && (m.fl & 1) == 0 && m.fl / 2 <= X4_THREADS &&
-        4 * 3 * m.fl <= 3 * X4_KC * X4_LD && !getenv("PM_XROWS_V2")) {
+    if (xrows_fills_rows(m, ws.scatter)) {
         const size_t smem4 = ((size_t)4 * X4_KC * X4_LD + 4 * X4_KC) * sizeof(double) + X4_KC * sizeof(int);
         static int u4 = 0;
         if (!u4) {
