@@ -109,7 +109,7 @@ struct pm_context {
     // chunk device buffers
     DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
         d_nbr, d_centre, d_rev, d_err;
-    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
+    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
         d_f, d_s;
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
@@ -689,11 +689,19 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         }
         zero_g = false;
     }
-    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s, zero_g);
+    // compact polynomial-variable rows for K4b v5 (single-type models); the padding entries [npv, 64) stay zero
+    double* dpv = nullptr;
+    if (d.n_type == 1 && d.npv_pad <= 64 && d.npv > 0) {
+        const size_t cap0 = c->d_dpv.cap;
+        c->d_dpv.ensure((size_t)h.n_atoms * 64);
+        if (c->d_dpv.cap != cap0) CK(cudaMemsetAsync(c->d_dpv.p, 0, c->d_dpv.cap * sizeof(double), s));
+        dpv = c->d_dpv.p;
+    }
+    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s, zero_g, dpv);
     tm.mark(ST_FEAT, 1);
 
     Workspace ws;
-    ws.PB = c->d_PB.p; ws.anc = c->d_anc.p; ws.agg = c->d_agg.p; ws.dfeat = c->d_dfeat.p; ws.Gbuf = c->d_G.p;
+    ws.PB = c->d_PB.p; ws.anc = c->d_anc.p; ws.agg = c->d_agg.p; ws.dfeat = c->d_dfeat.p; ws.dpv = dpv; ws.Gbuf = c->d_G.p;
     c->d_Xown.ensure((size_t)h.n_atoms * 3 * d.fl);
     c->d_S.ensure((size_t)h.n_atoms * 6 * d.fl);
     ws.Xown = c->d_Xown.p; ws.Sbuf = c->d_S.p; ws.errflag = c->d_err.p;
@@ -963,7 +971,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
-    c->d_PB.release(); c->d_dfeat.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
+    c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
     c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);

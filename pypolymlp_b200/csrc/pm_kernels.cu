@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
 template <int AT, int MO>
 __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                       double* __restrict__ dfeat, double* __restrict__ Gbuf,
-                                                      int nfull_max, int zero_g) {
+                                                      int nfull_max, int zero_g, double* __restrict__ dpv) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
     constexpr int NW = (MO + 1) / 2;
     const int i0 = blockIdx.x * AT;
@@ -814,9 +814,13 @@ __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, con
             if (lane < 8) {
                 const int fp = T.fsl_out[s * 8 + lane];
                 if (fp >= 0) {
+                    const int pv = dpv ? T.pad_pv[fp] : -1;
 #pragma unroll
                     for (int a = 0; a < AT; ++a)
-                        if (ty[a] == tt) dfeat[(size_t)(i0 + a) * m.fl + fp] = sum[a];
+                        if (ty[a] == tt) {
+                            dfeat[(size_t)(i0 + a) * m.fl + fp] = sum[a];
+                            if (pv >= 0) dpv[(size_t)(i0 + a) * 64 + pv] = sum[a];
+                        }
                 }
             }
         }
@@ -870,9 +874,25 @@ __global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, con
 
 static size_t g_feat_smem_set = 0, g_feat3_smem_set = 0;
 
+// compact polynomial-variable rows from dfeat (only after the fallback feature kernels; v3 writes them itself)
+__global__ void __launch_bounds__(256) k_dpv_gather(DevModel m, int n_atoms, const double* __restrict__ dfeat,
+                                                     double* __restrict__ dpv) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_atoms * 64) return;
+    const int atom = (int)(idx >> 6), a = (int)(idx & 63);
+    const int fa = a < m.npv_pad ? m.pv_fp[a] : -1;
+    dpv[idx] = fa >= 0 ? dfeat[(size_t)atom * m.fl + fa] : 0.0;
+}
+
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
-                     size_t smem_bytes, cudaStream_t s, bool zero_g) {
+                     size_t smem_bytes, cudaStream_t s, bool zero_g, double* dpv) {
     if (b.n_atoms == 0) return;
+    struct DpvFallback {   // runs when a fallback kernel (which does not know dpv) was used
+        const DevModel& m; const DevBatch& b; const double* dfeat; double* dpv; cudaStream_t s; bool armed = true;
+        ~DpvFallback() {
+            if (armed && dpv) k_dpv_gather<<<(int)(((long)b.n_atoms * 64 + 255) / 256), 256, 0, s>>>(m, b.n_atoms, dfeat, dpv);
+        }
+    } dpv_fallback{m, b, dfeat, dpv, s};
     // smem_bytes = bytes of one atom's full a_nlm array
     const int nfull_max = (int)(smem_bytes / sizeof(double2));
     constexpr int AT = 4;
@@ -887,13 +907,14 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     case MO_:                                                                                                    \
         if (smem4 > 48 * 1024 && g_feat3_smem_set != smem4)                                                      \
             cudaFuncSetAttribute(k_features_v3<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
-        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0);               \
+        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0, dpv);               \
         break;
         switch (mo) {
             PM_FEAT3_CASE(1) PM_FEAT3_CASE(2) PM_FEAT3_CASE(3) PM_FEAT3_CASE(4) PM_FEAT3_CASE(5) PM_FEAT3_CASE(6)
         }
 #undef PM_FEAT3_CASE
         if (smem4 > 48 * 1024) g_feat3_smem_set = smem4;
+        dpv_fallback.armed = false;
         return;
     }
     if (smem4 <= 96 * 1024 && mo <= 6) {

@@ -11,6 +11,7 @@ struct Workspace {
     double2* anc = nullptr;     // [n_atoms][hmax]
     double2* agg = nullptr;     // [n_atoms][hmax][9]
     double* dfeat = nullptr;    // [n_atoms][fl]
+    double* dpv = nullptr;      // [n_atoms][64] polynomial variables of each atom, compact (single-type models; else null)
     double* Gbuf = nullptr;     // [n_atoms][gstride]
     double* Lbuf = nullptr;     // [n_pairs * 3][fl]   (not used in scatter mode)
     double* Lpv = nullptr;      // [n_pairs * 3][npv_pad] derivative rows of the polynomial variables (scatter mode)
@@ -32,7 +33,8 @@ void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2
                  bool small_footprint = false);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
-                     size_t smem_bytes, cudaStream_t s, bool zero_g = true);
+                     size_t smem_bytes, cudaStream_t s, bool zero_g = true,
+                     double* dpv = nullptr);
 // K4a: per-centre derivative rows L = V . G
 void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s);
 bool scatter_mode_supported(const DevModel& m);

@@ -1613,15 +1613,15 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     return ok != 0;
 }
 
-__global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+__global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch b, const double* __restrict__ dpv,
                                                              const double* __restrict__ Lbuf,
                                                              const double* __restrict__ Xown, double* __restrict__ X,
                                                              int apply_w) {
     extern __shared__ __align__(128) double smem[];
     double* sD = smem;                          // [X4_KC][X4_LD]        D[c][a]
     double* sL = sD + X4_KC * X4_LD;            // [3][X4_KC][X4_LD]     Lambda_r[c][b]; later the lin scratch
-    double* ring = sL + 3 * X4_KC * X4_LD;      // [2 groups][X5_R][3 * fl]
-    const int slot_d = 3 * m.fl;
+    double* ring = sL + 3 * X4_KC * X4_LD;      // [2 groups][X5_R][3 * fl + 64]: 3 derivative rows + the centre's PV row
+    const int slot_d = 3 * m.fl + 64;
     const double** sSrc = reinterpret_cast<const double**>(ring + 2 * X5_R * slot_d);   // [X5_MAXC]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sSrc + X5_MAXC);   // [2][X5_R]
     int* sAtom = reinterpret_cast<int*>(bars + 2 * X5_R);                               // [X5_MAXC]
@@ -1664,7 +1664,7 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
 #pragma unroll
         for (int r = 0; r < 3; ++r) { acc[i][r][0] = 0.0; acc[i][r][1] = 0.0; }
 
-    const unsigned bytes = (unsigned)(slot_d * sizeof(double));
+    const unsigned bytes_l = (unsigned)(3 * m.fl * sizeof(double)), bytes_d = 64 * sizeof(double);
     double* myring = ring + (size_t)grp * X5_R * slot_d;
     const unsigned bar0 = smem_u32(bars + grp * X5_R);
     int jbase = 0;   // copies this group has consumed in earlier table passes (slot / phase bookkeeping)
@@ -1692,8 +1692,10 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
         auto issue = [&](int j) {
             const int slot = (jbase + j) % X5_R;
             const unsigned bar = bar0 + 8 * slot;
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(smem_u32(myring + (size_t)slot * slot_d), sSrc[2 * j + grp], bytes, bar);
+            mbar_expect_tx(bar, bytes_l + bytes_d);
+            double* dst = myring + (size_t)slot * slot_d;
+            bulk_g2s(smem_u32(dst), sSrc[2 * j + grp], bytes_l, bar);
+            bulk_g2s(smem_u32(dst + 3 * m.fl), dpv + (size_t)sAtom[2 * j + grp] * 64, bytes_d, bar);
         };
         if (gt == 0)
             for (int j = 0; j < min(X5_R, ng); ++j) issue(j);
@@ -1701,20 +1703,12 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
         for (int c0 = 0; c0 < nsc; c0 += X4_KC) {
             if (c0 > 0) __syncthreads();   // the previous chunk's DMMAs are done with sD / sL
             const int ncc = min(X4_KC, nsc - c0);
-            for (int e = tid; e < X4_KC * 64; e += X4_THREADS) {   // D tile
-                const int cc = e >> 6, a = e & 63;
-                double dv = 0.0;
-                if (cc < ncc && a < m.npv_pad) {
-                    const int fa = m.pv_fp[a];
-                    if (fa >= 0) dv = dfeat[(size_t)sAtom[c0 + cc] * m.fl + fa];
-                }
-                sD[cc * X4_LD + a] = dv;
-            }
-            {   // Lambda rows between ncc and the next multiple of 4 must be finite zeros
+            {   // D and Lambda rows between ncc and the next multiple of 4 must be finite zeros
                 const int ntail = ((ncc + 3) & ~3) - ncc;
-                for (int e = tid; e < 3 * ntail * X4_LD; e += X4_THREADS) {
+                for (int e = tid; e < 4 * ntail * X4_LD; e += X4_THREADS) {
                     const int r = e / (ntail * X4_LD), rem = e - r * ntail * X4_LD;
-                    sL[(r * X4_KC + ncc) * X4_LD + rem] = 0.0;
+                    if (r < 3) sL[(r * X4_KC + ncc) * X4_LD + rem] = 0.0;
+                    else sD[ncc * X4_LD + rem] = 0.0;
                 }
             }
             for (int cl = grp; cl < ncc; cl += 2) {   // c0 is even, so the group's centres are cl = grp, grp + 2, ..
@@ -1723,6 +1717,9 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
                 const int slot = use % X5_R;
                 const unsigned parity = (unsigned)(use / X5_R) & 1u;
                 while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+                if (gt < 32)   // the centre's polynomial variables (compact row, zero padded) -> D tile
+                    reinterpret_cast<double2*>(sD + cl * X4_LD)[gt] =
+                        reinterpret_cast<const double2*>(myring + (size_t)slot * slot_d + 3 * m.fl)[gt];
                 if (act) {
                     const double2* src = reinterpret_cast<const double2*>(myring + (size_t)slot * slot_d) + gt;
                     const double sg = (sc0 + c0 + cl == 0) ? 1.0 : -1.0;
@@ -1847,15 +1844,15 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         }
         auto kern = u4 == 2 ? k_xrows_v4<2> : k_xrows_v4<4>;
         static const bool use_v5 = getenv("PM_XROWS_V4") == nullptr;
-        const size_t smem5 = ((size_t)4 * X4_KC * X4_LD + 2 * X5_R * 3 * (size_t)m.fl + X5_MAXC + 2 * X5_R) * sizeof(double) +
+        const size_t smem5 = ((size_t)4 * X4_KC * X4_LD + 2 * X5_R * (3 * (size_t)m.fl + 64) + X5_MAXC + 2 * X5_R) * sizeof(double) +
                              X5_MAXC * sizeof(int) + 128;
-        if (use_v5 && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
+        if (use_v5 && ws.dpv && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
             static size_t set5_for = 0;   // the ring size depends on the model (fl)
             if (set5_for < smem5) {
                 cudaFuncSetAttribute(k_xrows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
                 set5_for = smem5;
             }
-            k_xrows_v5<<<b.n_atoms, X4_THREADS, smem5, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
+            k_xrows_v5<<<b.n_atoms, X4_THREADS, smem5, s>>>(m, b, ws.dpv, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
         } else {
             kern<<<b.n_atoms, X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
                                                       apply_weights ? 1 : 0);
