@@ -245,6 +245,41 @@ def fit_device(params_dict, train, test, alphas, weight_stress=0.1, batch_size=6
 
 
 # ---- multi-GPU: structures shard across ranks, one NCCL reduce of the packed accumulator ----------
+def compute_error(params_dict, scaled_coeffs, dataset: Dataset, stress_unit="eV", device=None, prop=None):
+    """Prediction errors of a fitted model on one dataset, through the device eval path with contiguous buffers.
+
+    Mirrors PolymlpEvalAccuracy.compute_error_single (PY/mlp_dev/core/eval_accuracy.py:49-140): RMSE / MAE of the
+    energy per atom, of the force components and of the stress (per atom in eV, or in GPa from the cell volumes).
+    scaled_coeffs = coefs / scales, as written to polymlp.yaml.  Returns the reference's error_dict keys."""
+    from .libmlpcpp import PotentialPropertiesFast
+
+    if prop is None:
+        prop = PotentialPropertiesFast(params_dict, scaled_coeffs, device=device)
+    e, f_list, s = prop._run(dataset.axis, dataset.positions_c, dataset.types)
+    n_atoms = np.asarray(dataset.total_n_atoms, dtype=float)
+
+    def _err(true, pred, normalize=None):
+        true, pred = np.asarray(true, dtype=float).reshape(-1), np.asarray(pred, dtype=float).reshape(-1)
+        if normalize is not None:
+            true, pred = true / normalize, pred / normalize
+        d = true - pred
+        return float(np.sqrt(np.mean(np.square(d)))), float(np.mean(np.abs(d)))
+
+    rmse_e, mae_e = _err(dataset.energies, e, n_atoms)
+    out = {"energy": rmse_e, "energy_mae": mae_e, "force": None, "force_mae": None, "stress": None, "stress_mae": None}
+    if dataset.include_force and dataset.forces is not None:
+        pred_f = np.concatenate([np.asarray(f).reshape(-1) for f in f_list]) if f_list else np.zeros(0)
+        out["force"], out["force_mae"] = _err(dataset.forces, pred_f)
+    if dataset.include_stress and dataset.stresses is not None:
+        if stress_unit == "GPa":
+            vol = np.array([abs(np.linalg.det(np.asarray(a, dtype=float))) for a in dataset.axis])
+            norm = np.repeat(vol, 6) / 160.21766208
+        else:
+            norm = np.repeat(n_atoms, 6)
+        out["stress"], out["stress_mae"] = _err(dataset.stresses, s, norm)
+    return out
+
+
 class _DevicePtr:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}

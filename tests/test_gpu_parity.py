@@ -359,6 +359,22 @@ def test_finalize_view_matches_copy():
     assert np.array_equal(a["xtx"], a["xtx"].T)
 
 
+def test_compute_error_matches_design_matrix_predictions():
+    """fit.compute_error (device eval over a dataset) against predictions X @ c of the same model:
+    energy RMSE per atom and force RMSE agree to 1e-9 relative."""
+    pd = make_params_dict(**cases.si_model_kwargs())
+    ds = _si_datasets(np.arange(12))
+    x = PotentialModel(pd, ds.axis, ds.positions_c, ds.types, [12], [True], [64] * 12).get_x()
+    coeffs = np.random.default_rng(3).normal(size=x.shape[1]) * 1e-3
+    err = fit.compute_error(pd, coeffs, ds)
+    pred = x @ coeffs
+    e_ref = np.sqrt(np.mean(np.square((ds.energies - pred[:12]) / 64)))
+    f_ref = np.sqrt(np.mean(np.square(ds.forces - pred[12 + 72:])))
+    assert abs(err["energy"] - e_ref) < 1e-9 * e_ref
+    assert abs(err["force"] - f_ref) < 1e-9 * f_ref
+    assert err["stress"] is None
+
+
 def test_pybind_dropin_module_gpu():
     """Same calls a reference user makes on `pypolymlp.cxx.lib.libmlpcpp`, through the pybind11 drop-in."""
     import importlib.util
