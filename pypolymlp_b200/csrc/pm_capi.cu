@@ -86,7 +86,7 @@ template <typename T> struct DevVec {
 };
 
 struct HostChunk {
-    int n_st = 0, n_atoms = 0, n_rows = 0, max_trans = 0;
+    int n_st = 0, n_atoms = 0, n_rows = 0, max_trans = 0, max_atoms = 0;
     std::vector<int> atom_off, st_of_atom, types, trans_off, force, erow, srow, frow;
     std::vector<double> x, y, z, trans, w, yv;
     std::vector<long> brow_e, brow_s, brow_f;  // rows in the caller's batch layout
@@ -109,6 +109,7 @@ struct pm_context {
     // chunk device buffers
     DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
         d_nbr, d_centre, d_rev, d_err;
+    DevVec<ulonglong2> d_masks;
     DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
         d_f, d_s;
     DevVec<double2> d_anc, d_agg;
@@ -520,6 +521,7 @@ static void prepare_chunk(const pm_context* c, const pm_structures* st, const st
         h.trans_off.push_back((int)(h.trans.size() / 3));
         h.max_trans = std::max(h.max_trans, (int)(ct.trans.size() / 3));
         h.atom_off.push_back(h.atom_off.back() + na);
+        h.max_atoms = std::max(h.max_atoms, na);
         h.force.push_back(st->force ? (st->force[s] != 0) : 0);
     }
     h.n_atoms = h.atom_off.back();
@@ -646,6 +648,17 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     c->d_err.ensure(1);
     CK(cudaMemsetAsync(c->d_counts.p + nseg, 0, sizeof(int), s));
     CK(cudaMemsetAsync(c->d_err.p, 0, sizeof(int), s));
+    // the count pass keeps its per-(i, j) hit masks (<= 128 translations) so that the fill pass does not repeat the
+    // distance sweep; skipped when the table would be large (very ragged or very big cells)
+    b.mask_stride = 0; b.masks = nullptr;
+    {
+        const size_t n_mask = (size_t)h.n_atoms * (size_t)h.max_atoms;
+        if (h.max_trans <= 128 && h.max_atoms > 0 && n_mask <= ((size_t)32 << 20)) {
+            c->d_masks.ensure(n_mask);
+            b.mask_stride = h.max_atoms;
+            b.masks = c->d_masks.p;
+        }
+    }
     launch_neighbor_count(d, b, c->d_counts.p, s);
     launch_scan_exclusive(c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
     int n_pairs = 0;
@@ -971,7 +984,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
-    c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
+    c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_masks.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
     c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1114,7 +1127,7 @@ int pm_fit_stage(pm_context* c, const pm_structures* st, const double* w, const 
             // keep only the metadata on the host
             HostChunk meta;
             meta.n_st = h.n_st; meta.n_atoms = h.n_atoms; meta.n_rows = h.n_rows; meta.force = h.force;
-            meta.max_trans = h.max_trans;
+            meta.max_trans = h.max_trans; meta.max_atoms = h.max_atoms;
             c->staged.push_back(std::move(meta));
         }
     });

@@ -121,6 +121,8 @@ __host__ __device__ inline int pb_y(const DevModel& m, int comp) { return 4 + 2 
 struct DevBatch {
     int n_st, n_atoms, n_pairs, n_rows;
     int max_trans;          // largest number of lattice translations of a structure in the chunk
+    int mask_stride;        // > 0: the count pass stores its hit masks at masks[i * mask_stride + j_local] for the fill pass
+    ulonglong2* masks;
     int need_agg;           // 1: K2b also builds the aggregated derivative rows (fit), 0: a_nlm only (eval)
     const int* atom_off;    // [n_st + 1]
     const int* st_of_atom;  // [n_atoms]

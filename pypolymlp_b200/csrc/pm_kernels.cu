@@ -102,17 +102,28 @@ __global__ void __launch_bounds__(256) k_neighbor_mask(DevModel m, DevBatch b, i
             double dxij = 0.0, dyij = 0.0, dzij = 0.0;
             const bool act = j < N && (nt == 1 || b.types[a0 + j] == u);
             if (act) {
-                dxij = __dsub_rn(b.x[a0 + j], xi);
-                dyij = __dsub_rn(b.y[a0 + j], yi);
-                dzij = __dsub_rn(b.z[a0 + j], zi);
-                for (int t = 0; t < T; ++t) {
-                    const double dx = __dadd_rn(dxij, tr[3 * t]);
-                    const double dy = __dadd_rn(dyij, tr[3 * t + 1]);
-                    const double dz = __dadd_rn(dzij, tr[3 * t + 2]);
-                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    if (r2 < cutoff_sq && r2 > tol_sq) {
-                        if (t < 64) m0 |= 1ull << t; else m1 |= 1ull << (t - 64);
+                if (FILL && b.mask_stride > 0) {   // hit masks were stored by the count pass: no second distance sweep
+                    const ulonglong2 mm = b.masks[(size_t)i * b.mask_stride + j];
+                    m0 = mm.x; m1 = mm.y;
+                    if (m0 | m1) {
+                        dxij = __dsub_rn(b.x[a0 + j], xi);
+                        dyij = __dsub_rn(b.y[a0 + j], yi);
+                        dzij = __dsub_rn(b.z[a0 + j], zi);
                     }
+                } else {
+                    dxij = __dsub_rn(b.x[a0 + j], xi);
+                    dyij = __dsub_rn(b.y[a0 + j], yi);
+                    dzij = __dsub_rn(b.z[a0 + j], zi);
+                    for (int t = 0; t < T; ++t) {
+                        const double dx = __dadd_rn(dxij, tr[3 * t]);
+                        const double dy = __dadd_rn(dyij, tr[3 * t + 1]);
+                        const double dz = __dadd_rn(dzij, tr[3 * t + 2]);
+                        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (r2 < cutoff_sq && r2 > tol_sq) {
+                            if (t < 64) m0 |= 1ull << t; else m1 |= 1ull << (t - 64);
+                        }
+                    }
+                    if (!FILL && b.mask_stride > 0) b.masks[(size_t)i * b.mask_stride + j] = make_ulonglong2(m0, m1);
                 }
             }
             const int mine = __popcll(m0) + __popcll(m1);
