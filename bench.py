@@ -292,21 +292,21 @@ def main():
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         # DRAM traffic of one SYRK launch from the committed ncu --set full capture (profiles/r01_ncu_kernels.json):
-        # dram__bytes_read.sum + dram__bytes_write.sum of a full-chunk launch (42 structures, as in the bench steps)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (K5 runs per block of <= 32768 X rows)
         traffic, traffic_alg = None, None
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]
-            met, n_cap = cap["metrics"], cap.get("structures_in_launch", 42)
+            met, rows_cap = cap["metrics"], cap.get("rows_in_launch", 32768)
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             traffic = sum(float(met[k]["value"]) * scale[met[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             fpad = (F + 1 + 127) // 128 * 128
-            traffic_alg = n_cap * 775 * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde chunk once + upper C tiles RMW
+            traffic_alg = rows_cap * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde rows once + upper C tiles RMW
         except Exception:
             pass
         roofline = {
             "bound": "tensor", "kernel": "k_syrk_sk (fp64 DMMA m8n8k4, stream-K SYRK)", "achieved": syrk_tflops, "peak": peak,
             "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
-            "traffic_note": "DRAM bytes of one full-chunk launch (42 structures; ncu --set full, "
+            "traffic_note": "DRAM bytes of one SYRK launch (a 32k-row block of a chunk; ncu --set full, "
                             "profiles/r01_ncu_kernels.json); algorithmic bytes of that launch in traffic_algorithmic",
             "traffic_algorithmic": traffic_alg,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "

@@ -789,7 +789,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
             launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
             if (t1) CK(cudaEventRecord(t1, s));
         }
-        tm.mark(ST_SYRK, 1);
+        tm.mark(ST_SYRK, syrk_launches(h.n_rows, d.fpad, c->simple_s));
         c->n_data += h.n_rows;
     }
 }

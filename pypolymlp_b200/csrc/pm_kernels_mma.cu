@@ -39,6 +39,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 constexpr int SY_BM = 128, SY_BK = 32, SY_STAGES = 3, SY_LD = SY_BM + 4;  // 132 == 4 (mod 16)
 constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LD;
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * sizeof(double);
+constexpr int SY_ROW_BLOCK = 32768;   // rows per SYRK launch (multiple of SY_BK)
 
 __global__ void __launch_bounds__(256, 1) k_syrk_mma(const double* __restrict__ X, int n_rows, int fpad,
                                                       double* __restrict__ C, int rows_per_split, int use_atomic) {
@@ -262,13 +263,22 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
     }
     const int ntile = fpad / SY_BM;
     const long tiles = (long)ntile * (ntile + 1) / 2;
-    const int nkb = (n_rows + SY_BK - 1) / SY_BK;
-    const long units = tiles * nkb;
-    const int grid = (int)std::min<long>(n_sm, units);
-    k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X, n_rows, fpad, C, nkb, units);
+    // Row blocks: the CTAs of one launch sweep the k range in step inside a window of (1 - tiles / n_sm) of its rows
+    // (see k_syrk_sk); blocks of <= 32768 rows keep that window (plus the C tiles) inside the 126 MB L2.
+    for (int r0 = 0; r0 < n_rows; r0 += SY_ROW_BLOCK) {
+        const int nr = std::min(SY_ROW_BLOCK, n_rows - r0);
+        const int nkb = (nr + SY_BK - 1) / SY_BK;
+        const long units = tiles * nkb;
+        const int grid = (int)std::min<long>(n_sm, units);
+        k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, units);
+    }
 }
 
-int syrk_launches(int n_rows, int fpad, bool simple) { return n_rows > 0 ? 1 : 0; }
+int syrk_launches(int n_rows, int fpad, bool simple) {
+    if (n_rows <= 0) return 0;
+    return simple ? 1 : (n_rows + SY_ROW_BLOCK - 1) / SY_ROW_BLOCK;
+}
+
 
 // ================================================================================================
 // K4a: L = V . G per centre atom (see pm_tables.hpp for the block-sparse layout of G).
