@@ -61,7 +61,12 @@ typedef struct {
     const int* n_terms;        /* [n_lcomb]                                                     */
     const int* lm_seq;         /* concatenated [n_terms][order] per l-comb, lm = l*l + l + m    */
     const double* lm_coeffs;   /* concatenated [n_terms] per l-comb                             */
+    int feature_type;          /* PM_FEATURE_GTINV (0) or PM_FEATURE_PAIR (1: radial sums only,
+                                  compute/local_pair.cpp:57-122; the gtinv arrays are ignored, n_lcomb may be 0,
+                                  model_type must be 1 or 2, polymlp_model_params_polynomial.cpp:40-56)   */
 } pm_feature_params;
+#define PM_FEATURE_GTINV 0
+#define PM_FEATURE_PAIR 1
 
 /* Builds all index tables on the host (replaces Features::Features, polymlp_features.cpp:27-58). */
 int pm_model_create(const pm_feature_params* fp, pm_model** out);

@@ -376,8 +376,9 @@ class Tables:
 
     def __init__(self, params_dict):
         model = params_dict["model"]
-        if model["feature_type"] != "gtinv":
-            raise ValueError("oracle restates the gtinv path only")
+        self.feature_type = model["feature_type"]
+        if self.feature_type not in ("gtinv", "pair"):
+            raise ValueError("feature_type must be 'gtinv' or 'pair'")
         self.n_type = nt = params_dict["n_type"]
         self.cutoff = float(model["cutoff"])
         self.maxl = int(model["max_l"])
@@ -386,8 +387,16 @@ class Tables:
         self.params = np.array(model["pair_params"], dtype=np.float64).reshape(-1, 2)
         self.n_fn = n_fn = len(self.params)
         cond = model.get("pair_params_conditional")
-        g = model["gtinv"]
-        l_comb, lm_seq, lm_coeffs = g["l_comb"], g["lm_seq"], g["lm_coeffs"]
+        if self.feature_type == "pair":
+            # pair features d_{n,tp} = sum_j f_n(r_ij) (compute/local_pair.cpp); the table code below only needs a
+            # single order-1 entry per (n, tp) -- its lm / coefficient content is not used by the pair numerics
+            if self.model_type > 2:
+                raise ValueError("Polymlp: Model type error.")  # polymlp_model_params_polynomial.cpp:42-45
+            self.maxl = 0
+            l_comb, lm_seq, lm_coeffs = [[0]], [[[0]]], [[1.0]]
+        else:
+            g = model["gtinv"]
+            l_comb, lm_seq, lm_coeffs = g["l_comb"], g["lm_seq"], g["lm_coeffs"]
 
         # type pairs (polymlp_mapping.cpp:36-56)
         self.type_pairs = np.zeros((nt, nt), int)
@@ -446,6 +455,10 @@ class Tables:
                 for n in n_list:
                     lin_by_n[n].append((n, lcid, tpc, order, t1))
         self.linear = [x for sub in lin_by_n for x in sub]
+        if self.feature_type == "pair":
+            # (tp, n) enumerated tp-major (polymlp_mapping.cpp:75-88 set_ntp_global_attrs)
+            self.linear = [x for tp in range(ntp) for n in self.tp_to_n[tp]
+                           for x in lin_by_n[n] if x[2][0] == tp]
         self.n_linear = len(self.linear)
 
         # per-type linear features: term lists over type-local ids into the full +-m array
@@ -577,6 +590,37 @@ def atom_features(tab, t1, a, deriv):
     return d, G
 
 
+def atom_pair_features(tab, types, off, nb, dx, dy, dz, i, deriv):
+    """Pair features d_{n,tp}(i) = sum_j f_n(r_ij) and their derivatives w.r.t. each pair vector,
+    g (3, F_local, M).  Restates LocalPair::pair / pair_d (compute/local_pair.cpp:17-55, 57-122):
+    no spherical harmonics, no 1e-20 skip rule."""
+    t1 = types[i]
+    feats = tab.features[t1]
+    sl = slice(off[i], off[i + 1])
+    js, x, y, z = nb[sl], dx[sl], dy[sl], dz[sl]
+    M = len(js)
+    d = np.zeros(len(feats))
+    g = np.zeros((3, len(feats), M)) if deriv else None
+    if M == 0:
+        return d, g
+    r = np.sqrt(x * x + y * y + z * z)
+    ok = r < tab.cutoff
+    tps = tab.type_pairs[t1, types[js]]
+    fn_all = {tp: radial(r, tab.tp_params[tp], tab.cutoff) for tp in set(tps.tolist())}
+    for f, (fid, _, _) in enumerate(feats):
+        n, _, tpc, _, _ = tab.linear[fid]
+        tp = tpc[0]
+        if tp not in fn_all:
+            continue
+        nid = tab.tpn_to_nid[tp][n]
+        mask = ok & (tps == tp)
+        d[f] = np.where(mask, fn_all[tp][0][:, nid], 0.0).sum()
+        if deriv:
+            fnd = np.where(mask, fn_all[tp][1][:, nid], 0.0)
+            g[0, f], g[1, f], g[2, f] = fnd * x / r, fnd * y / r, fnd * z / r
+    return d, g
+
+
 def structure_x(tab, axis, positions_c, types, force=True):
     """X rows of one structure: xe (F,), xf (3N, F), xs (6, F).
 
@@ -591,15 +635,19 @@ def structure_x(tab, axis, positions_c, types, force=True):
     xs = np.zeros((6, F)) if force else np.zeros((0, F))
     for i in range(n):
         t1 = types[i]
-        a, v = atom_anlm(tab, types, off, nb, dx, dy, dz, i, force)
-        d, G = atom_features(tab, t1, a, force)
+        if tab.feature_type == "pair":
+            d, g = atom_pair_features(tab, types, off, nb, dx, dy, dz, i, force)
+        else:
+            a, v = atom_anlm(tab, types, off, nb, dx, dy, dz, i, force)
+            d, G = atom_features(tab, t1, a, force)
         terms = tab.poly[t1]
         if force:
             sl = slice(off[i], off[i + 1])
             js = nb[sl]
             M = len(js)
             # derivative of each linear feature w.r.t. each pair vector: (3, Floc, M)
-            g = np.real(np.einsum("fh,ahm->afm", G, v)) if M else np.zeros((3, len(d), 0))
+            if tab.feature_type != "pair":
+                g = np.real(np.einsum("fh,ahm->afm", G, v)) if M else np.zeros((3, len(d), 0))
             Df = np.zeros((len(d), 3 * n))  # rows of X^T restricted to this centre
             Ds = np.zeros((len(d), 6))
             dl = np.stack([dx[sl], dy[sl], dz[sl]])

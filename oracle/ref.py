@@ -91,7 +91,7 @@ def _cond_arrays(params_dict):
 
 def _fp_args(params_dict):
     model = params_dict["model"]
-    g = model["gtinv"]
+    g = model["gtinv"] if model["feature_type"] != "pair" else {"order": 0, "max_l": []}
     params = _d(model["pair_params"]).reshape(-1, 2)
     off, val = _cond_arrays(params_dict)
     maxl = _i(list(g["max_l"]) + [0])

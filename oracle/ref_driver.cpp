@@ -65,10 +65,14 @@ feature_params make_fp(int n_type, int n_fn, const double* params,
         }
     fp.cutoff = cutoff;
     fp.pair_type = "gaussian";
-    fp.feature_type = "gtinv";
     fp.model_type = model_type;
     fp.maxp = maxp;
     fp.maxl = maxl;
+    if (gtinv_order <= 0) {   // feature_type "pair": the reference passes empty gtinv tables (params_utils.py:57-60)
+        fp.feature_type = "pair";
+        return fp;
+    }
+    fp.feature_type = "gtinv";
     vector1i ml(gtinv_maxl, gtinv_maxl + (gtinv_order > 1 ? gtinv_order - 1 : 0));
     Readgtinv rg(gtinv_order, ml, gtinv_version);
     fp.lm_array = rg.get_lm_seq();

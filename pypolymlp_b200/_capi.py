@@ -26,7 +26,7 @@ class FeatureParamsC(C.Structure):
         ("n_type", C.c_int), ("n_fn", C.c_int), ("pair_params", _dp), ("cond_offsets", _ip),
         ("cond_values", _ip), ("cutoff", C.c_double), ("model_type", C.c_int), ("max_p", C.c_int),
         ("max_l", C.c_int), ("n_lcomb", C.c_int), ("lcomb_order", _ip), ("l_comb", _ip),
-        ("n_terms", _ip), ("lm_seq", _ip), ("lm_coeffs", _dp),
+        ("n_terms", _ip), ("lm_seq", _ip), ("lm_coeffs", _dp), ("feature_type", C.c_int),
     ]
 
 

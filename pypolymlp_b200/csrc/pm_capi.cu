@@ -839,8 +839,9 @@ int pm_model_create(const pm_feature_params* p, pm_model** out) {
         for (int tp = 0; tp < ntp; ++tp)
             fp.cond.emplace_back(p->cond_values + p->cond_offsets[tp], p->cond_values + p->cond_offsets[tp + 1]);
         fp.cutoff = p->cutoff; fp.model_type = p->model_type; fp.maxp = p->max_p; fp.maxl = p->max_l;
+        fp.feature_type = p->feature_type;
         size_t o1 = 0, o2 = 0, o3 = 0;
-        for (int i = 0; i < p->n_lcomb; ++i) {
+        for (int i = 0; i < (fp.feature_type == PM_FEATURE_PAIR ? 0 : p->n_lcomb); ++i) {
             const int o = p->lcomb_order[i], nt_ = p->n_terms[i];
             fp.l_comb.emplace_back(p->l_comb + o1, p->l_comb + o1 + o);
             o1 += o;

@@ -42,6 +42,20 @@ void HostModel::build(const FeatureParams& fp_in) {
     if (nt < 1 || n_fn < 1) throw std::invalid_argument("invalid n_type / pair_params");
     if (fp.model_type < 1 || fp.model_type > 4) throw std::invalid_argument("Polymlp: Model type error.");
     if (fp.maxp < 1 || fp.maxp > 3) throw std::invalid_argument("Polymlp: maxp must be smaller than or equal to 3.");
+    const bool pair_features = fp.feature_type == 1;
+    if (pair_features) {
+        // feature_type = "pair" (compute/local_pair.cpp:57-122): d_{n,tp}(i) = sum_j f_n(r_ij).  Expressed through the
+        // same machinery as an l = 0, order-1 invariant: a_{n,00,tp} = Y_00 sum_j f_n, coefficient 1 / Y_00, with Y_00
+        // the constant k_pair_basis writes (s2pi * hs2).  Column order and polynomial rules differ (below).
+        if (fp.model_type > 2) throw std::invalid_argument("Polymlp: Model type error.");   // model_params_polynomial.cpp:42-45
+        const double y00 = 0.39894228040143267794 * 0.70710678118654752440;
+        fp.maxl = 0;
+        fp.l_comb = {{0}};
+        fp.lm_seq = {{{0}}};
+        fp.lm_coeffs = {{1.0 / y00}};
+    } else if (fp.feature_type != 0) {
+        throw std::invalid_argument("feature_type must be 0 (gtinv) or 1 (pair)");
+    }
     if (fp.l_comb.empty()) throw std::invalid_argument("gtinv tables are empty");
     n_lm_half = (fp.maxl + 1) * (fp.maxl + 2) / 2;
 
@@ -186,8 +200,17 @@ void HostModel::build(const FeatureParams& fp_in) {
         }
     }
     linear.clear();
-    for (auto& v : lin_by_n)
-        for (auto& x : v) linear.push_back(x);
+    if (pair_features) {
+        // pair models enumerate (tp, n) tp-major, n in the order of the type pair's active list
+        // (polymlp_mapping.cpp:75-88 set_ntp_global_attrs)
+        for (int tp = 0; tp < n_tp; ++tp)
+            for (int n : fp.cond[tp])
+                for (auto& x : lin_by_n[n])
+                    if (x.tp_comb[0] == tp) linear.push_back(x);
+    } else {
+        for (auto& v : lin_by_n)
+            for (auto& x : v) linear.push_back(x);
+    }
     n_linear = (int)linear.size();
 
     // ---- per-type features: term lists ---------------------------------------------------
@@ -196,7 +219,12 @@ void HostModel::build(const FeatureParams& fp_in) {
         T.max_order = order_max;
         T.term_off.push_back(0);
     }
-    for (int fid = 0; fid < n_linear; ++fid) {
+    // local feature order of a type = global order sorted by radial index (stable): gtinv models are n-major
+    // already; pair models (tp-major columns) are regrouped so that a feature tile still has ONE radial index
+    std::vector<int> fid_by_n(n_linear);
+    for (int k = 0; k < n_linear; ++k) fid_by_n[k] = k;
+    std::stable_sort(fid_by_n.begin(), fid_by_n.end(), [&](int a, int b) { return linear[a].n < linear[b].n; });
+    for (int fid : fid_by_n) {
         const LinearTerm& lt = linear[fid];
         const auto& lmlist = fp.lm_seq[lt.lcid];
         const auto& cf = fp.lm_coeffs[lt.lcid];

@@ -29,6 +29,7 @@ struct FeatureParams {
     std::vector<std::vector<int>> cond;         // per type pair (i<=j row-major): active radial ids
     double cutoff = 0.0;
     int model_type = 1, maxp = 1, maxl = 0;
+    int feature_type = 0;                       // 0 = gtinv, 1 = pair (radial sums only; compute/local_pair.cpp)
     std::vector<std::vector<int>> l_comb;               // [n_lcomb][order]
     std::vector<std::vector<std::vector<int>>> lm_seq;  // [n_lcomb][n_terms][order], lm = l*l+l+m
     std::vector<std::vector<double>> lm_coeffs;         // [n_lcomb][n_terms]

@@ -53,8 +53,10 @@ struct Model {
     explicit Model(const py::dict& params_dict) {
         const int n_type = params_dict["n_type"].cast<int>();
         const py::dict model = params_dict["model"].cast<py::dict>();
-        if (model["feature_type"].cast<std::string>() != "gtinv")
-            throw std::invalid_argument("pypolymlp_b200 implements feature_type='gtinv' only");
+        const std::string feature_type = model["feature_type"].cast<std::string>();
+        if (feature_type != "gtinv" && feature_type != "pair")
+            throw std::invalid_argument("feature_type must be 'gtinv' or 'pair'");
+        const bool pair = feature_type == "pair";
         const auto pair_params = model["pair_params"].cast<vector2d>();
         vector1d pp;
         for (const auto& p : pair_params) { pp.push_back(p.at(0)); pp.push_back(p.at(1)); }
@@ -67,10 +69,15 @@ struct Model {
                 off.push_back((int)val.size());
             }
         if (val.empty()) val.push_back(0);
-        const py::dict gtinv = model["gtinv"].cast<py::dict>();
-        const auto lm_seq = gtinv["lm_seq"].cast<vector3i>();
-        const auto l_comb = gtinv["l_comb"].cast<vector2i>();
-        const auto lm_coeffs = gtinv["lm_coeffs"].cast<vector2d>();
+        vector3i lm_seq;
+        vector2i l_comb;
+        vector2d lm_coeffs;
+        if (!pair) {
+            const py::dict gtinv = model["gtinv"].cast<py::dict>();
+            lm_seq = gtinv["lm_seq"].cast<vector3i>();
+            l_comb = gtinv["l_comb"].cast<vector2i>();
+            lm_coeffs = gtinv["lm_coeffs"].cast<vector2d>();
+        }
         vector1i lo, lc, nt, lm;
         vector1d cf;
         for (size_t i = 0; i < l_comb.size(); ++i) {
@@ -87,6 +94,7 @@ struct Model {
         fp.max_p = model["max_p"].cast<int>(); fp.max_l = model["max_l"].cast<int>();
         fp.n_lcomb = (int)l_comb.size(); fp.lcomb_order = lo.data(); fp.l_comb = lc.data();
         fp.n_terms = nt.data(); fp.lm_seq = lm.data(); fp.lm_coeffs = cf.data();
+        fp.feature_type = pair ? PM_FEATURE_PAIR : PM_FEATURE_GTINV;
         check(pm_model_create(&fp, &h));
     }
     ~Model() { pm_model_destroy(h); }

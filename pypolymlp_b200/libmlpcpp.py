@@ -60,8 +60,9 @@ class _Model:
 
     def __init__(self, params_dict):
         model = params_dict["model"]
-        if model["feature_type"] != "gtinv":
-            raise ValueError("pypolymlp_b200 implements feature_type='gtinv' only")
+        if model["feature_type"] not in ("gtinv", "pair"):
+            raise ValueError("feature_type must be 'gtinv' or 'pair'")
+        pair = model["feature_type"] == "pair"
         if model.get("pair_type", "gaussian") != "gaussian":
             raise ValueError("pypolymlp_b200 implements pair_type='gaussian' only")
         n_type = int(params_dict["n_type"])
@@ -73,8 +74,8 @@ class _Model:
                 lst = list(cond[(i, j)]) if cond else list(range(len(pp)))
                 val.extend(lst)
                 off.append(len(val))
-        g = model["gtinv"]
-        l_comb, lm_seq, lm_coeffs = g["l_comb"], g["lm_seq"], g["lm_coeffs"]
+        g = model.get("gtinv", {})
+        l_comb, lm_seq, lm_coeffs = ([], [], []) if pair else (g["l_comb"], g["lm_seq"], g["lm_coeffs"])
         lo = as_i([len(x) for x in l_comb])
         lc = as_i([v for x in l_comb for v in x])
         nt = as_i([len(x) for x in lm_seq])
@@ -84,7 +85,7 @@ class _Model:
         self._keep = (pp, off, val, lo, lc, nt, lm, cf)
         fp = FeatureParamsC(n_type, len(pp), pd(pp), pi(off), pi(val), float(model["cutoff"]),
                             int(model["model_type"]), int(model["max_p"]), int(model["max_l"]), len(l_comb),
-                            pi(lo), pi(lc), pi(nt), pi(lm), pd(cf))
+                            pi(lo), pi(lc), pi(nt), pi(lm), pd(cf), 1 if pair else 0)
         h = C.c_void_p()
         check(lib().pm_model_create(C.byref(fp), C.byref(h)))
         self.handle = h

@@ -30,11 +30,14 @@ def set_gaussian_params(params1=(1.0, 1.0, 1), params2=(0.0, 5.0, 7), n_gaussian
 
 def make_params_dict(n_type, cutoff, model_type, max_p, gtinv_order, gtinv_maxl, pair_params=None,
                      n_gaussians=None, gaussian_params1=(1.0, 1.0, 1), gaussian_params2=(0.0, 5.0, 7),
-                     pair_params_conditional=None, gtinv_version=1, print_memory=False):
-    """Build the params dict of a gtinv polymlp; gtinv tables come from Readgtinv."""
+                     pair_params_conditional=None, gtinv_version=1, print_memory=False, feature_type="gtinv"):
+    """Build the params dict of a polymlp; gtinv tables come from Readgtinv.  feature_type='pair' gives the
+    reference's empty gtinv block (order 0, max_l [] -> model.max_l = 0; params_utils.py:57-60)."""
     if pair_params is None:
         pair_params = set_gaussian_params(gaussian_params1, gaussian_params2, n_gaussians, cutoff)
-    rg = Readgtinv(gtinv_order, list(gtinv_maxl), gtinv_version)
+    if feature_type == "pair":
+        gtinv_order, gtinv_maxl = 0, []
+    rg = Readgtinv(gtinv_order, list(gtinv_maxl), gtinv_version) if feature_type != "pair" else None
     cond = pair_params_conditional is not None
     if not cond:
         pair_params_conditional = {
@@ -46,7 +49,7 @@ def make_params_dict(n_type, cutoff, model_type, max_p, gtinv_order, gtinv_maxl,
         "model": {
             "cutoff": float(cutoff),
             "pair_type": "gaussian",
-            "feature_type": "gtinv",
+            "feature_type": feature_type,
             "model_type": int(model_type),
             "max_p": int(max_p),
             "max_l": int(max(gtinv_maxl)) if len(gtinv_maxl) else 0,
@@ -57,9 +60,9 @@ def make_params_dict(n_type, cutoff, model_type, max_p, gtinv_order, gtinv_maxl,
                 "order": int(gtinv_order),
                 "max_l": list(gtinv_maxl),
                 "version": int(gtinv_version),
-                "lm_seq": rg.get_lm_seq(),
-                "l_comb": rg.get_l_comb(),
-                "lm_coeffs": rg.get_lm_coeffs(),
+                "lm_seq": rg.get_lm_seq() if rg else [],
+                "l_comb": rg.get_l_comb() if rg else [],
+                "lm_coeffs": rg.get_lm_coeffs() if rg else [],
             },
         },
     }

@@ -41,6 +41,26 @@ def ternary_p3_model_kwargs():
                 pair_params=[[1.0, 0.0], [0.0, 0.0]])
 
 
+def pair_model_kwargs(n_type=2, model_type=2, max_p=2):
+    # feature_type = "pair" (radial sums only); binary: conditional radial sets as in binary_model_kwargs
+    cond = {(0, 0): [0, 1, 2, 5], (0, 1): [1, 2, 3, 4, 5], (1, 1): [0, 2, 4, 5]} if n_type == 2 else None
+    return dict(n_type=n_type, cutoff=5.0, model_type=model_type, max_p=max_p, gtinv_order=0, gtinv_maxl=[],
+                pair_params=[[1.0, m] for m in np.linspace(0, 4, 5)] + [[0.0, 0.0]],
+                pair_params_conditional=cond, feature_type="pair")
+
+
+def mgo_model_kwargs(feature_type):
+    # the reference's tests/test_calc/files/mlps/polymlp.yaml.{pair,gtinv}.MgO
+    kw = dict(n_type=2, cutoff=8.0, max_p=2, pair_params=[[1.0, float(m)] for m in range(8)] + [[0.0, 0.0]])
+    if feature_type == "pair":
+        return dict(kw, model_type=2, gtinv_order=0, gtinv_maxl=[], feature_type="pair")
+    return dict(kw, model_type=3, gtinv_order=3, gtinv_maxl=[4, 4])
+
+
+def load_mgo():
+    return np.load(os.path.join(GOLDEN, "mgo.npz"))
+
+
 def skewed_cell(n_type, n_atom=9, seed=1):
     rng = np.random.default_rng(seed)
     axis = np.array([[5.0, 2.6, 0.3], [0.1, 4.5, 2.4], [0.0, 0.2, 5.5]])

@@ -102,6 +102,44 @@ out["cfg3_xe"], out["cfg3_xs"] = xe, xs
 out["cfg3_xf_rows"] = xf[::6]
 out["cfg3_xf_colsum"], out["cfg3_xf_colsqsum"] = xf.sum(axis=0), np.square(xf).sum(axis=0)
 
+# ---- pair features (feature_type = "pair", compute/local_pair.cpp): binary conditional model -----------
+pd = make_params_dict(**cases.pair_model_kwargs(2))
+rm = ref.RefModel(pd)
+ax, pc, ty = cases.skewed_cell(2)
+xe, xf, xs = rm.run(ax, pc, ty, True)
+out["pair_xe"], out["pair_xf"], out["pair_xs"] = xe, xf, xs
+coeffs = np.random.default_rng(13).normal(size=rm.n_features)
+e, f, s = ref.RefEval(pd, coeffs).eval(ax, pc, ty)
+out["pair_coeffs"], out["pair_e"], out["pair_f"], out["pair_s"] = coeffs, np.array([e]), f, s
+
 np.savez_compressed(os.path.join(cases.GOLDEN, "ref_vectors.npz"), **out)
+
+# ---- the reference's MgO fixtures (tests/test_calc/files): structures and published coefficients --------
+# Known answers that go with them are quoted in tests/ (test_calc/test_compute_features.py:45-58,
+# test_calc/test_properties_MgO.py:9-97).
+
+
+def read_poscar(path):
+    with open(path) as fh:
+        ln = fh.read().split("\n")
+    scale = float(ln[1])
+    lattice = np.array([[float(v) for v in ln[k].split()] for k in (2, 3, 4)]) * scale
+    counts = [int(v) for v in ln[6].split()]
+    n = sum(counts)
+    frac = np.array([[float(v) for v in ln[8 + k].split()[:3]] for k in range(n)])
+    axis_ = lattice.T
+    types_ = np.concatenate([np.full(c, k, np.int32) for k, c in enumerate(counts)])
+    return axis_, axis_ @ frac.T, types_
+
+
+fdir = "/root/reference/tests/test_calc/files/"
+mgo = {}
+for key, name in (("rs", "POSCAR.RS.MgO"), ("st1", "POSCAR-00001.MgO"), ("st2", "POSCAR-00002.MgO")):
+    mgo[key + "_axis"], mgo[key + "_pos"], mgo[key + "_types"] = read_poscar(fdir + "poscars/" + name)
+for key in ("pair", "gtinv"):
+    with open(fdir + "mlps/polymlp.yaml." + key + ".MgO") as fh:
+        mgo[key + "_coeffs"] = np.array(yaml.safe_load(fh)["coeffs"], dtype=np.float64)
+np.savez_compressed(os.path.join(cases.GOLDEN, "mgo.npz"), **mgo)
+
 for k, v in out.items():
     print(k, v.shape)

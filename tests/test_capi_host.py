@@ -96,9 +96,59 @@ def test_invalid_model_arguments():
     with pytest.raises(ValueError):
         _Model(pd)
     pd = make_params_dict(**cases.si_model_kwargs())
-    pd["model"]["feature_type"] = "pair"
+    pd["model"]["feature_type"] = "triple"
     with pytest.raises(ValueError):
         _Model(pd)
+    # pair models stop at model_type 2 (polymlp_model_params_polynomial.cpp:42-45)
+    with pytest.raises(ValueError):
+        _Model(make_params_dict(**cases.pair_model_kwargs(2, model_type=3)))
+
+
+@pytest.mark.parametrize("kw", [cases.pair_model_kwargs(1), cases.pair_model_kwargs(2),
+                                cases.pair_model_kwargs(3, max_p=3), cases.mgo_model_kwargs("pair")])
+def test_pair_model_tables_match_oracle(kw):
+    """feature_type = 'pair': column count and, per centre type, the polynomial terms as sets of global linear ids
+    (the local feature order differs on purpose: ours is regrouped by radial index)."""
+    pd = make_params_dict(**kw)
+    tab, m = po.Tables(pd), _Model(pd)
+    assert m.n_features == tab.n_variables and m.info()["n_linear"] == tab.n_linear
+    for t in range(kw["n_type"]):
+        col, order, ids = m.polynomial(t)
+        l2g = {int(ids[k][0]): int(col[k]) for k in range(len(col)) if order[k] == 1}
+        mine = {int(col[k]): sorted(l2g[int(x)] for x in ids[k][: order[k]]) for k in range(len(col))}
+        o_l2g = {lids[0]: c for c, lids in tab.poly[t] if len(lids) == 1}
+        assert mine == {c: sorted(o_l2g[x] for x in lids) for c, lids in tab.poly[t]}
+
+
+def test_polymlp_yaml_round_trip(tmp_path):
+    """save_mlp_yaml -> load_mlp_yaml (format of src/pypolymlp/core/io_polymlp_yaml.py:17-161)."""
+    from pypolymlp_b200.io_yaml import load_mlp_yaml, save_mlp_yaml
+
+    for kw, elements in ((cases.binary_model_kwargs(), ["Mg", "O"]), (cases.pair_model_kwargs(2), ["Sr", "Ti"])):
+        pd = make_params_dict(**kw)
+        n = _Model(pd).n_features
+        rng = np.random.default_rng(3)
+        coeffs, scales = rng.normal(size=n), rng.uniform(0.5, 2.0, n)
+        path = str(tmp_path / "polymlp.yaml")
+        save_mlp_yaml(pd, coeffs, scales, elements, path)
+        pd2, c2, meta = load_mlp_yaml(path)
+        assert meta["elements"] == elements and meta["type_full"]
+        np.testing.assert_allclose(c2, coeffs / scales, rtol=1e-15)
+        assert pd2["model"] == pd["model"] and pd2["n_type"] == pd["n_type"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests/test_calc/files/mlps"), reason="reference tree not mounted")
+def test_polymlp_yaml_reads_reference_files():
+    from pypolymlp_b200.io_yaml import load_mlp_yaml
+
+    M = cases.load_mgo()
+    for kind in ("pair", "gtinv"):
+        pd, coeffs, meta = load_mlp_yaml("/root/reference/tests/test_calc/files/mlps/polymlp.yaml.%s.MgO" % kind)
+        assert meta["elements"] == ["Mg", "O"]
+        assert np.array_equal(coeffs, M[kind + "_coeffs"])
+        want = make_params_dict(**cases.mgo_model_kwargs(kind))["model"]
+        want["pair_conditional"] = True  # the loader always passes explicit per-pair lists (io_polymlp_yaml.py:139)
+        assert pd["model"] == want
 
 
 def test_flop_count_config2():

@@ -439,3 +439,79 @@ def test_device_ridge_solve_matches_host():
         # summation order of the accumulator (RED.F64 partial tiles) shows up at the 1e-5 eV/A level there
         assert np.sqrt(np.mean(np.square(ph[:20] - pdv[:20]))) / 64 < 1e-6
         assert np.sqrt(np.mean(np.square(ph[140:] - pdv[140:]))) < (1e-4 if alphas[k] < 1e-2 else 1e-5)
+
+
+# ---- feature_type = "pair" (compute/local_pair.cpp) and the reference's published MgO answers ---------------
+@pytest.mark.parametrize("flags", FLAVOURS)
+def test_pair_features_x_xtx_eval(flags):
+    pd = make_params_dict(**cases.pair_model_kwargs(2))
+    ax, pc, ty = cases.skewed_cell(2)
+    pm = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [9], flags=flags)
+    full = np.vstack([G["pair_xe"][None], G["pair_xs"], G["pair_xf"]])
+    assert pm.get_x().shape == full.shape
+    assert cases.x_rel_err(pm.get_x(), full) < 1e-10
+    # energy-only structure next to a force structure, then the fused accumulation against numpy on the oracle's X
+    tab = po.Tables(pd)
+    sts = [cases.skewed_cell(2, n_atom=6, seed=s) for s in (4, 5, 6)]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    force = [True, False, True]
+    X = po.build_x(tab, axis, pcs, tys, force)
+    rng = np.random.default_rng(2)
+    w, t = rng.uniform(0.1, 1.0, X.shape[0]), rng.normal(size=X.shape[0])
+    xtx, xty, ysq, xe_sum, xe_sq = po.accumulate(X, 3, w, t)
+    acc = PotentialXtX(pd, flags=flags)
+    acc.add(axis, pcs, tys, force, w, w * t)
+    res = acc.finalize()
+    assert np.abs(res["xtx"] - xtx).max() < 1e-10 * np.abs(xtx).max()
+    assert np.abs(res["xty"] - xty).max() < 1e-10 * np.abs(xty).max()
+    assert np.abs(res["xe_sum"] - xe_sum).max() < 1e-10 * np.abs(xe_sum).max()
+    prop = PotentialPropertiesFast(pd, G["pair_coeffs"], flags=flags)
+    prop.eval(ax, pc, ty)
+    assert abs(prop.get_e() - G["pair_e"][0]) < 1e-10 * abs(G["pair_e"][0])
+    assert np.abs(prop.get_f() - G["pair_f"]).max() < 1e-10 * np.abs(G["pair_f"]).max()
+    assert np.abs(prop.get_s() - G["pair_s"]).max() < 1e-10 * np.abs(G["pair_s"]).max()
+
+
+@pytest.mark.parametrize("kw", [cases.pair_model_kwargs(1), cases.pair_model_kwargs(3, max_p=3),
+                                cases.pair_model_kwargs(2, model_type=1, max_p=1)])
+def test_pair_features_other_shapes_vs_oracle(kw):
+    pd = make_params_dict(**kw)
+    tab = po.Tables(pd)
+    ax, pc, ty = cases.skewed_cell(kw["n_type"], n_atom=7, seed=3)
+    X = po.build_x(tab, [ax], [pc], [ty], [True])
+    pm = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [7])
+    assert cases.x_rel_err(pm.get_x(), X) < 1e-10
+
+
+@pytest.mark.parametrize("kind", ["pair", "gtinv"])
+def test_mgo_published_answers_gpu(kind):
+    """The reference's own known answers for its bundled MgO potentials: feature sums
+    (tests/test_calc/test_compute_features.py:45-58) and E / F / stress of the displaced rocksalt cell
+    (tests/test_calc/test_properties_MgO.py:9-97: E rel 1e-8, F atol 1e-6 eV/A, stress atol 1e-5 GPa)."""
+    from test_oracle_golden import MGO_FEATURES, check_mgo_eval
+
+    M = cases.load_mgo()
+    pd = make_params_dict(**cases.mgo_model_kwargs(kind))
+    pm = PotentialModel(pd, [M["st1_axis"], M["st2_axis"]], [M["st1_pos"], M["st2_pos"]],
+                        [M["st1_types"], M["st2_types"]], [2], [False], [64, 64])
+    x = pm.get_x()
+    ncol, total, diff = MGO_FEATURES[kind]
+    assert x.shape == (2, ncol)
+    assert np.sum(x) == pytest.approx(total, rel=1e-6)
+    assert np.sum(x[0] - x[1]) == pytest.approx(diff, rel=1e-6)
+    pmf = PotentialModel(pd, [M["st1_axis"], M["st2_axis"]], [M["st1_pos"], M["st2_pos"]],
+                         [M["st1_types"], M["st2_types"]], [2], [True], [64, 64])
+    assert pmf.get_x().shape == (398, ncol)  # test_compute_features.py:68-72
+    assert cases.x_rel_err(pmf.get_x()[:2], x) < 1e-12
+    prop = PotentialPropertiesFast(pd, M[kind + "_coeffs"])
+    vol = np.linalg.det(M["rs_axis"])
+    prop.eval(M["rs_axis"], M["rs_pos"], M["rs_types"])
+    check_mgo_eval(kind, prop.get_e(), prop.get_f(), prop.get_s(), vol)
+    prop.eval_multiple([M["rs_axis"]] * 2, [M["rs_pos"]] * 2, [M["rs_types"]] * 2)  # test_properties_MgO.py:89-97
+    for k in range(2):
+        check_mgo_eval(kind, prop.get_e_array()[k], prop.get_f_array()[k], prop.get_s_array()[k], vol)
+    # and against the oracle at full precision
+    e, f, s = po.eval_structure(po.Tables(pd), M[kind + "_coeffs"], M["rs_axis"], M["rs_pos"], M["rs_types"])
+    assert abs(prop.get_e() - e) < 1e-10 * abs(e)
+    assert np.abs(prop.get_f() - f).max() < 1e-10 * np.abs(f).max()
+    assert np.abs(prop.get_s() - s).max() < 1e-10 * np.abs(s).max()

@@ -130,3 +130,67 @@ def test_si_train_column_sums_published_goldens():
     assert np.abs(a - G["si3_atom5_anlm"]).max() < 1e-12 * np.abs(G["si3_atom5_anlm"]).max()
     d, _ = po.atom_features(tab, 0, a, False)
     assert np.abs(d - G["si3_atom5_d"]).max() < 1e-12 * np.abs(G["si3_atom5_d"]).max()
+
+
+# ---- feature_type = "pair" and the reference's MgO fixtures -------------------------------------------
+EV_TO_GPA = 160.21766208  # src/pypolymlp/core/units.py:22
+
+
+def test_pair_features_vs_reference_vectors():
+    pd = make_params_dict(**cases.pair_model_kwargs(2))
+    tab = po.Tables(pd)
+    assert tab.n_variables == 88
+    ax, pc, ty = cases.skewed_cell(2)
+    xe, xf, xs = po.structure_x(tab, ax, pc, ty, True)
+    assert cases.x_rel_err(np.vstack([xe[None], xs, xf]), np.vstack([G["pair_xe"][None], G["pair_xs"], G["pair_xf"]])) < 1e-10
+    e, f, s = po.eval_structure(tab, G["pair_coeffs"], ax, pc, ty)
+    assert abs(e - G["pair_e"][0]) < 1e-10 * abs(G["pair_e"][0])
+    assert np.abs(f - G["pair_f"]).max() < 1e-10 * np.abs(G["pair_f"]).max()
+    assert np.abs(s - G["pair_s"]).max() < 1e-10 * np.abs(G["pair_s"]).max()
+    with pytest.raises(ValueError):  # pair models stop at model_type 2 (polymlp_model_params_polynomial.cpp:42-45)
+        po.Tables(make_params_dict(**cases.pair_model_kwargs(2, model_type=3)))
+
+
+# published in the reference: tests/test_calc/test_properties_MgO.py:9-97 (POSCAR.RS.MgO, polymlp.yaml.{pair,gtinv}.MgO)
+MGO_EVAL = {
+    "pair": (-40.22469744315832,
+             [[-0.03962958, -0.01188776, -0.07928375], [-0.00459307, 0.00331611, 0.02210267],
+              [0.01105381, -0.00137797, 0.022104], [0.01105096, 0.00331545, -0.00918516],
+              [0.00978188, 0.00177061, 0.01180386], [0.00590284, 0.00293358, 0.01180553],
+              [0.00589926, 0.00176979, 0.01958533], [0.0005339, 0.00016018, 0.00106752]],
+             [-0.17379186, -0.17521681, -0.16909401, 0.00004465, 0.00008926, 0.00029751]),
+    "gtinv": (-40.223320043232334,
+              [[-0.03882777, -0.0116472, -0.07768031], [-0.00302382, 0.00324809, 0.02165033],
+               [0.01082712, -0.00090718, 0.02165147], [0.01082468, 0.00324753, -0.00604679],
+               [0.00925154, 0.00182258, 0.01215086], [0.00607581, 0.00277448, 0.01215188],
+               [0.00607362, 0.00182207, 0.0185246], [-0.00120118, -0.00036037, -0.00240204]],
+              [-2.78575100e-02, -2.91029804e-02, -2.37508486e-02, 1.32744242e-05, 2.65114887e-05, 8.83338671e-05]),
+}
+# tests/test_calc/test_compute_features.py:45-58 (POSCAR-0000{1,2}.MgO, energy rows only)
+MGO_FEATURES = {"pair": (324, 997193.0146734761, -6.428600229143143), "gtinv": (1899, 237100.3979091199, -1.9717588279337908)}
+
+
+def check_mgo_eval(kind, e, f, s, volume):
+    e_true, f_true, s_true = MGO_EVAL[kind]
+    assert e == pytest.approx(e_true, rel=1e-8)
+    np.testing.assert_allclose(np.asarray(f), f_true, atol=1e-6)
+    np.testing.assert_allclose(np.asarray(s) * EV_TO_GPA / volume, s_true, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["pair", "gtinv"])
+def test_mgo_published_properties(kind):
+    M = cases.load_mgo()
+    tab = po.Tables(make_params_dict(**cases.mgo_model_kwargs(kind)))
+    e, f, s = po.eval_structure(tab, M[kind + "_coeffs"], M["rs_axis"], M["rs_pos"], M["rs_types"])
+    check_mgo_eval(kind, e, f, s, np.linalg.det(M["rs_axis"]))
+
+
+def test_mgo_published_pair_feature_sums():
+    M = cases.load_mgo()
+    tab = po.Tables(make_params_dict(**cases.mgo_model_kwargs("pair")))
+    x = po.build_x(tab, [M["st1_axis"], M["st2_axis"]], [M["st1_pos"], M["st2_pos"]], [M["st1_types"], M["st2_types"]],
+                   [False, False])
+    ncol, total, diff = MGO_FEATURES["pair"]
+    assert x.shape == (2, ncol)
+    assert np.sum(x) == pytest.approx(total, rel=1e-6)
+    assert np.sum(x[0] - x[1]) == pytest.approx(diff, rel=1e-6)

@@ -16,6 +16,10 @@ pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not bui
     (dict(n_type=1, cutoff=5.0, model_type=4, max_p=2, gtinv_order=3, gtinv_maxl=[2, 2], n_gaussians=4), 1),
     (cases.binary_model_kwargs(), 2),
     (dict(n_type=3, cutoff=4.5, model_type=3, max_p=2, gtinv_order=4, gtinv_maxl=[2, 2, 1], n_gaussians=3), 3),
+    (cases.pair_model_kwargs(1), 1),
+    (cases.pair_model_kwargs(2), 2),
+    (cases.pair_model_kwargs(3, model_type=2, max_p=3), 3),
+    (cases.pair_model_kwargs(2, model_type=1, max_p=1), 2),
 ])
 def test_x_and_eval(kwargs, n_type):
     pd = make_params_dict(**kwargs)
