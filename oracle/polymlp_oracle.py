@@ -686,6 +686,42 @@ def build_x(tab, axis_list, positions_c_list, types_list, force_st):
     return X
 
 
+def build_x_hybrid(tabs, type_full, type_indices, axis_list, positions_c_list, types_list, force_st):
+    """Hybrid design matrix: sub-model blocks side by side, each evaluated on its own subset of atoms.
+
+    Restates PyHybridModel (compute/py_hybrid_model.cpp:58-114) and find_active_atoms (:116-156): a sub-model
+    with type_full = False sees only atoms whose type is in its type_indices, renumbered to the position in
+    that list; its force rows go back to rows 3 * (original atom) + alpha of the full structure."""
+    n_st = len(axis_list)
+    n_atoms = [np.asarray(p).shape[1] for p in positions_c_list]
+    rows_s = 6 * sum(bool(f) for f in force_st)
+    rows_f = sum(3 * n for n, f in zip(n_atoms, force_st) if f)
+    X = np.zeros((n_st + rows_s + rows_f, sum(t.n_variables for t in tabs)))
+    c0 = 0
+    for tab, full, tind in zip(tabs, type_full, type_indices):
+        isb, ifb = n_st, n_st + rows_s
+        for s in range(n_st):
+            ty = np.asarray(types_list[s], int)
+            pc = np.asarray(positions_c_list[s], float)
+            if full:
+                act, ty_a = np.arange(len(ty)), ty
+            else:
+                act = np.array([a for a in range(len(ty)) if ty[a] in tind], int)
+                ty_a = ty[act].copy()
+                for rep, t in enumerate(tind):  # std::replace, in list order
+                    ty_a[ty_a == t] = rep
+            xe, xf, xs = structure_x(tab, axis_list[s], pc[:, act], ty_a, bool(force_st[s]))
+            X[s, c0:c0 + tab.n_variables] = xe
+            if force_st[s]:
+                X[isb:isb + 6, c0:c0 + tab.n_variables] = xs
+                isb += 6
+                for k, a in enumerate(act):
+                    X[ifb + 3 * a:ifb + 3 * a + 3, c0:c0 + tab.n_variables] = xf[3 * k:3 * k + 3]
+                ifb += 3 * n_atoms[s]
+        c0 += tab.n_variables
+    return X
+
+
 def eval_structure(tab, coeffs, axis, positions_c, types):
     """E (eV/cell), F (N,3), stress (6: xx,yy,zz,xy,yz,zx; eV/cell) of a trained model.
 

@@ -10,6 +10,8 @@
 //       .get_e() .get_f() .get_s() .get_e_array() .get_f_array() .get_s_array() (pybind11_mlp.cpp:51-67)
 //   Readgtinv(order, maxl, version) .get_lm_seq() .get_l_comb() .get_lm_coeffs() (pybind11_mlp.cpp:84-94)
 //   FeaturesAttr(params_dict) .get_n_features()                                  (subset of :70-82)
+//   PotentialHybridModel(params_dict_array, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all)
+//       .get_x() .get_fbegin() .get_sbegin() .get_cumulative_n_features() .get_n_data()  (pybind11_mlp.cpp:30-49)
 // Additive: PotentialXtX(params_dict) .add(...) .finalize() -- the fused feature + X^T X accumulation.
 // Errors: C-ABI status PM_ERR_INVALID -> ValueError, anything else -> RuntimeError (as pybind11 maps
 // std::invalid_argument / std::runtime_error in the reference).  No CPU fallback.
@@ -17,7 +19,9 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstdlib>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -101,32 +105,90 @@ struct Model {
     Model(const Model&) = delete;
 };
 
+using darray = py::array_t<double, py::array::c_style | py::array::forcecast>;
+using iarray = py::array_t<int, py::array::c_style | py::array::forcecast>;
+
+// Structures of a call, flattened for the C ABI.  The reference's casters turn every structure into nested
+// std::vectors element by element (pybind11_mlp.cpp:12-19 with pybind11/stl.h); its Python producers hand over lists
+// of NumPy arrays (mlp_dev/core/features.py:13-44, calculator/properties_single.py:118-121), so each item is taken
+// through the buffer protocol instead (nested lists still work: forcecast converts them) -- SURVEY 8(f)-3.
 struct Batch {
     vector1d axis, pos;
     vector1i types, n_atoms, force;
     pm_structures st{};
-    Batch(const vector3d& axis_a, const vector3d& pos_a, const vector2i& types_a, const std::vector<bool>& force_st) {
-        const size_t n = axis_a.size();
-        if (pos_a.size() != n || types_a.size() != n || force_st.size() != n)
+    Batch(const py::sequence& axis_a, const py::sequence& pos_a, const py::sequence& types_a,
+          const std::vector<bool>& force_st) {
+        const size_t n = py::len(axis_a);
+        if (py::len(pos_a) != n || py::len(types_a) != n || force_st.size() != n)
             throw std::invalid_argument("inconsistent number of structures");
+        axis.reserve(9 * n);
+        n_atoms.reserve(n);
         for (size_t s = 0; s < n; ++s) {
-            if (axis_a[s].size() != 3 || pos_a[s].size() != 3) throw std::invalid_argument("axis/positions_c must be 3 x .");
-            for (int i = 0; i < 3; ++i) {
-                if (axis_a[s][i].size() != 3) throw std::invalid_argument("axis must be 3 x 3");
-                axis.insert(axis.end(), axis_a[s][i].begin(), axis_a[s][i].end());
-            }
-            const size_t na = types_a[s].size();
-            for (int i = 0; i < 3; ++i) {
-                if (pos_a[s][i].size() != na) throw std::invalid_argument("positions_c must be (3, N) with N == len(types)");
-                pos.insert(pos.end(), pos_a[s][i].begin(), pos_a[s][i].end());
-            }
-            types.insert(types.end(), types_a[s].begin(), types_a[s].end());
-            n_atoms.push_back((int)na);
+            const darray ax = darray::ensure(axis_a[s]);
+            const darray pc = darray::ensure(pos_a[s]);
+            const iarray ty = iarray::ensure(types_a[s]);
+            if (!ax || !pc || !ty) throw std::invalid_argument("axis / positions_c / types must be numeric arrays");
+            if (ax.ndim() != 2 || ax.shape(0) != 3 || ax.shape(1) != 3) throw std::invalid_argument("axis must be 3 x 3");
+            if (pc.ndim() != 2 || pc.shape(0) != 3) throw std::invalid_argument("axis/positions_c must be 3 x .");
+            if (ty.ndim() != 1 || ty.shape(0) != pc.shape(1))
+                throw std::invalid_argument("positions_c must be (3, N) with N == len(types)");
+            axis.insert(axis.end(), ax.data(), ax.data() + 9);
+            pos.insert(pos.end(), pc.data(), pc.data() + pc.size());
+            types.insert(types.end(), ty.data(), ty.data() + ty.size());
+            n_atoms.push_back((int)ty.size());
             force.push_back(force_st[s] ? 1 : 0);
         }
-        st.n_st = (int)n; st.axis = axis.data(); st.positions_c = pos.data(); st.types = types.data();
+        finish();
+    }
+    // already flattened (hybrid sub-models)
+    Batch(const vector1d& axis_flat, const vector3d& pos_a, const vector2i& types_a, const std::vector<bool>& force_st)
+        : axis(axis_flat) {
+        for (size_t s = 0; s < types_a.size(); ++s) {
+            for (int i = 0; i < 3; ++i) pos.insert(pos.end(), pos_a[s][i].begin(), pos_a[s][i].end());
+            types.insert(types.end(), types_a[s].begin(), types_a[s].end());
+            n_atoms.push_back((int)types_a[s].size());
+            force.push_back(force_st[s] ? 1 : 0);
+        }
+        finish();
+    }
+    void finish() {
+        st.n_st = (int)n_atoms.size(); st.axis = axis.data(); st.positions_c = pos.data(); st.types = types.data();
         st.n_atoms = n_atoms.data(); st.force = force.data();
     }
+    Batch(const Batch&) = delete;
+};
+
+// row bookkeeping of PyModel::set_index / PyHybridModel::set_index (compute/py_model.cpp:58-106,
+// compute/py_hybrid_model.cpp:158-203): energies | stress (6 per force structure) | forces (3N per force structure)
+struct RowIndex {
+    std::vector<bool> force_st;
+    vector1i fbegin, sbegin, n_data, xs_begin, xf_begin;
+    RowIndex(const vector1i& n_st_dataset, const std::vector<bool>& force_dataset, const vector1i& n_atoms_all) {
+        if (force_dataset.size() != n_st_dataset.size()) throw std::invalid_argument("force_dataset / n_st_dataset mismatch");
+        for (size_t i = 0; i < n_st_dataset.size(); ++i)
+            for (int k = 0; k < n_st_dataset[i]; ++k) force_st.push_back(force_dataset[i]);
+        const int n_st = (int)force_st.size();
+        if ((int)n_atoms_all.size() < n_st) throw std::invalid_argument("n_atoms_all is shorter than the number of structures");
+        fbegin.assign(n_st_dataset.size(), -1);
+        sbegin.assign(n_st_dataset.size(), -1);
+        xs_begin.assign(n_st, -1);
+        xf_begin.assign(n_st, -1);
+        n_data = {n_st, 0, 0};
+        int ist = n_st, k = 0;
+        for (size_t i = 0; i < n_st_dataset.size(); ++i) {
+            if (force_dataset[i]) { sbegin[i] = ist; n_data[2] += 6 * n_st_dataset[i]; }
+            for (int j = 0; j < n_st_dataset[i]; ++j, ++k)
+                if (force_dataset[i]) { xs_begin[k] = ist; ist += 6; }
+        }
+        int ifo = ist;
+        k = 0;
+        for (size_t i = 0; i < n_st_dataset.size(); ++i) {
+            if (force_dataset[i]) fbegin[i] = ifo;
+            for (int j = 0; j < n_st_dataset[i]; ++j, ++k)
+                if (force_dataset[i]) { xf_begin[k] = ifo; ifo += 3 * n_atoms_all[k]; n_data[1] += 3 * n_atoms_all[k]; }
+        }
+    }
+    int n_rows() const { return n_data[0] + n_data[1] + n_data[2]; }
 };
 
 class PyModel {
@@ -136,26 +198,12 @@ class PyModel {
     vector1i fbegin, sbegin, n_data;
 
   public:
-    PyModel(const py::dict& params_dict, const vector3d& axis, const vector3d& positions_c, const vector2i& types,
+    PyModel(const py::dict& params_dict, const py::sequence& axis, const py::sequence& positions_c, const py::sequence& types,
             const vector1i& n_st_dataset, const std::vector<bool>& force_dataset, const vector1i& n_atoms_all)
         : model(params_dict) {
-        std::vector<bool> force_st;
-        for (size_t i = 0; i < n_st_dataset.size(); ++i)
-            for (int k = 0; k < n_st_dataset[i]; ++k) force_st.push_back(force_dataset[i]);
-        // row bookkeeping of PyModel::set_index (compute/py_model.cpp:58-106)
-        const int n_st = (int)force_st.size();
-        fbegin.assign(n_st_dataset.size(), -1);
-        sbegin.assign(n_st_dataset.size(), -1);
-        n_data = {n_st, 0, 0};
-        int ist = n_st;
-        for (size_t i = 0; i < n_st_dataset.size(); ++i)
-            if (force_dataset[i]) { sbegin[i] = ist; ist += 6 * n_st_dataset[i]; n_data[2] += 6 * n_st_dataset[i]; }
-        int ifo = ist, k = 0;
-        for (size_t i = 0; i < n_st_dataset.size(); ++i) {
-            if (force_dataset[i]) fbegin[i] = ifo;
-            for (int j = 0; j < n_st_dataset[i]; ++j, ++k)
-                if (force_dataset[i]) { ifo += 3 * n_atoms_all.at(k); n_data[1] += 3 * n_atoms_all.at(k); }
-        }
+        const RowIndex idx(n_st_dataset, force_dataset, n_atoms_all);
+        const std::vector<bool>& force_st = idx.force_st;
+        fbegin = idx.fbegin; sbegin = idx.sbegin; n_data = idx.n_data;
         Batch b(axis, positions_c, types, force_st);
         check(pm_context_create(model.h, default_device(), 0, 0, &ctx));
         const py::ssize_t rows = (py::ssize_t)pm_batch_rows(&b.st), F = pm_model_n_features(model.h);
@@ -166,6 +214,94 @@ class PyModel {
     py::array_t<double> get_x() { return x; }
     const vector1i& get_fbegin() const { return fbegin; }
     const vector1i& get_sbegin() const { return sbegin; }
+    const vector1i& get_n_data() const { return n_data; }
+};
+
+// PotentialHybridModel (pybind11_mlp.cpp:30-49, compute/py_hybrid_model.cpp:11-156): sub-model blocks side by side,
+// each computed by the CUDA path on the atoms of its own element subset and scattered back to the full rows.
+class PyHybridModel {
+    py::array_t<double> x;
+    vector1i fbegin, sbegin, n_data, cumulative;
+
+  public:
+    PyHybridModel(const std::vector<py::dict>& params_dict_array, const py::sequence& axis_a, const py::sequence& pos_a,
+                  const py::sequence& types_a, const vector1i& n_st_dataset, const std::vector<bool>& force_dataset,
+                  const vector1i& n_atoms_all) {
+        const RowIndex idx(n_st_dataset, force_dataset, n_atoms_all);
+        fbegin = idx.fbegin; sbegin = idx.sbegin; n_data = idx.n_data;
+        const Batch all(axis_a, pos_a, types_a, idx.force_st);   // validates shapes, flattens through the buffer protocol
+        const size_t n_st = (size_t)all.st.n_st;
+        vector2i types(n_st);
+        vector3d positions_c(n_st, vector2d(3));
+        for (size_t s = 0, ao = 0; s < n_st; ao += all.n_atoms[s], ++s) {
+            const int na = all.n_atoms[s];
+            types[s].assign(all.types.begin() + ao, all.types.begin() + ao + na);
+            for (int c = 0; c < 3; ++c)
+                positions_c[s][c].assign(all.pos.begin() + 3 * ao + (size_t)c * na, all.pos.begin() + 3 * ao + (size_t)(c + 1) * na);
+        }
+        if (idx.force_st.size() != n_st) throw std::invalid_argument("n_st_dataset does not match the number of structures");
+        std::vector<std::unique_ptr<Model>> models;
+        int n_features = 0;
+        for (const auto& p : params_dict_array) {
+            models.emplace_back(new Model(p));
+            n_features += pm_model_n_features(models.back()->h);
+            cumulative.push_back(n_features);
+        }
+        x = py::array_t<double>({(py::ssize_t)idx.n_rows(), (py::ssize_t)n_features});
+        double* xa = x.mutable_data();
+        std::fill(xa, xa + (size_t)idx.n_rows() * n_features, 0.0);
+        int n_force_st = 0;
+        for (bool f : idx.force_st) n_force_st += f ? 1 : 0;
+        for (size_t n = 0; n < models.size(); ++n) {
+            const py::dict& p = params_dict_array[n];
+            const bool type_full = p["type_full"].cast<bool>();
+            const vector1i type_indices = p["type_indices"].cast<vector1i>();
+            const int first = n == 0 ? 0 : cumulative[n - 1], F = cumulative[n] - first;
+            // active atoms of every structure (find_active_atoms, py_hybrid_model.cpp:116-156)
+            vector2i active(n_st), types_a(n_st);
+            vector3d pos_a(n_st, vector2d(3));
+            for (size_t s = 0; s < n_st; ++s) {
+                if (positions_c[s].size() != 3) throw std::invalid_argument("positions_c must be 3 x N");
+                for (int a = 0; a < (int)types[s].size(); ++a) {
+                    int t = types[s][a];
+                    if (!type_full) {
+                        const auto it = std::find(type_indices.begin(), type_indices.end(), t);
+                        if (it == type_indices.end()) continue;
+                    }
+                    active[s].push_back(a);
+                    types_a[s].push_back(t);
+                    for (int c = 0; c < 3; ++c) pos_a[s][c].push_back(positions_c[s][c].at(a));
+                }
+                if (!type_full)   // std::replace in list order, on the partly renumbered array
+                    for (int rep = 0; rep < (int)type_indices.size(); ++rep)
+                        std::replace(types_a[s].begin(), types_a[s].end(), type_indices[rep], rep);
+            }
+            Batch b(all.axis, pos_a, types_a, idx.force_st);
+            pm_context* ctx = nullptr;
+            check(pm_context_create(models[n]->h, default_device(), 0, 0, &ctx));
+            std::vector<double> xn((size_t)pm_batch_rows(&b.st) * F + 1);
+            const int status = pm_features_x(ctx, &b.st, xn.data());
+            pm_context_destroy(ctx);
+            check(status);
+            auto copy_row = [&](size_t src, size_t dst) {
+                std::copy(xn.begin() + src * F, xn.begin() + (src + 1) * F, xa + dst * n_features + first);
+            };
+            size_t isb = n_st, ifb = n_st + 6 * (size_t)n_force_st;
+            for (size_t s = 0; s < n_st; ++s) {
+                copy_row(s, s);
+                if (!idx.force_st[s]) continue;
+                for (int r = 0; r < 6; ++r) copy_row(isb + r, idx.xs_begin[s] + r);
+                isb += 6;
+                for (size_t k = 0; k < active[s].size(); ++k)
+                    for (int c = 0; c < 3; ++c) copy_row(ifb + 3 * k + c, idx.xf_begin[s] + 3 * active[s][k] + c);
+                ifb += 3 * active[s].size();
+            }
+        }
+    }
+    py::array_t<double> get_x() { return x; }
+    const vector1i& get_fbegin() const { return fbegin; }
+    const vector1i& get_sbegin() const { return sbegin; }
+    const vector1i& get_cumulative_n_features() const { return cumulative; }
     const vector1i& get_n_data() const { return n_data; }
 };
 
@@ -181,7 +317,7 @@ class PyXtX {
         F = pm_model_n_features(model.h);
     }
     ~PyXtX() { pm_context_destroy(ctx); }
-    void add(const vector3d& axis, const vector3d& positions_c, const vector2i& types, const std::vector<bool>& force_st,
+    void add(const py::sequence& axis, const py::sequence& positions_c, const py::sequence& types, const std::vector<bool>& force_st,
              py::array_t<double, py::array::c_style | py::array::forcecast> w,
              py::array_t<double, py::array::c_style | py::array::forcecast> y) {
         Batch b(axis, positions_c, types, force_st);
@@ -205,52 +341,56 @@ class PyPropertiesFast {
     Model model;
     pm_context* ctx = nullptr;
     double energy = 0.0;
-    vector2d force;
-    vector1d stress;
-    vector1d e_array;
-    vector3d f_array;
-    vector2d s_array;
+    py::array_t<double> force, stress;       // (N, 3), (6)
+    py::array_t<double> e_array, s_array;    // (n_st), (n_st, 6)
+    py::list f_array;                        // n_st arrays (N_s, 3)
 
-    void run(const vector3d& axis, const vector3d& pos, const vector2i& types, vector1d& e, vector3d& f, vector2d& s) {
-        Batch b(axis, pos, types, std::vector<bool>(axis.size(), true));
-        const size_t n = axis.size();
+    // Results come back as NumPy arrays instead of the reference's nested lists (pybind11_mlp.cpp:56-67 via stl.h): its
+    // consumers wrap them in np.array(...) anyway (calculator/properties_single.py:122-125)
+    void run(const py::sequence& axis, const py::sequence& pos, const py::sequence& types, py::array_t<double>& e,
+             py::list& f, py::array_t<double>& s) {
+        const size_t n = py::len(axis);
+        Batch b(axis, pos, types, std::vector<bool>(n, true));
         size_t na = 0;
         for (int v : b.n_atoms) na += v;
-        vector1d eb(n), fb(3 * na + 1), sb(6 * n + 1);
-        check(pm_eval(ctx, &b.st, eb.data(), fb.data(), sb.data()));
-        e = eb;
-        f.assign(n, {});
-        s.assign(n, vector1d(6));
+        e = py::array_t<double>((py::ssize_t)n);
+        s = py::array_t<double>({(py::ssize_t)n, (py::ssize_t)6});
+        vector1d fb(3 * na + 1);
+        check(pm_eval(ctx, &b.st, e.mutable_data(), fb.data(), s.mutable_data()));
+        f = py::list();
         size_t off = 0;
         for (size_t k = 0; k < n; ++k) {
-            f[k].assign(b.n_atoms[k], vector1d(3));
-            for (int a = 0; a < b.n_atoms[k]; ++a)
-                for (int c = 0; c < 3; ++c) f[k][a][c] = fb[3 * (off + a) + c];
+            py::array_t<double> fk({(py::ssize_t)b.n_atoms[k], (py::ssize_t)3});
+            std::copy(fb.begin() + 3 * off, fb.begin() + 3 * (off + b.n_atoms[k]), fk.mutable_data());
+            f.append(fk);
             off += b.n_atoms[k];
-            for (int c = 0; c < 6; ++c) s[k][c] = sb[6 * k + c];
         }
     }
 
   public:
-    PyPropertiesFast(const py::dict& params_dict, const vector1d& coeffs) : model(params_dict) {
+    PyPropertiesFast(const py::dict& params_dict, const darray& coeffs) : model(params_dict) {
         check(pm_context_create(model.h, default_device(), 0, 0, &ctx));
         check(pm_eval_set_coeffs(ctx, coeffs.data(), (int)coeffs.size()));
     }
     ~PyPropertiesFast() { pm_context_destroy(ctx); }
-    void eval(const vector2d& axis, const vector2d& positions_c, const vector1i& types, const bool) {
-        vector1d e; vector3d f; vector2d s;
-        run({axis}, {positions_c}, {types}, e, f, s);
-        energy = e[0]; force = f[0]; stress = s[0];
+    void eval(const py::object& axis, const py::object& positions_c, const py::object& types, const bool) {
+        py::array_t<double> e, s;
+        py::list f;
+        run(py::make_tuple(axis), py::make_tuple(positions_c), py::make_tuple(types), e, f, s);
+        energy = e.at(0);
+        force = f[0].cast<py::array_t<double>>();
+        stress = py::array_t<double>((py::ssize_t)6);
+        std::copy(s.data(), s.data() + 6, stress.mutable_data());
     }
-    void eval_multiple(const vector3d& axis, const vector3d& positions_c, const vector2i& types) {
+    void eval_multiple(const py::sequence& axis, const py::sequence& positions_c, const py::sequence& types) {
         run(axis, positions_c, types, e_array, f_array, s_array);
     }
-    const double& get_e() const { return energy; }
-    const vector2d& get_f() const { return force; }
-    const vector1d& get_s() const { return stress; }
-    const vector1d& get_e_array() const { return e_array; }
-    const vector3d& get_f_array() const { return f_array; }
-    const vector2d& get_s_array() const { return s_array; }
+    double get_e() const { return energy; }
+    py::array_t<double> get_f() const { return force; }
+    py::array_t<double> get_s() const { return stress; }
+    py::array_t<double> get_e_array() const { return e_array; }
+    py::list get_f_array() const { return f_array; }
+    py::array_t<double> get_s_array() const { return s_array; }
 };
 
 class PyReadgtinv {
@@ -294,26 +434,34 @@ class PyFeaturesAttr {
 PYBIND11_MODULE(libmlpcpp, m) {
     m.doc() = "B200-native drop-in for pypolymlp.cxx.lib.libmlpcpp (hot path only)";
     py::class_<PyModel>(m, "PotentialModel")
-        .def(py::init<const py::dict&, const vector3d&, const vector3d&, const vector2i&, const vector1i&,
+        .def(py::init<const py::dict&, const py::sequence&, const py::sequence&, const py::sequence&, const vector1i&,
                       const std::vector<bool>&, const vector1i&>())
         .def("get_x", &PyModel::get_x)
         .def("get_fbegin", &PyModel::get_fbegin, py::return_value_policy::reference_internal)
         .def("get_sbegin", &PyModel::get_sbegin, py::return_value_policy::reference_internal)
         .def("get_n_data", &PyModel::get_n_data, py::return_value_policy::reference_internal);
+    py::class_<PyHybridModel>(m, "PotentialHybridModel")
+        .def(py::init<const std::vector<py::dict>&, const py::sequence&, const py::sequence&, const py::sequence&, const vector1i&,
+                      const std::vector<bool>&, const vector1i&>())
+        .def("get_x", &PyHybridModel::get_x)
+        .def("get_fbegin", &PyHybridModel::get_fbegin, py::return_value_policy::reference_internal)
+        .def("get_sbegin", &PyHybridModel::get_sbegin, py::return_value_policy::reference_internal)
+        .def("get_cumulative_n_features", &PyHybridModel::get_cumulative_n_features, py::return_value_policy::reference_internal)
+        .def("get_n_data", &PyHybridModel::get_n_data, py::return_value_policy::reference_internal);
     py::class_<PyXtX>(m, "PotentialXtX")
         .def(py::init<const py::dict&>())
         .def("add", &PyXtX::add)
         .def("finalize", &PyXtX::finalize);
     py::class_<PyPropertiesFast>(m, "PotentialPropertiesFast")
-        .def(py::init<const py::dict&, const vector1d&>())
+        .def(py::init<const py::dict&, const darray&>())
         .def("eval", &PyPropertiesFast::eval)
         .def("eval_multiple", &PyPropertiesFast::eval_multiple)
-        .def("get_e", &PyPropertiesFast::get_e, py::return_value_policy::reference_internal)
-        .def("get_f", &PyPropertiesFast::get_f, py::return_value_policy::reference_internal)
-        .def("get_s", &PyPropertiesFast::get_s, py::return_value_policy::reference_internal)
-        .def("get_e_array", &PyPropertiesFast::get_e_array, py::return_value_policy::reference_internal)
-        .def("get_f_array", &PyPropertiesFast::get_f_array, py::return_value_policy::reference_internal)
-        .def("get_s_array", &PyPropertiesFast::get_s_array, py::return_value_policy::reference_internal);
+        .def("get_e", &PyPropertiesFast::get_e)
+        .def("get_f", &PyPropertiesFast::get_f)
+        .def("get_s", &PyPropertiesFast::get_s)
+        .def("get_e_array", &PyPropertiesFast::get_e_array)
+        .def("get_f_array", &PyPropertiesFast::get_f_array)
+        .def("get_s_array", &PyPropertiesFast::get_s_array);
     py::class_<PyReadgtinv>(m, "Readgtinv")
         .def(py::init<const int, const vector1i&, const int>())
         .def("get_lm_seq", &PyReadgtinv::get_lm_seq, py::return_value_policy::reference_internal)

@@ -253,6 +253,88 @@ class PotentialModel:
         return self._n_data
 
 
+def find_active_atoms(type_full, type_indices, types, positions_c):
+    """Atoms a hybrid sub-model sees (PyHybridModel::find_active_atoms, compute/py_hybrid_model.cpp:116-156):
+    all of them when type_full, else those whose type is listed in type_indices, renumbered by position in it."""
+    types = np.asarray(types, dtype=np.int32)
+    positions_c = np.asarray(positions_c, dtype=np.float64)
+    if type_full:
+        return np.arange(len(types)), types, positions_c
+    type_indices = list(type_indices)
+    active = np.array([a for a, t in enumerate(types) if t in type_indices], dtype=np.int64)
+    # std::replace runs in list order on the already partly renumbered array: reproduce it literally
+    ta = types[active].copy()
+    for t_rep, t in enumerate(type_indices):
+        ta[ta == t] = t_rep
+    return active, ta, positions_c[:, active]
+
+
+class PotentialHybridModel:
+    """PotentialHybridModel(params_dict_array, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all)
+    (reference: pybind11_mlp.cpp:30-49, compute/py_hybrid_model.cpp:11-114): the design matrices of the
+    sub-models side by side, each computed on the atoms of its own element subset (type_indices / type_full)
+    and scattered back to the rows of the full structure.  Every sub-model runs through the same CUDA path."""
+
+    def __init__(self, params_dict_array, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all,
+                 device=None, flags=0):
+        if len(axis) != sum(n_st_dataset):
+            raise ValueError("n_st_dataset does not match the number of structures")
+        force_st = _force_per_structure(n_st_dataset, force_dataset)
+        self._fbegin, self._sbegin, self._n_data = _set_index(n_st_dataset, force_dataset, n_atoms_all)
+        n_st = len(axis)
+        # first X row of every structure's stress / force block in the full layout
+        xs_begin, xf_begin = [-1] * n_st, [-1] * n_st
+        ist = n_st
+        for k in range(n_st):
+            if force_st[k]:
+                xs_begin[k] = ist
+                ist += 6
+        for k in range(n_st):
+            if force_st[k]:
+                xf_begin[k] = ist
+                ist += 3 * int(n_atoms_all[k])
+        models = [_Model(p) for p in params_dict_array]
+        self._cumulative = list(np.cumsum([m.n_features for m in models]).astype(int))
+        self._x = np.zeros((sum(self._n_data), self._cumulative[-1] if models else 0))
+        if params_dict_array and params_dict_array[0].get("print_memory", False):
+            print(" matrix shape (X):", self._x.shape, flush=True)
+        for n, (p, model) in enumerate(zip(params_dict_array, models)):
+            first = 0 if n == 0 else self._cumulative[n - 1]
+            cols = slice(first, self._cumulative[n])
+            act = [find_active_atoms(p["type_full"], p["type_indices"], types[k], positions_c[k]) for k in range(n_st)]
+            ctx = _Context(model, device, flags=flags)
+            batch = StructureBatch(axis, [a[2] for a in act], [a[1] for a in act], force_st)
+            xn = np.zeros((batch.n_rows, model.n_features))
+            check(lib().pm_features_x(ctx.handle, C.byref(batch.c), pd(xn)))
+            self._x[:n_st, cols] = xn[:n_st]
+            isb = n_st
+            ifb = n_st + 6 * sum(force_st)
+            for k in range(n_st):
+                if not force_st[k]:
+                    continue
+                self._x[xs_begin[k]:xs_begin[k] + 6, cols] = xn[isb:isb + 6]
+                isb += 6
+                active = act[k][0]
+                rows = (xf_begin[k] + 3 * active[:, None] + np.arange(3)[None, :]).reshape(-1)
+                self._x[rows, cols] = xn[ifb:ifb + 3 * len(active)]
+                ifb += 3 * len(active)
+
+    def get_x(self):
+        return self._x
+
+    def get_fbegin(self):
+        return self._fbegin
+
+    def get_sbegin(self):
+        return self._sbegin
+
+    def get_cumulative_n_features(self):
+        return self._cumulative
+
+    def get_n_data(self):
+        return self._n_data
+
+
 class PotentialXtX:
     """Fused feature + X^T X / X^T y accumulation on the GPU (additive entry point).
 

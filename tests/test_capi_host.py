@@ -249,6 +249,8 @@ def test_pybind_dropin_module_host_side():
                          ("PotentialPropertiesFast", ("eval", "eval_multiple", "get_e", "get_f", "get_s",
                                                       "get_e_array", "get_f_array", "get_s_array")),
                          ("Readgtinv", ("get_lm_seq", "get_l_comb", "get_lm_coeffs")),
+                         ("PotentialHybridModel", ("get_x", "get_fbegin", "get_sbegin", "get_cumulative_n_features",
+                                                   "get_n_data")),
                          ("FeaturesAttr", ("get_n_features",)), ("PotentialXtX", ("add", "finalize"))):
         assert all(hasattr(getattr(m, cls), k) for k in methods), cls
     rg = m.Readgtinv(3, [4, 4], 1)
@@ -257,6 +259,7 @@ def test_pybind_dropin_module_host_side():
     assert rg.get_lm_coeffs() == ours.get_lm_coeffs()
     pd = make_params_dict(**cases.si_model_kwargs())
     assert m.FeaturesAttr(pd).get_n_features() == 168
+    assert m.FeaturesAttr(make_params_dict(**cases.mgo_model_kwargs("pair"))).get_n_features() == 324
     with pytest.raises(ValueError):
         m.Readgtinv(9, [1], 1)
     bad = make_params_dict(**cases.si_model_kwargs())

@@ -398,6 +398,25 @@ def test_pybind_dropin_module_gpu():
     assert np.abs(np.array(prop.get_s_array())[1] - G["bin_s"]).max() < 1e-10 * np.abs(G["bin_s"]).max()
     with pytest.raises(ValueError):
         libmlpcpp.PotentialPropertiesFast(pd, [0.0, 1.0])
+    # the producers of the reference hand over lists of NumPy arrays (mlp_dev/core/features.py:13-44): same result
+    # through the buffer protocol, and a shape error instead of a crash for a malformed structure
+    obj2 = libmlpcpp.PotentialModel(pd, [ax], [pc], [ty], [1], [True], [9])
+    assert np.array_equal(np.asarray(obj2.get_x()), np.asarray(obj.get_x()))
+    prop.eval_multiple([ax, ax], [pc, pc[:, ::-1]], [ty, ty[::-1]])
+    e2, f2 = np.array(prop.get_e_array()), [np.array(f) for f in prop.get_f_array()]
+    assert abs(e2[0] - e2[1]) < 1e-12 * abs(e2[0]) and np.abs(f2[0] - f2[1][::-1]).max() < 1e-10
+    with pytest.raises(ValueError):
+        libmlpcpp.PotentialModel(pd, [ax], [pc[:, :5]], [ty], [1], [True], [9])
+    # hybrid drop-in class against the Python mirror
+    from pypolymlp_b200.libmlpcpp import PotentialHybridModel
+
+    pd1 = dict(pd, type_full=True, type_indices=[0, 1])
+    pd2 = dict(make_params_dict(**cases.pair_model_kwargs(1)), type_full=False, type_indices=[1])
+    args = ([pd1, pd2], [ax, ax], [pc, pc], [ty, ty], [1, 1], [True, False], [9, 9])
+    hm, hm_py = libmlpcpp.PotentialHybridModel(*args), PotentialHybridModel(*args)
+    assert np.array_equal(np.asarray(hm.get_x()), hm_py.get_x())
+    assert hm.get_cumulative_n_features() == hm_py.get_cumulative_n_features() and hm.get_n_data() == hm_py.get_n_data()
+    assert hm.get_fbegin() == hm_py.get_fbegin() and hm.get_sbegin() == hm_py.get_sbegin()
 
 
 def test_device_ridge_solve_matches_host():
@@ -515,3 +534,26 @@ def test_mgo_published_answers_gpu(kind):
     assert abs(prop.get_e() - e) < 1e-10 * abs(e)
     assert np.abs(prop.get_f() - f).max() < 1e-10 * np.abs(f).max()
     assert np.abs(prop.get_s() - s).max() < 1e-10 * np.abs(s).max()
+
+
+def test_hybrid_model_vs_oracle():
+    """PotentialHybridModel (compute/py_hybrid_model.cpp): a full binary gtinv model next to a pair model that only
+    sees element 1, on a mixed force / energy-only batch (one structure has a single atom of element 1)."""
+    from pypolymlp_b200.libmlpcpp import PotentialHybridModel
+
+    pd1 = dict(make_params_dict(**cases.binary_model_kwargs()), type_full=True, type_indices=[0, 1])
+    pd2 = dict(make_params_dict(**cases.pair_model_kwargs(1)), type_full=False, type_indices=[1])
+    sts = [cases.skewed_cell(2, n_atom=n, seed=s) for n, s in ((7, 1), (5, 2), (6, 3))]
+    sts[1][2][:] = 0
+    sts[1][2][3] = 1
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    hm = PotentialHybridModel([pd1, pd2], axis, pcs, tys, [2, 1], [True, False], [7, 5, 6])
+    tabs = [po.Tables(pd1), po.Tables(pd2)]
+    X = po.build_x_hybrid(tabs, [True, False], [[0, 1], [1]], axis, pcs, tys, [True, True, False])
+    assert hm.get_x().shape == X.shape
+    assert hm.get_cumulative_n_features() == [tabs[0].n_variables, tabs[0].n_variables + tabs[1].n_variables]
+    assert hm.get_n_data() == [3, 36, 12] and hm.get_sbegin() == [3, -1] and hm.get_fbegin() == [15, -1]
+    assert cases.x_rel_err(hm.get_x(), X) < 1e-10
+    # a sub-model alone equals the plain model on the same atoms
+    pm = PotentialModel(pd1, axis, pcs, tys, [2, 1], [True, False], [7, 5, 6])
+    assert np.array_equal(hm.get_x()[:, : tabs[0].n_variables], pm.get_x())
