@@ -321,7 +321,7 @@ static void build_device_model(pm_context* c) {
             };
             std::vector<int4> fmeta, emeta;
             std::vector<int> fout;
-            std::vector<int2> eout;
+            std::vector<int2> eout, efh;
             bool ids_fit = T.n_full < 32768;
             // features: rows of 8, 4 k-lanes
             {
@@ -390,9 +390,17 @@ static void build_device_model(pm_context* c) {
                     const size_t base = scoef.size();
                     grow(base + (size_t)mx * 32);
                     emeta.push_back(make_int4((int)base, mx, cn_of[idx[p0]], 0));
-                    for (int r = 0; r < 32; ++r)
+                    for (int r = 0; r < 32; ++r) {
                         eout.push_back(p0 + r < p1 ? make_int2(T.ent_pos_re[idx[p0 + r]], T.ent_pos_im[idx[p0 + r]])
                                                    : make_int2(-1, -1));
+                        int2 fh = make_int2(-1, -1);
+                        if (p0 + r < p1) {   // pos_re = 32 * block + 4 * (feature inside the tile) + 2 * (head inside the block)
+                            const int pos = T.ent_pos_re[idx[p0 + r]];
+                            const auto& blk = T.blocks[pos / 32];
+                            fh = make_int2(blk.tile * 8 + (pos % 32) / 4, (blk.seg << 20) | (4 * blk.kchunk + pos % 4));
+                        }
+                        efh.push_back(fh);
+                    }
                     for (int p = p0; p < p1; ++p) {
                         const int e = idx[p], row = p - p0;
                         for (int q = T.ent_off[e], k = 0; q < T.ent_off[e + 1]; ++q, ++k) {
@@ -418,9 +426,13 @@ static void build_device_model(pm_context* c) {
                 perm.resize(emeta.size());
                 for (size_t k = 0; k < perm.size(); ++k) perm[k] = (int)k;
                 std::stable_sort(perm.begin(), perm.end(), [&](int a, int b2) { return by_len(emeta[a], emeta[b2]); });
-                std::vector<int4> em2; std::vector<int2> eo2;
-                for (int k : perm) { em2.push_back(emeta[k]); eo2.insert(eo2.end(), eout.begin() + 32 * k, eout.begin() + 32 * k + 32); }
-                emeta.swap(em2); eout.swap(eo2);
+                std::vector<int4> em2; std::vector<int2> eo2, ef2;
+                for (int k : perm) {
+                    em2.push_back(emeta[k]);
+                    eo2.insert(eo2.end(), eout.begin() + 32 * k, eout.begin() + 32 * k + 32);
+                    ef2.insert(ef2.end(), efh.begin() + 32 * k, efh.begin() + 32 * k + 32);
+                }
+                emeta.swap(em2); eout.swap(eo2); efh.swap(ef2);
             }
             D.n_fsl = ids_fit ? (int)fmeta.size() : 0;
             D.n_esl = ids_fit ? (int)emeta.size() : 0;
@@ -429,7 +441,7 @@ static void build_device_model(pm_context* c) {
             std::vector<unsigned> flat;
             for (auto& w : sw) flat.insert(flat.end(), w.begin(), w.end());
             D.fsl_meta = upload(c, fmeta); D.fsl_out = upload(c, fout);
-            D.esl_meta = upload(c, emeta); D.esl_out = upload(c, eout);
+            D.esl_meta = upload(c, emeta); D.esl_out = upload(c, eout); D.esl_fh = upload(c, efh);
             D.sl_coeff = upload(c, scoef); D.sl_ids = upload(c, flat);
             if (getenv("PM_DEBUG_TABLES"))
                 fprintf(stderr, "[pm] type %d: %d feature slices, %d entry slices, %ld slots (terms %zu, contribs %zu)\n",
@@ -691,11 +703,12 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
 
     // ---- K3 ------------------------------------------------------------------------------------
     c->d_dfeat.ensure((size_t)h.n_atoms * d.fl);
-    c->d_G.ensure(any_force ? (size_t)h.n_atoms * d.gstride : 1);
+    const bool eval_fused = mode == MODE_EVAL && !c->simple_s && eval_fused_supported(d, c->feat_smem);
+    c->d_G.ensure(any_force && !eval_fused ? (size_t)h.n_atoms * d.gstride : 1);
     // single-type models: every atom slot of G has the same zero pattern, so the buffer is cleared once per
     // allocation and the kernel only writes the non-zero entries afterwards
     bool zero_g = true;
-    if (d.n_type == 1 && any_force) {
+    if (d.n_type == 1 && any_force && !eval_fused) {
         if (c->g_zero_cap != c->d_G.cap) {
             CK(cudaMemsetAsync(c->d_G.p, 0, c->d_G.cap * sizeof(double), s));
             c->g_zero_cap = c->d_G.cap;
@@ -710,8 +723,8 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         if (c->d_dpv.cap != cap0) CK(cudaMemsetAsync(c->d_dpv.p, 0, c->d_dpv.cap * sizeof(double), s));
         dpv = c->d_dpv.p;
     }
-    launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s, zero_g, dpv);
-    tm.mark(ST_FEAT, 1);
+    if (!eval_fused) launch_features(d, b, c->d_anc.p, c->d_dfeat.p, c->d_G.p, c->feat_smem, s, zero_g, dpv);
+    tm.mark(ST_FEAT, eval_fused ? 0 : 1);
 
     Workspace ws;
     ws.PB = c->d_PB.p; ws.anc = c->d_anc.p; ws.agg = c->d_agg.p; ws.dfeat = c->d_dfeat.p; ws.dpv = dpv; ws.Gbuf = c->d_G.p;
@@ -729,7 +742,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         CK(cudaMemsetAsync(c->d_e.p, 0, h.n_st * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_f.p, 0, ((size_t)h.n_atoms * 3 + 1) * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_s.p, 0, (size_t)h.n_st * 6 * sizeof(double), s));
-        launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s);
+        launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s, eval_fused ? c->feat_smem : 0);
         tm.mark(ST_EVAL, 5);
         return;
     }

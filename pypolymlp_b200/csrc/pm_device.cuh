@@ -57,6 +57,8 @@ struct DevType {
     const int* fsl_out;           // [n_fsl][8] padded feature id or -1
     const int4* esl_meta;         // [n_esl] (first slot, iterations, number of ids, 0)
     const int2* esl_out;          // [n_esl][32] (pos_re, pos_im) in the atom's G buffer, or (-1, -1)
+    const int2* esl_fh;           // [n_esl][32] (padded feature id, segment << 20 | real position inside the segment's
+                                  //  head list) of the entry, or (-1, -1): the eval path folds G into the head adjoint
     const double* sl_coeff;       // [n_slots]
     const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;

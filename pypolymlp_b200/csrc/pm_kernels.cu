@@ -1335,14 +1335,254 @@ __global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, c
     }
 }
 
-void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
-                         double* energies, double* forces, double* stresses, cudaStream_t s) {
-    if (b.n_atoms == 0) return;
+
+// Fused eval front end (single launch instead of K3 + k_eval_atom, no G buffer): for AT atoms per CTA
+//   (1) linear invariants d_f from the sliced term tables (as k_features_v3),
+//   (2) E_i and w_f = dE_i/dd_f from the polynomial terms (shared-memory atomics),
+//   (3) the head adjoint Ah[h] = sum_f w_f dd_f/da_h accumulated straight from the sliced contribution tables --
+//       the 48 KB / atom G matrix of the fit path is never written (polymlp_eval.cpp:182-290 restated in adjoint form).
+template <int AT, int MO>
+__global__ void __launch_bounds__(256) k_eval_features(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                        const double* __restrict__ coeffs, double* __restrict__ Ah,
+                                                        int ah_stride, double* __restrict__ energies, int nfull_max) {
+    extern __shared__ double2 afull[];   // [AT][nfull_max] | sd [AT][fl] | sw [AT][fl] | sah [AT][ah_stride]
+    double* sd = reinterpret_cast<double*>(afull + (size_t)AT * nfull_max);
+    double* sw = sd + (size_t)AT * m.fl;
+    double* sah = sw + (size_t)AT * m.fl;
+    __shared__ double s_e[AT];
+    constexpr int NW = (MO + 1) / 2;
+    const int i0 = blockIdx.x * AT;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int segstride = ah_stride / m.n_type;
+    int ty[AT];
+#pragma unroll
+    for (int a = 0; a < AT; ++a) ty[a] = i0 + a < b.n_atoms ? b.types[i0 + a] : -1;
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        if (ty[a] < 0) continue;
+        const DevType& T = m.types[ty[a]];
+        for (int k = tid; k < T.n_full; k += nthr) {
+            double2 v = anc[(size_t)(i0 + a) * m.hmax + T.full_head[k]];
+            if (T.full_conj[k]) {
+                const double cc = T.full_cc[k];
+                v = make_double2(cc * v.x, -cc * v.y);
+            }
+            afull[(size_t)a * nfull_max + k] = v;
+        }
+    }
+    for (int k = tid; k < AT * m.fl; k += nthr) { sd[k] = 0.0; sw[k] = 0.0; }
+    for (int k = tid; k < AT * ah_stride; k += nthr) sah[k] = 0.0;
+    if (tid < AT) s_e[tid] = 0.0;
+    __syncthreads();
+    // (1) linear invariants
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        bool any = false;
+#pragma unroll
+        for (int a = 0; a < AT; ++a) any = any || ty[a] == tt;
+        if (!any) continue;
+        const DevType& T = m.types[tt];
+        const double* __restrict__ coef = T.sl_coeff;
+        const unsigned* __restrict__ ids = T.sl_ids;
+        const long ns = T.n_slots;
+        for (int s = warp; s < T.n_fsl; s += nwarp) {
+            const int4 meta = T.fsl_meta[s];
+            const int o = meta.z;
+            double sum[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) sum[a] = 0.0;
+#pragma unroll 2
+            for (int it = 0; it < meta.y; ++it) {
+                const long slot = meta.x + it * 32 + lane;
+                const double cf = coef[slot];
+                int id[2 * NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned v = ids[w * ns + slot];
+                    id[2 * w] = v & 0xffffu;
+                    id[2 * w + 1] = v >> 16;
+                }
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = af[id[0]];
+#pragma unroll
+                    for (int k = 1; k < MO; ++k)
+                        if (k < o) pr = cmul(pr, af[id[k]]);
+                    sum[a] += cf * pr.x;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], 8);
+                sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], 16);
+            }
+            if (lane < 8) {
+                const int fp = T.fsl_out[s * 8 + lane];
+                if (fp >= 0) {
+#pragma unroll
+                    for (int a = 0; a < AT; ++a)
+                        if (ty[a] == tt) sd[a * m.fl + fp] = sum[a];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // (2) polynomial: energy and w_f
+    double e[AT];
+#pragma unroll
+    for (int a = 0; a < AT; ++a) e[a] = 0.0;
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        bool any = false;
+#pragma unroll
+        for (int a = 0; a < AT; ++a) any = any || ty[a] == tt;
+        if (!any) continue;
+        const DevPolyTerm* __restrict__ ct = m.types[tt].colterm;
+        for (int col = tid; col < m.n_variables; col += nthr) {
+            const DevPolyTerm tm = ct[col];
+            if (!tm.order) continue;
+            const double c = coeffs[col];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                if (ty[a] != tt) continue;
+                const double* d = sd + a * m.fl;
+                double* w = sw + a * m.fl;
+                if (tm.order == 1) {
+                    e[a] += c * d[tm.fp0];
+                    atomicAdd(w + tm.fp0, c);
+                } else if (tm.order == 2) {
+                    const double d0 = d[tm.fp0], d1 = d[tm.fp1];
+                    e[a] += c * d0 * d1;
+                    atomicAdd(w + tm.fp0, c * d1);
+                    atomicAdd(w + tm.fp1, c * d0);
+                } else {
+                    const double d0 = d[tm.fp0], d1 = d[tm.fp1], d2 = d[tm.fp2];
+                    e[a] += c * d0 * d1 * d2;
+                    atomicAdd(w + tm.fp0, c * d1 * d2);
+                    atomicAdd(w + tm.fp1, c * d0 * d2);
+                    atomicAdd(w + tm.fp2, c * d0 * d1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) e[a] += __shfl_xor_sync(0xffffffffu, e[a], dlt);
+        if (lane == 0 && ty[a] >= 0) atomicAdd(&s_e[a], e[a]);
+    }
+    __syncthreads();
+    if (tid < AT && ty[tid] >= 0) atomicAdd(energies + b.st_of_atom[i0 + tid], s_e[tid]);
+    // (3) head adjoint from the contribution slices
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        bool any = false;
+#pragma unroll
+        for (int a = 0; a < AT; ++a) any = any || ty[a] == tt;
+        if (!any) continue;
+        const DevType& T = m.types[tt];
+        const double* __restrict__ coef = T.sl_coeff;
+        const unsigned* __restrict__ ids = T.sl_ids;
+        const long ns = T.n_slots;
+        for (int s = warp; s < T.n_esl; s += nwarp) {
+            const int4 meta = T.esl_meta[s];
+            const int cn = meta.z;
+            double gr[AT], gi[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) { gr[a] = 0.0; gi[a] = 0.0; }
+#pragma unroll 2
+            for (int it = 0; it < meta.y; ++it) {
+                const long slot = meta.x + it * 32 + lane;
+                const double cf = coef[slot];
+                int id[2 * NW];
+                unsigned w0 = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned v = ids[w * ns + slot];
+                    if (w == 0) w0 = v;
+                    id[2 * w] = v & 0xffffu;
+                    id[2 * w + 1] = (v >> 16) & 0x7fffu;
+                }
+                const double cfi = (w0 & 0x80000000u) ? -cf : cf;
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    const double2* af = afull + (size_t)a * nfull_max;
+                    double2 pr = make_double2(1.0, 0.0);
+                    if (MO > 1 && cn > 0) pr = af[id[0]];
+#pragma unroll
+                    for (int qq = 1; qq < MO - 1; ++qq)
+                        if (qq < cn) pr = cmul(pr, af[id[qq]]);
+                    gr[a] += cf * pr.x;
+                    gi[a] += cfi * pr.y;
+                }
+            }
+            const int2 fh = T.esl_fh[s * 32 + lane];
+            if (fh.x >= 0) {
+                const int pos = (fh.y >> 20) * segstride + (fh.y & 0xfffff);
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    const double wf = sw[a * m.fl + fh.x];
+                    atomicAdd(sah + a * ah_stride + pos, wf * gr[a]);
+                    atomicAdd(sah + a * ah_stride + pos + 1, -wf * gi[a]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+        if (ty[a] < 0) continue;
+        double* ah = Ah + (size_t)(i0 + a) * ah_stride;
+        for (int k = tid; k < ah_stride; k += nthr) ah[k] = sah[a * ah_stride + k];
+    }
+}
+
+constexpr int EVF_AT = 4;
+static int eval_ah_stride(const DevModel& m) {
     int maxseg = 0;
     for (int t = 0; t < m.n_type; ++t)
         for (int u = 0; u < m.n_type; ++u) maxseg = max(maxseg, m.types[t].seg_len[u]);
-    const int ah_stride = m.n_type * 2 * maxseg;
-    k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
+    return m.n_type * 2 * maxseg;
+}
+static size_t eval_fused_smem(const DevModel& m, size_t feat_smem) {
+    return EVF_AT * (feat_smem + (2ull * m.fl + eval_ah_stride(m)) * sizeof(double));
+}
+bool eval_fused_supported(const DevModel& m, size_t feat_smem) {
+    int mo = 1;
+    for (int t = 0; t < m.n_type; ++t) {
+        mo = max(mo, m.types[t].max_order);
+        if (m.types[t].n_fsl <= 0 || m.types[t].n_esl <= 0) return false;
+    }
+    return mo <= 6 && eval_fused_smem(m, feat_smem) <= 160 * 1024;
+}
+
+void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
+                         double* energies, double* forces, double* stresses, cudaStream_t s, size_t feat_smem) {
+    if (b.n_atoms == 0) return;
+    const int ah_stride = eval_ah_stride(m);
+    if (feat_smem > 0) {
+        const size_t smem = eval_fused_smem(m, feat_smem);
+        const int nfull_max = (int)(feat_smem / sizeof(double2));
+        const int grid = (b.n_atoms + EVF_AT - 1) / EVF_AT;
+        int mo = 1;
+        for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
+        static size_t set_for = 0;
+#define PM_EVF_CASE(MO_)                                                                                              \
+    case MO_:                                                                                                         \
+        if (smem > 48 * 1024 && set_for != smem)                                                                      \
+            cudaFuncSetAttribute(k_eval_features<EVF_AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_eval_features<EVF_AT, MO_><<<grid, 256, smem, s>>>(m, b, ws.anc, coeffs, ws.Ah, ah_stride, energies, nfull_max); \
+        break;
+        switch (mo) {
+            PM_EVF_CASE(1) PM_EVF_CASE(2) PM_EVF_CASE(3) PM_EVF_CASE(4) PM_EVF_CASE(5) PM_EVF_CASE(6)
+        }
+#undef PM_EVF_CASE
+        if (smem > 48 * 1024) set_for = smem;
+    } else {
+        k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
+    }
     if (b.n_pairs > 0) {
         if (m.n_fn <= EV_MAXFN)
             k_eval_pairs_v2<<<(b.n_pairs + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);

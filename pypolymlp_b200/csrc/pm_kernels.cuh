@@ -49,8 +49,11 @@ void launch_scan_exclusive(const int* in, int* out, int n, cudaStream_t s);
 void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s);
 int syrk_launches(int n_rows, int fpad, bool simple);
 // eval: E/F/S through contraction with coefficients
+// feat_smem > 0: fused feature + polynomial-adjoint kernel (no G buffer, no separate K3 launch); it must be the
+// bytes of one atom's full a_nlm array and eval_fused_supported() must hold
 void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
-                         double* energies, double* forces, double* stresses, cudaStream_t s);
+                         double* energies, double* forces, double* stresses, cudaStream_t s, size_t feat_smem = 0);
+bool eval_fused_supported(const DevModel& m, size_t feat_smem);
 // micro-benchmarks (TFLOP/s)
 double microbench_fp64(int which, cudaStream_t s);
 

@@ -29,6 +29,22 @@ prop.eval_multiple(axis, pcs, tys)
 for k, (ms, ln) in prop._ctx.profile_get().items():
     if ms > 0:
         print("   %-12s %9.3f ms" % (k, ms))
+# the pybind11 drop-in (lists of NumPy arrays in through the buffer protocol, NumPy arrays out)
+import importlib.util  # noqa: E402
+
+from pypolymlp_b200.build import pybind_module_path  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("libmlpcpp", pybind_module_path())
+libmlpcpp = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(libmlpcpp)
+pp = libmlpcpp.PotentialPropertiesFast(pd, coeffs)
+pp.eval_multiple(axis[:4], pcs[:4], tys[:4])
+t0 = time.perf_counter()
+pp.eval_multiple(axis, pcs, tys)
+ea_pb = np.array(pp.get_e_array())
+fa_pb = [np.array(f) for f in pp.get_f_array()]
+dt = time.perf_counter() - t0
+print(f"pybind drop-in eval_multiple + getters: {dt * 1e3:.1f} ms -> {n_st * 512 / dt:.3e} atoms/s")
 from oracle import ref  # noqa: E402
 
 if ref.available():
