@@ -19,6 +19,7 @@ namespace pm {
 void set_features_smem(size_t smem_bytes);
 void set_lrows_kmax(int kmax);
 size_t lrows_mma_smem(const DevModel& m);
+bool lrows_big_supported(const DevModel& m);
 size_t xrows_mma_smem(const DevModel& m);
 double microbench_dgemm(int n, cudaStream_t s);
 double microbench_red(int n_rows, cudaStream_t s);
@@ -470,7 +471,7 @@ static void build_device_model(pm_context* c) {
     if (c->feat_smem > 48 * 1024) set_features_smem(c->feat_smem);
     const bool force_simple = (c->flags & PM_FLAG_SIMPLE_KERNELS) != 0;
     c->simple_s = force_simple;
-    c->simple_l = force_simple || lrows_mma_smem(d) > 200 * 1024;
+    c->simple_l = force_simple || (lrows_mma_smem(d) > 200 * 1024 && !lrows_big_supported(d));
     c->simple_x = force_simple || hm.has_order3 || xrows_mma_smem(d) > 200 * 1024;
     c->scatter = !c->simple_l && !c->simple_x && scatter_mode_supported(d) && (c->flags & PM_FLAG_SCATTER);
 }

@@ -15,6 +15,7 @@
 #include "pm_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cublas_v2.h>
 
@@ -437,6 +438,189 @@ __global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4a for large angular expansions (max_l ~ 12: 92 heads = 184 reals per radial group, hundreds of feature
+// tiles per radial index), where neither the per-warp V tiles of k_lrows_mma nor the register-resident B
+// fragments of k_lrows_v3 fit.  One CTA (8 warps) per centre atom, two CTAs per SM.  Per (neighbour-type
+// segment, chunk of up to 8*MRT rows, radial index):
+//   1. all threads build the V tile [2*heads][rows] of the radial index in shared memory straight from the
+//      pair-basis records (L2; lane = row, so a warp reads ~11 consecutive pairs of one item),
+//   2. the warps split the feature tiles of the radial index; per tile a warp walks the tile's non-zero
+//      blocks of G (coalesced 256 B B-fragment loads, four in flight) and issues one DMMA per active row tile.
+// The nine aggregated rows (own x/y/z + six virial rows, fed from the K2b sums) ride behind the pair rows
+// of every segment and are accumulated over the segments into Xown / Sbuf.
+// Only the row tiles that hold rows are multiplied, so ragged segments cost what they contain.
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_THREADS = 256;
+
+template <int MRT>
+__global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                            const double2* __restrict__ agg,
+                                                            const double* __restrict__ Gbuf, double* __restrict__ Lbuf,
+                                                            double* __restrict__ Xown, double* __restrict__ Sbuf, int ldv) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int MR = 8 * MRT;                      // rows per chunk
+    constexpr int NKL = LB_THREADS / 32;             // one k-lane per warp in the V build
+    const int i = blockIdx.x;
+    if (!b.force[b.st_of_atom[i]]) return;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const int nt = m.n_type;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* V = smem;                                // [2 * heads of the radial group][ldv]
+    const double* G = Gbuf + (size_t)i * m.gstride;
+    const int oy = pb_y(m, 0);
+    for (int e = tid; e < 3 * m.fl; e += LB_THREADS) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
+    for (int e = tid; e < 6 * m.fl; e += LB_THREADS) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
+
+    for (int u = 0; u < nt; ++u) {
+        const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
+        if (p1 == p0) continue;              // no neighbour of this type: its heads carry exact zeros
+        const int nrow = 3 * (p1 - p0);
+        const int nrow_all = nrow + 9;
+        const int* skey = T.seg_key[u];
+        const int* sh = T.seg_heads[u];
+        const int* snoff = T.seg_n_off[u];
+        const int* snid = T.seg_nid[u];
+        const int* tboff = T.tile_blk_off[u];
+        // equal chunks: ceil(rows / chunks) rounded up to row tiles
+        const int nchunk = (nrow_all + MR - 1) / MR;
+        const int crow = ((nrow_all + nchunk - 1) / nchunk + 7) & ~7;
+        for (int row0 = 0; row0 < nrow_all; row0 += crow) {
+            const int rows_here = min(crow, nrow_all - row0);
+            const int n_rt = (rows_here + 7) >> 3;
+            // V build: each warp owns one k-lane; its lanes cover the rows of the chunk in passes of 32
+            for (int n = 0; n < m.n_fn; ++n) {
+                const int h0 = snoff[n], h1 = snoff[n + 1];
+                const int tile_b = T.tile_n_off[n], tile_e = T.tile_n_off[n + 1];
+                if (h1 == h0) {  // radial index inactive for this type pair: the pair rows are exactly zero
+                    for (int tile = tile_b + warp; tile < tile_e; tile += NKL)
+#pragma unroll
+                        for (int rt = 0; rt < MRT; ++rt) {
+                            const int r = row0 + rt * 8 + g;
+                            if (rt < n_rt && r < nrow)
+                                *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q) =
+                                    make_double2(0.0, 0.0);
+                        }
+                    continue;
+                }
+                const int nid = snid[n];
+                __syncthreads();  // the previous V tile is fully consumed
+                for (int rl = lane; rl < 8 * n_rt; rl += 32) {
+                    const int row = row0 + rl;
+                    double* vcol = V + rl;
+                    if (row < nrow) {
+                        const int pl = row / 3, al = row - 3 * pl;
+                        const PBRec rec = pb_rec(PB, p0 + pl, m.pbstride);
+                        const double fn = rec[4 + nid];
+                        const double c1 = rec[4 + m.n_fn + nid] * (rec[al] * rec[3]);
+                        const PBRec ry = rec + oy, rya = rec + pb_y(m, 1 + al);
+#pragma unroll 4
+                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                            const int key = skey[hq];
+                            double vr = 0.0, vi = 0.0;
+                            if (key >= 0) {
+                                vr = c1 * ry[2 * key] + fn * rya[2 * key];
+                                vi = c1 * ry[2 * key + 1] + fn * rya[2 * key + 1];
+                            }
+                            vcol[(size_t)(2 * (hq - h0)) * ldv] = vr;
+                            vcol[(size_t)(2 * (hq - h0) + 1) * ldv] = vi;
+                        }
+                    } else if (row < nrow_all) {
+                        const int ra = row - nrow;
+                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                            const int h = sh[hq];
+                            double2 v = make_double2(0.0, 0.0);
+                            if (h >= 0) v = agg[((size_t)i * m.hmax + h) * 9 + ra];
+                            vcol[(size_t)(2 * (hq - h0)) * ldv] = v.x;
+                            vcol[(size_t)(2 * (hq - h0) + 1) * ldv] = v.y;
+                        }
+                    } else {
+                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                            vcol[(size_t)(2 * (hq - h0)) * ldv] = 0.0;
+                            vcol[(size_t)(2 * (hq - h0) + 1) * ldv] = 0.0;
+                        }
+                    }
+                }
+                __syncthreads();
+                const int kc0 = h0 >> 1;
+                for (int tile = tile_b + warp; tile < tile_e; tile += NKL) {
+                    double acc[MRT][2];
+#pragma unroll
+                    for (int rt = 0; rt < MRT; ++rt) { acc[rt][0] = 0.0; acc[rt][1] = 0.0; }
+                    const int b1 = tboff[tile + 1];
+                    for (int bk = tboff[tile]; bk < b1; bk += 4) {
+                        double bf[4];
+                        int kcl[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool on = bk + j < b1;
+                            bf[j] = on ? G[32 * (size_t)(bk + j) + lane] : 0.0;
+                            kcl[j] = on ? T.blk_kchunk[bk + j] - kc0 : 0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (bk + j < b1) {
+                                const double* va = V + (size_t)(4 * kcl[j] + q) * ldv + g;
+#pragma unroll
+                                for (int rt = 0; rt < MRT; ++rt)
+                                    if (rt < n_rt) dmma(acc[rt][0], acc[rt][1], va[rt * 8], bf[j]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int rt = 0; rt < MRT; ++rt) {
+                        if (rt >= n_rt) continue;
+                        const int r = row0 + rt * 8 + g;
+                        if (r < nrow) {
+                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q) =
+                                make_double2(acc[rt][0], acc[rt][1]);
+                        } else if (r < nrow_all) {
+                            const int ra = r - nrow;
+                            double* dst = (ra < 3 ? Xown + ((size_t)i * 3 + ra) * m.fl : Sbuf + ((size_t)i * 6 + (ra - 3)) * m.fl) +
+                                          tile * 8 + 2 * q;
+                            double2 v = *reinterpret_cast<double2*>(dst);
+                            v.x += acc[rt][0]; v.y += acc[rt][1];
+                            *reinterpret_cast<double2*>(dst) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int g_lrows_kmax = 0;
+static int lrows_big_ldv(int mrt) { return mrt == 8 ? 68 : (mrt == 9 ? 76 : 100); }   // >= 8 * mrt, == 4 or 12 (mod 16)
+static size_t lrows_big_smem(int mrt) { return (size_t)g_lrows_kmax * lrows_big_ldv(mrt) * sizeof(double); }
+bool lrows_big_supported(const DevModel& m) { return lrows_big_smem(8) <= 226 * 1024; }
+
+template <int MRT>
+static void launch_lrows_big_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    const size_t smem = lrows_big_smem(MRT);
+    static size_t set_for = 0;
+    if (set_for != smem) {
+        cudaFuncSetAttribute(k_lrows_big<MRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set_for = smem;
+    }
+    k_lrows_big<MRT><<<b.n_atoms, LB_THREADS, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
+                                                       lrows_big_ldv(MRT));
+}
+
+static void launch_lrows_big(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
+    // rows of a typical segment = 3 * pairs per (atom, neighbour type) + 9; take the chunk height (64 or 72 rows, both
+    // leave two CTAs per SM when they fit) that needs fewer chunks, then fewer row tiles
+    const double rows = 3.0 * b.n_pairs / std::max(1, b.n_atoms * m.n_type) + 9.0;
+    auto cost = [&](int mrt) {
+        const int nch = (int)std::ceil(rows / (8.0 * mrt));
+        return nch * 1000 + (int)std::ceil(rows / nch / 8.0) * nch;
+    };
+    const bool fits9 = 2 * (lrows_big_smem(9) + 1024) <= 228 * 1024 || lrows_big_smem(8) > 113 * 1024;
+    if (fits9 && lrows_big_smem(9) <= 226 * 1024 && cost(9) < cost(8)) launch_lrows_big_t<9>(m, b, ws, s);
+    else launch_lrows_big_t<8>(m, b, ws, s);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4a fast path for models whose radial groups are small (<= TPN feature tiles, <= KPN k-chunks):
 // per (row chunk, radial group) a warp (1) prefetches its B fragments (blocks of G) into registers,
 // (2) builds the V tile in its private shared memory, (3) issues TPN*KPN*4 DMMAs from registers and
@@ -768,7 +952,6 @@ static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspac
 }
 
 // set by the context at model upload (max over types/segments/radial groups of 2 * padded heads)
-static int g_lrows_kmax = 0;
 void set_lrows_kmax(int kmax) { g_lrows_kmax = kmax; }
 size_t lrows_mma_smem(const DevModel& m) {
     return ((size_t)m.pbstride * LR_PLD + 4ull * g_lrows_kmax * LR_LD) * sizeof(double);
@@ -777,6 +960,7 @@ size_t lrows_mma_smem(const DevModel& m) {
 void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
     if (launch_lrows_v2(m, b, ws, apply_w, s)) return;
     const size_t smem = lrows_mma_smem(m);
+    if (smem > 200 * 1024) { launch_lrows_big(m, b, ws, s); return; }
     static size_t set_for = 0;
     if (set_for != smem) {
         cudaFuncSetAttribute(k_lrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
