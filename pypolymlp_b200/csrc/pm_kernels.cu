@@ -742,8 +742,8 @@ __global__ void __launch_bounds__(256) k_features_v2(DevModel m, DevBatch b, con
 // v3: same work split as v2 (AT atoms per CTA share every table read) but the term / contribution tables are
 // read through the sliced copies (DevType::fsl_* / esl_*): every warp iteration loads 32 consecutive slots
 // (coefficient + packed 16-bit ids), so table reads are coalesced and independent of the accumulation chain.
-template <int AT, int MO>
-__global__ void __launch_bounds__(256) k_features_v3(DevModel m, DevBatch b, const double2* __restrict__ anc,
+template <int AT, int MO, int NT>
+__global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                       double* __restrict__ dfeat, double* __restrict__ Gbuf,
                                                       int nfull_max, int zero_g, double* __restrict__ dpv) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
@@ -910,21 +910,39 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     const size_t smem4 = smem_bytes * AT;
     int mo = 1;
     for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
-    bool sliced = mo <= 6 && smem4 <= 96 * 1024;
+    bool sliced = mo <= 6;
     for (int t = 0; t < m.n_type; ++t) sliced = sliced && m.types[t].n_fsl > 0;
     if (sliced) {
-        const int grid = (b.n_atoms + AT - 1) / AT;
-#define PM_FEAT3_CASE(MO_)                                                                                       \
-    case MO_:                                                                                                    \
-        if (smem4 > 48 * 1024 && g_feat3_smem_set != smem4)                                                      \
-            cudaFuncSetAttribute(k_features_v3<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
-        k_features_v3<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0, dpv);               \
+        // atoms per CTA: as many as fit (every table read is shared by the CTA's atoms).  Small models: 4 atoms,
+        // 256 threads, several CTAs per SM; big a_nlm arrays (max_l ~ 12): one 512-thread CTA per SM with 4, 2 or 1 atoms
+        const size_t cap = 226 * 1024;
+        const int at = smem4 <= cap ? 4 : (2 * smem_bytes <= cap ? 2 : 1);
+        const bool big = smem4 > 96 * 1024;
+        const size_t smem = smem_bytes * at;
+        const int grid = (b.n_atoms + at - 1) / at;
+        static const void* set_fn = nullptr;
+        static size_t set_sz = 0;
+#define PM_FEAT3_LAUNCH(AT_, MO_, NT_)                                                                              \
+    {                                                                                                              \
+        const void* fn = (const void*)k_features_v3<AT_, MO_, NT_>;                                                \
+        if (smem > 48 * 1024 && (set_fn != fn || set_sz != smem)) {                                                \
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
+            set_fn = fn; set_sz = smem;                                                                            \
+        }                                                                                                          \
+        k_features_v3<AT_, MO_, NT_><<<grid, NT_, smem, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0, dpv); \
+    }
+#define PM_FEAT3_CASE(MO_)                                                                                          \
+    case MO_:                                                                                                      \
+        if (!big) PM_FEAT3_LAUNCH(4, MO_, 256)                                                                     \
+        else if (at == 4) PM_FEAT3_LAUNCH(4, MO_, 512)                                                             \
+        else if (at == 2) PM_FEAT3_LAUNCH(2, MO_, 512)                                                             \
+        else PM_FEAT3_LAUNCH(1, MO_, 512)                                                                          \
         break;
         switch (mo) {
             PM_FEAT3_CASE(1) PM_FEAT3_CASE(2) PM_FEAT3_CASE(3) PM_FEAT3_CASE(4) PM_FEAT3_CASE(5) PM_FEAT3_CASE(6)
         }
 #undef PM_FEAT3_CASE
-        if (smem4 > 48 * 1024) g_feat3_smem_set = smem4;
+#undef PM_FEAT3_LAUNCH
         dpv_fallback.armed = false;
         return;
     }
