@@ -987,7 +987,7 @@ __global__ void __launch_bounds__(256) k_xrows_mma(DevModel m, DevBatch b, const
                                                     const double* __restrict__ Lbuf, const double* __restrict__ Xown,
                                                     const double* __restrict__ Sbuf, double* __restrict__ X,
                                                     double* __restrict__ xe_sum, double* __restrict__ xe_sq,
-                                                    int mode, int apply_w) {
+                                                    int mode, int apply_w, int skip_linear) {
     extern __shared__ __align__(16) double smem[];
     double* sD = smem;                            // [XR_KC][XR_LD]  D[c][a]  (a-tile)
     double* sL = sD + XR_KC * XR_LD;              // [XR_KC][XR_LD]  Lambda[c][b] (b-tile)
@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(256) k_xrows_mma(DevModel m, DevBatch b, const
         double* xr = X + (size_t)row * m.fpad;
 
         // ---- linear columns: one thread per global linear feature -------------------------------
-        for (int col = tid; col < m.n_linear; col += 256) {
+        for (int col = tid; col < (skip_linear ? 0 : m.n_linear); col += 256) {
             double val = 0.0;
             for (int c = 0; c < n_cent; ++c) {
                 int atom; const double* lam; double sgn = 1.0;
@@ -2068,6 +2068,140 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Linear columns of K4b for models with thousands of linear features (the generic k_xrows_mma walks the centres
+// one dependent load at a time per column).  Force rows: CTA per row atom k, the centre list (own row + reverse
+// pairs) staged in shared memory, thread = column, the three Cartesian rows summed together, four centres
+// (12 loads) in flight.  Energy / virial rows: grid (structure, block of 256 columns), seven sums per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int XL_KC = 128;
+
+__device__ __forceinline__ int xl_pick(int t, int f0, int f1, int f2, int f3) {
+    return t == 0 ? f0 : (t == 1 ? f1 : (t == 2 ? f2 : f3));
+}
+
+__global__ void __launch_bounds__(256) k_xlin_force(DevModel m, DevBatch b, const double* __restrict__ Lbuf,
+                                                     const double* __restrict__ Xown, double* __restrict__ X, int apply_w) {
+    __shared__ const double* sBase[XL_KC];
+    __shared__ double sSgn[XL_KC];
+    __shared__ int sTy[XL_KC];
+    const int k_atom = blockIdx.x, tid = threadIdx.x, nt = m.n_type;
+    const int s = b.st_of_atom[k_atom];
+    if (!b.force[s]) return;
+    const int p0 = b.seg_off[k_atom * nt];
+    const int n_cent = 1 + b.seg_off[k_atom * nt + nt] - p0;
+    const int row0 = b.frow[s] + 3 * (k_atom - b.atom_off[s]);
+    double w[3];
+#pragma unroll
+    for (int al = 0; al < 3; ++al) w[al] = apply_w ? b.w[row0 + al] : 1.0;
+    double* xr = X + (size_t)row0 * m.fpad;
+    const size_t fl = m.fl;
+    for (int c0 = 0; c0 < n_cent; c0 += XL_KC) {
+        const int ncc = min(XL_KC, n_cent - c0);
+        __syncthreads();
+        if (tid < ncc) {
+            const int c = c0 + tid;
+            if (c == 0) {
+                sBase[tid] = Xown + (size_t)k_atom * 3 * fl; sSgn[tid] = 1.0; sTy[tid] = b.types[k_atom];
+            } else {
+                const int p = p0 + c - 1;
+                sBase[tid] = Lbuf + (size_t)b.rev[p] * 3 * fl; sSgn[tid] = -1.0; sTy[tid] = b.types[b.nbr[p]];
+            }
+        }
+        __syncthreads();
+        for (int col = tid; col < m.n_linear; col += 256) {
+            int fpt[MAXT];
+#pragma unroll
+            for (int t = 0; t < MAXT; ++t) {
+                fpt[t] = -1;
+                if (t < nt) {
+                    const DevPolyTerm tm = m.types[t].colterm[col];
+                    if (tm.order) fpt[t] = tm.fp0;
+                }
+            }
+            double v[3] = {0.0, 0.0, 0.0};
+            int cc = 0;
+            for (; cc + 4 <= ncc; cc += 4) {
+                double x[4][3];
+                double sg[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int fp = xl_pick(sTy[cc + u], fpt[0], fpt[1], fpt[2], fpt[3]);
+                    sg[u] = fp >= 0 ? sSgn[cc + u] : 0.0;
+                    const double* base = sBase[cc + u] + max(fp, 0);
+#pragma unroll
+                    for (int al = 0; al < 3; ++al) x[u][al] = base[al * fl];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int al = 0; al < 3; ++al) v[al] += sg[u] * x[u][al];
+            }
+            for (; cc < ncc; ++cc) {
+                const int fp = xl_pick(sTy[cc], fpt[0], fpt[1], fpt[2], fpt[3]);
+                if (fp >= 0) {
+                    const double* base = sBase[cc] + fp;
+#pragma unroll
+                    for (int al = 0; al < 3; ++al) v[al] += sSgn[cc] * base[al * fl];
+                }
+            }
+#pragma unroll
+            for (int al = 0; al < 3; ++al) {
+                double* dst = xr + (size_t)al * m.fpad + col;
+                *dst = c0 == 0 ? w[al] * v[al] : *dst + w[al] * v[al];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_xlin_struct(DevModel m, DevBatch b, const double* __restrict__ dfeat,
+                                                      const double* __restrict__ Sbuf, double* __restrict__ X,
+                                                      double* __restrict__ xe_sum, double* __restrict__ xe_sq, int apply_w) {
+    const int s = blockIdx.x, col = blockIdx.y * 256 + threadIdx.x, nt = m.n_type;
+    if (col >= m.n_linear) return;
+    const bool force = b.force[s] != 0;
+    const int a0 = b.atom_off[s], a1 = b.atom_off[s + 1];
+    int fpt[MAXT];
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+        fpt[t] = -1;
+        if (t < nt) {
+            const DevPolyTerm tm = m.types[t].colterm[col];
+            if (tm.order) fpt[t] = tm.fp0;
+        }
+    }
+    const size_t fl = m.fl;
+    double e = 0.0, sv[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int a = a0; a < a1; a += 2) {
+        double xe[2], xs[2][6];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int atom = min(a + u, a1 - 1);
+            const int fp = xl_pick(b.types[atom], fpt[0], fpt[1], fpt[2], fpt[3]);
+            const bool on = fp >= 0 && a + u < a1;
+            xe[u] = on ? dfeat[(size_t)atom * fl + fp] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) xs[u][r] = (on && force) ? Sbuf[((size_t)atom * 6 + r) * fl + fp] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            e += xe[u];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) sv[r] += xs[u][r];
+        }
+    }
+    if (xe_sum) { atomicAdd(xe_sum + col, e); atomicAdd(xe_sq + col, e * e); }
+    const int er = b.erow[s];
+    X[(size_t)er * m.fpad + col] = (apply_w ? b.w[er] : 1.0) * e;
+    if (force) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int row = b.srow[s] + r;
+            X[(size_t)row * m.fpad + col] = (apply_w ? b.w[row] : 1.0) * sv[r];
+        }
+    }
+}
+
 size_t xrows_mma_smem(const DevModel& m) {
     return (2ull * XR_KC * XR_LD + (size_t)m.npv_pad * (m.npv_pad + 1)) * sizeof(double) + 2 * XR_KC * sizeof(int);
 }
@@ -2081,10 +2215,17 @@ void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws,
         cudaFuncSetAttribute(k_xrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set_for = smem;
     }
+    // thousands of linear columns: dedicated gather kernels, k_xrows_mma keeps the polynomial part only
+    const int big = m.n_linear >= 1024 ? 1 : 0;
+    if (big) {
+        k_xlin_force<<<b.n_atoms, 256, 0, s>>>(m, b, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
+        k_xlin_struct<<<dim3(b.n_st, (m.n_linear + 255) / 256), 256, 0, s>>>(m, b, ws.dfeat, ws.Sbuf, ws.X, xe_sum, xe_sq,
+                                                                            apply_weights ? 1 : 0);
+    }
     k_xrows_mma<<<b.n_atoms, 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
-                                             apply_weights ? 1 : 0);
+                                             apply_weights ? 1 : 0, big);
     k_xrows_mma<<<dim3(b.n_st, 7), 256, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
-                                                   apply_weights ? 1 : 0);
+                                                   apply_weights ? 1 : 0, big);
 }
 
 // ================================================================================================
