@@ -17,7 +17,7 @@
 
 namespace pm {
 void set_features_smem(size_t smem_bytes);
-void set_lrows_kmax(int kmax);
+void set_lrows_kmax(int kmax, int runmax, int tilemax);
 size_t lrows_mma_smem(const DevModel& m);
 bool lrows_big_supported(const DevModel& m);
 size_t xrows_mma_smem(const DevModel& m);
@@ -98,6 +98,7 @@ struct pm_context {
     int device = 0;
     int flags = 0;
     size_t ws_cap = 0;
+    size_t ws_cap_max = 0;   // > ws_cap: plan_chunks may grow the workspace for large models (default workspace only)
     cudaStream_t stream = nullptr;
     DevModel dm{};
     std::vector<void*> table_allocs;
@@ -179,7 +180,21 @@ static void build_device_model(pm_context* c) {
         for (int u = 0; u < d.n_type; ++u)
             for (int n = 0; n < d.n_fn; ++n) kmax = std::max(kmax, 2 * (T.seg_n_off[u][n + 1] - T.seg_n_off[u][n]));
     }
-    set_lrows_kmax(kmax);
+    {   // longest run of G blocks / most feature tiles of one (type, neighbour type, radial index): table sizes of k_lrows_big
+        int runmax = 1, tilemax = 1;
+        for (const auto& T : hm.types) {
+            const int ntile = T.n_fpad / 8;
+            std::vector<int> first(d.n_fn + 1, ntile);
+            for (int tile = ntile - 1; tile >= 0; --tile) first[T.tile_n[tile]] = tile;
+            for (int n = d.n_fn - 1; n >= 0; --n) first[n] = std::min(first[n], first[n + 1]);
+            for (int n = 0; n < d.n_fn; ++n) {
+                tilemax = std::max(tilemax, first[n + 1] - first[n]);
+                for (int u = 0; u < d.n_type; ++u)
+                    runmax = std::max(runmax, T.tile_blk_off[u][first[n + 1]] - T.tile_blk_off[u][first[n]]);
+            }
+        }
+        set_lrows_kmax(kmax, runmax, tilemax);
+    }
     {   // fast-path template selection for K4a: (tiles per radial index, k-chunks per radial group)
         int tpn = 1;
         for (const auto& T : hm.types) {
@@ -271,7 +286,7 @@ static void build_device_model(pm_context* c) {
         D.tile_n_off = upload(c, tile_n_off);
         for (int u = 0; u < MAXT; ++u) {
             D.seg_heads[u] = nullptr; D.seg_len[u] = 0; D.seg_key[u] = nullptr; D.seg_n_off[u] = nullptr;
-            D.seg_nid[u] = nullptr; D.tile_blk_off[u] = nullptr; D.blkmap[u] = nullptr;
+            D.seg_nid[u] = nullptr; D.tile_blk_off[u] = nullptr; D.blkmap[u] = nullptr; D.tile_order[u] = nullptr;
         }
         for (int u = 0; u < d.n_type; ++u) {
             D.seg_heads[u] = upload(c, T.seg_heads[u]);
@@ -285,6 +300,15 @@ static void build_device_model(pm_context* c) {
             for (int n = 0; n < d.n_fn; ++n) nid[n] = hm.tp_nid[T.seg_tp[u]][n];
             D.seg_nid[u] = upload(c, nid);
             D.tile_blk_off[u] = upload(c, T.tile_blk_off[u]);
+            {
+                std::vector<int> ord(D.n_tiles);
+                for (int tile = 0; tile < D.n_tiles; ++tile) ord[tile] = tile;
+                const auto& tb = T.tile_blk_off[u];
+                for (int n = 0; n < d.n_fn; ++n)
+                    std::stable_sort(ord.begin() + tile_n_off[n], ord.begin() + tile_n_off[n + 1],
+                                     [&](int a, int b2) { return tb[a + 1] - tb[a] > tb[b2 + 1] - tb[b2]; });
+                D.tile_order[u] = upload(c, ord);
+            }
             D.blkmap[u] = nullptr;
             if (d.kpn > 0) {
                 std::vector<int> bm((size_t)D.n_tiles * d.kpn, -1);
@@ -584,9 +608,16 @@ static std::vector<std::pair<int, int>> plan_chunks(const pm_context* c, const p
     std::vector<std::pair<int, int>> chunks;
     int s0 = 0;
     double bytes = 0.0;
+    // Large models (MBs of G and L per atom) would get chunks of a few hundred atoms out of the default workspace:
+    // too few CTAs for 148 SMs.  Unless the caller fixed the workspace, grow it to ~2400 atoms per chunk (bounded).
+    double cap = (double)c->ws_cap;
+    if (c->ws_cap_max > c->ws_cap && st->n_st > 0 && st->n_atoms[0] > 0) {
+        const double b0 = est_bytes_per_structure(c, st->axis, st->n_atoms[0], st->force && st->force[0]);
+        cap = std::min((double)c->ws_cap_max, std::max(cap, b0 / st->n_atoms[0] * 2400.0));
+    }
     for (int s = 0; s < st->n_st; ++s) {
         const double bs = est_bytes_per_structure(c, st->axis + 9 * (size_t)s, st->n_atoms[s], st->force && st->force[s]);
-        if (s > s0 && bytes + bs > (double)c->ws_cap) {
+        if (s > s0 && bytes + bs > cap) {
             chunks.push_back({s0, s});
             s0 = s;
             bytes = 0.0;
@@ -981,6 +1012,12 @@ int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int
         build_device_model(c.get());
         const DevModel& d = c->dm;
         c->acc_n = (size_t)d.fpad * d.fpad + 2 * (size_t)d.fpad + 1;
+        if (!workspace_bytes && !getenv("PM_WORKSPACE_GB")) {
+            size_t fr = 0, tot = 0;
+            CK(cudaMemGetInfo(&fr, &tot));
+            const double avail = 0.5 * ((double)fr - 2.0 * (double)c->acc_n * sizeof(double));
+            if (avail > (double)c->ws_cap) c->ws_cap_max = (size_t)std::min(avail, 64.0 * (1ull << 30));
+        }
         *out = c.release();
     });
 }

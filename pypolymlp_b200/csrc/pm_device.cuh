@@ -63,6 +63,7 @@ struct DevType {
     const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;
     const int* tile_blk_off[MAXT];
+    const int* tile_order[MAXT];  // [n_tiles] tiles of each radial index sorted by decreasing block count in segment u
     const int* pad_gid;     // [n_fpad] global linear column of a padded feature id or -1
     const int* pad_pv;      // [n_fpad] polynomial-variable index of a padded feature id or -1
     const DevPolyTerm* colterm;

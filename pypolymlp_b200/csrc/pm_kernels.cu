@@ -748,6 +748,7 @@ __global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, cons
                                                       int nfull_max, int zero_g, double* __restrict__ dpv) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
     constexpr int NW = (MO + 1) / 2;
+    constexpr int UN = NT > 256 ? 4 : 2;   // table slots in flight per lane (the 512-thread CTAs run alone on their SM)
     const int i0 = blockIdx.x * AT;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, cons
             double sum[AT];
 #pragma unroll
             for (int a = 0; a < AT; ++a) sum[a] = 0.0;
-#pragma unroll 2
+#pragma unroll UN
             for (int it = 0; it < meta.y; ++it) {
                 const long slot = meta.x + it * 32 + lane;
                 const double cf = coef[slot];
@@ -842,7 +843,7 @@ __global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, cons
             double gr[AT], gi[AT];
 #pragma unroll
             for (int a = 0; a < AT; ++a) { gr[a] = 0.0; gi[a] = 0.0; }
-#pragma unroll 2
+#pragma unroll UN
             for (int it = 0; it < meta.y; ++it) {
                 const long slot = meta.x + it * 32 + lane;
                 const double cf = coef[slot];

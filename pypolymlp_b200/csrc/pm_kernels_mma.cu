@@ -450,16 +450,22 @@ __global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const
 // of every segment and are accumulated over the segments into Xown / Sbuf.
 // Only the row tiles that hold rows are multiplied, so ragged segments cost what they contain.
 // ------------------------------------------------------------------------------------------------
-constexpr int LB_THREADS = 256;
+// asynchronous L2 prefetch of a contiguous global range (one instruction; bytes is a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
+}
 
-template <int MRT>
-__global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatch b, const double* __restrict__ PB,
-                                                            const double2* __restrict__ agg,
-                                                            const double* __restrict__ Gbuf, double* __restrict__ Lbuf,
-                                                            double* __restrict__ Xown, double* __restrict__ Sbuf, int ldv) {
+// MRT row tiles (8 rows each) per chunk, NT threads; (8 | 9, 256): two CTAs per SM, (12, 512): one CTA per SM whose
+// chunk holds a whole ~96-row segment, so that G is walked once per segment
+template <int MRT, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_lrows_big(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                                    const double2* __restrict__ agg,
+                                                                    const double* __restrict__ Gbuf, double* __restrict__ Lbuf,
+                                                                    double* __restrict__ Xown, double* __restrict__ Sbuf,
+                                                                    int ldv, int kmax, int runmax, int tilemax) {
     extern __shared__ __align__(16) double smem[];
     constexpr int MR = 8 * MRT;                      // rows per chunk
-    constexpr int NKL = LB_THREADS / 32;             // one k-lane per warp in the V build
+    constexpr int NW = NT / 32;                      // warps; one k-lane per warp in the V build
     const int i = blockIdx.x;
     if (!b.force[b.st_of_atom[i]]) return;
     const int t = b.types[i];
@@ -468,10 +474,13 @@ __global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatc
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     double* V = smem;                                // [2 * heads of the radial group][ldv]
+    int* sKc = reinterpret_cast<int*>(V + (size_t)kmax * ldv);   // [runmax] k-chunk of each block of the run, relative
+    int* sTb = sKc + runmax;                                     // [tiles of the radial index + 1] block offsets, relative
+    int* sOrd = sTb + tilemax + 1;                               // [tiles of the radial index] tiles by decreasing block count
     const double* G = Gbuf + (size_t)i * m.gstride;
     const int oy = pb_y(m, 0);
-    for (int e = tid; e < 3 * m.fl; e += LB_THREADS) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
-    for (int e = tid; e < 6 * m.fl; e += LB_THREADS) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
+    for (int e = tid; e < 3 * m.fl; e += NT) Xown[(size_t)i * 3 * m.fl + e] = 0.0;
+    for (int e = tid; e < 6 * m.fl; e += NT) Sbuf[(size_t)i * 6 * m.fl + e] = 0.0;
 
     for (int u = 0; u < nt; ++u) {
         const int p0 = b.seg_off[i * nt + u], p1 = b.seg_off[i * nt + u + 1];
@@ -483,29 +492,46 @@ __global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatc
         const int* snoff = T.seg_n_off[u];
         const int* snid = T.seg_nid[u];
         const int* tboff = T.tile_blk_off[u];
+        // the blocks of G that one (segment, radial index) needs are contiguous: fetch the next run into L2 while
+        // the current one is multiplied
+        auto prefetch_run = [&](int n_) {
+            if (tid != 0 || n_ >= m.n_fn) return;
+            const int bb = tboff[T.tile_n_off[n_]], be = tboff[T.tile_n_off[n_ + 1]];
+            if (be > bb) bulk_prefetch_l2(G + 32 * (size_t)bb, (unsigned)(be - bb) * 256u);
+        };
         // equal chunks: ceil(rows / chunks) rounded up to row tiles
         const int nchunk = (nrow_all + MR - 1) / MR;
         const int crow = ((nrow_all + nchunk - 1) / nchunk + 7) & ~7;
         for (int row0 = 0; row0 < nrow_all; row0 += crow) {
             const int rows_here = min(crow, nrow_all - row0);
             const int n_rt = (rows_here + 7) >> 3;
-            // V build: each warp owns one k-lane; its lanes cover the rows of the chunk in passes of 32
+            prefetch_run(0);
             for (int n = 0; n < m.n_fn; ++n) {
                 const int h0 = snoff[n], h1 = snoff[n + 1];
                 const int tile_b = T.tile_n_off[n], tile_e = T.tile_n_off[n + 1];
                 if (h1 == h0) {  // radial index inactive for this type pair: the pair rows are exactly zero
-                    for (int tile = tile_b + warp; tile < tile_e; tile += NKL)
+                    for (int tile = tile_b + warp; tile < tile_e; tile += NW)
 #pragma unroll
                         for (int rt = 0; rt < MRT; ++rt) {
                             const int r = row0 + rt * 8 + g;
                             if (rt < n_rt && r < nrow)
-                                *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q) =
-                                    make_double2(0.0, 0.0);
+                                __stcs(reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q),
+                                       make_double2(0.0, 0.0));
                         }
                     continue;
                 }
                 const int nid = snid[n];
-                __syncthreads();  // the previous V tile is fully consumed
+                const int ntile_n = tile_e - tile_b;
+                const int run0 = tboff[tile_b];
+                const int kc0 = h0 >> 1;
+                __syncthreads();  // the previous V tile and block tables are fully consumed
+                {   // block tables of the run (short-latency LDS in the multiply loop instead of dependent global loads)
+                    const int run_len = tboff[tile_e] - run0;
+                    for (int e = tid; e < run_len; e += NT) sKc[e] = T.blk_kchunk[run0 + e] - kc0;
+                    for (int e = tid; e <= ntile_n; e += NT) sTb[e] = tboff[tile_b + e] - run0;
+                    for (int e = tid; e < ntile_n; e += NT) sOrd[e] = T.tile_order[u][tile_b + e] - tile_b;
+                }
+                // V build: each warp owns one k-lane; its lanes cover the rows of the chunk in passes of 32
                 for (int rl = lane; rl < 8 * n_rt; rl += 32) {
                     const int row = row0 + rl;
                     double* vcol = V + rl;
@@ -516,7 +542,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatc
                         const double c1 = rec[4 + m.n_fn + nid] * (rec[al] * rec[3]);
                         const PBRec ry = rec + oy, rya = rec + pb_y(m, 1 + al);
 #pragma unroll 4
-                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                        for (int hq = h0 + warp; hq < h1; hq += NW) {
                             const int key = skey[hq];
                             double vr = 0.0, vi = 0.0;
                             if (key >= 0) {
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatc
                         }
                     } else if (row < nrow_all) {
                         const int ra = row - nrow;
-                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                        for (int hq = h0 + warp; hq < h1; hq += NW) {
                             const int h = sh[hq];
                             double2 v = make_double2(0.0, 0.0);
                             if (h >= 0) v = agg[((size_t)i * m.hmax + h) * 9 + ra];
@@ -536,88 +562,126 @@ __global__ void __launch_bounds__(LB_THREADS, 2) k_lrows_big(DevModel m, DevBatc
                             vcol[(size_t)(2 * (hq - h0) + 1) * ldv] = v.y;
                         }
                     } else {
-                        for (int hq = h0 + warp; hq < h1; hq += NKL) {
+                        for (int hq = h0 + warp; hq < h1; hq += NW) {
                             vcol[(size_t)(2 * (hq - h0)) * ldv] = 0.0;
                             vcol[(size_t)(2 * (hq - h0) + 1) * ldv] = 0.0;
                         }
                     }
                 }
                 __syncthreads();
-                const int kc0 = h0 >> 1;
-                for (int tile = tile_b + warp; tile < tile_e; tile += NKL) {
+                prefetch_run(n + 1);
+                // multiply: the warp walks its tiles; the B fragments of the next group of four blocks (of this tile or
+                // of the warp's next tile) are in flight while the current group is multiplied
+                const double* Grun = G + 32 * (size_t)run0 + lane;
+                double bf[4];
+                int kc[4];
+                auto load_group = [&](double (&f)[4], int (&k)[4], int bk, int b1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool on = bk + j < b1;
+                        f[j] = on ? __ldcs(Grun + 32 * (size_t)(bk + j)) : 0.0;   // streamed: L2 is kept for the pair records
+                        k[j] = on ? sKc[bk + j] : 0;
+                    }
+                };
+                // tiles are dealt to the warps in decreasing block count, back and forth (slot r * NW + w, reversed in odd
+                // rounds), so that the warps reach the barrier together
+                int slot = warp, round = 0, bk = 0, b1 = 0, tl = 0;
+                if (slot < ntile_n) { tl = sOrd[slot]; bk = sTb[tl]; b1 = sTb[tl + 1]; load_group(bf, kc, bk, b1); }
+                while (slot < ntile_n) {
                     double acc[MRT][2];
 #pragma unroll
                     for (int rt = 0; rt < MRT; ++rt) { acc[rt][0] = 0.0; acc[rt][1] = 0.0; }
-                    const int b1 = tboff[tile + 1];
-                    for (int bk = tboff[tile]; bk < b1; bk += 4) {
-                        double bf[4];
-                        int kcl[4];
+                    ++round;
+                    const int slot_n = round * NW + ((round & 1) ? NW - 1 - warp : warp);
+                    const int tln = slot_n < ntile_n ? sOrd[slot_n] : 0;
+                    int bk_n = 0, b1_n = 0;
+                    for (;;) {
+                        double bfn[4];
+                        int kcn[4];
+                        const int nx = bk + 4;
+                        const bool more = nx < b1;
+                        if (more) {
+                            load_group(bfn, kcn, nx, b1);
+                        } else if (slot_n < ntile_n) {
+                            bk_n = sTb[tln]; b1_n = sTb[tln + 1];
+                            load_group(bfn, kcn, bk_n, b1_n);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const bool on = bk + j < b1;
-                            bf[j] = on ? G[32 * (size_t)(bk + j) + lane] : 0.0;
-                            kcl[j] = on ? T.blk_kchunk[bk + j] - kc0 : 0;
+                            for (int j = 0; j < 4; ++j) { bfn[j] = 0.0; kcn[j] = 0; }
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (bk + j < b1) {
-                                const double* va = V + (size_t)(4 * kcl[j] + q) * ldv + g;
+                                const double* va = V + (size_t)(4 * kc[j] + q) * ldv + g;
 #pragma unroll
                                 for (int rt = 0; rt < MRT; ++rt)
                                     if (rt < n_rt) dmma(acc[rt][0], acc[rt][1], va[rt * 8], bf[j]);
                             }
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { bf[j] = bfn[j]; kc[j] = kcn[j]; }
+                        if (!more) break;
+                        bk = nx;
                     }
+                    const int tile = tile_b + tl;
 #pragma unroll
                     for (int rt = 0; rt < MRT; ++rt) {
                         if (rt >= n_rt) continue;
                         const int r = row0 + rt * 8 + g;
                         if (r < nrow) {
-                            *reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q) =
-                                make_double2(acc[rt][0], acc[rt][1]);
+                            __stcs(reinterpret_cast<double2*>(Lbuf + ((size_t)p0 * 3 + r) * m.fl + tile * 8 + 2 * q),
+                                   make_double2(acc[rt][0], acc[rt][1]));
                         } else if (r < nrow_all) {
+                            // aggregated rows: summed over the segments with RED.F64 (no read-modify-write latency)
                             const int ra = r - nrow;
                             double* dst = (ra < 3 ? Xown + ((size_t)i * 3 + ra) * m.fl : Sbuf + ((size_t)i * 6 + (ra - 3)) * m.fl) +
                                           tile * 8 + 2 * q;
-                            double2 v = *reinterpret_cast<double2*>(dst);
-                            v.x += acc[rt][0]; v.y += acc[rt][1];
-                            *reinterpret_cast<double2*>(dst) = v;
+                            atomicAdd(dst, acc[rt][0]);
+                            atomicAdd(dst + 1, acc[rt][1]);
                         }
                     }
+                    slot = slot_n; tl = tln; bk = bk_n; b1 = b1_n;
                 }
             }
         }
     }
 }
 
-static int g_lrows_kmax = 0;
-static int lrows_big_ldv(int mrt) { return mrt == 8 ? 68 : (mrt == 9 ? 76 : 100); }   // >= 8 * mrt, == 4 or 12 (mod 16)
-static size_t lrows_big_smem(int mrt) { return (size_t)g_lrows_kmax * lrows_big_ldv(mrt) * sizeof(double); }
+static int g_lrows_kmax = 0, g_lrows_runmax = 0, g_lrows_tilemax = 0;
+static int lrows_big_ldv(int mrt) { return mrt == 8 ? 68 : (mrt == 9 ? 76 : (mrt == 12 ? 100 : 132)); }   // >= 8 * mrt, == 4 or 12 (mod 16)
+static size_t lrows_big_smem(int mrt) {
+    return (size_t)g_lrows_kmax * lrows_big_ldv(mrt) * sizeof(double) + ((size_t)g_lrows_runmax + 2 * g_lrows_tilemax + 2) * sizeof(int);
+}
 bool lrows_big_supported(const DevModel& m) { return lrows_big_smem(8) <= 226 * 1024; }
 
-template <int MRT>
+template <int MRT, int NT>
 static void launch_lrows_big_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
     const size_t smem = lrows_big_smem(MRT);
     static size_t set_for = 0;
     if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_big<MRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lrows_big<MRT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set_for = smem;
     }
-    k_lrows_big<MRT><<<b.n_atoms, LB_THREADS, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
-                                                       lrows_big_ldv(MRT));
+    k_lrows_big<MRT, NT><<<b.n_atoms, NT, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
+                                                   lrows_big_ldv(MRT), g_lrows_kmax, g_lrows_runmax, g_lrows_tilemax);
 }
 
 static void launch_lrows_big(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
-    // rows of a typical segment = 3 * pairs per (atom, neighbour type) + 9; take the chunk height (64 or 72 rows, both
-    // leave two CTAs per SM when they fit) that needs fewer chunks, then fewer row tiles
+    // rows of a typical segment = 3 * pairs per (atom, neighbour type) + 9.  Up to 72 rows: one chunk of 8 or 9 row
+    // tiles, two CTAs per SM.  More: 12 row tiles in a 512-thread CTA (one per SM), so that a ~96-row segment walks G once.
     const double rows = 3.0 * b.n_pairs / std::max(1, b.n_atoms * m.n_type) + 9.0;
-    auto cost = [&](int mrt) {
-        const int nch = (int)std::ceil(rows / (8.0 * mrt));
-        return nch * 1000 + (int)std::ceil(rows / nch / 8.0) * nch;
-    };
-    const bool fits9 = 2 * (lrows_big_smem(9) + 1024) <= 228 * 1024 || lrows_big_smem(8) > 113 * 1024;
-    if (fits9 && lrows_big_smem(9) <= 226 * 1024 && cost(9) < cost(8)) launch_lrows_big_t<9>(m, b, ws, s);
-    else launch_lrows_big_t<8>(m, b, ws, s);
+    static const int force_mrt = getenv("PM_LROWS_MRT") ? atoi(getenv("PM_LROWS_MRT")) : 0;
+    const bool two9 = 2 * (lrows_big_smem(9) + 1024) <= 228 * 1024;
+    int mrt = 8;
+    if (rows > 64.0 && rows <= 72.0 && two9) mrt = 9;
+    else if (rows > 84.0 && lrows_big_smem(16) <= 226 * 1024) mrt = 16;     // segments around 96 rows: 12 tiles would split half of them
+    else if (rows > 72.0 && lrows_big_smem(12) <= 226 * 1024) mrt = 12;
+    if ((force_mrt == 8 || force_mrt == 9 || force_mrt == 12 || force_mrt == 16) && lrows_big_smem(force_mrt) <= 226 * 1024)
+        mrt = force_mrt;
+    if (mrt == 16) launch_lrows_big_t<16, 512>(m, b, ws, s);
+    else if (mrt == 12) launch_lrows_big_t<12, 512>(m, b, ws, s);
+    else if (mrt == 9) launch_lrows_big_t<9, 256>(m, b, ws, s);
+    else launch_lrows_big_t<8, 256>(m, b, ws, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -952,7 +1016,7 @@ static bool launch_lrows_v2(const DevModel& m, const DevBatch& b, const Workspac
 }
 
 // set by the context at model upload (max over types/segments/radial groups of 2 * padded heads)
-void set_lrows_kmax(int kmax) { g_lrows_kmax = kmax; }
+void set_lrows_kmax(int kmax, int runmax, int tilemax) { g_lrows_kmax = kmax; g_lrows_runmax = runmax; g_lrows_tilemax = tilemax; }
 size_t lrows_mma_smem(const DevModel& m) {
     return ((size_t)m.pbstride * LR_PLD + 4ull * g_lrows_kmax * LR_LD) * sizeof(double);
 }
