@@ -914,10 +914,16 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
     bool sliced = mo <= 6;
     for (int t = 0; t < m.n_type; ++t) sliced = sliced && m.types[t].n_fsl > 0;
     if (sliced) {
-        // atoms per CTA: as many as fit (every table read is shared by the CTA's atoms).  Small models: 4 atoms,
-        // 256 threads, several CTAs per SM; big a_nlm arrays (max_l ~ 12): one 512-thread CTA per SM with 4, 2 or 1 atoms
+        // atoms per CTA (every table read is shared by the CTA's atoms).  Small models: 4 atoms, 256 threads, several
+        // CTAs per SM; big a_nlm arrays (max_l ~ 12): 512-thread CTAs with 4, 2 or 1 atoms, two per SM when they fit
         const size_t cap = 226 * 1024;
-        const int at = smem4 <= cap ? 4 : (2 * smem_bytes <= cap ? 2 : 1);
+        // measured (config 3 / 4): two 512-thread CTAs per SM beat one CTA with twice the atoms (latency-bound gathers)
+        const size_t half = 113 * 1024;
+        int at = smem4 <= half ? 4 : (2 * smem_bytes <= half ? 2 : (smem_bytes <= half ? 1 : (2 * smem_bytes <= cap ? 2 : 1)));
+        if (smem4 > 96 * 1024 && getenv("PM_FEAT_AT")) {
+            const int want = atoi(getenv("PM_FEAT_AT"));
+            if ((want == 1 || want == 2 || want == 4) && want * smem_bytes <= cap) at = want;
+        }
         const bool big = smem4 > 96 * 1024;
         const size_t smem = smem_bytes * at;
         const int grid = (b.n_atoms + at - 1) / at;

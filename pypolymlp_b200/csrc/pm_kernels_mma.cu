@@ -670,7 +670,7 @@ static void launch_lrows_big(const DevModel& m, const DevBatch& b, const Workspa
     // rows of a typical segment = 3 * pairs per (atom, neighbour type) + 9.  Up to 72 rows: one chunk of 8 or 9 row
     // tiles, two CTAs per SM.  More: 12 row tiles in a 512-thread CTA (one per SM), so that a ~96-row segment walks G once.
     const double rows = 3.0 * b.n_pairs / std::max(1, b.n_atoms * m.n_type) + 9.0;
-    static const int force_mrt = getenv("PM_LROWS_MRT") ? atoi(getenv("PM_LROWS_MRT")) : 0;
+    const int force_mrt = getenv("PM_LROWS_MRT") ? atoi(getenv("PM_LROWS_MRT")) : 0;
     const bool two9 = 2 * (lrows_big_smem(9) + 1024) <= 228 * 1024;
     int mrt = 8;
     if (rows > 64.0 && rows <= 72.0 && two9) mrt = 9;

@@ -182,6 +182,41 @@ def test_x_config3_binary_order4_maxl12():
     assert np.abs(res["xty"] - xw.T @ y).max() < 1e-10 * np.abs(xw.T @ y).max()
 
 
+@pytest.mark.parametrize("mrt", ["8", "9", "12", "16", ""])
+def test_x_large_model_kernels_ragged_vs_straightforward(mrt, monkeypatch):
+    """Large-model kernels (k_lrows_big in all its row-tile variants, the 512-thread sliced feature kernel, the
+    staged linear-column gathers) against the straightforward kernels -- which the reference goldens pin on this
+    model (test above) -- on what the goldens do not cover: ragged neighbour-type segments, a structure without
+    atoms of one type (empty segments), an energy-only structure, segments longer than one chunk."""
+    if mrt:
+        monkeypatch.setenv("PM_LROWS_MRT", mrt)
+    else:
+        monkeypatch.delenv("PM_LROWS_MRT", raising=False)
+    pd = make_params_dict(**cases.cfg3_model_kwargs())
+    sts = [cases.skewed_cell(2, n_atom=5, seed=11), cases.skewed_cell(1, n_atom=3, seed=12),
+           cases.skewed_cell(2, n_atom=2, seed=13), cases.bcc_supercell(rep=(2, 2, 1), a=3.2, n_type=2, seed=14)]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    n_atoms = [len(t) for t in tys]
+    args = (pd, axis, pcs, tys, [2, 1, 1], [True, False, True], n_atoms)
+    x_ref = PotentialModel(*args, flags=PM_FLAG_SIMPLE_KERNELS).get_x()
+    x = PotentialModel(*args).get_x()
+    assert x.shape == x_ref.shape and np.isfinite(x).all()
+    assert cases.x_rel_err(x, x_ref) < 1e-10
+    rows = x.shape[0]
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.2, 1.0, rows)
+    y = w * rng.normal(size=rows)
+    force = [True, True, False, True]
+    ra = PotentialXtX(pd, flags=PM_FLAG_SIMPLE_KERNELS)
+    ra.add(axis, pcs, tys, force, w, y)
+    r0 = ra.finalize()
+    rb = PotentialXtX(pd)
+    rb.add(axis, pcs, tys, force, w, y)
+    r1 = rb.finalize()
+    for k in ("xtx", "xty", "xe_sum", "xe_sq_sum"):
+        assert np.abs(r1[k] - r0[k]).max() <= 1e-10 * np.abs(r0[k]).max(), k
+
+
 def _si_datasets(ids):
     axis, positions_c, forces, energies = cases.load_si_dataset()
     return fit.Dataset([axis] * len(ids), [positions_c[i] for i in ids], [np.zeros(64, np.int32)] * len(ids),
