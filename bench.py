@@ -293,7 +293,7 @@ def main():
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         # DRAM traffic of one SYRK launch from the committed ncu --set full capture (profiles/r01_ncu_kernels.json):
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (K5 runs per block of <= 32768 X rows)
-        traffic, traffic_alg = None, None
+        traffic, traffic_alg, rows_cap = None, None, 0
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]
             met, rows_cap = cap["metrics"], cap.get("rows_in_launch", 32768)
@@ -306,7 +306,7 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": "k_syrk_sk (fp64 DMMA m8n8k4, stream-K SYRK)", "achieved": syrk_tflops, "peak": peak,
             "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
-            "traffic_note": "DRAM bytes of one SYRK launch (a 32k-row block of a chunk; ncu --set full, "
+            "traffic_note": "DRAM bytes of the captured SYRK launch (%d X rows; ncu --set full, " % (rows_cap if traffic else 0) +
                             "profiles/r01_ncu_kernels.json); algorithmic bytes of that launch in traffic_algorithmic",
             "traffic_algorithmic": traffic_alg,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
