@@ -39,6 +39,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // ================================================================================================
 constexpr int SY_BM = 128, SY_BK = 32, SY_STAGES = 3, SY_LD = SY_BM + 4;  // 132 == 4 (mod 16)
 constexpr int SY_STAGE_DOUBLES = 2 * SY_BK * SY_LD;
+constexpr int SY_ISSUE_AT = 2;          // k-step of a k-block behind which the next cp.async stage is issued
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * SY_STAGE_DOUBLES * sizeof(double);
 constexpr int SY_ROW_BLOCK = 32768;   // rows per SYRK launch (multiple of SY_BK)
 
@@ -207,17 +208,19 @@ __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_r
         for (int kt = 0; kt < nk; ++kt) {
             cp_async_wait<SY_STAGES - 2>();
             __syncthreads();
-            {
-                const int nx = kt + SY_STAGES - 1;
-                if (nx < nk) load_stage(nx, nx % SY_STAGES);
-                cp_async_commit();
-            }
             const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
             const double* sB = diag ? sA : sA + SY_BK * SY_LD;
             const double* pa = sA + q * SY_LD + wm * 64 + g;
             const double* pb = sB + q * SY_LD + wn * 32 + g;
 #pragma unroll
             for (int ks = 0; ks < SY_BK / 4; ++ks) {
+                if (ks == SY_ISSUE_AT) {
+                    // the copies of k-block kt + 2 are issued behind the first DMMAs of this k-block (the slot they
+                    // overwrite was released by the barrier above), so the tensor pipe is fed right after the barrier
+                    const int nx = kt + SY_STAGES - 1;
+                    if (nx < nk) load_stage(nx, nx % SY_STAGES);
+                    cp_async_commit();
+                }
                 double af[8], bf[4];
 #pragma unroll
                 for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
