@@ -31,6 +31,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
 }
+// asynchronous L2 prefetch of a contiguous global range (one instruction; bytes is a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
@@ -453,11 +458,6 @@ __global__ void __launch_bounds__(128) k_lrows_mma(DevModel m, DevBatch b, const
 // of every segment and are accumulated over the segments into Xown / Sbuf.
 // Only the row tiles that hold rows are multiplied, so ragged segments cost what they contain.
 // ------------------------------------------------------------------------------------------------
-// asynchronous L2 prefetch of a contiguous global range (one instruction; bytes is a multiple of 16)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
-}
-
 // MRT row tiles (8 rows each) per chunk, NT threads; (8 | 9, 256): two CTAs per SM, (12, 512): one CTA per SM whose
 // chunk holds a whole ~96-row segment, so that G is walked once per segment
 template <int MRT, int NT>
