@@ -116,6 +116,13 @@ int64_t pm_batch_rows(const pm_structures* st);
 int pm_neighbor_full(pm_context* c, const double* axis, const double* positions_c, const int* types,
                      int n_atom, int* offsets, int* neigh, double* dx, double* dy, double* dz);
 
+/* ---- lattice translations / cell reduction (NeighborCell, compute/neighbor_cell.cpp:11-19,126-168,203-256) ----
+ * Host only (no device needed).  positions_c: (3, n_atom) row-major.  axis_out[9] / positions_out (same shape) receive
+ * the possibly refined cell and the atoms wrapped into it; *n_trans is always set, trans[cap][3] is filled when
+ * cap >= *n_trans.  Same translation order as the reference. */
+int pm_cell_translations(const double* axis, const double* positions_c, int n_atom, double cutoff, double* axis_out,
+                         double* positions_out, int* n_trans, double* trans, int cap);
+
 /* ---- design matrix (PotentialModel::get_x, compute/py_model.cpp:10-54) -----------------------------
  * x: row-major (pm_batch_rows, n_features) in HOST memory, unweighted. */
 int pm_features_x(pm_context* c, const pm_structures* st, double* x);

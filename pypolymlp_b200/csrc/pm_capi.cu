@@ -1048,6 +1048,20 @@ void pm_context_destroy(pm_context* c) {
     delete c;
 }
 
+int pm_cell_translations(const double* axis, const double* positions_c, int n_atom, double cutoff, double* axis_out,
+                         double* positions_out, int* n_trans, double* trans, int cap) {
+    return guarded([&] {
+        if (!axis || !n_trans || n_atom < 0 || (n_atom > 0 && !positions_c)) throw std::invalid_argument("null argument");
+        std::vector<double> pos(positions_c, positions_c + 3 * (size_t)n_atom);
+        CellTranslations ct;
+        find_translations(axis, pos.data(), n_atom, cutoff, ct);
+        *n_trans = (int)(ct.trans.size() / 3);
+        if (axis_out) std::copy(ct.axis, ct.axis + 9, axis_out);
+        if (positions_out) std::copy(pos.begin(), pos.end(), positions_out);
+        if (trans && cap >= *n_trans) std::copy(ct.trans.begin(), ct.trans.end(), trans);
+    });
+}
+
 int64_t pm_batch_rows(const pm_structures* st) {
     int64_t r = st->n_st;
     for (int s = 0; s < st->n_st; ++s)

@@ -10,6 +10,7 @@
 //       .get_e() .get_f() .get_s() .get_e_array() .get_f_array() .get_s_array() (pybind11_mlp.cpp:51-67)
 //   Readgtinv(order, maxl, version) .get_lm_seq() .get_l_comb() .get_lm_coeffs() (pybind11_mlp.cpp:84-94)
 //   FeaturesAttr(params_dict) .get_n_features()                                  (subset of :70-82)
+//   Neighbor / NeighborHalf / NeighborFull / NeighborCell test hooks             (pybind11_mlp.cpp:96-142)
 //   PotentialHybridModel(params_dict_array, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all)
 //       .get_x() .get_fbegin() .get_sbegin() .get_cumulative_n_features() .get_n_data()  (pybind11_mlp.cpp:30-49)
 // Additive: PotentialXtX(params_dict) .add(...) .finalize() -- the fused feature + X^T X accumulation.
@@ -20,6 +21,7 @@
 #include <pybind11/stl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <memory>
 #include <stdexcept>
@@ -35,6 +37,7 @@ using vector3i = std::vector<vector2i>;
 using vector1d = std::vector<double>;
 using vector2d = std::vector<vector1d>;
 using vector3d = std::vector<vector2d>;
+using vector4d = std::vector<vector3d>;
 
 namespace {
 
@@ -429,6 +432,146 @@ class PyFeaturesAttr {
     int get_n_features() const { return pm_model_n_features(model.h); }
 };
 
+// ---- test hooks of the reference on the neighbour-list row (pybind11_mlp.cpp:96-142) ---------------------------
+// NeighborCell is host code (lattice translations, cell reduction); Neighbor / NeighborFull / NeighborHalf run the device
+// neighbour kernels (K1) through pm_neighbor_full on a throw-away context whose model only carries n_type and the cutoff.
+class PyNeighborCell {
+    vector2d axis_, pos_, trans_;
+
+  public:
+    PyNeighborCell(const vector2d& axis, const vector2d& positions_c, const double cutoff) {
+        if (axis.size() != 3 || positions_c.size() != 3) throw std::invalid_argument("axis must be 3x3, positions_c 3xN");
+        const int n = (int)positions_c[0].size();
+        vector1d a(9), p(3 * (size_t)n), ao(9), po(3 * (size_t)n);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) a[3 * r + c] = axis[r].at(c);
+            for (int k = 0; k < n; ++k) p[(size_t)r * n + k] = positions_c[r].at(k);
+        }
+        int nt = 0;
+        check(pm_cell_translations(a.data(), p.data(), n, cutoff, ao.data(), po.data(), &nt, nullptr, 0));
+        vector1d tr(3 * (size_t)std::max(nt, 1));
+        check(pm_cell_translations(a.data(), p.data(), n, cutoff, nullptr, nullptr, &nt, tr.data(), nt));
+        axis_.assign(3, vector1d(3));
+        pos_.assign(3, vector1d(n));
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) axis_[r][c] = ao[3 * r + c];
+            for (int k = 0; k < n; ++k) pos_[r][k] = po[(size_t)r * n + k];
+        }
+        for (int k = 0; k < nt; ++k) trans_.push_back({tr[3 * k], tr[3 * k + 1], tr[3 * k + 2]});
+    }
+    const vector2d& get_axis() const { return axis_; }
+    const vector2d& get_positions_cartesian() const { return pos_; }
+    const vector2d& get_translations() const { return trans_; }
+};
+
+struct NeighborList {
+    int n_atom = 0;
+    vector1i off, nbr;
+    vector1d dx, dy, dz;
+    // full list with the atoms typed as given (entries of an atom: by neighbour type, then (j, translation))
+    void build(const vector2d& axis, const vector2d& positions_c, const vector1i& types, int n_type, double cutoff) {
+        if (axis.size() != 3 || positions_c.size() != 3) throw std::invalid_argument("axis must be 3x3, positions_c 3xN");
+        n_atom = (int)positions_c[0].size();
+        if ((int)types.size() != n_atom) throw std::invalid_argument("types / positions size mismatch");
+        vector1d a(9), p(3 * (size_t)n_atom);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) a[3 * r + c] = axis[r].at(c);
+            for (int k = 0; k < n_atom; ++k) p[(size_t)r * n_atom + k] = positions_c[r].at(k);
+        }
+        // minimal pair-feature model: one cutoff-only radial function for every type pair
+        const int ntp = n_type * (n_type + 1) / 2;
+        vector1d pp{0.0, 0.0};
+        vector1i offs(ntp + 1), vals(ntp, 0);
+        for (int k = 0; k <= ntp; ++k) offs[k] = k;
+        pm_feature_params fp{};
+        fp.n_type = n_type; fp.n_fn = 1; fp.pair_params = pp.data(); fp.cond_offsets = offs.data(); fp.cond_values = vals.data();
+        fp.cutoff = cutoff; fp.model_type = 1; fp.max_p = 1; fp.max_l = 0; fp.feature_type = PM_FEATURE_PAIR;
+        pm_model* mh = nullptr;
+        check(pm_model_create(&fp, &mh));
+        std::unique_ptr<pm_model, void (*)(pm_model*)> mg(mh, pm_model_destroy);
+        pm_context* ch = nullptr;
+        check(pm_context_create(mh, default_device(), (size_t)1 << 28, 0, &ch));
+        std::unique_ptr<pm_context, void (*)(pm_context*)> cg(ch, pm_context_destroy);
+        off.assign(n_atom + 1, 0);
+        check(pm_neighbor_full(ch, a.data(), p.data(), types.data(), n_atom, off.data(), nullptr, nullptr, nullptr, nullptr));
+        const int P = off[n_atom];
+        nbr.assign(std::max(P, 1), 0); dx.assign(std::max(P, 1), 0.0); dy = dx; dz = dx;
+        check(pm_neighbor_full(ch, a.data(), p.data(), types.data(), n_atom, off.data(), nbr.data(), dx.data(), dy.data(), dz.data()));
+    }
+    // [atom][type of the neighbour][k] views of the list (reference: Neighbor / NeighborFull::get_*_array)
+    vector3d distances(int n_type, const vector1i& types) const {
+        vector3d out(n_atom, vector2d(n_type));
+        for (int i = 0; i < n_atom; ++i)
+            for (int k = off[i]; k < off[i + 1]; ++k)
+                out[i][types.at(nbr[k])].push_back(std::sqrt(dx[k] * dx[k] + dy[k] * dy[k] + dz[k] * dz[k]));
+        return out;
+    }
+    vector4d differences(int n_type, const vector1i& types) const {
+        vector4d out(n_atom, vector3d(n_type));
+        for (int i = 0; i < n_atom; ++i)
+            for (int k = off[i]; k < off[i + 1]; ++k) out[i][types.at(nbr[k])].push_back({dx[k], dy[k], dz[k]});
+        return out;
+    }
+    vector3i indices(int n_type, const vector1i& types) const {
+        vector3i out(n_atom, vector2i(n_type));
+        for (int i = 0; i < n_atom; ++i)
+            for (int k = off[i]; k < off[i + 1]; ++k) out[i][types.at(nbr[k])].push_back(nbr[k]);
+        return out;
+    }
+};
+
+class PyNeighbor {   // Neighbor(axis, positions_c, types, n_type, cutoff): pybind11_mlp.cpp:96-108
+    NeighborList nl;
+    vector1i types_;
+    int n_type_;
+
+  public:
+    PyNeighbor(const vector2d& axis, const vector2d& positions_c, const vector1i& types, const int& n_type, const double& cutoff)
+        : types_(types), n_type_(n_type) {
+        nl.build(axis, positions_c, types, n_type, cutoff);
+    }
+    vector3d get_distances() const { return nl.distances(n_type_, types_); }
+    vector4d get_differences() const { return nl.differences(n_type_, types_); }
+    vector3i get_neighbor_indices() const { return nl.indices(n_type_, types_); }
+};
+
+class PyNeighborFull {   // NeighborFull(axis, positions_c, cutoff), getters take (n_type, types): pybind11_mlp.cpp:120-131
+    NeighborList nl;
+
+  public:
+    PyNeighborFull(const vector2d& axis, const vector2d& positions_c, const double cutoff) {
+        nl.build(axis, positions_c, vector1i(positions_c.size() == 3 ? positions_c[0].size() : 0, 0), 1, cutoff);
+    }
+    vector3d get_distances(const int n_type, const vector1i& types) const { return nl.distances(n_type, types); }
+    vector4d get_differences(const int n_type, const vector1i& types) const { return nl.differences(n_type, types); }
+    vector3i get_neighbor_indices(const int n_type, const vector1i& types) const { return nl.indices(n_type, types); }
+};
+
+class PyNeighborHalf {   // NeighborHalf(axis, positions_c, cutoff, use_openmp): compute/neighbor_half.cpp:11-83
+    vector2i half_;
+    vector3d diff_;
+
+  public:
+    PyNeighborHalf(const vector2d& axis, const vector2d& positions_c, const double cutoff, const bool) {
+        NeighborList nl;
+        nl.build(axis, positions_c, vector1i(positions_c.size() == 3 ? positions_c[0].size() : 0, 0), 1, cutoff);
+        const double tol = 1e-10;
+        half_.resize(nl.n_atom);
+        diff_.resize(nl.n_atom);
+        for (int i = 0; i < nl.n_atom; ++i)
+            for (int k = nl.off[i]; k < nl.off[i + 1]; ++k) {
+                const int j = nl.nbr[k];
+                const double x = nl.dx[k], y = nl.dy[k], z = nl.dz[k];
+                bool keep = j < i;
+                if (j == i)   // periodic images of the atom itself: the half space z > 0, then y > 0, then x > 0
+                    keep = z >= tol || (std::fabs(z) < tol && y >= tol) || (std::fabs(z) < tol && std::fabs(y) < tol && x >= tol);
+                if (keep) { half_[i].push_back(j); diff_[i].push_back({x, y, z}); }
+            }
+    }
+    const vector3d& get_differences() const { return diff_; }
+    const vector2i& get_neighbor_indices() const { return half_; }
+};
+
 }  // namespace
 
 PYBIND11_MODULE(libmlpcpp, m) {
@@ -470,4 +613,23 @@ PYBIND11_MODULE(libmlpcpp, m) {
     py::class_<PyFeaturesAttr>(m, "FeaturesAttr")
         .def(py::init<const py::dict&>())
         .def("get_n_features", &PyFeaturesAttr::get_n_features);
+    py::class_<PyNeighbor>(m, "Neighbor")
+        .def(py::init<const vector2d&, const vector2d&, const vector1i&, const int&, const double&>())
+        .def("get_distances", &PyNeighbor::get_distances)
+        .def("get_differences", &PyNeighbor::get_differences)
+        .def("get_neighbor_indices", &PyNeighbor::get_neighbor_indices);
+    py::class_<PyNeighborHalf>(m, "NeighborHalf")
+        .def(py::init<const vector2d&, const vector2d&, const double, const bool>())
+        .def("get_differences", &PyNeighborHalf::get_differences, py::return_value_policy::reference_internal)
+        .def("get_neighbor_indices", &PyNeighborHalf::get_neighbor_indices, py::return_value_policy::reference_internal);
+    py::class_<PyNeighborFull>(m, "NeighborFull")
+        .def(py::init<const vector2d&, const vector2d&, const double>())
+        .def("get_distances", &PyNeighborFull::get_distances)
+        .def("get_differences", &PyNeighborFull::get_differences)
+        .def("get_neighbor_indices", &PyNeighborFull::get_neighbor_indices);
+    py::class_<PyNeighborCell>(m, "NeighborCell")
+        .def(py::init<const vector2d&, const vector2d&, const double>())
+        .def("get_axis", &PyNeighborCell::get_axis, py::return_value_policy::reference_internal)
+        .def("get_positions_cartesian", &PyNeighborCell::get_positions_cartesian, py::return_value_policy::reference_internal)
+        .def("get_translations", &PyNeighborCell::get_translations, py::return_value_policy::reference_internal);
 }

@@ -266,3 +266,28 @@ def test_pybind_dropin_module_host_side():
     bad["model"]["max_p"] = 7
     with pytest.raises(ValueError):
         m.FeaturesAttr(bad)
+
+
+def test_neighbor_cell_hook_reference_known_answers():
+    """NeighborCell test hook (host code, pm_cell_translations): the reference's translation counts for
+    POSCAR-rocksalt (tests/test_cxx/test_neighbor.py:189-207), the unrefined cell handed back unchanged, and the
+    skewed-cell reduction against the oracle's restatement of compute/neighbor_cell.cpp."""
+    m = _pybind_module()
+    axis = np.eye(3) * 4.0
+    frac = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [0, 0, .5], [0, .5, 0], [.5, 0, 0], [.5, .5, .5]]).T
+    pc = axis @ frac
+    for cutoff, n in ((6.0, 147), (8.0, 203), (16.0, 751)):
+        nc = m.NeighborCell(axis.tolist(), pc.tolist(), cutoff)
+        assert len(nc.get_translations()) == n
+        np.testing.assert_allclose(np.array(nc.get_positions_cartesian()), pc)
+        np.testing.assert_allclose(np.array(nc.get_axis()), axis)
+    ax, pcs, _ = cases.skewed_cell(1, n_atom=5, seed=3)
+    ref = po.NeighborCell(ax, pcs, 6.0)
+    nc = m.NeighborCell(ax.tolist(), pcs.tolist(), 6.0)
+    assert np.array_equal(np.array(nc.get_translations()), np.asarray(ref.trans))
+    assert np.array_equal(np.array(nc.get_axis()), np.asarray(ref.axis))
+    assert np.array_equal(np.array(nc.get_positions_cartesian()), np.asarray(ref.pos))
+    for cls, methods in (("Neighbor", ("get_distances", "get_differences", "get_neighbor_indices")),
+                         ("NeighborFull", ("get_distances", "get_differences", "get_neighbor_indices")),
+                         ("NeighborHalf", ("get_differences", "get_neighbor_indices"))):
+        assert all(hasattr(getattr(m, cls), k) for k in methods), cls

@@ -592,3 +592,40 @@ def test_hybrid_model_vs_oracle():
     # a sub-model alone equals the plain model on the same atoms
     pm = PotentialModel(pd1, axis, pcs, tys, [2, 1], [True, False], [7, 5, 6])
     assert np.array_equal(hm.get_x()[:, : tabs[0].n_variables], pm.get_x())
+
+
+def test_neighbor_test_hooks_reference_known_answers():
+    """The reference's own neighbour-list tests (tests/test_cxx/test_neighbor.py:14-186, POSCAR-rocksalt, cutoff 6)
+    replayed on the pybind drop-in's Neighbor / NeighborFull / NeighborHalf hooks, which run the device kernels (K1)."""
+    import importlib.util
+
+    from pypolymlp_b200.build import pybind_module_path
+
+    spec = importlib.util.spec_from_file_location("libmlpcpp", pybind_module_path())
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    axis = np.eye(3) * 4.0
+    frac = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0], [0, 0, .5], [0, .5, 0], [.5, 0, 0], [.5, .5, .5]]).T
+    pc = (axis @ frac).tolist()
+    types = [0, 0, 0, 0, 1, 1, 1, 1]
+    full = m.NeighborFull(axis.tolist(), pc, 6.0)
+    plain = m.Neighbor(axis.tolist(), pc, types, 2, 6.0)
+    for dist, diff, nbr in ((plain.get_distances(), plain.get_differences(), plain.get_neighbor_indices()),
+                            (full.get_distances(2, types), full.get_differences(2, types),
+                             full.get_neighbor_indices(2, types))):
+        assert len(dist) == 8 and len(dist[0][0]) == 54 and len(dist[0][1]) == 38
+        d00, d01 = np.array(dist[0][0]), np.array(dist[0][1])
+        assert np.isclose(d00, 2.8284271247461903).sum() == 12 and np.isclose(d00, 4.0).sum() == 6
+        assert np.isclose(d00, 4.898979485566356).sum() == 24 and np.isclose(d00, 5.656854249492381).sum() == 12
+        assert np.isclose(d01, 2.0).sum() == 6 and np.isclose(d01, 3.46410162).sum() == 8
+        assert np.isclose(d01, 4.47213595).sum() == 24
+        assert np.sum(np.square(diff[0][0])) == pytest.approx(1152) and np.sum(np.square(diff[0][1])) == pytest.approx(600)
+        assert np.sum(np.square(diff[4][0])) == pytest.approx(600) and np.sum(np.square(diff[4][1])) == pytest.approx(1152)
+        sums = [(np.sum(nbr[i][0]), np.sum(nbr[i][1])) for i in range(8)]
+        assert sums == [(72, 206), (78, 208), (84, 210), (90, 212), (54, 288), (56, 294), (58, 300), (60, 306)]
+    half = m.NeighborHalf(axis.tolist(), pc, 6.0, True)
+    diffs, nb = half.get_differences(), half.get_neighbor_indices()
+    assert [len(x) for x in nb] == [9, 21, 33, 45, 47, 59, 71, 83]
+    assert [np.array(x).shape for x in diffs] == [(n, 3) for n in (9, 21, 33, 45, 47, 59, 71, 83)]
+    assert diffs[2][5] == pytest.approx([-2.0, 4.0, 2.0])
+    assert [int(np.sum(x)) for x in nb] == [0, 9, 30, 63, 90, 149, 220, 303]
