@@ -327,6 +327,22 @@ def test_eval_binary_and_fcc(flags):
         PotentialPropertiesFast(pd, G["fcc_coeffs"][:-1])
 
 
+def test_eval_large_model_matches_design_matrix():
+    """E / F / S evaluation of the config-3 model (max_l 12: the unfused eval path with the G buffer, 512-thread
+    feature kernel) against X @ c of the design matrix the reference goldens pin (energy, force and stress rows)."""
+    pd = make_params_dict(**cases.cfg3_model_kwargs())
+    ax, pc, ty = cases.bcc_supercell(rep=(2, 2, 2), a=3.2, n_type=2, seed=5)
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [16]).get_x()
+    coeffs = np.random.default_rng(9).normal(size=x.shape[1]) * 1e-3
+    pred = x @ coeffs
+    prop = PotentialPropertiesFast(pd, coeffs)
+    prop.eval(ax, pc, ty, True)
+    scale_f = np.abs(pred[7:]).max()
+    assert abs(prop.get_e() - pred[0]) < 1e-10 * max(abs(pred[0]), np.abs(x[0] * coeffs).max())
+    assert np.abs(np.asarray(prop.get_f()).reshape(-1) - pred[7:]).max() < 1e-10 * scale_f
+    assert np.abs(np.asarray(prop.get_s()) - pred[1:7]).max() < 1e-10 * max(np.abs(pred[1:7]).max(), np.abs(x[1:7] * coeffs).max())
+
+
 def test_config2_full_size_properties():
     """BASELINE config-2 shapes (256-atom fcc, F = 2030): size-independent properties of the fused path:
     tensor-core and straightforward kernels agree, accumulation is additive over structures and independent
