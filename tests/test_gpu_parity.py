@@ -382,6 +382,43 @@ def test_config2_full_size_properties():
     assert np.abs(r3["xtx"] - r1["xtx"]).max() < 1e-11 * sc  # RED.F64 summation order varies run to run
 
 
+def test_config3_full_size_properties():
+    """BASELINE config-3 shapes (216-atom bcc 6x6x3, binary, F = 9385): the large-model tensor-core kernels against the
+    straightforward kernels at full structure size, chunking independence (one structure per chunk vs all in one),
+    symmetry, and X^T y / xe_sum consistency with the materialised X of one structure."""
+    pd = make_params_dict(**cases.cfg3_model_kwargs())
+    n = 3
+    sts = [cases.bcc_supercell(rep=(6, 6, 3), a=3.2, n_type=2, seed=100 + s) for s in range(n)]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    rows = n * 655
+    rng = np.random.default_rng(6)
+    w = rng.uniform(0.2, 1.0, rows)
+    y = w * rng.normal(size=rows)
+    a1 = PotentialXtX(pd)
+    a1.add(axis, pcs, tys, [True] * n, w, y)
+    r1 = a1.finalize()
+    a2 = PotentialXtX(pd, flags=PM_FLAG_SIMPLE_KERNELS, workspace_bytes=1 << 30)   # one structure per chunk
+    a2.add(axis, pcs, tys, [True] * n, w, y)
+    r2 = a2.finalize()
+    sc = np.abs(r2["xtx"]).max()
+    assert np.abs(r1["xtx"] - r2["xtx"]).max() < 1e-10 * sc
+    assert np.abs(r1["xty"] - r2["xty"]).max() < 1e-10 * np.abs(r2["xty"]).max()
+    assert np.abs(r1["xe_sum"] - r2["xe_sum"]).max() < 1e-10 * np.abs(r2["xe_sum"]).max()
+    assert np.abs(r1["xtx"] - r1["xtx"].T).max() == 0.0
+    assert r1["total_n_data"] == rows
+    # first structure alone: materialised X (PyModel layout of a 1-structure batch: E, 6 S, 648 F rows)
+    x = PotentialModel(pd, axis[:1], pcs[:1], tys[:1], [1], [True], [216]).get_x()
+    sel = np.r_[0, n + np.arange(6), n + 6 * n + np.arange(648)]     # rows of structure 0 in the 3-structure batch
+    a3 = PotentialXtX(pd)
+    a3.add(axis[:1], pcs[:1], tys[:1], [True], w[sel], y[sel])
+    r3 = a3.finalize()
+    xw = x * w[sel][:, None]
+    ref = xw.T @ xw
+    assert np.abs(r3["xtx"] - ref).max() < 1e-10 * np.abs(ref).max()
+    assert np.abs(r3["xty"] - xw.T @ y[sel]).max() < 1e-10 * np.abs(xw.T @ y[sel]).max()
+    assert np.abs(r3["xe_sum"] - x[0]).max() < 1e-10 * np.abs(x[0]).max()
+
+
 def test_error_paths():
     pd = make_params_dict(**cases.si_model_kwargs())
     ax, pc, ty = cases.skewed_cell(1)
