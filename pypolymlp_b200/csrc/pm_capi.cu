@@ -604,11 +604,10 @@ static void batch_layout(const pm_structures* st, std::vector<size_t>& aoff, std
     n_rows = ifo;
 }
 
-static std::vector<std::pair<int, int>> plan_chunks(const pm_context* c, const pm_structures* st, long max_atoms = 0) {
+static std::vector<std::pair<int, int>> plan_chunks(const pm_context* c, const pm_structures* st) {
     std::vector<std::pair<int, int>> chunks;
     int s0 = 0;
     double bytes = 0.0;
-    long atoms = 0;
     // Large models (MBs of G and L per atom) would get chunks of a few hundred atoms out of the default workspace:
     // too few CTAs for 148 SMs.  Unless the caller fixed the workspace, grow it to ~2400 atoms per chunk (bounded).
     double cap = (double)c->ws_cap;
@@ -618,14 +617,12 @@ static std::vector<std::pair<int, int>> plan_chunks(const pm_context* c, const p
     }
     for (int s = 0; s < st->n_st; ++s) {
         const double bs = est_bytes_per_structure(c, st->axis + 9 * (size_t)s, st->n_atoms[s], st->force && st->force[s]);
-        if (s > s0 && (bytes + bs > cap || (max_atoms > 0 && atoms + st->n_atoms[s] > max_atoms))) {
+        if (s > s0 && bytes + bs > cap) {
             chunks.push_back({s0, s});
             s0 = s;
             bytes = 0.0;
-            atoms = 0;
         }
         bytes += bs;
-        atoms += st->n_atoms[s];
     }
     if (st->n_st > s0) chunks.push_back({s0, st->n_st});
     return chunks;
@@ -1101,15 +1098,7 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
     const int F = d.n_variables;
     StageTimer tm(c);
     // The host prepares chunk k+1 (translations, row maps) while the GPU still works on chunk k.
-    // Evaluation has no accumulator to amortise: cut the batch into ~4 chunks (>= 4096 atoms each) so that the host
-    // preparation of chunk k+1 and the result copies of chunk k overlap the kernels
-    long eval_atoms = 0;
-    if (mode == MODE_EVAL) {
-        long tot = 0;
-        for (int s = 0; s < st->n_st; ++s) tot += st->n_atoms[s];
-        eval_atoms = std::max<long>(4096, (tot + 3) / 4);
-    }
-    const auto chunks = plan_chunks(c, st, eval_atoms);
+    const auto chunks = plan_chunks(c, st);
     HostChunk h_next;
     auto prepare = [&](size_t k, HostChunk& out) {
         prepare_chunk(c, st, aoff, be, bs, bf, chunks[k].first, chunks[k].second, w, y, out);
