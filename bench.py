@@ -247,7 +247,7 @@ def main():
     # ---- secondary metric: atoms/s of E/F/S evaluation (BASELINE config 5), sharded by structure -----------
     from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
 
-    n_ev = 32
+    n_ev = int(os.environ.get("PM_BENCH_NEV", "32"))   # structures per evaluation call and GPU (config 5 holds 10 000)
     ev_sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + rank * n_ev + k) for k in range(n_ev)]
     ev_axis, ev_pcs, ev_tys = [x[0] for x in ev_sts], [x[1] for x in ev_sts], [x[2] for x in ev_sts]
     prop = PotentialPropertiesFast(pd, np.random.default_rng(12).normal(size=F) * 1e-3, device=local_rank)

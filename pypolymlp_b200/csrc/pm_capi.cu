@@ -112,7 +112,7 @@ struct pm_context {
     DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
         d_nbr, d_centre, d_rev, d_err;
     DevVec<ulonglong2> d_masks;
-    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_e,
+    DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_cmat, d_e,
         d_f, d_s;
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
@@ -128,6 +128,7 @@ struct pm_context {
     int64_t stage_launches[ST_COUNT] = {0};
     cudaEvent_t ev[ST_COUNT + 1] = {nullptr};
     bool has_coeffs = false;
+    bool has_cmat = false;
     // K5 runs on its own stream: the host-side work and the first kernels of the next chunk overlap the SYRK of the
     // previous chunk.  (Measured: the FP64-heavy small kernels make little progress next to the DMMA-saturating SYRK
     // CTA -- the FP64 pipe is the shared resource -- so the gain is ~1 % on the device and ~2 % end to end.)
@@ -774,6 +775,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         CK(cudaMemsetAsync(c->d_e.p, 0, h.n_st * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_f.p, 0, ((size_t)h.n_atoms * 3 + 1) * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_s.p, 0, (size_t)h.n_st * 6 * sizeof(double), s));
+        ws.cmat = c->has_cmat ? c->d_cmat.p : nullptr;
         launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s, eval_fused ? c->feat_smem : 0);
         tm.mark(ST_EVAL, 5);
         return;
@@ -1037,7 +1039,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
     c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_masks.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
-    c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
+    c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_cmat.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -1455,6 +1457,25 @@ int pm_eval_set_coeffs(pm_context* c, const double* coeffs, int n) {
         c->d_coeffs.ensure(n);
         CK(cudaMemcpy(c->d_coeffs.p, coeffs, n * sizeof(double), cudaMemcpyHostToDevice));
         c->has_coeffs = true;
+        // dense order-2 coefficient matrix over the polynomial variables for the fused eval kernel (max_p = 2, <= 64
+        // variables, one column per unordered pair): C'[a][b] = C'[b][a] = c_col, diagonal doubled (d E / d d_a)
+        const HostModel& hm = c->model->hm;
+        c->has_cmat = false;
+        if (c->dm.pair_colof && !hm.has_order3 && c->dm.npv_pad <= 64) {
+            const int nt = c->dm.n_type;
+            std::vector<double> cm((size_t)nt * 4096, 0.0);
+            for (const auto& pt : hm.pair_terms) {
+                const int col = pt[0], a = pt[1], b2 = pt[2];
+                for (int t = 0; t < nt; ++t) {
+                    if (hm.colterm[t][col].order != 2) continue;
+                    if (a == b2) cm[(size_t)t * 4096 + a * 64 + a] = 2.0 * coeffs[col];
+                    else { cm[(size_t)t * 4096 + a * 64 + b2] = coeffs[col]; cm[(size_t)t * 4096 + b2 * 64 + a] = coeffs[col]; }
+                }
+            }
+            c->d_cmat.ensure(cm.size());
+            CK(cudaMemcpy(c->d_cmat.p, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
+            c->has_cmat = true;
+        }
     });
 }
 

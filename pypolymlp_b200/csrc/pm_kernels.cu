@@ -1369,8 +1369,10 @@ __global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, c
 template <int AT, int MO>
 __global__ void __launch_bounds__(256) k_eval_features(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                         const double* __restrict__ coeffs, double* __restrict__ Ah,
-                                                        int ah_stride, double* __restrict__ energies, int nfull_max) {
+                                                        int ah_stride, double* __restrict__ energies, int nfull_max,
+                                                        const double* __restrict__ cmat) {
     extern __shared__ double2 afull[];   // [AT][nfull_max] | sd [AT][fl] | sw [AT][fl] | sah [AT][ah_stride]
+    __shared__ double s_dpv[AT * 64];
     double* sd = reinterpret_cast<double*>(afull + (size_t)AT * nfull_max);
     double* sw = sd + (size_t)AT * m.fl;
     double* sah = sw + (size_t)AT * m.fl;
@@ -1458,6 +1460,55 @@ __global__ void __launch_bounds__(256) k_eval_features(DevModel m, DevBatch b, c
     double e[AT];
 #pragma unroll
     for (int a = 0; a < AT; ++a) e[a] = 0.0;
+    if (cmat) {
+        // max_p = 2 with <= 64 polynomial variables: w = c_lin + C' d over the polynomial variables, C' the symmetric
+        // matrix of the order-2 coefficients with a doubled diagonal (pm_eval_set_coeffs); E_2 = d . C' d / 2.
+        // No two threads touch the same w entry, so no atomics (the CAS loops of the generic branch below took more
+        // than half of this kernel: ~10 retries per update on the 60 hot entries).
+        for (int k = tid; k < AT * 64; k += nthr) {
+            const int a = k >> 6, pv = k & 63;
+            double v = 0.0;
+            if (ty[a] >= 0 && pv < m.npv_pad) {
+                const int fp = m.pv_fp[(size_t)ty[a] * m.npv_pad + pv];
+                if (fp >= 0) v = sd[a * m.fl + fp];
+            }
+            s_dpv[k] = v;
+        }
+        for (int tt = 0; tt < m.n_type; ++tt) {
+            bool any = false;
+#pragma unroll
+            for (int a = 0; a < AT; ++a) any = any || ty[a] == tt;
+            if (!any) continue;
+            const DevPolyTerm* __restrict__ ct = m.types[tt].colterm;
+            for (int col = tid; col < m.n_linear; col += nthr) {
+                const DevPolyTerm tm = ct[col];
+                if (tm.order != 1) continue;
+                const double c = coeffs[col];
+#pragma unroll
+                for (int a = 0; a < AT; ++a) {
+                    if (ty[a] != tt) continue;
+                    e[a] += c * sd[a * m.fl + tm.fp0];
+                    sw[a * m.fl + tm.fp0] = c;
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < AT * 64; k += nthr) {
+            const int a = k >> 6, pv = k & 63;
+            if (ty[a] < 0 || pv >= m.npv_pad) continue;
+            const int fp = m.pv_fp[(size_t)ty[a] * m.npv_pad + pv];
+            if (fp < 0) continue;
+            const double* __restrict__ cm = cmat + (size_t)ty[a] * 4096 + pv;   // column pv = row pv (symmetric): coalesced
+            const double* dv = s_dpv + a * 64;
+            double w2 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 64; ++q) w2 += cm[q * 64] * dv[q];
+            sw[a * m.fl + fp] += w2;
+#pragma unroll
+            for (int a2 = 0; a2 < AT; ++a2)
+                if (a2 == a) e[a2] += 0.5 * dv[pv] * w2;
+        }
+    } else
     for (int tt = 0; tt < m.n_type; ++tt) {
         bool any = false;
 #pragma unroll
@@ -1598,7 +1649,7 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
     case MO_:                                                                                                         \
         if (smem > 48 * 1024 && set_for != smem)                                                                      \
             cudaFuncSetAttribute(k_eval_features<EVF_AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_eval_features<EVF_AT, MO_><<<grid, 256, smem, s>>>(m, b, ws.anc, coeffs, ws.Ah, ah_stride, energies, nfull_max); \
+        k_eval_features<EVF_AT, MO_><<<grid, 256, smem, s>>>(m, b, ws.anc, coeffs, ws.Ah, ah_stride, energies, nfull_max, ws.cmat); \
         break;
         switch (mo) {
             PM_EVF_CASE(1) PM_EVF_CASE(2) PM_EVF_CASE(3) PM_EVF_CASE(4) PM_EVF_CASE(5) PM_EVF_CASE(6)

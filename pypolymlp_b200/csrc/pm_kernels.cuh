@@ -20,6 +20,7 @@ struct Workspace {
     double* Sbuf = nullptr;     // [n_atoms][6][fl]
     double* X = nullptr;        // [n_rows][fpad]
     double* Ah = nullptr;       // [n_atoms][ah_stride] head adjoints (eval)
+    const double* cmat = nullptr;  // [n_type][64][64] order-2 coefficient matrix over the polynomial variables (eval, max_p = 2) or null
     int* errflag = nullptr;     // device error flag
 };
 
