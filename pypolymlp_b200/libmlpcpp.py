@@ -466,3 +466,49 @@ class PotentialPropertiesFast:
 
     def get_s_array(self):
         return self._s_array
+
+
+def _pair_basis_record(params_dict, dvec):
+    """Pair-basis record (device kernel k_pair_basis, K2a) of the single pair 0 -> 1 of a two-atom cell whose lattice
+    is far larger than the cutoff: items dx dy dz 1/r | f_n | f_n' | Y (re, im) | dY/dx | dY/dy | dY/dz."""
+    model = _Model(params_dict)
+    ctx = _Context(model)
+    rc = float(params_dict["model"]["cutoff"])
+    axis = np.eye(3) * (4.0 * rc + 10.0)
+    pos = np.zeros((3, 2))
+    pos[:, 1] = dvec
+    st = StructureBatch([axis], [pos], [np.zeros(2, np.int32)], [True])
+    x = np.zeros((int(lib().pm_batch_rows(C.byref(st.c))), model.n_features))
+    check(lib().pm_features_x(ctx.handle, C.byref(st.c), pd(x)))
+    raw = ctx.debug_fetch(2)
+    if raw.size == 0:
+        raise ValueError("the pair is not inside the cutoff")
+    n_fn = len(params_dict["model"]["pair_params"])
+    L = int(params_dict["model"]["max_l"])
+    nh = (L + 1) * (L + 2) // 2
+    stride = 4 + 2 * n_fn + 8 * nh
+    return raw.reshape(-1, stride, 32)[0, :, 0], n_fn, nh     # pair 0 of block 0 = (atom 0 -> atom 1)
+
+
+def get_fn(dis, params, cutoff):
+    """Test hook of the reference (pybind11_mlp.cpp:158-167, get_fn_): Gaussian x cosine-cutoff radial functions and
+    their derivatives at distance `dis`, computed by the device pair-basis kernel."""
+    from .params import make_params_dict
+
+    pd_ = make_params_dict(n_type=1, cutoff=cutoff, model_type=2, max_p=1, gtinv_order=0, gtinv_maxl=[],
+                           pair_params=[list(map(float, p)) for p in params], feature_type="pair")
+    rec, n_fn, _ = _pair_basis_record(pd_, np.array([0.0, 0.0, float(dis)]))
+    return rec[4:4 + n_fn].copy(), rec[4 + n_fn:4 + 2 * n_fn].copy()
+
+
+def get_ylm(x, y, z, lmax, r=1.0):
+    """Test hook of the reference (pybind11_mlp.cpp:169-181, get_ylm_): Y_lm(m <= 0) of the direction (x, y, z) / r and
+    its Cartesian gradient at distance r, computed by the device pair-basis kernel."""
+    from .params import make_params_dict
+
+    pd_ = make_params_dict(n_type=1, cutoff=max(6.0, 2.0 * r), model_type=2, max_p=1, gtinv_order=2, gtinv_maxl=[lmax],
+                           pair_params=[[0.0, 0.0]])
+    rec, n_fn, nh = _pair_basis_record(pd_, np.array([x, y, z], dtype=float))
+    o = 4 + 2 * n_fn
+    out = [rec[o + k * 2 * nh:o + (k + 1) * 2 * nh].copy().view(np.complex128) for k in range(4)]
+    return tuple(out)

@@ -682,3 +682,24 @@ def test_neighbor_test_hooks_reference_known_answers():
     assert [np.array(x).shape for x in diffs] == [(n, 3) for n in (9, 21, 33, 45, 47, 59, 71, 83)]
     assert diffs[2][5] == pytest.approx([-2.0, 4.0, 2.0])
     assert [int(np.sum(x)) for x in nb] == [0, 9, 30, 63, 90, 149, 220, 303]
+
+
+def test_get_fn_get_ylm_hooks_reference_known_answers():
+    """The reference's tests of the radial functions and spherical harmonics (tests/test_cxx/test_functions.py:14-50)
+    replayed on the device pair-basis kernel (K2a) through the get_fn / get_ylm hooks."""
+    from pypolymlp_b200.libmlpcpp import get_fn, get_ylm
+
+    fn, fn_d = get_fn(1.2, [[1.0, 0.0], [1.0, 1.0], [1.0, 2.0]], 6.0)
+    np.testing.assert_allclose(fn, [0.21430317094756238, 0.8690422117212636, 0.4769404780495180], rtol=1e-12)
+    np.testing.assert_allclose(fn_d, [-0.5507864848009192, -0.495464911460655, 0.6819640474131319], rtol=1e-12)
+    x, y, z = 0.173723561607389, 0.446843340790007, 0.877582561890373
+    ylm, ylm_dx, ylm_dy, ylm_dz = get_ylm(x, y, z, 10)
+    assert len(ylm) == len(ylm_dx) == len(ylm_dy) == len(ylm_dz) == 66
+    assert ylm.sum() == pytest.approx(-3.094632553138235 + 0.09510814961092404j, rel=1e-6)
+    assert ylm_dx.sum() == pytest.approx(-6.916830463136405 - 1.910490992920798j, rel=1e-6)
+    assert ylm_dy.sum() == pytest.approx(12.686387327323297 + 23.645024627283863j, rel=1e-6)
+    assert ylm_dz.sum() == pytest.approx(-5.090360117438893 - 11.661266919165213j, rel=1e-6)
+    # against the oracle's restatement of polymlp_spherical_harmonics.cpp, element by element
+    o = po.ylm_der(np.array([x]), np.array([y]), np.array([z]), 10)
+    for a, b_ in zip((ylm, ylm_dx, ylm_dy, ylm_dz), o):
+        assert np.abs(a - b_[:, 0]).max() < 1e-12 * max(1.0, np.abs(b_).max())
