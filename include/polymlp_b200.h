@@ -81,6 +81,14 @@ int pm_model_type_info(const pm_model* m, int type, int64_t out[12]);
 /* polynomial terms of a centre type: global column, order, local feature ids (-1 padded).
  * Returns the count through *n; buffers may be NULL. */
 int pm_model_polynomial(const pm_model* m, int type, int* n, int* col, int* order, int* local_ids3);
+/* FeaturesAttr getters (compute/py_features_attr.cpp:11-63, pybind11_mlp.cpp:70-82; consumed by get_features_attr /
+ * get_num_features, PY/mlp_dev/core/features_attr.py:11-49).  Per linear feature, in column order: the radial index,
+ * the l-combination id (gtinv models only: n_gtinv_ids = 0 for pair models) and its type-pair combination (CSR
+ * tcomb_off[n_linear+1] / tcomb_ids); the polynomial columns (comb2 then comb3) as global linear ids (CSR poly_off /
+ * poly_ids); type_pairs[n_type * n_type].  sizes[0]=n_linear, [1]=n_gtinv_ids, [2]=len(tcomb_ids), [3]=n_poly,
+ * [4]=len(poly_ids), [5]=n_type.  Every buffer may be NULL (size query). */
+int pm_model_feature_attrs(const pm_model* m, int64_t sizes[6], int* radial_ids, int* gtinv_ids, int* tcomb_off,
+                           int* tcomb_ids, int* poly_off, int* poly_ids, int* type_pairs);
 /* Algorithmic FLOPs of one structure given its neighbour statistics:
  * pairs_tt[t*n_type+u] = number of ordered pairs with centre type t, neighbour type u;
  * atoms_t[t] = atoms of type t.  out[0]=W_syrk, [1]=W_xty, [2]=W_poly, [3]=W_deriv, [4]=W_anlm. */

@@ -197,6 +197,28 @@ class RefModel:
         lib().ref_model_polynomial(self._h, t, _pi(g), _pi(l3))
         return g, l3
 
+    def feature_attrs(self):
+        """(radial_ids, gtinv_ids, tcomb_ids, polynomial_ids, type_pairs) of the reference's FeaturesAttr."""
+        L = lib()
+        L.ref_model_feature_attrs.restype = C.c_long
+        n = L.ref_model_feature_attrs(self._h, None)
+        v = np.zeros(n, np.int32)
+        L.ref_model_feature_attrs(self._h, _pi(v))
+        v = v.tolist()
+        pos, radial, gtinv, tcomb, poly = 1, [], [], [], []
+        for _ in range(v[0]):
+            radial.append(v[pos])
+            if v[pos + 1] >= 0:
+                gtinv.append(v[pos + 1])
+            tcomb.append(v[pos + 3:pos + 3 + v[pos + 2]])
+            pos += 3 + v[pos + 2]
+        n_poly, pos = v[pos], pos + 1
+        for _ in range(n_poly):
+            poly.append(v[pos + 1:pos + 1 + v[pos]])
+            pos += 1 + v[pos]
+        nt, pos = v[pos], pos + 1
+        return radial, gtinv, tcomb, poly, [v[pos + i * nt:pos + (i + 1) * nt] for i in range(nt)]
+
     def run(self, axis, positions_c, types, force=True):
         axis, pos, ty = _d(axis), _d(positions_c), _i(types)
         n, F = pos.shape[1], self.n_features

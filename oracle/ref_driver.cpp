@@ -279,6 +279,40 @@ int ref_model_polynomial(void* h, int t, int* global_id, int* local_ids3) {
     return i;
 }
 
+// Feature attributes as the reference's FeaturesAttr reports them (pybind11_mlp.cpp:70-82): flattened to one int
+// stream so the test can compare with pm_model_feature_attrs.  Layout of `out` (returned length; out may be NULL):
+//   n_linear, then per linear feature: radial id, gtinv id (-1 for pair models), len, tp ids...;
+//   n_poly, then per polynomial column (comb2 then comb3): len, linear ids...;  n_type, type_pairs row-major.
+long ref_model_feature_attrs(void* h, int* out) {
+    auto* m = static_cast<RefModel*>(h);
+    PolymlpAPI api;                       // as compute/py_features_attr.cpp:16-19 does: a fresh API object,
+    api.set_model_parameters(m->fp);      // model parameters only (Model itself goes through set_features)
+    const auto& mp = api.get_model_params();
+    auto& maps = api.get_maps();
+    std::vector<int> v;
+    if (m->fp.feature_type == "pair") {
+        v.push_back((int)maps.ntp_attrs.size());
+        for (const auto& a : maps.ntp_attrs) { v.push_back(a.n); v.push_back(-1); v.push_back(1); v.push_back(a.tp); }
+    } else {
+        const auto& lin = mp.get_linear_terms();
+        const auto& tpc = mp.get_tp_combs();
+        v.push_back((int)lin.size());
+        for (const auto& t : lin) {
+            const auto& c = tpc[t.order][t.tp_comb_id];
+            v.push_back(t.n); v.push_back(t.lm_comb_id); v.push_back((int)c.size());
+            v.insert(v.end(), c.begin(), c.end());
+        }
+    }
+    v.push_back((int)(mp.get_comb2().size() + mp.get_comb3().size()));
+    for (const auto* combs : {&mp.get_comb2(), &mp.get_comb3()})
+        for (const auto& c : *combs) { v.push_back((int)c.size()); v.insert(v.end(), c.begin(), c.end()); }
+    const int nt = (int)maps.type_pairs.size();
+    v.push_back(nt);
+    for (const auto& row : maps.type_pairs) v.insert(v.end(), row.begin(), row.end());
+    if (out) std::copy(v.begin(), v.end(), out);
+    return (long)v.size();
+}
+
 // X rows of one structure: xe[F], xf[3N*F] (row-major rows 3*atom+alpha), xs[6*F]
 int ref_model_run(void* h, const double* axis9, const double* pos3n, const int* types, int n_atom,
                   int force, double* xe, double* xf, double* xs) {

@@ -41,7 +41,7 @@ _lib = None
 
 EXPORTS = [
     "pm_last_error", "pm_version", "pm_gtinv_read", "pm_model_create", "pm_model_destroy",
-    "pm_model_n_features", "pm_model_info", "pm_model_type_info", "pm_model_polynomial",
+    "pm_model_n_features", "pm_model_info", "pm_model_type_info", "pm_model_polynomial", "pm_model_feature_attrs",
     "pm_model_count_flops", "pm_device_count", "pm_context_create", "pm_context_destroy",
     "pm_batch_rows", "pm_neighbor_full", "pm_features_x", "pm_fit_reset", "pm_fit_accumulate",
     "pm_fit_stage", "pm_fit_accumulate_staged", "pm_fit_accumulator", "pm_fit_fpad",

@@ -942,6 +942,55 @@ int pm_model_polynomial(const pm_model* m, int type, int* n, int* col, int* orde
     });
 }
 
+int pm_model_feature_attrs(const pm_model* m, int64_t sizes[6], int* radial_ids, int* gtinv_ids, int* tcomb_off,
+                           int* tcomb_ids, int* poly_off, int* poly_ids, int* type_pairs) {
+    return guarded([&] {
+        if (!m || !sizes) throw std::invalid_argument("null model");
+        const HostModel& hm = m->hm;
+        const bool gtinv = hm.fp.feature_type == 0;
+        const int nt = hm.fp.n_type;
+        int64_t n_tc = 0;
+        for (const auto& lt : hm.linear) n_tc += (int64_t)lt.tp_comb.size();
+        sizes[0] = hm.n_linear; sizes[1] = gtinv ? hm.n_linear : 0; sizes[2] = n_tc;
+        sizes[3] = (int64_t)(hm.comb2.size() + hm.comb3.size());
+        sizes[4] = (int64_t)(2 * hm.comb2.size() + 3 * hm.comb3.size()); sizes[5] = nt;
+        int pos = 0;
+        for (int k = 0; k < hm.n_linear; ++k) {
+            const LinearTerm& lt = hm.linear[k];
+            if (radial_ids) radial_ids[k] = lt.n;
+            if (gtinv && gtinv_ids) gtinv_ids[k] = lt.lcid;
+            if (tcomb_off) tcomb_off[k] = pos;
+            for (int tp : lt.tp_comb) {
+                if (tcomb_ids) tcomb_ids[pos] = tp;
+                ++pos;
+            }
+        }
+        if (tcomb_off) tcomb_off[hm.n_linear] = pos;
+        int row = 0;
+        pos = 0;
+        for (const auto& c : hm.comb2) {
+            if (poly_off) poly_off[row] = pos;
+            for (int v : c) {
+                if (poly_ids) poly_ids[pos] = v;
+                ++pos;
+            }
+            ++row;
+        }
+        for (const auto& c : hm.comb3) {
+            if (poly_off) poly_off[row] = pos;
+            for (int v : c) {
+                if (poly_ids) poly_ids[pos] = v;
+                ++pos;
+            }
+            ++row;
+        }
+        if (poly_off) poly_off[row] = pos;
+        if (type_pairs)
+            for (int i = 0; i < nt; ++i)
+                for (int j = 0; j < nt; ++j) type_pairs[i * nt + j] = hm.type_pairs[i][j];
+    });
+}
+
 int pm_model_count_flops(const pm_model* m, const int64_t* atoms_t, const int64_t* pairs_tt, int force, double out[5]) {
     return guarded([&] {
         if (!m) throw std::invalid_argument("null model");

@@ -426,10 +426,38 @@ class PyReadgtinv {
 
 class PyFeaturesAttr {
     Model model;
+    vector1i radial_ids, gtinv_ids;
+    vector2i tcomb_ids, polynomial_ids, type_pairs;
+
+    static vector2i rows(const vector1i& off, const vector1i& val, const size_t n) {
+        vector2i out(n);
+        for (size_t k = 0; k < n; ++k) out[k].assign(val.begin() + off[k], val.begin() + off[k + 1]);
+        return out;
+    }
 
   public:
-    explicit PyFeaturesAttr(const py::dict& params_dict) : model(params_dict) {}
+    // compute/py_features_attr.cpp:11-45: the attribute lists are built once in the constructor
+    explicit PyFeaturesAttr(const py::dict& params_dict) : model(params_dict) {
+        int64_t sz[6];
+        check(pm_model_feature_attrs(model.h, sz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        const size_t n_lin = (size_t)sz[0], n_poly = (size_t)sz[3], nt = (size_t)sz[5];
+        radial_ids.resize(n_lin);
+        gtinv_ids.resize((size_t)sz[1]);
+        vector1i tc_off(n_lin + 1), tc((size_t)sz[2]), p_off(n_poly + 1), pv((size_t)sz[4]), tps(nt * nt);
+        check(pm_model_feature_attrs(model.h, sz, radial_ids.data(), gtinv_ids.data(), tc_off.data(), tc.data(),
+                                     p_off.data(), pv.data(), tps.data()));
+        tcomb_ids = rows(tc_off, tc, n_lin);
+        polynomial_ids = rows(p_off, pv, n_poly);
+        type_pairs.assign(nt, vector1i(nt));
+        for (size_t i = 0; i < nt; ++i)
+            for (size_t j = 0; j < nt; ++j) type_pairs[i][j] = tps[i * nt + j];
+    }
     int get_n_features() const { return pm_model_n_features(model.h); }
+    const vector1i& get_radial_ids() const { return radial_ids; }
+    const vector1i& get_gtinv_ids() const { return gtinv_ids; }
+    const vector2i& get_tcomb_ids() const { return tcomb_ids; }
+    const vector2i& get_polynomial_ids() const { return polynomial_ids; }
+    const vector2i& get_type_pairs() const { return type_pairs; }
 };
 
 // ---- test hooks of the reference on the neighbour-list row (pybind11_mlp.cpp:96-142) ---------------------------
@@ -612,7 +640,12 @@ PYBIND11_MODULE(libmlpcpp, m) {
         .def("get_lm_coeffs", &PyReadgtinv::get_lm_coeffs, py::return_value_policy::reference_internal);
     py::class_<PyFeaturesAttr>(m, "FeaturesAttr")
         .def(py::init<const py::dict&>())
-        .def("get_n_features", &PyFeaturesAttr::get_n_features);
+        .def("get_n_features", &PyFeaturesAttr::get_n_features)
+        .def("get_radial_ids", &PyFeaturesAttr::get_radial_ids, py::return_value_policy::reference_internal)
+        .def("get_gtinv_ids", &PyFeaturesAttr::get_gtinv_ids, py::return_value_policy::reference_internal)
+        .def("get_tcomb_ids", &PyFeaturesAttr::get_tcomb_ids, py::return_value_policy::reference_internal)
+        .def("get_polynomial_ids", &PyFeaturesAttr::get_polynomial_ids, py::return_value_policy::reference_internal)
+        .def("get_type_pairs", &PyFeaturesAttr::get_type_pairs, py::return_value_policy::reference_internal);
     py::class_<PyNeighbor>(m, "Neighbor")
         .def(py::init<const vector2d&, const vector2d&, const vector1i&, const int&, const double&>())
         .def("get_distances", &PyNeighbor::get_distances)

@@ -53,7 +53,7 @@ def load_mlp_yaml(filename="polymlp.yaml"):
     return pd, np.asarray(yml["coeffs"], dtype=np.float64), meta
 
 
-def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml"):
+def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml", mass=None):
     """Writes coeffs / scales with the key order and number format of the reference writer."""
     model = params_dict["model"]
     coeffs = np.asarray(coeffs, float) / np.asarray(scales, float)
@@ -75,7 +75,8 @@ def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml"
             print("gtinv_version:", int(g.get("version", 1)), file=f)
             print(file=f)
         print("electrostatic:", 0, file=f)
-        print("mass:         ", [_MASS.get(e, 1.0) for e in elements], file=f)
+        print("mass:         ", [float(m) for m in mass] if mass is not None else [_MASS.get(e, 1.0) for e in elements],
+              file=f)
         print(file=f)
         print("n_pair_params:", len(model["pair_params"]), file=f)
         print("pair_params:", file=f)

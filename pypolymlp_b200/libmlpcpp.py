@@ -127,15 +127,46 @@ class _Model:
 
 
 class FeaturesAttr:
-    """Subset of FeaturesAttr (compute/py_features_attr.cpp) needed by get_num_features."""
+    """FeaturesAttr(params_dict) with the reference's five getters (compute/py_features_attr.cpp:11-63,
+    pybind11_mlp.cpp:70-82) plus `get_n_features`; host tables only, no device needed."""
 
     def __init__(self, params_dict):
-        self._model = _Model(params_dict)
+        self._model = m = _Model(params_dict)
+        sizes = (C.c_int64 * 6)()
+        check(lib().pm_model_feature_attrs(m.handle, sizes, None, None, None, None, None, None, None))
+        n_lin, n_gt, n_tc, n_poly, n_pv, nt = (int(v) for v in sizes)
+        radial, gt = np.zeros(max(n_lin, 1), np.int32), np.zeros(max(n_gt, 1), np.int32)
+        tc_off, tc = np.zeros(n_lin + 1, np.int32), np.zeros(max(n_tc, 1), np.int32)
+        p_off, pv = np.zeros(n_poly + 1, np.int32), np.zeros(max(n_pv, 1), np.int32)
+        tps = np.zeros(nt * nt, np.int32)
+        check(lib().pm_model_feature_attrs(m.handle, sizes, pi(radial), pi(gt), pi(tc_off), pi(tc), pi(p_off), pi(pv),
+                                           pi(tps)))
+        self._radial_ids = radial[:n_lin].tolist()
+        self._gtinv_ids = gt[:n_gt].tolist()
+        self._tcomb_ids = [tc[tc_off[k]:tc_off[k + 1]].tolist() for k in range(n_lin)]
+        self._polynomial_ids = [pv[p_off[k]:p_off[k + 1]].tolist() for k in range(n_poly)]
+        self._type_pairs = tps.reshape(nt, nt).tolist()
 
     def get_n_features(self):
         return self._model.n_features
 
-    def get_polynomial_ids(self, t=0):
+    def get_radial_ids(self):
+        return self._radial_ids
+
+    def get_gtinv_ids(self):
+        return self._gtinv_ids
+
+    def get_tcomb_ids(self):
+        return self._tcomb_ids
+
+    def get_polynomial_ids(self):
+        return self._polynomial_ids
+
+    def get_type_pairs(self):
+        return self._type_pairs
+
+    def get_polynomial_terms(self, t=0):
+        """(column, order, local ids) of centre type t's polynomial terms (additive; not in the reference class)."""
         return self._model.polynomial(t)
 
 

@@ -291,3 +291,29 @@ def test_neighbor_cell_hook_reference_known_answers():
                          ("NeighborFull", ("get_distances", "get_differences", "get_neighbor_indices")),
                          ("NeighborHalf", ("get_differences", "get_neighbor_indices"))):
         assert all(hasattr(getattr(m, cls), k) for k in methods), cls
+
+
+# ---- FeaturesAttr: the reference's five getters (compute/py_features_attr.cpp:11-63) -------------------------------
+@pytest.mark.parametrize("kw", [cases.si_model_kwargs(), cases.cfg2_model_kwargs(), cases.binary_model_kwargs(),
+                                cases.ternary_p3_model_kwargs(), cases.pair_model_kwargs(2),
+                                cases.pair_model_kwargs(3, max_p=3), cases.mgo_model_kwargs("gtinv"),
+                                cases.cfg3_model_kwargs()])
+def test_features_attr_getters_match_reference(kw):
+    """radial / gtinv / type-pair-combination ids per linear feature, polynomial combinations and the type-pair table,
+    from the ctypes mirror (pm_model_feature_attrs) and from the compiled pybind11 drop-in, against the reference's
+    own FeaturesAttr construction run in oracle/_ref."""
+    from oracle import ref
+    from pypolymlp_b200 import dropin
+    from pypolymlp_b200.libmlpcpp import FeaturesAttr
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    pd = make_params_dict(**kw)
+    radial, gtinv, tcomb, poly, type_pairs = ref.RefModel(pd).feature_attrs()
+    assert len(radial) + len(poly) == FeaturesAttr(pd).get_n_features()
+    for impl in (FeaturesAttr(pd), dropin.load_extension().FeaturesAttr(pd)):
+        assert list(impl.get_radial_ids()) == radial
+        assert list(impl.get_gtinv_ids()) == gtinv  # empty for pair models, as in the reference
+        assert [list(v) for v in impl.get_tcomb_ids()] == tcomb
+        assert [list(v) for v in impl.get_polynomial_ids()] == poly
+        assert [list(v) for v in impl.get_type_pairs()] == type_pairs
