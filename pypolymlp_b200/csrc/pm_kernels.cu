@@ -314,7 +314,10 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
     // angular
     const int L = LT >= 0 ? LT : m.maxl;
     constexpr int NHT = LT >= 0 ? (LT + 1) * (LT + 2) / 2 : MAX_NH;
-    const double ct = dz * rinv;
+    // a true division, as the reference does (polymlp_functions_interface.cpp:124 cos_theta = z / r): dz * rinv can be
+    // 1 - 1 ulp for a neighbour exactly on the z axis, and st = sqrt(1 - ct^2) then comes out as 1.5e-8 instead of 0
+    // (seen as 6e-8 eV/A residual forces in the ideal perovskite cell, where the reference gives 1e-16)
+    const double ct = dz / r;
     const double rho = hypot(dx, dy);
     double cp = 1.0, sp = 0.0;
     if (rho > 0.0) { cp = dx / rho; sp = dy / rho; }

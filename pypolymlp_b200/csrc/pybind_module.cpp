@@ -16,12 +16,14 @@
 // Additive: PotentialXtX(params_dict) .add(...) .finalize() -- the fused feature + X^T X accumulation.
 // Errors: C-ABI status PM_ERR_INVALID -> ValueError, anything else -> RuntimeError (as pybind11 maps
 // std::invalid_argument / std::runtime_error in the reference).  No CPU fallback.
+#include <pybind11/complex.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <memory>
 #include <stdexcept>
@@ -600,6 +602,92 @@ class PyNeighborHalf {   // NeighborHalf(axis, positions_c, cutoff, use_openmp):
     const vector2i& get_neighbor_indices() const { return half_; }
 };
 
+// ---- test hooks FeatureParams / get_fn / get_ylm (pybind11_mlp.cpp:145-181) ---------------------------------------
+// FeatureParams is the reference's plain feature_params record (polymlp_mlpcpp.h:54-68); get_fn only reads its cutoff
+// and pair_type (cxx/wrapper/api_functions.py:8-14).  Both functions run the device pair-basis kernel (K2a) on the
+// single pair 0 -> 1 of a two-atom cell far larger than the cutoff and read its record back through pm_debug_fetch:
+// items dx dy dz 1/r | f_n | f_n' | Y (re, im per m <= 0 head) | dY/dx | dY/dy | dY/dz, 32 pairs per block.
+struct FeatureParamsHook {
+    int n_type = 1;
+    bool force = false;
+    vector2d params;
+    vector3i params_conditional;
+    double cutoff = 0.0;
+    std::string pair_type = "gaussian", feature_type = "gtinv";
+    int model_type = 1, maxp = 1, maxl = 0;
+    vector3i lm_array;
+    vector2i l_comb;
+    vector2d lm_coeffs;
+};
+
+vector1d pair_basis_record(pm_feature_params& fp, const double x, const double y, const double z) {
+    pm_model* mh = nullptr;
+    check(pm_model_create(&fp, &mh));
+    std::unique_ptr<pm_model, void (*)(pm_model*)> mg(mh, pm_model_destroy);
+    pm_context* ch = nullptr;
+    check(pm_context_create(mh, default_device(), (size_t)1 << 28, 0, &ch));
+    std::unique_ptr<pm_context, void (*)(pm_context*)> cg(ch, pm_context_destroy);
+    const double box = 4.0 * fp.cutoff + 10.0;
+    const double axis[9] = {box, 0, 0, 0, box, 0, 0, 0, box};
+    const double pos[6] = {0.0, x, 0.0, y, 0.0, z};   // (3, 2) row-major: atom 0 at the origin, atom 1 at (x, y, z)
+    const int types[2] = {0, 0}, n_atoms[1] = {2}, force[1] = {1};
+    pm_structures st{};
+    st.n_st = 1; st.axis = axis; st.positions_c = pos; st.types = types; st.n_atoms = n_atoms; st.force = force;
+    vector1d X((size_t)pm_batch_rows(&st) * (size_t)pm_model_n_features(mh));
+    check(pm_features_x(ch, &st, X.data()));
+    size_t n = 0;
+    check(pm_debug_fetch(ch, 2, nullptr, 0, &n));
+    if (n == 0) throw std::invalid_argument("the pair is not inside the cutoff");
+    vector1d raw(n);
+    check(pm_debug_fetch(ch, 2, raw.data(), raw.size(), &n));
+    const int nh = (fp.max_l + 1) * (fp.max_l + 2) / 2;
+    const size_t stride = 4 + 2 * (size_t)fp.n_fn + 8 * (size_t)nh;
+    vector1d rec(stride);
+    for (size_t item = 0; item < stride; ++item) rec[item] = raw.at(item * 32);   // pair 0 of block 0
+    return rec;
+}
+
+py::tuple hook_get_fn(const double dis, const FeatureParamsHook& fph, const vector2d& params) {
+    if (fph.pair_type != "gaussian") throw std::invalid_argument("pair_type must be 'gaussian'");
+    vector1d pp;
+    for (const auto& p : params) { pp.push_back(p.at(0)); pp.push_back(p.at(1)); }
+    const int n_fn = (int)params.size();
+    vector1i offs{0, n_fn}, vals(n_fn);
+    for (int k = 0; k < n_fn; ++k) vals[k] = k;
+    pm_feature_params fp{};
+    fp.n_type = 1; fp.n_fn = n_fn; fp.pair_params = pp.data(); fp.cond_offsets = offs.data(); fp.cond_values = vals.data();
+    fp.cutoff = fph.cutoff; fp.model_type = 2; fp.max_p = 1; fp.max_l = 0; fp.feature_type = PM_FEATURE_PAIR;
+    const vector1d rec = pair_basis_record(fp, 0.0, 0.0, dis);
+    return py::make_tuple(vector1d(rec.begin() + 4, rec.begin() + 4 + n_fn),
+                          vector1d(rec.begin() + 4 + n_fn, rec.begin() + 4 + 2 * n_fn));
+}
+
+py::tuple hook_get_ylm(const double r, const double x, const double y, const double z, const int lmax) {
+    // an order-2 gtinv model with max_l = lmax and one cutoff-only radial function carries every Y_lm up to lmax
+    const vector1i maxl{lmax};
+    int64_t sz[4];
+    const char* dir = std::getenv("POLYMLP_B200_GTINV_DIR");
+    check(pm_gtinv_read(dir, 2, maxl.data(), 1, 1, sz, nullptr, nullptr, nullptr, nullptr, nullptr));
+    vector1i lo(sz[0]), lc(sz[1] + 1), nt(sz[0]), lm(sz[3] + 1);
+    vector1d cf(sz[2] + 1);
+    check(pm_gtinv_read(dir, 2, maxl.data(), 1, 1, sz, lo.data(), lc.data(), nt.data(), lm.data(), cf.data()));
+    vector1d pp{0.0, 0.0};
+    vector1i offs{0, 1}, vals{0};
+    pm_feature_params fp{};
+    fp.n_type = 1; fp.n_fn = 1; fp.pair_params = pp.data(); fp.cond_offsets = offs.data(); fp.cond_values = vals.data();
+    fp.cutoff = std::max(6.0, 2.0 * r); fp.model_type = 2; fp.max_p = 1; fp.max_l = lmax;
+    fp.n_lcomb = (int)sz[0]; fp.lcomb_order = lo.data(); fp.l_comb = lc.data();
+    fp.n_terms = nt.data(); fp.lm_seq = lm.data(); fp.lm_coeffs = cf.data();
+    fp.feature_type = PM_FEATURE_GTINV;
+    const vector1d rec = pair_basis_record(fp, x, y, z);
+    const int nh = (lmax + 1) * (lmax + 2) / 2;
+    std::vector<std::vector<std::complex<double>>> out(4, std::vector<std::complex<double>>(nh));
+    for (int k = 0; k < 4; ++k)
+        for (int h = 0; h < nh; ++h)
+            out[k][h] = {rec[6 + (size_t)k * 2 * nh + 2 * h], rec[6 + (size_t)k * 2 * nh + 2 * h + 1]};
+    return py::make_tuple(out[0], out[1], out[2], out[3]);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(libmlpcpp, m) {
@@ -665,4 +753,21 @@ PYBIND11_MODULE(libmlpcpp, m) {
         .def("get_axis", &PyNeighborCell::get_axis, py::return_value_policy::reference_internal)
         .def("get_positions_cartesian", &PyNeighborCell::get_positions_cartesian, py::return_value_policy::reference_internal)
         .def("get_translations", &PyNeighborCell::get_translations, py::return_value_policy::reference_internal);
+    py::class_<FeatureParamsHook>(m, "FeatureParams")
+        .def(py::init<>())
+        .def_readwrite("n_type", &FeatureParamsHook::n_type)
+        .def_readwrite("force", &FeatureParamsHook::force)
+        .def_readwrite("params", &FeatureParamsHook::params)
+        .def_readwrite("params_conditional", &FeatureParamsHook::params_conditional)
+        .def_readwrite("cutoff", &FeatureParamsHook::cutoff)
+        .def_readwrite("pair_type", &FeatureParamsHook::pair_type)
+        .def_readwrite("feature_type", &FeatureParamsHook::feature_type)
+        .def_readwrite("model_type", &FeatureParamsHook::model_type)
+        .def_readwrite("maxp", &FeatureParamsHook::maxp)
+        .def_readwrite("maxl", &FeatureParamsHook::maxl)
+        .def_readwrite("lm_array", &FeatureParamsHook::lm_array)
+        .def_readwrite("l_comb", &FeatureParamsHook::l_comb)
+        .def_readwrite("lm_coeffs", &FeatureParamsHook::lm_coeffs);
+    m.def("get_fn", &hook_get_fn, py::arg("dis"), py::arg("fp"), py::arg("params"));
+    m.def("get_ylm", &hook_get_ylm, py::arg("r"), py::arg("x"), py::arg("y"), py::arg("z"), py::arg("lmax"));
 }

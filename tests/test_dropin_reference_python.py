@@ -30,7 +30,8 @@ def test_module_is_ours_and_exports_the_boundary(ext):
 
     assert libmlpcpp is ext and "pypolymlp_b200" in ext.__file__
     for name in ("PotentialModel", "PotentialHybridModel", "PotentialPropertiesFast", "Readgtinv", "FeaturesAttr",
-                 "Neighbor", "NeighborHalf", "NeighborFull", "NeighborCell"):  # pybind11_mlp.cpp:12-142
+                 "Neighbor", "NeighborHalf", "NeighborFull", "NeighborCell",   # pybind11_mlp.cpp:12-142
+                 "FeatureParams", "get_fn", "get_ylm"):                         # :145-181
         assert hasattr(libmlpcpp, name), name
 
 
@@ -90,3 +91,22 @@ def test_compute_entry_points_need_a_device(ext):
         ext.PotentialModel(pd, [ax], [pc], [ty], [1], [True], [len(ty)])
     with pytest.raises(RuntimeError):
         ext.PotentialPropertiesFast(pd, [0.0] * 168)
+    # the radial / spherical-harmonic hooks run the device pair-basis kernel: through the reference's own wrapper
+    from pypolymlp.cxx.wrapper.api_functions import get_fn, get_ylm
+
+    with pytest.raises(RuntimeError):
+        get_fn(1.2, [[1.0, 0.0]], 6.0)
+    with pytest.raises(RuntimeError):
+        get_ylm(0.3, -0.5, 0.81, 4)
+
+
+def test_feature_params_record(ext):
+    """FeatureParams is the reference's plain feature_params record (pybind11_mlp.cpp:145-160): every field
+    readable and writable."""
+    fp = ext.FeatureParams()
+    values = dict(n_type=2, force=True, params=[[1.0, 0.5]], params_conditional=[[[0]], [[0]]], cutoff=6.5,
+                  pair_type="gaussian", feature_type="gtinv", model_type=3, maxp=2, maxl=4,
+                  lm_array=[[[0]]], l_comb=[[0]], lm_coeffs=[[1.0]])
+    for key, val in values.items():
+        setattr(fp, key, val)
+        assert getattr(fp, key) == val, key
