@@ -110,3 +110,36 @@ def test_feature_params_record(ext):
     for key, val in values.items():
         setattr(fp, key, val)
         assert getattr(fp, key) == val, key
+
+
+def test_reference_call_sites_reach_the_device_step(ext):
+    """The reference's own producers hand their objects to the three compute classes
+    (mlp_dev/core/features.py:120,193 Features / FeaturesHybrid; calculator/properties_single.py:41): with no CUDA
+    device the calls must get past argument conversion and table construction and stop at context creation
+    (RuntimeError 'no CPU fallback'), never at a TypeError of the binding."""
+    import ctypes
+    import glob
+
+    try:
+        ctypes.CDLL("libcuda.so.1")
+        pytest.skip("a CUDA driver is present")
+    except OSError:
+        pass
+    from pypolymlp.calculator.properties import Properties
+    from pypolymlp.core.interface_vasp import Poscar
+    from pypolymlp.core.io_polymlp import load_mlp, load_mlps
+    from pypolymlp.core.params import PolymlpParams
+    from pypolymlp.mlp_dev.core.features import Features, FeaturesHybrid
+
+    files = "/root/reference/tests/test_calc/files/"
+    mgo = Poscar(files + "poscars/POSCAR-00001.MgO").structure
+    srtio3 = Poscar(files + "poscars/POSCAR.perovskite.SrTiO3").structure
+    params, _ = load_mlp(MLPS + "polymlp.yaml.gtinv.MgO")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Features(PolymlpParams(params), structures=[mgo], print_memory=False)
+    hybrid, _ = load_mlps(sorted(glob.glob(MLPS + "polymlp.yaml.flexible.*.SrTiO3")))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FeaturesHybrid(hybrid, structures=[srtio3], print_memory=False)
+    for pot in ("polymlp.lammps.gtinv.SrTiO3", "polymlp.lammps.pair.cond.SrTiO3"):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Properties(pot=MLPS + pot)
