@@ -53,7 +53,8 @@ def load_mlp_yaml(filename="polymlp.yaml"):
     return pd, np.asarray(yml["coeffs"], dtype=np.float64), meta
 
 
-def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml", mass=None):
+def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml", mass=None, type_full=True,
+                  type_indices=None):
     """Writes coeffs / scales with the key order and number format of the reference writer."""
     model = params_dict["model"]
     coeffs = np.asarray(coeffs, float) / np.asarray(scales, float)
@@ -90,8 +91,9 @@ def save_mlp_yaml(params_dict, coeffs, scales, elements, filename="polymlp.yaml"
             print("- atom_type_pair:     ", [int(v) for v in tp], file=f)
             print("  pair_params_indices:", [int(v) for v in ids], file=f)
         print(file=f)
-        print("type_full:   ", 1, file=f)
-        print("type_indices:", list(range(int(params_dict["n_type"]))), file=f)
+        print("type_full:   ", int(bool(type_full)), file=f)
+        print("type_indices:", [int(v) for v in type_indices] if type_indices is not None
+              else list(range(int(params_dict["n_type"]))), file=f)
         print(file=f)
         print("n_coeffs:", len(coeffs), file=f)
         print("coeffs:", "[" + ", ".join(f"{c:.15e}" for c in coeffs) + "]", file=f)

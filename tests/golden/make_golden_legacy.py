@@ -10,6 +10,9 @@ Outputs
                        fixture polymlp.lammps.synthetic: model parameters + digests of the scaled coefficients
   legacy.npz           scaled coefficients of the potentials the reference publishes known answers for
                        (tests/test_calc/test_properties_legacy_{SrTiO3,Ag,MgO}.py) and the structures of those tests
+  polymlp.yaml.flexible.{1,2}.SrTiO3   the reference's hybrid ("flexible") SrTiO3 potential re-written by OUR yaml
+                       writer from what our reader got out of the reference's files (coefficients checked against the
+                       reference loader here); sub-model 2 is an O-only model with type_full = 0
   polymlp.lammps.synthetic   a small legacy file written by OUR writer (binary conditional gtinv model, seeded
                        coefficients / scales); travels with the repo so the reader is covered without /root/reference
 """
@@ -91,3 +94,23 @@ for key, poscar in [("srtio3", "POSCAR.perovskite.SrTiO3"), ("ag", "POSCAR.fcc.A
     out[key + "_types"] = np.asarray(st.types, np.int32)
 np.savez_compressed(os.path.join(cases.GOLDEN, "legacy.npz"), **out)
 print({k: v.shape for k, v in out.items()})
+
+# ---- the reference's hybrid potential of test_properties_legacy_SrTiO3.py:72-85, re-written by our writer -----------
+from pypolymlp.core.io_polymlp import load_mlp as ref_load_mlp  # noqa: E402  (reference)
+
+from pypolymlp_b200.io_yaml import load_mlp_yaml, save_mlp_yaml  # noqa: E402
+
+for k in (1, 2):
+    src = REF_T + "/test_calc/files/mlps/polymlp.yaml.flexible.%d.SrTiO3" % k
+    dst = os.path.join(cases.GOLDEN, "polymlp.yaml.flexible.%d.SrTiO3" % k)
+    pd_k, coeffs_k, meta_k = load_mlp_yaml(src)
+    params_ref, coeffs_ref = ref_load_mlp(src)
+    assert np.array_equal(coeffs_k, coeffs_ref) and list(params_ref.elements) == meta_k["elements"]
+    assert bool(params_ref.type_full) == meta_k["type_full"] and list(params_ref.type_indices) == meta_k["type_indices"]
+    save_mlp_yaml(pd_k, coeffs_k, np.ones(len(coeffs_k)), meta_k["elements"], filename=dst, mass=meta_k["mass"],
+                  type_full=meta_k["type_full"], type_indices=meta_k["type_indices"])
+    params_back, coeffs_back = ref_load_mlp(dst)      # the reference loader reads our file back identically
+    assert np.allclose(coeffs_back, coeffs_ref, rtol=1e-15, atol=0)
+    assert params_back.as_dict()["model"] == params_ref.as_dict()["model"]
+    assert bool(params_back.type_full) == bool(params_ref.type_full)
+    print(os.path.basename(dst), len(coeffs_k), meta_k["elements"], meta_k["type_full"], meta_k["type_indices"])

@@ -1,0 +1,40 @@
+"""GPU cases written after this round's GPU budget was used up: they have NOT run on hardware yet.  They are marked
+xfail(strict=False) so that a surprise cannot turn the verified suite red; an XPASS in the report means they pass on
+the box, and the mark goes away next round (tests/test_gpu_legacy_hooks.py went through the same step and was
+promoted after its B200 run).  The file sorts last on purpose.  CPU side of the same cases: tests/test_calc_properties.py."""
+
+import numpy as np
+import pytest
+
+from pypolymlp_b200 import calc
+from test_calc_properties import FLEX, FLEX_ENERGY, SRTIO3_ELEMENTS
+from test_legacy_io import load_legacy_golden
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on a B200")]
+
+
+def test_hybrid_flexible_published_energy_gpu():
+    """The reference's hybrid SrTiO3 potential (sub-model 2: O only, max_l 8, model_type 4) through calc.Properties on
+    the device: published energy (test_properties_legacy_SrTiO3.py:72-85), vanishing forces, additivity."""
+    L = load_legacy_golden()
+    axis, pos = L["srtio3_axis"], L["srtio3_pos"]
+    prop = calc.Properties(pot=FLEX)
+    e, f, s = prop.eval(axis, pos, SRTIO3_ELEMENTS)
+    assert e == pytest.approx(FLEX_ENERGY, rel=1e-8)
+    assert f.shape == (3, 5) and np.abs(f).max() < 1e-10
+    p1, p2 = calc.PropertiesSingle(pot=FLEX[0]), calc.PropertiesSingle(pot=FLEX[1])
+    e1, f1, s1 = p1.eval(axis, pos, SRTIO3_ELEMENTS)
+    e2, f2, s2 = p2.eval(axis, pos, SRTIO3_ELEMENTS)
+    assert e == pytest.approx(e1 + e2, rel=1e-13)
+    np.testing.assert_allclose(s, s1 + s2, rtol=1e-12, atol=1e-13)
+    # displaced cell, shuffled atoms: same energy, permuted forces; the O-only model leaves Sr / Ti forces untouched
+    rng = np.random.default_rng(5)
+    posd = pos + rng.normal(scale=0.05, size=(3, 5))
+    order = [3, 0, 2, 4, 1]
+    ea, fa, sa = prop.eval(axis, posd, SRTIO3_ELEMENTS)
+    eb, fb, sb = prop.eval(axis, posd[:, order], [SRTIO3_ELEMENTS[i] for i in order])
+    assert ea == pytest.approx(eb, rel=1e-12)
+    np.testing.assert_allclose(fb, fa[:, order], rtol=1e-9, atol=1e-11)
+    e2d, f2d, _ = p2.eval(axis, posd, SRTIO3_ELEMENTS)
+    assert np.all(f2d[:, :2] == 0.0) and np.abs(f2d[:, 2:]).max() > 0.0
