@@ -114,3 +114,39 @@ for k in (1, 2):
     assert params_back.as_dict()["model"] == params_ref.as_dict()["model"]
     assert bool(params_back.type_full) == bool(params_ref.type_full)
     print(os.path.basename(dst), len(coeffs_k), meta_k["elements"], meta_k["type_full"], meta_k["type_indices"])
+
+# ---- cell-shape invariance set of tests/test_calc/test_check_neighbors.py:39-75 ---------------------------------------
+# ideal rocksalt MgO re-expressed in 25 unimodular (mostly very skewed) cells.  The reference builds them with
+# phonopy (utils/supercell_utils.py:26-53; phonopy is not installed here); for det H = 1 the supercell is the same
+# crystal in the lattice A' = A H with fractional coordinates H^-1 x wrapped into [0, 1) (refine rule of :19-23)
+def supercell(st, hnf):
+    assert round(np.linalg.det(hnf)) == 1
+    frac = np.linalg.solve(hnf.astype(float), np.asarray(st.positions, float))
+    frac -= np.floor(frac)
+    frac[frac > 1 - 1e-13] -= 1.0
+
+    class _S:
+        axis, positions, types = np.asarray(st.axis, float) @ hnf, frac, st.types
+    return _S
+
+
+unitcell = Poscar(REF_T + "/test_calc/files/poscars/POSCAR.RS.idealMgO").structure
+expansions = [
+    [[1, 0, 0], [0, 1, 0], [0, 0, 1]], [[1, 0, 0], [1, 1, 0], [1, 1, 1]], [[1, 0, 0], [1, 1, 0], [0, 0, 1]],
+    [[1, 1, 0], [0, 1, 0], [0, 0, 1]], [[1, 0, 0], [0, 1, 0], [1, 0, 1]], [[1, 0, 0], [0, 1, 0], [0, 1, 1]],
+    [[1, 0, 0], [-1, 1, 0], [0, 0, 1]], [[1, 0, 0], [-1, 1, 0], [-1, -1, 1]], [[1, 0, 0], [-3, 1, 0], [3, 3, 1]],
+    [[1, 0, 0], [3, 1, 0], [3, 3, 1]], [[1, 0, 0], [-3, 1, 0], [-3, -3, 1]], [[1, 0, 0], [5, 1, 0], [5, 5, 1]],
+    [[1, 0, 0], [-5, 1, 0], [-5, -5, 1]], [[1, 0, 0], [10, 1, 0], [10, 10, 1]], [[1, 0, 0], [-10, 1, 0], [-10, -10, 1]],
+    [[1, 3, 3], [0, 1, 3], [0, 0, 1]], [[1, 4, 4], [0, 1, 4], [0, 0, 1]], [[1, 5, 5], [0, 1, 5], [0, 0, 1]],
+    [[1, -5, -5], [0, 1, -5], [0, 0, 1]], [[1, 10, 10], [0, 1, 10], [0, 0, 1]], [[1, -10, -10], [0, 1, -10], [0, 0, 1]],
+    [[1, 0, 0], [5, 1, 0], [0, 0, 1]], [[1, 0, 0], [-5, 1, 0], [0, 0, 1]], [[1, 0, 0], [10, 1, 0], [0, 0, 1]],
+    [[1, 0, 0], [-10, 1, 0], [0, 0, 1]],
+]
+cells = {}
+for k, hnf in enumerate(expansions):
+    st = supercell(unitcell, np.array(hnf))
+    cells["axis_%02d" % k] = np.asarray(st.axis, np.float64)
+    cells["pos_%02d" % k] = np.asarray(st.axis @ st.positions, np.float64)
+    cells["types_%02d" % k] = np.asarray(st.types, np.int32)
+np.savez_compressed(os.path.join(cases.GOLDEN, "mgo_cell_shapes.npz"), **cells)
+print("mgo_cell_shapes", len(expansions), cells["pos_08"].shape, cells["axis_13"])

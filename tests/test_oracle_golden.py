@@ -194,3 +194,24 @@ def test_mgo_published_pair_feature_sums():
     assert x.shape == (2, ncol)
     assert np.sum(x) == pytest.approx(total, rel=1e-6)
     assert np.sum(x[0] - x[1]) == pytest.approx(diff, rel=1e-6)
+
+
+# ---- cell-shape invariance (tests/test_calc/test_check_neighbors.py:39-75) -------------------------------------------
+MGO_IDEAL_ENERGY = -40.225125687168706
+
+
+def load_mgo_cell_shapes():
+    S = np.load(os.path.join(cases.GOLDEN, "mgo_cell_shapes.npz"))
+    return [(S["axis_%02d" % k], S["pos_%02d" % k], S["types_%02d" % k]) for k in range(25)]
+
+
+def test_mgo_cell_shape_invariance_published_energy():
+    """Ideal rocksalt MgO in 25 unimodular cells, most of them far too skewed for the plain image search (lattice
+    vectors up to 60 A long): the reference publishes one energy for all of them, atol 1e-12; exercises the cell
+    reduction of NeighborCell (compute/neighbor_cell.cpp:126-168)."""
+    M = cases.load_mgo()
+    tab = po.Tables(make_params_dict(**cases.mgo_model_kwargs("pair")))
+    for axis, pos, types in load_mgo_cell_shapes():
+        e, f, s = po.eval_structure(tab, M["pair_coeffs"], axis, pos, types)
+        assert abs(e - MGO_IDEAL_ENERGY) < 1e-12
+        assert np.abs(f).max() < 1e-10

@@ -38,3 +38,20 @@ def test_hybrid_flexible_published_energy_gpu():
     np.testing.assert_allclose(fb, fa[:, order], rtol=1e-9, atol=1e-11)
     e2d, f2d, _ = p2.eval(axis, posd, SRTIO3_ELEMENTS)
     assert np.all(f2d[:, :2] == 0.0) and np.abs(f2d[:, 2:]).max() > 0.0
+
+
+def test_mgo_cell_shape_invariance_published_energy_gpu():
+    """tests/test_calc/test_check_neighbors.py:39-75 on the device: ideal rocksalt MgO in 25 unimodular, mostly very
+    skewed cells (host cell reduction + device neighbour kernels + eval), one published energy, atol 1e-12."""
+    import cases
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+    from pypolymlp_b200.params import make_params_dict
+    from test_oracle_golden import MGO_IDEAL_ENERGY, load_mgo_cell_shapes
+
+    cells = load_mgo_cell_shapes()
+    prop = PotentialPropertiesFast(make_params_dict(**cases.mgo_model_kwargs("pair")), cases.load_mgo()["pair_coeffs"])
+    prop.eval_multiple([c[0] for c in cells], [c[1] for c in cells], [c[2] for c in cells])
+    np.testing.assert_allclose(prop.get_e_array(), MGO_IDEAL_ENERGY, atol=1e-12, rtol=0)
+    assert max(np.abs(f).max() for f in prop.get_f_array()) < 1e-10
+    s = np.asarray(prop.get_s_array())
+    np.testing.assert_allclose(s, np.broadcast_to(s[0], s.shape), atol=1e-10, rtol=0)
