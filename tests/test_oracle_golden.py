@@ -215,3 +215,41 @@ def test_mgo_cell_shape_invariance_published_energy():
         e, f, s = po.eval_structure(tab, M["pair_coeffs"], axis, pos, types)
         assert abs(e - MGO_IDEAL_ENERGY) < 1e-12
         assert np.abs(f).max() < 1e-10
+
+
+# ---- intermediates pinned by the reference's PolymlpAPI test (tests/test_cxx/test_polymlp_api.py:53-101) ---------------
+def _api_test_anlmtp(tab, t):
+    """compute_anlmtp_conjugate(arange, arange, type) of the reference (polymlp_api.cpp:63-86): m <= 0 entries take
+    k + ik in local order, partners cc * conj; an m = 0 entry is its own partner and is written last, i.e. conjugated."""
+    full = tab.local[t]["full"]
+    a = np.zeros(len(full), complex)
+    k = 0
+    for i, (_, _, m, _, _, conj, _, _) in enumerate(full):
+        if not conj:
+            a[i] = complex(k, -k if m == 0 else k)
+            k += 1
+    for i, (_, _, _, _, _, conj, cc, src) in enumerate(full):
+        if conj:
+            a[i] = cc * np.conj(a[src])
+    return a, k
+
+
+def test_polymlp_api_known_answers():
+    """MgO gtinv model (1899 columns): 450 order parameters / 270 without conjugates per type, the reference's sums of
+    the conjugate expansion, of the 891 invariants and of their derivative contractions."""
+    tab = po.Tables(make_params_dict(**cases.mgo_model_kwargs("gtinv")))
+    assert tab.n_variables == 1899
+    for t in (0, 1):
+        a, n_noconj = _api_test_anlmtp(tab, t)
+        assert (len(a), n_noconj) == (450, 270)
+        assert a.sum() == 31581 + 17199j
+        d, G = po.atom_features(tab, t, a, True)
+        assert d.shape == (891,)
+        assert d.sum() == pytest.approx(849391612.5622855, rel=1e-14)
+    a, _ = _api_test_anlmtp(tab, 0)
+    _, G = po.atom_features(tab, 0, a, True)
+    dfx, dfy, dfz, ds = np.ones((450, 8)), -2.0 * np.ones((450, 8)), 0.5 * np.ones((450, 8)), -np.ones((450, 6))
+    dfy[200, 3], dfz[100, 3], ds[300, 3] = 0.02, -0.05, 0.03
+    for arr, want in ((dfx, -14716083.219391469), (dfy, 29122027.72943048), (dfz, -7326280.333739502),
+                      (ds, 10734296.686030138)):
+        assert np.real(G @ arr.astype(complex)).sum() == pytest.approx(want, rel=1e-13)
