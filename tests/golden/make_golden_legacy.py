@@ -150,3 +150,9 @@ for k, hnf in enumerate(expansions):
     cells["types_%02d" % k] = np.asarray(st.types, np.int32)
 np.savez_compressed(os.path.join(cases.GOLDEN, "mgo_cell_shapes.npz"), **cells)
 print("mgo_cell_shapes", len(expansions), cells["pos_08"].shape, cells["axis_13"])
+
+# ---- the skewed BiGd2 cell of tests/test_cxx/test_neighbor_variants.py (tests/files/POSCAR-BiGd2) -------------------
+st = Poscar(REF_T + "/files/POSCAR-BiGd2").structure
+np.savez_compressed(os.path.join(cases.GOLDEN, "bigd2.npz"), axis=np.asarray(st.axis, np.float64),
+                    positions=np.asarray(st.positions, np.float64), types=np.asarray(st.types, np.int32))
+print("bigd2", np.asarray(st.positions).shape, st.n_atoms)

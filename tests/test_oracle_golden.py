@@ -253,3 +253,48 @@ def test_polymlp_api_known_answers():
     for arr, want in ((dfx, -14716083.219391469), (dfy, 29122027.72943048), (dfz, -7326280.333739502),
                       (ds, 10734296.686030138)):
         assert np.real(G @ arr.astype(complex)).sum() == pytest.approx(want, rel=1e-13)
+
+
+# ---- skewed BiGd2 cell (tests/test_cxx/test_neighbor_variants.py:17-66) -----------------------------------------------
+BIGD2_FULL = {  # (atom, neighbour type): (count, sum of distances or None, sum of squared differences, sum of indices)
+    (0, 0): (8, 38.163579855514044, 187.52873463482072, 15), (0, 1): (None, 83.65951693527006, 415.3567695554637, 325),
+    (15, 0): (None, None, 207.80873466782282, 32), (15, 1): (17, None, 381.07889949085563, 302),
+}
+
+
+def load_bigd2():
+    B = np.load(os.path.join(cases.GOLDEN, "bigd2.npz"))
+    return B["axis"], B["axis"] @ B["positions"], B["types"]
+
+
+def check_bigd2_full(off, nb, dx, dy, dz, types):
+    assert len(off) == 31
+    for (i, t), (count, dist_sum, sq_sum, idx_sum) in BIGD2_FULL.items():
+        sl = slice(off[i], off[i + 1])
+        pick = types[nb[sl]] == t
+        r2 = (dx[sl] ** 2 + dy[sl] ** 2 + dz[sl] ** 2)[pick]
+        if count is not None:
+            assert pick.sum() == count
+        if dist_sum is not None:
+            assert np.sqrt(r2).sum() == pytest.approx(dist_sum)
+        assert r2.sum() == pytest.approx(sq_sum)
+        assert nb[sl][pick].sum() == idx_sum
+
+
+def test_bigd2_neighbor_full_known_answers():
+    axis, pc, types = load_bigd2()
+    check_bigd2_full(*po.neighbor_full(axis, pc, 6.0), types)
+
+
+def test_bigd2_neighbor_cell_known_answers_compiled_dropin():
+    """NeighborCell of the compiled drop-in (host code, pm_cell_translations): cell and positions unchanged, 91 / 117 /
+    281 translations at cutoff 6 / 8 / 16 (test_neighbor_variants.py:50-66); the oracle counts agree."""
+    from pypolymlp_b200 import dropin
+
+    ext = dropin.load_extension()
+    axis, pc, _ = load_bigd2()
+    for cutoff, n_trans in ((6.0, 91), (8.0, 117), (16.0, 281)):
+        nc = ext.NeighborCell(axis.tolist(), pc.tolist(), cutoff)
+        assert len(nc.get_translations()) == n_trans
+        np.testing.assert_allclose(nc.get_axis(), axis)
+        np.testing.assert_allclose(nc.get_positions_cartesian(), pc)

@@ -55,3 +55,32 @@ def test_mgo_cell_shape_invariance_published_energy_gpu():
     assert max(np.abs(f).max() for f in prop.get_f_array()) < 1e-10
     s = np.asarray(prop.get_s_array())
     np.testing.assert_allclose(s, np.broadcast_to(s[0], s.shape), atol=1e-10, rtol=0)
+
+
+def test_bigd2_neighbor_full_known_answers_gpu():
+    """tests/test_cxx/test_neighbor_variants.py:17-47 on the device neighbour kernels through the compiled drop-in's
+    NeighborFull hook, and bit-exact against the oracle list."""
+    from oracle import polymlp_oracle as po
+    from pypolymlp_b200 import dropin
+    from test_oracle_golden import BIGD2_FULL, load_bigd2
+
+    axis, pc, types = load_bigd2()
+    full = dropin.load_extension().NeighborFull(axis.tolist(), pc.tolist(), 6.0)
+    dist = full.get_distances(2, types.tolist())
+    diff = full.get_differences(2, types.tolist())
+    nbr = full.get_neighbor_indices(2, types.tolist())
+    assert len(dist) == 30 and len(dist[0]) == 2
+    for (i, t), (count, dist_sum, sq_sum, idx_sum) in BIGD2_FULL.items():
+        if count is not None:
+            assert len(dist[i][t]) == count
+        if dist_sum is not None:
+            assert np.sum(dist[i][t]) == pytest.approx(dist_sum)
+        assert np.sum(np.square(diff[i][t])) == pytest.approx(sq_sum)
+        assert np.sum(nbr[i][t]) == idx_sum
+    off, nb, dx, dy, dz = po.neighbor_full(axis, pc, 6.0)
+    for i in range(30):
+        for t in range(2):
+            pick = types[nb[off[i]:off[i + 1]]] == t
+            assert np.array_equal(np.asarray(nbr[i][t]), nb[off[i]:off[i + 1]][pick])
+            want = np.stack([dx, dy, dz], axis=1)[off[i]:off[i + 1]][pick]
+            assert np.array_equal(np.asarray(diff[i][t]).reshape(-1, 3), want)
