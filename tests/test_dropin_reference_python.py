@@ -143,3 +143,18 @@ def test_reference_call_sites_reach_the_device_step(ext):
     for pot in ("polymlp.lammps.gtinv.SrTiO3", "polymlp.lammps.pair.cond.SrTiO3"):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             Properties(pot=MLPS + pot)
+
+
+def test_reference_neighbor_cell_test_on_the_dropin(ext):
+    """tests/test_cxx/test_neighbor_variants.py:50-66 verbatim in spirit: the reference's own wrapper
+    (cxx/wrapper/api_neighbor.py NeighborCell) and Poscar reader, our NeighborCell underneath (host code)."""
+    from pypolymlp.core.interface_vasp import Poscar
+    from pypolymlp.cxx.wrapper.api_neighbor import NeighborCell
+
+    str1 = Poscar("/root/reference/tests/files/POSCAR-BiGd2").structure
+    neigh = NeighborCell(str1, cutoff=6.0)
+    np.testing.assert_allclose(neigh.axis, str1.axis)
+    np.testing.assert_allclose(neigh.positions_cartesian, str1.axis @ str1.positions)
+    assert len(neigh.translations) == 91
+    assert len(NeighborCell(str1, cutoff=8.0).translations) == 117
+    assert len(NeighborCell(str1, cutoff=16.0).translations) == 281
