@@ -4,8 +4,12 @@ TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline leg may import this module; the product (pypolymlp_b200) never
 does.  Parity status: PINNED -- checked against the reference's golden vectors
 (tests/test_oracle_golden.py: get_fn, Y_lm sums, translation counts, Si design
-matrix column sums) and against the unmodified reference C++ compiled into
-oracle/_ref (tests/test_oracle_vs_ref.py).
+matrix column sums, the MgO potentials' published E / F / stress and feature
+sums, the PolymlpAPI sums of tests/test_cxx/test_polymlp_api.py, the skewed
+BiGd2 neighbour lists, the 25-cell shape-invariance energy of
+tests/test_calc/test_check_neighbors.py; tests/test_legacy_io.py: the published
+answers of the bundled legacy SrTiO3 / Ag / MgO potentials) and against the
+unmodified reference C++ compiled into oracle/_ref (tests/test_oracle_vs_ref.py).
 
 The restatement is deliberately written in a different algebraic form from the
 reference (neighbour-sparse derivatives through G = d(feature)/d(a_nlm)), so
