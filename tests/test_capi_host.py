@@ -317,3 +317,18 @@ def test_features_attr_getters_match_reference(kw):
         assert [list(v) for v in impl.get_tcomb_ids()] == tcomb
         assert [list(v) for v in impl.get_polynomial_ids()] == poly
         assert [list(v) for v in impl.get_type_pairs()] == type_pairs
+
+
+def test_count_flops_tool_config2():
+    """tools/count_flops.py reproduces SURVEY 8(d)'s config-2 figures: 13 824 ordered pairs, 775 rows,
+    W = 4.33 GFLOP per structure (SYRK 3.195e9)."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "count_flops.py"), "2"], capture_output=True,
+                         text=True, check=True).stdout.strip().splitlines()[-1]
+    rec = json.loads(out)
+    assert (rec["n_features"], rec["atoms"], rec["ordered_pairs"], rec["rows"]) == (2030, 256, 13824, 775)
+    assert rec["flops"]["syrk"] == pytest.approx(775 * 2030 * 2031, rel=1e-3)
+    assert rec["flops_per_structure"] == pytest.approx(4.327e9, rel=1e-3)
