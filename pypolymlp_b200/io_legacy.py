@@ -196,3 +196,38 @@ def convert_to_yaml(txt="polymlp.lammps", yaml="polymlp.yaml"):
     pd, coeffs, meta = load_mlp_lammps(txt)
     save_mlp_yaml(pd, coeffs, np.ones(len(coeffs)), meta["elements"], filename=yaml, mass=meta["mass"])
     return yaml
+
+
+def load_mlps(file_list_or_file):
+    """One file or a list of files (hybrid models) -> lists of (params_dict, coeffs, meta), one entry per sub-model
+    (io_polymlp.py:78-104 returns PolymlpParams + a coefficient list; here the boundary dicts take their place)."""
+    if isinstance(file_list_or_file, (str, io.IOBase)):
+        files = [file_list_or_file]
+    elif isinstance(file_list_or_file, (list, tuple, np.ndarray)):
+        files = list(file_list_or_file)
+    else:
+        raise RuntimeError("Input object not appropriate for load_mlps.")
+    if not files:
+        raise RuntimeError("Input object not appropriate for load_mlps.")
+    loaded = [load_mlp(f) for f in files]
+    return [x[0] for x in loaded], [x[1] for x in loaded], [x[2] for x in loaded]
+
+
+def find_mlps(path):
+    """polymlp.yaml* files of a directory, else polymlp.lammps* files, sorted; None if neither (io_polymlp.py:107-117)."""
+    import glob
+
+    for pattern in ("/polymlp.yaml*", "/polymlp.lammps*"):
+        files = glob.glob(path + pattern)
+        if files:
+            return sorted(files)
+    return None
+
+
+def is_hybrid(filename="polymlp.yaml"):
+    """True for a list of more than one potential file (io_polymlp.py:159-175)."""
+    if isinstance(filename, (str, io.IOBase)):
+        return False
+    if isinstance(filename, (list, tuple, np.ndarray)):
+        return len(filename) > 1
+    raise RuntimeError("filename must be strings or array-type.")

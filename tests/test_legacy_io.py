@@ -220,3 +220,31 @@ def test_legacy_mgo_pair_published_answers():
         {k: v for k, v in want.items() if k != "pair_conditional"}
     e, f, s = po.eval_structure(po.Tables(pd), L["mgo_pair_coeffs"], M["rs_axis"], M["rs_pos"], M["rs_types"])
     check_mgo_eval("pair", e, f, s, np.linalg.det(M["rs_axis"]))
+
+
+def test_load_mlps_find_mlps_is_hybrid(tmp_path):
+    """io_polymlp.py:78-117,159-175: lists of potential files (hybrid models), directory lookup, hybrid predicate."""
+    import shutil
+
+    from pypolymlp_b200.io_legacy import find_mlps, is_hybrid, load_mlps
+
+    flex = [os.path.join(cases.GOLDEN, "polymlp.yaml.flexible.%d.SrTiO3" % k) for k in (1, 2)]
+    pds, coeffs, metas = load_mlps(flex)
+    assert [m["elements"] for m in metas] == [["Sr", "Ti", "O"], ["O"]]
+    assert [m["type_full"] for m in metas] == [True, False] and metas[1]["type_indices"] == [2]
+    assert [len(c) for c in coeffs] == [5452, 2220] and [p["n_type"] for p in pds] == [3, 1]
+    one = load_mlps(SYNTHETIC)
+    assert len(one[0]) == 1 and np.array_equal(one[1][0], load_mlp(SYNTHETIC)[1])
+    assert is_hybrid(flex) and not is_hybrid(flex[:1]) and not is_hybrid(flex[0])
+    with pytest.raises(RuntimeError):
+        is_hybrid(3)
+    with pytest.raises(RuntimeError):
+        load_mlps(3)
+    assert find_mlps(str(tmp_path)) is None
+    shutil.copy(SYNTHETIC, tmp_path / "polymlp.lammps")
+    assert find_mlps(str(tmp_path)) == [str(tmp_path / "polymlp.lammps")]
+    for k, f in enumerate(flex):
+        shutil.copy(f, tmp_path / ("polymlp.yaml.%d" % (k + 1)))
+    found = find_mlps(str(tmp_path))  # yaml files take precedence over legacy ones
+    assert found == [str(tmp_path / "polymlp.yaml.1"), str(tmp_path / "polymlp.yaml.2")]
+    assert [len(c) for c in load_mlps(found)[1]] == [5452, 2220]
