@@ -56,3 +56,22 @@ def test_readgtinv():
     for order, maxl in ((2, [6]), (3, [4, 4]), (4, [4, 2, 2])):
         a, b = po.readgtinv(order, maxl, d), ref.readgtinv(order, maxl)
         assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+
+
+def test_neighbor_cell_of_the_dropin_is_bit_equal_on_skewed_cells():
+    """NeighborCell of the compiled drop-in (host C++, pm_cell_translations) against the reference's NeighborCell in
+    oracle/_ref on the 25 unimodular MgO cells of test_check_neighbors.py (lattice vectors up to 60 A: every one needs the
+    cell reduction) and on the BiGd2 cell: reduced axis, wrapped positions and the translation list, exactly."""
+    from pypolymlp_b200 import dropin
+    from test_oracle_golden import load_bigd2, load_mgo_cell_shapes
+
+    ext = dropin.load_extension()
+    cells = [(a, p, 8.0) for a, p, _ in load_mgo_cell_shapes()]
+    axis, pc, _ = load_bigd2()
+    cells += [(axis, pc, rc) for rc in (6.0, 8.0, 16.0)]
+    for axis, pos, cutoff in cells:
+        nc = ext.NeighborCell(axis.tolist(), pos.tolist(), cutoff)
+        trans, axis_ref, pos_ref = ref.neighbor_cell(axis, pos, cutoff)
+        assert np.array_equal(np.asarray(nc.get_translations()), trans)
+        assert np.array_equal(np.asarray(nc.get_axis()), axis_ref)
+        assert np.array_equal(np.asarray(nc.get_positions_cartesian()), pos_ref)
