@@ -75,3 +75,14 @@ def test_neighbor_cell_of_the_dropin_is_bit_equal_on_skewed_cells():
         assert np.array_equal(np.asarray(nc.get_translations()), trans)
         assert np.array_equal(np.asarray(nc.get_axis()), axis_ref)
         assert np.array_equal(np.asarray(nc.get_positions_cartesian()), pos_ref)
+
+
+def test_oracle_neighbor_lists_on_skewed_cells_bit_equal():
+    """numpy oracle vs reference NeighborFull / NeighborHalf on the skewed MgO cells and BiGd2 (cell reduction path)."""
+    from test_oracle_golden import load_bigd2, load_mgo_cell_shapes
+
+    cells = [(a, p, 8.0) for a, p, _ in load_mgo_cell_shapes()[::3]] + [load_bigd2()[:2] + (6.0,)]
+    for axis, pos, cutoff in cells:
+        for kind, fn in (("full", po.neighbor_full), ("half", po.neighbor_half)):
+            for a, b in zip(fn(axis, pos, cutoff), ref.neighbor(kind, axis, pos, cutoff)):
+                assert np.array_equal(a, b)
