@@ -90,6 +90,7 @@ struct HostChunk {
     int n_st = 0, n_atoms = 0, n_rows = 0, max_trans = 0, max_atoms = 0;
     std::vector<int> atom_off, st_of_atom, types, trans_off, force, erow, srow, frow;
     std::vector<double> x, y, z, trans, w, yv;
+    std::vector<double> we;   // fit: true weights of the energy rows (w[erow] is 1 on the device, see k_xe_reduce)
     std::vector<long> brow_e, brow_s, brow_f;  // rows in the caller's batch layout
 };
 
@@ -113,7 +114,7 @@ struct pm_context {
         d_nbr, d_centre, d_rev, d_err;
     DevVec<ulonglong2> d_masks;
     DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_cmat, d_e,
-        d_f, d_s;
+        d_f, d_s, d_we;
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
     DevBatch last_batch{};
@@ -143,6 +144,7 @@ struct pm_context {
     double* pinned = nullptr;   // host (pinned) copy of the packed result of pm_fit_finalize
     size_t pinned_n = 0;
     double* packed = nullptr;   // device: [xtx F*F | xty F | xe_sum F | xe_sq F | y_sq_norm | n_data]
+    SyrkScratch syrk_scr{};     // parked partial tiles + per-tile arrival counters of the deterministic SYRK fix-up
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -209,6 +211,22 @@ static void build_device_model(pm_context* c) {
         if (d.tpn == 0) d.kpn = 0;
         d.dense = 1;
         for (const auto& T : hm.types) d.dense = d.dense && T.dense_blocks;
+        // k_lrows_v4 forms its A operands from the Y_lm arrays directly: position inside a radial group == Y_lm key
+        d.front2 = d.n_type == 1 ? 1 : 0;
+        if (d.front2) {
+            const TypeTables& T = hm.types[0];
+            for (int n = 0; n < d.n_fn && d.front2; ++n) {
+                const int o0 = T.seg_n_off[0][n], o1 = T.seg_n_off[0][n + 1];
+                int real = 0;
+                for (int pos = o0; pos < o1; ++pos) {
+                    const int h = T.seg_heads[0][pos];
+                    if (h < 0) continue;
+                    ++real;
+                    if (T.head_key[h] != pos - o0) d.front2 = 0;
+                }
+                if (real != 0 && real != hm.n_lm_half) d.front2 = 0;
+            }
+        }
     }
     std::vector<double> tpp((size_t)d.n_tp * d.n_fn * 2, 0.0);
     std::vector<int> tpn(d.n_tp, 0), tpairs((size_t)d.n_type * d.n_type);
@@ -528,7 +546,7 @@ static double est_bytes_per_structure(const pm_context* c, const double* axis, i
     double bytes = pairs * (d.pbstride * 8.0 + 12.0);
     bytes += n_atoms * (d.hmax * 16.0 * 10 + d.fl * 8.0 * 10 + 64);
     if (force) {
-        bytes += pairs * 3.0 * (c->scatter ? d.npv_pad : d.fl) * 8.0;
+        bytes += (pairs + n_atoms) * 3.0 * (c->scatter ? d.npv_pad : d.fl) * 8.0;
         bytes += (double)n_atoms * d.gstride * 8.0;
         bytes += (7.0 + 3.0 * n_atoms) * d.fpad * 8.0;
     } else {
@@ -580,9 +598,12 @@ static void prepare_chunk(const pm_context* c, const pm_structures* st, const st
     h.n_rows = ifo;
     h.w.assign(h.n_rows, 1.0);
     h.yv.assign(h.n_rows, 0.0);
+    h.we.assign(h.n_st, 1.0);
     if (w && y) {
         for (int k = 0; k < h.n_st; ++k) {
-            h.w[h.erow[k]] = w[h.brow_e[k]]; h.yv[h.erow[k]] = y[h.brow_e[k]];
+            // the energy rows leave K4b unweighted (device weight 1): k_xe_reduce takes the unweighted column sums
+            // xe_sum / xe_sq_sum from them in structure order and applies the weight afterwards
+            h.we[k] = w[h.brow_e[k]]; h.yv[h.erow[k]] = y[h.brow_e[k]];
             if (h.force[k]) {
                 for (int r = 0; r < 6; ++r) { h.w[h.srow[k] + r] = w[h.brow_s[k] + r]; h.yv[h.srow[k] + r] = y[h.brow_s[k] + r]; }
                 const int nf = 3 * (h.atom_off[k + 1] - h.atom_off[k]);
@@ -656,6 +677,28 @@ struct StageTimer {
 
 enum Mode { MODE_FIT = 0, MODE_X = 1, MODE_EVAL = 2, MODE_NEIGH = 3 };
 
+__global__ void k_add_scalar(double* dst, double v) { *dst += v; }
+
+// xe_sum / xe_sq_sum (src/pypolymlp/mlp_dev/core/data_sequential.py:128-132: sums of the UNWEIGHTED energy rows and of
+// their squares): one thread per column walks the chunk's energy rows in structure order -- a fixed summation
+// order, unlike the atomics this replaces -- and then applies the energy-row weight that K4b left out.
+__global__ void __launch_bounds__(128) k_xe_reduce(double* __restrict__ X, int fpad, int F, const int* __restrict__ erow,
+                                                   const double* __restrict__ we, int n_st, double* __restrict__ xe_sum,
+                                                   double* __restrict__ xe_sq) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= F) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < n_st; ++s) {
+        double* px = X + (size_t)erow[s] * fpad + col;
+        const double v = *px;
+        s1 += v;
+        s2 += v * v;
+        *px = we[s] * v;
+    }
+    xe_sum[col] += s1;
+    xe_sq[col] += s2;
+}
+
 // makes the main stream wait for the SYRK that is still running on stream2 (no host sync)
 static void join_syrk(pm_context* c) {
     if (!c->syrk_pending) return;
@@ -674,7 +717,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         h2d(c->d_trans_off, h.trans_off, s); h2d(c->d_force, h.force, s); h2d(c->d_erow, h.erow, s);
         h2d(c->d_srow, h.srow, s); h2d(c->d_frow, h.frow, s);
         h2d(c->d_x, h.x, s); h2d(c->d_y, h.y, s); h2d(c->d_z, h.z, s); h2d(c->d_trans, h.trans, s);
-        h2d(c->d_w, h.w, s); h2d(c->d_yv, h.yv, s);
+        h2d(c->d_w, h.w, s); h2d(c->d_yv, h.yv, s); h2d(c->d_we, h.we, s);
     }
     DevBatch b{};
     b.n_st = h.n_st; b.n_atoms = h.n_atoms; b.n_pairs = 0; b.n_rows = h.n_rows; b.max_trans = h.max_trans;
@@ -684,7 +727,18 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     b.force = c->d_force.p; b.erow = c->d_erow.p; b.srow = c->d_srow.p; b.frow = c->d_frow.p;
     b.w = c->d_w.p; b.yv = c->d_yv.p;
     tm.mark(ST_H2D, 0);
-    if (h.n_atoms == 0) { c->last_batch = b; c->last_pairs = 0; return; }
+    if (h.n_atoms == 0) {
+        // structures without (active) atoms: every X row is zero.  The fit still counts the rows and their targets
+        // (y^T y); pm_features_x zero-fills the caller's rows in process_batch.
+        c->last_batch = b; c->last_pairs = 0;
+        if (mode == MODE_FIT && h.n_rows > 0) {
+            double ysq = 0.0;
+            for (double v : h.yv) ysq += v * v;
+            k_add_scalar<<<1, 1, 0, s>>>(c->acc + (size_t)d.n_variables * d.fpad + d.n_variables, ysq);
+            c->n_data += h.n_rows;
+        }
+        return;
+    }
 
     // ---- K1 ------------------------------------------------------------------------------------
     const size_t nseg = (size_t)h.n_atoms * nt;
@@ -785,6 +839,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     // that K4a of this chunk does not have to wait for the previous chunk's SYRK (which still reads X)
     const bool fit = mode == MODE_FIT;
     ws.scatter = c->scatter;
+    ws.lt = !c->simple_l && !c->simple_x && !c->scatter && dpv != nullptr && front_v2_supported(d);
     auto prep_X = [&] {
         join_syrk(c);
         c->d_X.ensure((size_t)std::max(h.n_rows, 1) * d.fpad);
@@ -799,7 +854,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
             c->d_Lpv.ensure(np1 * 3 * d.npv_pad);
             ws.Lpv = c->d_Lpv.p;
         } else {
-            c->d_L.ensure(np1 * 3 * d.fl);
+            c->d_L.ensure((np1 + (ws.lt ? (size_t)h.n_atoms : 0)) * 3 * d.fl);
             ws.Lbuf = c->d_L.p;
         }
         launch_lrows(d, b, ws, c->simple_l, fit, s);
@@ -807,10 +862,13 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     }
     // ---- K4b -------------------------------------------------------------------------------------
     if (!ws.scatter) prep_X();
-    double* xe_sum = fit ? c->acc + (size_t)d.fpad * d.fpad : nullptr;
-    double* xe_sq = fit ? xe_sum + d.fpad : nullptr;
-    launch_xrows(d, b, ws, xe_sum, xe_sq, c->simple_x, fit, s);
-    tm.mark(ST_XROWS, 3);
+    launch_xrows(d, b, ws, nullptr, nullptr, c->simple_x, fit, s);
+    if (fit) {
+        double* xe_sum = c->acc + (size_t)d.fpad * d.fpad;
+        k_xe_reduce<<<(d.n_variables + 127) / 128, 128, 0, s>>>(ws.X, d.fpad, d.n_variables, b.erow, c->d_we.p, h.n_st,
+                                                               xe_sum, xe_sum + d.fpad);
+    }
+    tm.mark(ST_XROWS, fit ? 4 : 3);
     // ---- K5 --------------------------------------------------------------------------------------
     if (fit) {
         cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -827,13 +885,13 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
             CK(cudaEventRecord(c->ev_x, s));
             CK(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
             if (t0) CK(cudaEventRecord(t0, c->stream2));
-            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, c->stream2);
+            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, c->stream2, &c->syrk_scr);
             if (t1) CK(cudaEventRecord(t1, c->stream2));
             CK(cudaEventRecord(c->ev_s, c->stream2));
             c->syrk_pending = true;
         } else {
             if (t0) CK(cudaEventRecord(t0, s));
-            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s);
+            launch_syrk(ws.X, h.n_rows, d.fpad, c->acc, c->simple_s, s, &c->syrk_scr);
             if (t1) CK(cudaEventRecord(t1, s));
         }
         tm.mark(ST_SYRK, syrk_launches(h.n_rows, d.fpad, c->simple_s));
@@ -1083,10 +1141,12 @@ void pm_context_destroy(pm_context* c) {
     if (c->ev_s) cudaEventDestroy(c->ev_s);
     for (void* p : c->table_allocs) cudaFree(p);
     if (c->acc) cudaFree(c->acc);
+    if (c->syrk_scr.partials) cudaFree(c->syrk_scr.partials);
+    if (c->syrk_scr.counters) cudaFree(c->syrk_scr.counters);
     c->d_atom_off.release(); c->d_st_of_atom.release(); c->d_types.release(); c->d_trans_off.release();
     c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
-    c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release();
+    c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release(); c->d_we.release();
     c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_masks.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
     c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_cmat.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
@@ -1126,6 +1186,16 @@ static void ensure_acc(pm_context* c) {
         CK(cudaMemsetAsync(c->acc, 0, c->acc_n * sizeof(double), c->stream));
         c->n_data = 0;
     }
+    if (!c->syrk_scr.partials) {
+        int n_sm = 0;
+        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device));
+        const long nt = c->dm.fpad / 128;
+        c->syrk_scr.n_slots = 2L * std::max(n_sm, 1);
+        c->syrk_scr.n_counters = nt * (nt + 1) / 2;
+        CK(cudaMalloc(&c->syrk_scr.partials, (size_t)c->syrk_scr.n_slots * 128 * 128 * sizeof(double)));
+        CK(cudaMalloc(&c->syrk_scr.counters, (size_t)c->syrk_scr.n_counters * sizeof(int)));
+        CK(cudaMemsetAsync(c->syrk_scr.counters, 0, (size_t)c->syrk_scr.n_counters * sizeof(int), c->stream));
+    }
 }
 
 int pm_fit_reset(pm_context* c) {
@@ -1161,7 +1231,12 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
         const int s0 = chunks[ck].first;
         HostChunk h = std::move(h_next);
         run_chunk(c, h, mode, true, tm);
-        if (mode == MODE_X) {
+        if (mode == MODE_X && h.n_atoms == 0) {
+            for (int k = 0; k < h.n_st; ++k) {   // no atoms: zero rows, as the reference returns them
+                std::fill_n(x_out + (size_t)h.brow_e[k] * F, (size_t)F, 0.0);
+                if (h.force[k]) std::fill_n(x_out + (size_t)h.brow_s[k] * F, (size_t)6 * F, 0.0);
+            }
+        } else if (mode == MODE_X) {
             for (int k = 0; k < h.n_st; ++k) {
                 CK(cudaMemcpy2DAsync(x_out + (size_t)h.brow_e[k] * F, F * sizeof(double), c->d_X.p + (size_t)h.erow[k] * d.fpad,
                                      d.fpad * sizeof(double), F * sizeof(double), 1, cudaMemcpyDeviceToHost, c->stream));
@@ -1240,6 +1315,7 @@ int pm_fit_stage(pm_context* c, const pm_structures* st, const double* w, const 
             put(h.srow.data(), h.srow.size() * 4); put(h.frow.data(), h.frow.size() * 4);
             put(h.x.data(), h.x.size() * 8); put(h.y.data(), h.y.size() * 8); put(h.z.data(), h.z.size() * 8);
             put(h.trans.data(), h.trans.size() * 8); put(h.w.data(), h.w.size() * 8); put(h.yv.data(), h.yv.size() * 8);
+            put(h.we.data(), h.we.size() * 8);
             c->staged_dev.push_back(dev);
             // keep only the metadata on the host
             HostChunk meta;
@@ -1264,11 +1340,12 @@ int pm_fit_accumulate_staged(pm_context* c) {
             auto save = [&](auto& vec) { saved.push_back({vec.p, vec.cap}); };
             save(c->d_atom_off); save(c->d_st_of_atom); save(c->d_types); save(c->d_trans_off); save(c->d_force);
             save(c->d_erow); save(c->d_srow); save(c->d_frow); save(c->d_x); save(c->d_y); save(c->d_z); save(c->d_trans);
-            save(c->d_w); save(c->d_yv);
+            save(c->d_w); save(c->d_yv); save(c->d_we);
             swap_in(c->d_atom_off, dev[0]); swap_in(c->d_st_of_atom, dev[1]); swap_in(c->d_types, dev[2]);
             swap_in(c->d_trans_off, dev[3]); swap_in(c->d_force, dev[4]); swap_in(c->d_erow, dev[5]);
             swap_in(c->d_srow, dev[6]); swap_in(c->d_frow, dev[7]); swap_in(c->d_x, dev[8]); swap_in(c->d_y, dev[9]);
             swap_in(c->d_z, dev[10]); swap_in(c->d_trans, dev[11]); swap_in(c->d_w, dev[12]); swap_in(c->d_yv, dev[13]);
+            swap_in(c->d_we, dev[14]);
             std::exception_ptr ex;
             try {
                 run_chunk(c, c->staged[k], MODE_FIT, false, tm);
@@ -1277,7 +1354,7 @@ int pm_fit_accumulate_staged(pm_context* c) {
             auto restore = [&](auto& vec) { vec.p = reinterpret_cast<decltype(vec.p)>(saved[q].p); vec.cap = saved[q].cap; ++q; };
             restore(c->d_atom_off); restore(c->d_st_of_atom); restore(c->d_types); restore(c->d_trans_off);
             restore(c->d_force); restore(c->d_erow); restore(c->d_srow); restore(c->d_frow); restore(c->d_x);
-            restore(c->d_y); restore(c->d_z); restore(c->d_trans); restore(c->d_w); restore(c->d_yv);
+            restore(c->d_y); restore(c->d_z); restore(c->d_trans); restore(c->d_w); restore(c->d_yv); restore(c->d_we);
             if (ex) std::rethrow_exception(ex);
         }
         join_syrk(c);

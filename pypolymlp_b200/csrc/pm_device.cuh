@@ -78,6 +78,7 @@ struct DevModel {
     int dense;     // 1 if every type stores dense blocks (B fragments addressed as base + (tile*kc_n + kc)*32)
     int kpn;       // k-chunks (2 heads) per radial group, padded to the fast-path template value (0 = no fast path)
     int tpn;       // max feature tiles per radial index, padded likewise
+    int front2;    // 1: single-type model whose radial groups list all m <= 0 heads in Y_lm key order (k_lrows_v4 / k_xrows_v6)
     long gstride;  // doubles per atom in the G buffer
     double cutoff;
     const double* tp_params;  // [n_tp][n_fn][2], compacted by radial id of the pair

@@ -1676,7 +1676,7 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
 void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_weights, cudaStream_t s);
 void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                       bool apply_weights, cudaStream_t s);
-void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s);
+void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s, const SyrkScratch* scr);
 
 void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s) {
     if (b.n_atoms == 0) return;
@@ -1695,13 +1695,13 @@ void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, dou
     }
 }
 
-void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s) {
+void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s, const SyrkScratch* scr) {
     if (n_rows == 0) return;
     if (simple) {
         const int nt = fpad / 64;
         k_syrk_simple<<<nt * (nt + 1) / 2, 256, 0, s>>>(X, n_rows, fpad, C);
     } else {
-        launch_syrk_mma(X, n_rows, fpad, C, s);
+        launch_syrk_mma(X, n_rows, fpad, C, s, scr);
     }
 }
 

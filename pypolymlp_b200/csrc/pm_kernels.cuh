@@ -14,6 +14,8 @@ struct Workspace {
     double* dpv = nullptr;      // [n_atoms][64] polynomial variables of each atom, compact (single-type models; else null)
     double* Gbuf = nullptr;     // [n_atoms][gstride]
     double* Lbuf = nullptr;     // [n_pairs * 3][fl]   (not used in scatter mode)
+    bool lt = false;            // Lbuf is target-major ("Lt", k_lrows_v4 -> k_xrows_v6): [(n_pairs + n_atoms) * 3][fl], block of
+                                // atom k starts at row 3 * (seg_off[k] + k): own row, then the negated rows of its neighbours
     double* Lpv = nullptr;      // [n_pairs * 3][npv_pad] derivative rows of the polynomial variables (scatter mode)
     bool scatter = false;       // K4a adds the linear columns straight into X with RED.F64, K4b only does the GEMM part
     double* Xown = nullptr;     // [n_atoms][3][fl]
@@ -39,6 +41,10 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
 // K4a: per-centre derivative rows L = V . G
 void launch_lrows(const DevModel& m, const DevBatch& b, const Workspace& ws, bool simple, bool apply_weights, cudaStream_t s);
 bool scatter_mode_supported(const DevModel& m);
+// second-generation front end (pm_kernels_front.cu): K4a writes target-major rows, K4b streams them
+bool front_v2_supported(const DevModel& m);
+bool launch_lrows_v4(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s);
+void launch_xrows_v6(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_weights, cudaStream_t s);
 // K4b: gather + polynomial expansion -> weighted X-tilde rows
 void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, double* xe_sum, double* xe_sq,
                   bool simple, bool apply_weights, cudaStream_t s);
@@ -46,8 +52,16 @@ void launch_xrows(const DevModel& m, const DevBatch& b, const Workspace& ws, dou
 bool xrows_fills_rows(const DevModel& m, bool scatter);
 // exclusive prefix sum (segment offsets of the neighbour list)
 void launch_scan_exclusive(const int* in, int* out, int n, cudaStream_t s);
-// K5: C += Xt^T Xt (upper tiles)
-void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s);
+// K5: C += Xt^T Xt (upper tiles).  The scratch holds the parked partial tiles of the deterministic stream-K fix-up
+// (2 slots of 128 x 128 doubles per CTA) and one arrival counter per tile (zero between launches).
+struct SyrkScratch {
+    double* partials = nullptr;
+    int* counters = nullptr;
+    long n_slots = 0;
+    long n_counters = 0;
+};
+void launch_syrk(const double* X, int n_rows, int fpad, double* C, bool simple, cudaStream_t s,
+                 const SyrkScratch* scratch = nullptr);
 int syrk_launches(int n_rows, int fpad, bool simple);
 // eval: E/F/S through contraction with coefficients
 // feat_smem > 0: fused feature + polynomial-adjoint kernel (no G buffer, no separate K3 launch); it must be the

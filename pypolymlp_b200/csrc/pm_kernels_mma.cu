@@ -13,6 +13,7 @@
 //                      G read as ready-made B fragments from the block-sparse buffer (L1/L2)
 //   k_xrows_mma   K4b  gather GEMM C[a,b] = sum_centres d_a Lambda_b, then X = C + C^T per polynomial term
 #include "pm_kernels.cuh"
+#include "pm_mma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -20,24 +21,6 @@
 #include <cublas_v2.h>
 
 namespace pm {
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
-}
-// asynchronous L2 prefetch of a contiguous global range (one instruction; bytes is a multiple of 16)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ================================================================================================
 // K5: SYRK.  grid = (upper tiles, k-splits).  8 warps as 2 (M) x 4 (N), warp tile 64 x 32.
@@ -261,10 +244,219 @@ __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_r
     }
 }
 
-void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s) {
+// ------------------------------------------------------------------------------------------------
+// Stream-K SYRK, second version.  Differences to k_syrk_sk:
+//  * DETERMINISTIC: a CTA that owns only part of a tile's k range parks its partial tile in a workspace slot
+//    instead of adding it to C with RED.F64; the last contributor to arrive (per-tile counter) sums the parts in
+//    k order -- a fixed order, whoever does it -- and is the only one that touches the C tile.
+//  * diagonal tiles compute their upper triangle only (136 of 256 8x8 blocks): the warps are remapped so that each SM
+//    sub-partition keeps <= 36 of 64 DMMAs per k-step, and the stream-K split weighs a diagonal k-block 9/16 of a
+//    full one.  Diagonal tiles come first in the tile order.
+// ------------------------------------------------------------------------------------------------
+constexpr int SY_TILE_D = SY_BM * SY_BM;
+constexpr long SY_COST_DIAG = 9, SY_COST_FULL = 16;
+
+__device__ __forceinline__ long sy_unit_of_cost(long y, long nD, long Dc, long nU) {
+    const long u = y <= Dc ? y / SY_COST_DIAG : nD + (y - Dc) / SY_COST_FULL;
+    return u < nU ? u : nU;
+}
+__device__ __forceinline__ int sy_cta_of_unit(long x, long nD, long Dc, long cper) {
+    const long y = x < nD ? SY_COST_DIAG * x + (SY_COST_DIAG - 1) : Dc + SY_COST_FULL * (x - nD) + (SY_COST_FULL - 1);
+    return (int)(y / cper);
+}
+
+__global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_rows, int fpad,
+                                             double* __restrict__ C, int nkb, double* __restrict__ part,
+                                             int* __restrict__ counters) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_first, s_np;
+    const int ntile = fpad / SY_BM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const long nD = (long)ntile * nkb;
+    const long nU = (long)ntile * (ntile + 1) / 2 * nkb;
+    const long Dc = SY_COST_DIAG * nD;
+    const long Ctot = Dc + SY_COST_FULL * (nU - nD);
+    const long cper = (Ctot + gridDim.x - 1) / gridDim.x;
+    long u = sy_unit_of_cost((long)blockIdx.x * cper, nD, Dc, nU);
+    const long u_end = sy_unit_of_cost((long)(blockIdx.x + 1) * cper, nD, Dc, nU);
+    long first_u = -1;   // see k_syrk_sk: the run that starts mid-tile is done last (k-blocks swept upwards in step)
+    if (u < u_end && u % nkb != 0) {
+        first_u = u;
+        u = min(u_end, (u / nkb + 1) * (long)nkb);
+    }
+
+    while (u < u_end || first_u >= 0) {
+        long cur = u, cur_end = u_end;
+        if (u >= u_end) {
+            cur = first_u;
+            cur_end = min(u_end, (first_u / nkb + 1) * (long)nkb);
+            first_u = -1;
+        }
+        const int tile = (int)(cur / nkb);
+        const int kb0 = (int)(cur - (long)tile * nkb);
+        const int kb1 = (int)min((long)nkb, (long)kb0 + (cur_end - cur));
+        const bool diag = tile < ntile;
+        int ti = tile, tj = tile;
+        if (!diag) {
+            int rem = tile - ntile;
+            ti = 0;
+            while (rem >= ntile - 1 - ti) { rem -= ntile - 1 - ti; ++ti; }
+            tj = ti + 1 + rem;
+        }
+        // warp tile (64 x 32) inside the 128 x 128 tile; diagonal tiles: (0,3) (0,2) (0,1) (0,0) | (1,0) (1,1) (1,2) (1,3)
+        const int wm = warp >> 2;
+        const int wn = diag ? (warp < 4 ? 3 - warp : warp - 4) : (warp & 3);
+        unsigned mask = 0xffffffffu;
+        if (diag) {
+            mask = 0u;
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (wm * 8 + a <= wn * 4 + b) mask |= 1u << (a * 4 + b);
+        }
+        const int r_begin = kb0 * SY_BK;
+        const int r_end = min(n_rows, kb1 * SY_BK);
+        const int nk = kb1 - kb0;
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+        auto load_stage = [&](int kt, int slot) {
+            double* sA = smem + (size_t)slot * SY_STAGE_DOUBLES;
+            double* sB = sA + SY_BK * SY_LD;
+            const int r0 = r_begin + kt * SY_BK;
+#pragma unroll
+            for (int it = 0; it < SY_BK / 4; ++it) {
+                const int e = tid + it * 256;
+                const int rr = e >> 6, cc = (e & 63) * 2;
+                const int r = r0 + rr;
+                const bool ok = r < r_end;
+                const double* src = X + (size_t)(ok ? r : r_begin) * fpad;
+                cp_async16(sA + rr * SY_LD + cc, src + ti * SY_BM + cc, ok ? 16 : 0);
+                if (!diag) cp_async16(sB + rr * SY_LD + cc, src + tj * SY_BM + cc, ok ? 16 : 0);
+            }
+        };
+        __syncthreads();  // previous segment's smem reads are finished
+#pragma unroll
+        for (int s = 0; s < SY_STAGES - 1; ++s) {
+            if (s < nk) load_stage(s, s);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < nk; ++kt) {
+            cp_async_wait<SY_STAGES - 2>();
+            __syncthreads();
+            const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
+            const double* sB = diag ? sA : sA + SY_BK * SY_LD;
+            const double* pa = sA + q * SY_LD + wm * 64 + g;
+            const double* pb = sB + q * SY_LD + wn * 32 + g;
+#pragma unroll
+            for (int ks = 0; ks < SY_BK / 4; ++ks) {
+                if (ks == SY_ISSUE_AT) {
+                    const int nx = kt + SY_STAGES - 1;
+                    if (nx < nk) load_stage(nx, nx % SY_STAGES);
+                    cp_async_commit();
+                }
+                if (!diag) {
+                    double af[8], bf[4];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                } else if (mask) {
+                    double af[8], bf[4];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (mask & (1u << (a * 4 + b))) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        const bool whole = kb0 == 0 && kb1 == nkb;
+        bool reduce = whole;
+        if (!whole) {
+            // park the partial tile: thread-major fragment order, coalesced
+            double* ws = part + ((size_t)blockIdx.x * 2 + (kb0 == 0 ? 1 : 0)) * SY_TILE_D + tid;
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    __stcg(ws + ((a * 4 + b) * 2) * 256, acc[a][b][0]);
+                    __stcg(ws + ((a * 4 + b) * 2 + 1) * 256, acc[a][b][1]);
+                }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const long t0 = (long)tile * nkb;
+                const int first = sy_cta_of_unit(t0, nD, Dc, cper);
+                const int last = sy_cta_of_unit(t0 + nkb - 1, nD, Dc, cper);
+                const int np = last - first + 1;
+                const int old = atomicAdd(counters + tile, 1);
+                s_first = old == np - 1 ? first : -1;
+                s_np = np;
+                if (old == np - 1) counters[tile] = 0;   // ready for the next launch
+            }
+            __syncthreads();
+            if (s_first >= 0) {   // last contributor: sum the parts in k order
+                __threadfence();
+                reduce = true;
+                const int first = s_first, np = s_np;
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+                for (int p = 0; p < np; ++p) {
+                    const double* src = part + ((size_t)(first + p) * 2 + (p == 0 ? 1 : 0)) * SY_TILE_D + tid;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            acc[a][b][0] += __ldcg(src + ((a * 4 + b) * 2) * 256);
+                            acc[a][b][1] += __ldcg(src + ((a * 4 + b) * 2 + 1) * 256);
+                        }
+                }
+            }
+        }
+        if (reduce) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int row = ti * SY_BM + wm * 64 + a * 8 + g;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (!(mask & (1u << (a * 4 + b)))) continue;
+                    const int col = tj * SY_BM + wn * 32 + b * 8 + 2 * q;
+                    double2* dst = reinterpret_cast<double2*>(C + (size_t)row * fpad + col);
+                    double2 v = *dst;
+                    v.x += acc[a][b][0];
+                    v.y += acc[a][b][1];
+                    *dst = v;
+                }
+            }
+        }
+        if (cur == u) u += nk;
+    }
+}
+
+void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s, const SyrkScratch* scr) {
     static int n_sm = 0;
+    const bool use_v1 = getenv("PM_SYRK_V1") != nullptr;   // read per call (tests compare both)
     if (n_sm == 0) {
         cudaFuncSetAttribute(k_syrk_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
+        cudaFuncSetAttribute(k_syrk_sk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -272,6 +464,7 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
     }
     const int ntile = fpad / SY_BM;
     const long tiles = (long)ntile * (ntile + 1) / 2;
+    const bool v2 = !use_v1 && scr && scr->partials && scr->counters && scr->n_slots >= 2 * n_sm && scr->n_counters >= tiles;
     // Row blocks: the CTAs of one launch sweep the k range in step inside a window of (1 - tiles / n_sm) of its rows
     // (see k_syrk_sk); blocks of <= 32768 rows keep that window (plus the C tiles) inside the 126 MB L2.
     for (int r0 = 0; r0 < n_rows; r0 += SY_ROW_BLOCK) {
@@ -279,7 +472,8 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
         const int nkb = (nr + SY_BK - 1) / SY_BK;
         const long units = tiles * nkb;
         const int grid = (int)std::min<long>(n_sm, units);
-        k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, units);
+        if (v2) k_syrk_sk2<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, scr->partials, scr->counters);
+        else k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, units);
     }
 }
 
@@ -694,11 +888,6 @@ static void launch_lrows_big(const DevModel& m, const DevBatch& b, const Workspa
 // shared memory only.  The 9 aggregated rows (own x/y/z + 6 virial) ride in the last row chunk of each
 // neighbour-type segment, so no separate pass is needed.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
-}
-
 constexpr int LR_MAXW = 8;  // max warps per CTA
 
 // ------------------------------------------------------------------------------------------------
@@ -1025,6 +1214,10 @@ size_t lrows_mma_smem(const DevModel& m) {
 }
 
 void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_w, cudaStream_t s) {
+    if (ws.lt) {
+        if (!launch_lrows_v4(m, b, ws, s)) fprintf(stderr, "[pm] internal error: no k_lrows_v4 instance for this model\n");
+        return;
+    }
     if (launch_lrows_v2(m, b, ws, apply_w, s)) return;
     const size_t smem = lrows_mma_smem(m);
     if (smem > 200 * 1024) { launch_lrows_big(m, b, ws, s); return; }
@@ -1852,28 +2045,6 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v4(DevModel m, DevBatch
 constexpr int X5_R = 3;        // ring slots per group
 constexpr int X5_MAXC = 128;   // centres per pointer-table pass
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-
 __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch b, const double* __restrict__ dpv,
                                                              const double* __restrict__ Lbuf,
                                                              const double* __restrict__ Xown, double* __restrict__ X,
@@ -1911,7 +2082,7 @@ __global__ void __launch_bounds__(X4_THREADS, 2) k_xrows_v5(DevModel m, DevBatch
     }
     if (tid == 0) {
         for (int k = 0; k < 2 * X5_R; ++k) mbar_init(smem_u32(bars + k), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     int ta[X4_SLOTS], tb[X4_SLOTS];
 #pragma unroll
@@ -2107,7 +2278,9 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         static const bool use_v5 = getenv("PM_XROWS_V4") == nullptr;
         const size_t smem5 = ((size_t)4 * X4_KC * X4_LD + 2 * X5_R * (3 * (size_t)m.fl + 64) + X5_MAXC + 2 * X5_R) * sizeof(double) +
                              X5_MAXC * sizeof(int) + 128;
-        if (use_v5 && ws.dpv && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
+        if (ws.lt) {
+            launch_xrows_v6(m, b, ws, apply_weights, s);
+        } else if (use_v5 && ws.dpv && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
             static size_t set5_for = 0;   // the ring size depends on the model (fl)
             if (set5_for < smem5) {
                 cudaFuncSetAttribute(k_xrows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);

@@ -1,6 +1,7 @@
 // pm_solver.cu -- ridge regression on the device-resident accumulator (cuSOLVER Cholesky + cuBLAS).
 // Reference: src/pypolymlp/mlp_dev/core/utils_scales.py:6-40, data_sequential.py:72-92,
 // src/pypolymlp/mlp_dev/standard/solvers.py:9-84, src/pypolymlp/mlp_dev/core/utils_model_selection.py:37-72.
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -16,11 +17,12 @@ namespace pm {
 __global__ void k_scale_system(const double* __restrict__ C, int fpad, int F, const double* __restrict__ sinv,
                                const int* __restrict__ zero, double* __restrict__ A, double* __restrict__ rhs) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
     if (j >= F) return;
-    const bool z = zero[i] || zero[j];
-    if (j >= i) A[(size_t)i * F + j] = z ? 0.0 : C[(size_t)i * fpad + j] * sinv[i] * sinv[j];
-    if (j == 0) rhs[i] = zero[i] ? 0.0 : C[(size_t)i * fpad + F] * sinv[i];
+    for (int i = blockIdx.y; i < F; i += gridDim.y) {   // rows strided over gridDim.y (<= 65535)
+        const bool z = zero[i] || zero[j];
+        if (j >= i) A[(size_t)i * F + j] = z ? 0.0 : C[(size_t)i * fpad + j] * sinv[i] * sinv[j];
+        if (j == 0) rhs[i] = zero[i] ? 0.0 : C[(size_t)i * fpad + F] * sinv[i];
+    }
 }
 
 __global__ void k_add_diag(double* __restrict__ A, int F, double v) {
@@ -80,7 +82,8 @@ void solve_ridge_device(const double* C, int fpad, int F, const double* xe_sum_h
         SOLVER_CK(cudaMemcpyAsync(d_sinv, sinv.data(), F * sizeof(double), cudaMemcpyHostToDevice, stream), "h2d");
         SOLVER_CK(cudaMemcpyAsync(d_zero, zero.data(), F * sizeof(int), cudaMemcpyHostToDevice, stream), "h2d");
         SOLVER_CK(cudaMemsetAsync(A0, 0, nA * sizeof(double), stream), "memset");
-        k_scale_system<<<dim3((F + 255) / 256, F), 256, 0, stream>>>(C, fpad, F, d_sinv, d_zero, A0, rhs);
+        k_scale_system<<<dim3((F + 255) / 256, std::min(F, 32768)), 256, 0, stream>>>(C, fpad, F, d_sinv, d_zero, A0, rhs);
+        SOLVER_CK(cudaGetLastError(), "k_scale_system launch");
         SOLVER_CK(cusolverDnCreate(&sol), "cusolverDnCreate");
         SOLVER_CK(cusolverDnSetStream(sol, stream), "cusolverDnSetStream");
         SOLVER_CK(cublasCreate(&blas), "cublasCreate");
@@ -94,6 +97,7 @@ void solve_ridge_device(const double* C, int fpad, int F, const double* xe_sum_h
         for (int k = 0; k < n_alpha; ++k) {
             // incremental diagonal update on the pristine matrix (solvers.py:76-83), then factorise a copy
             k_add_diag<<<(F + 255) / 256, 256, 0, stream>>>(A0, F, alphas[k] - alpha_prev);
+            SOLVER_CK(cudaGetLastError(), "k_add_diag launch");
             alpha_prev = alphas[k];
             SOLVER_CK(cudaMemcpyAsync(A, A0, nA * sizeof(double), cudaMemcpyDeviceToDevice, stream), "copy");
             SOLVER_CK(cudaMemcpyAsync(x, rhs, F * sizeof(double), cudaMemcpyDeviceToDevice, stream), "copy");
