@@ -194,8 +194,9 @@ int pm_eval(pm_context* c, const pm_structures* st, double* energies, double* fo
  * what: 0 = a_nlm heads (complex, [atom][n_head_max]), 1 = linear features d ([atom][fl]),
  *       2 = pair basis records, 3 = X-tilde chunk ([rows][fpad]).  *n returns the number of doubles. */
 int pm_debug_fetch(pm_context* c, int what, double* out, size_t cap, size_t* n);
-/* micro-benchmarks: which = 0 DFMA, 1 DMMA (mma.sync m8n8k4 f64), 2 both interleaved, 3 cuBLAS DGEMM n^3.
- * Returns TFLOP/s. */
+/* micro-benchmarks: which = 0 DFMA, 1 DMMA (mma.sync m8n8k4 f64), 2 both interleaved, 3 cuBLAS DGEMM n^3 (TFLOP/s);
+ * 4: fp64 RED throughput (giga atomics / s); 5: DMMA dependent-issue probe, n = 100 * warps + independent chains per
+ * warp on one SM, returns SM cycles per DMMA of one warp. */
 int pm_microbench(pm_context* c, int which, int n, double* tflops);
 
 #ifdef __cplusplus

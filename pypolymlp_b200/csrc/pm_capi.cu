@@ -23,6 +23,7 @@ bool lrows_big_supported(const DevModel& m);
 size_t xrows_mma_smem(const DevModel& m);
 double microbench_dgemm(int n, cudaStream_t s);
 double microbench_red(int n_rows, cudaStream_t s);
+double microbench_dmma_chain(int code, cudaStream_t s);
 void solve_ridge_device(const double* C, int fpad, int F, const double* xe_sum_h, const double* xe_sq_h,
                         double y_sq_norm, long n_data, const double* alphas, int n_alpha, const double* scales_in,
                         long n_energy, bool include_force, double threshold, double* scales_out, double* coefs,
@@ -1639,6 +1640,7 @@ int pm_microbench(pm_context* c, int which, int n, double* tflops) {
         CK(cudaSetDevice(c->device));
         if (which == 3) *tflops = microbench_dgemm(n > 0 ? n : 8192, c->stream);
         else if (which == 4) *tflops = microbench_red(n > 16 ? n : 768, c->stream);  // giga fp64 atomics / s
+        else if (which == 5) *tflops = microbench_dmma_chain(n, c->stream);          // cycles per DMMA of one warp; n = 100 * warps + chains
         else *tflops = microbench_fp64(which, c->stream);
         CK(cudaGetLastError());
     });

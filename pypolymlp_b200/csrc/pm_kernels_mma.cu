@@ -254,32 +254,101 @@ __global__ void __maxnreg__(192) k_syrk_sk(const double* __restrict__ X, int n_r
 //    full one.  Diagonal tiles come first in the tile order.
 // ------------------------------------------------------------------------------------------------
 constexpr int SY_TILE_D = SY_BM * SY_BM;
-constexpr long SY_COST_DIAG = 9, SY_COST_FULL = 16;
+constexpr long SY_COST_FULL = 16;   // cost of a full k-block; a diagonal k-block costs cost_diag (<= 16, kernel argument)
 
-__device__ __forceinline__ long sy_unit_of_cost(long y, long nD, long Dc, long nU) {
-    const long u = y <= Dc ? y / SY_COST_DIAG : nD + (y - Dc) / SY_COST_FULL;
+__device__ __forceinline__ long sy_unit_of_cost(long y, long nD, long Dc, long nU, long cd) {
+    const long u = y <= Dc ? y / cd : nD + (y - Dc) / SY_COST_FULL;
     return u < nU ? u : nU;
 }
-__device__ __forceinline__ int sy_cta_of_unit(long x, long nD, long Dc, long cper) {
-    const long y = x < nD ? SY_COST_DIAG * x + (SY_COST_DIAG - 1) : Dc + SY_COST_FULL * (x - nD) + (SY_COST_FULL - 1);
+__device__ __forceinline__ int sy_cta_of_unit(long x, long nD, long Dc, long cper, long cd) {
+    const long y = x < nD ? cd * x + (cd - 1) : Dc + SY_COST_FULL * (x - nD) + (SY_COST_FULL - 1);
     return (int)(y / cper);
+}
+
+// one pipeline stage: rows [r0, r0 + 32) of the column blocks ti (A tile) and tj (B tile; skipped on diagonal tiles).
+// Thread t copies row t >> 3, 16-byte chunks (t & 7) + 8 * it, it = 0..7: the eight copies of a thread sit at constant
+// 128-byte steps from ONE source / destination pointer pair (immediate offsets: no per-copy address arithmetic, whose
+// registers the LSU holds until the LDGSTS has issued), and a warp instruction still covers four full 128-byte lines.
+struct SyLoader {
+    const double* srcA;   // row r_begin + (tid >> 3), column ti * 128 + (tid & 7) * 2
+    const double* srcB;
+    unsigned dst;         // shared address of stage 0, tile A, row tid >> 3, column (tid & 7) * 2
+    int row;              // r_begin + (tid >> 3)
+};
+__device__ __forceinline__ void sy_load_stage(const SyLoader& L, int fpad, int slot, int kt, int r_end, bool diag) {
+    const int r = L.row + kt * SY_BK;
+    const int bytes = r < r_end ? 16 : 0;
+    const size_t adv = (size_t)(r < r_end ? kt : 0) * SY_BK * fpad;
+    const double* a = L.srcA + adv;
+    const double* b = L.srcB + adv;
+    const unsigned d = L.dst + (unsigned)slot * (SY_STAGE_DOUBLES * 8);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d + it * 128), "l"(a + it * 16), "r"(bytes));
+        if (!diag)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d + SY_BK * SY_LD * 8 + it * 128),
+                         "l"(b + it * 16), "r"(bytes));
+    }
+}
+
+// k loop of one (tile, k range) run.  OFF selects which 8x8 blocks (a, b) of the warp's 64 x 32 tile are computed:
+// b >= a - OFF (OFF >= 7: all 32; 4: 26; 0: 10; < -3: none) -- compile-time, so skipped DMMAs are not issued at all
+// (a predicated-off DMMA still occupies the tensor pipe: measured).
+template <int OFF>
+__device__ __forceinline__ void sy_mainloop(double (&acc)[8][4][2], const double* __restrict__ smem, const SyLoader& L,
+                                            int fpad, int nk, int r_end, bool diag, int wm, int wn, int g, int q) {
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<SY_STAGES - 2>();
+        __syncthreads();
+        const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
+        const double* sB = diag ? sA : sA + SY_BK * SY_LD;
+        const double* pa = sA + q * SY_LD + wm * 64 + g;
+        const double* pb = sB + q * SY_LD + wn * 32 + g;
+#pragma unroll
+        for (int ks = 0; ks < SY_BK / 4; ++ks) {
+            if (ks == SY_ISSUE_AT) {
+                // the copies of k-block kt + 2 are issued behind the first DMMAs of this k-block (the slot they overwrite
+                // was released by the barrier above), so the tensor pipe is fed right after the barrier
+                const int nx = kt + SY_STAGES - 1;
+                if (nx < nk) sy_load_stage(L, fpad, nx % SY_STAGES, nx, r_end, diag);
+                cp_async_commit();
+            }
+            if (OFF > -4) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (a - OFF <= 3) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (b >= a - OFF) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+        }
+    }
 }
 
 __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_rows, int fpad,
                                              double* __restrict__ C, int nkb, double* __restrict__ part,
-                                             int* __restrict__ counters) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_first, s_np;
+                                             int* __restrict__ counters, int cost_diag, int full_diag) {
+    // no static shared variables here: they would shift the dynamic array off its 128-byte alignment, and LDGSTS into
+    // 16-byte-aligned-only rows fetched every global sector twice (ncu: 2x lts__t_sectors_srcunit_tex_op_read)
+    extern __shared__ __align__(128) double smem[];
+    int& s_first = *reinterpret_cast<int*>(smem + SY_STAGES * SY_STAGE_DOUBLES);
+    int& s_np = *(reinterpret_cast<int*>(smem + SY_STAGES * SY_STAGE_DOUBLES) + 1);
     const int ntile = fpad / SY_BM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const long nD = (long)ntile * nkb;
     const long nU = (long)ntile * (ntile + 1) / 2 * nkb;
-    const long Dc = SY_COST_DIAG * nD;
+    const long cd = cost_diag;
+    const long Dc = cd * nD;
     const long Ctot = Dc + SY_COST_FULL * (nU - nD);
     const long cper = (Ctot + gridDim.x - 1) / gridDim.x;
-    long u = sy_unit_of_cost((long)blockIdx.x * cper, nD, Dc, nU);
-    const long u_end = sy_unit_of_cost((long)(blockIdx.x + 1) * cper, nD, Dc, nU);
+    long u = sy_unit_of_cost((long)blockIdx.x * cper, nD, Dc, nU, cd);
+    const long u_end = sy_unit_of_cost((long)(blockIdx.x + 1) * cper, nD, Dc, nU, cd);
     long first_u = -1;   // see k_syrk_sk: the run that starts mid-tile is done last (k-blocks swept upwards in step)
     if (u < u_end && u % nkb != 0) {
         first_u = u;
@@ -296,26 +365,26 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
         const int tile = (int)(cur / nkb);
         const int kb0 = (int)(cur - (long)tile * nkb);
         const int kb1 = (int)min((long)nkb, (long)kb0 + (cur_end - cur));
-        const bool diag = tile < ntile;
+        bool diag = tile < ntile;
         int ti = tile, tj = tile;
-        if (!diag) {
+        if (full_diag == 3) {   // A/B switch: the row-major tile order of k_syrk_sk (needs cost_diag == 16)
+            int rem = tile;
+            ti = 0;
+            while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
+            tj = ti + rem;
+            diag = ti == tj;
+        } else if (!diag) {
             int rem = tile - ntile;
             ti = 0;
             while (rem >= ntile - 1 - ti) { rem -= ntile - 1 - ti; ++ti; }
             tj = ti + 1 + rem;
         }
-        // warp tile (64 x 32) inside the 128 x 128 tile; diagonal tiles: (0,3) (0,2) (0,1) (0,0) | (1,0) (1,1) (1,2) (1,3)
+        // warp tile (64 x 32) inside the 128 x 128 tile; diagonal tiles: (0,3) (0,2) (0,1) (0,0) | (1,0) (1,1) (1,2) (1,3),
+        // i.e. 32 | 32 | 26 + 10 | 10 + 26 blocks on the four SM sub-partitions (warps w and w + 4 share one)
+        const bool tri = diag && full_diag != 1 && full_diag != 3;   // full_diag = 1: A/B switch, diagonal tiles computed in full
         const int wm = warp >> 2;
-        const int wn = diag ? (warp < 4 ? 3 - warp : warp - 4) : (warp & 3);
-        unsigned mask = 0xffffffffu;
-        if (diag) {
-            mask = 0u;
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (wm * 8 + a <= wn * 4 + b) mask |= 1u << (a * 4 + b);
-        }
+        const int wn = tri ? (warp < 4 ? 3 - warp : warp - 4) : (warp & 3);
+        const int off = tri ? 4 * wn - 8 * wm : 12;   // block (a, b) of the warp tile is on or above the diagonal iff b >= a - off
         const int r_begin = kb0 * SY_BK;
         const int r_end = min(n_rows, kb1 * SY_BK);
         const int nk = kb1 - kb0;
@@ -326,69 +395,40 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
 #pragma unroll
             for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-        auto load_stage = [&](int kt, int slot) {
-            double* sA = smem + (size_t)slot * SY_STAGE_DOUBLES;
-            double* sB = sA + SY_BK * SY_LD;
-            const int r0 = r_begin + kt * SY_BK;
-#pragma unroll
-            for (int it = 0; it < SY_BK / 4; ++it) {
-                const int e = tid + it * 256;
-                const int rr = e >> 6, cc = (e & 63) * 2;
-                const int r = r0 + rr;
-                const bool ok = r < r_end;
-                const double* src = X + (size_t)(ok ? r : r_begin) * fpad;
-                cp_async16(sA + rr * SY_LD + cc, src + ti * SY_BM + cc, ok ? 16 : 0);
-                if (!diag) cp_async16(sB + rr * SY_LD + cc, src + tj * SY_BM + cc, ok ? 16 : 0);
-            }
-        };
+        SyLoader L;
+        L.row = r_begin + (tid >> 3);
+        {
+            const int rr = min(L.row, max(r_end - 1, r_begin));   // rows past the end: any valid address, 0 bytes copied
+            L.srcA = X + (size_t)rr * fpad + ti * SY_BM + (tid & 7) * 2;
+            L.srcB = X + (size_t)rr * fpad + tj * SY_BM + (tid & 7) * 2;
+            L.dst = smem_u32(smem + (tid >> 3) * SY_LD + (tid & 7) * 2);
+        }
         __syncthreads();  // previous segment's smem reads are finished
 #pragma unroll
         for (int s = 0; s < SY_STAGES - 1; ++s) {
-            if (s < nk) load_stage(s, s);
+            if (s < nk) sy_load_stage(L, fpad, s, s, r_end, diag);
             cp_async_commit();
         }
-        for (int kt = 0; kt < nk; ++kt) {
-            cp_async_wait<SY_STAGES - 2>();
-            __syncthreads();
-            const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
-            const double* sB = diag ? sA : sA + SY_BK * SY_LD;
-            const double* pa = sA + q * SY_LD + wm * 64 + g;
-            const double* pb = sB + q * SY_LD + wn * 32 + g;
-#pragma unroll
-            for (int ks = 0; ks < SY_BK / 4; ++ks) {
-                if (ks == SY_ISSUE_AT) {
-                    const int nx = kt + SY_STAGES - 1;
-                    if (nx < nk) load_stage(nx, nx % SY_STAGES);
-                    cp_async_commit();
-                }
-                if (!diag) {
-                    double af[8], bf[4];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-                } else if (mask) {
-                    double af[8], bf[4];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) af[a] = pa[ks * 4 * SY_LD + a * 8];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            if (mask & (1u << (a * 4 + b))) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-                }
-            }
-        }
+        if (off >= 7) sy_mainloop<12>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
+        else if (off == 4) sy_mainloop<4>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
+        else if (off == 0) sy_mainloop<0>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
+        else sy_mainloop<-8>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
         cp_async_wait<0>();
         const bool whole = kb0 == 0 && kb1 == nkb;
         bool reduce = whole;
-        if (!whole) {
+        if (!whole && full_diag == 2) {   // A/B switch: the old RED.F64 fix-up (non-deterministic)
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int row = ti * SY_BM + wm * 64 + a * 8 + g;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    if (b < a - off) continue;
+                    double* dst = C + (size_t)row * fpad + tj * SY_BM + wn * 32 + b * 8 + 2 * q;
+                    atomicAdd(dst, acc[a][b][0]);
+                    atomicAdd(dst + 1, acc[a][b][1]);
+                }
+            }
+        } else if (!whole) {
             // park the partial tile: thread-major fragment order, coalesced
             double* ws = part + ((size_t)blockIdx.x * 2 + (kb0 == 0 ? 1 : 0)) * SY_TILE_D + tid;
 #pragma unroll
@@ -402,8 +442,8 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
             __syncthreads();
             if (tid == 0) {
                 const long t0 = (long)tile * nkb;
-                const int first = sy_cta_of_unit(t0, nD, Dc, cper);
-                const int last = sy_cta_of_unit(t0 + nkb - 1, nD, Dc, cper);
+                const int first = sy_cta_of_unit(t0, nD, Dc, cper, cd);
+                const int last = sy_cta_of_unit(t0 + nkb - 1, nD, Dc, cper, cd);
                 const int np = last - first + 1;
                 const int old = atomicAdd(counters + tile, 1);
                 s_first = old == np - 1 ? first : -1;
@@ -437,7 +477,7 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
                 const int row = ti * SY_BM + wm * 64 + a * 8 + g;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    if (!(mask & (1u << (a * 4 + b)))) continue;
+                    if (b < a - off) continue;
                     const int col = tj * SY_BM + wn * 32 + b * 8 + 2 * q;
                     double2* dst = reinterpret_cast<double2*>(C + (size_t)row * fpad + col);
                     double2 v = *dst;
@@ -456,7 +496,7 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
     const bool use_v1 = getenv("PM_SYRK_V1") != nullptr;   // read per call (tests compare both)
     if (n_sm == 0) {
         cudaFuncSetAttribute(k_syrk_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
-        cudaFuncSetAttribute(k_syrk_sk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
+        cudaFuncSetAttribute(k_syrk_sk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM + 16);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -472,7 +512,17 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
         const int nkb = (nr + SY_BK - 1) / SY_BK;
         const long units = tiles * nkb;
         const int grid = (int)std::min<long>(n_sm, units);
-        if (v2) k_syrk_sk2<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, scr->partials, scr->counters);
+        if (v2) {
+            const char* ec = getenv("PM_SYRK_DIAGCOST");
+            const int full_diag = getenv("PM_SYRK_ROWMAJOR") ? 3 : (getenv("PM_SYRK_FULLDIAG") ? 1 : (getenv("PM_SYRK_ATOMIC") ? 2 : 0));
+            const int cost = ec ? std::max(1, std::min(16, atoi(ec))) : ((full_diag == 1 || full_diag == 3) ? 16 : 10);   // 10/16 measured best (9/16 = DMMA count alone)
+            // every CTA must own at least one k-block (the fix-up counts the contributors of a tile by CTA index):
+            // cost per CTA >= the cost of a full k-block
+            const long ctot = (long)cost * ntile * nkb + SY_COST_FULL * (units - (long)ntile * nkb);
+            const int grid2 = (int)std::max<long>(1, std::min<long>(n_sm, ctot / SY_COST_FULL));
+            k_syrk_sk2<<<grid2, 256, SY_SMEM + 16, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, scr->partials, scr->counters, cost,
+                                                  full_diag);
+        }
         else k_syrk_sk<<<grid, 256, SY_SMEM, s>>>(X + (size_t)r0 * fpad, nr, fpad, C, nkb, units);
     }
 }
@@ -2595,6 +2645,58 @@ double microbench_fp64(int which, cudaStream_t s) {
     cudaEventDestroy(e1);
     cudaFree(out);
     return flops / (best * 1e-3) * 1e-12;
+}
+
+// DMMA issue / latency probe: one CTA on one SM, `blockDim.x / 32` warps, each running NACC independent accumulator
+// chains round-robin (NACC = 1: every DMMA depends on the previous one).  Returns SM cycles per DMMA of one warp:
+// NACC = 1 -> the dependent-issue latency; large NACC with 1 warp per sub-partition -> the pipe's issue interval.
+template <int NACC>
+__global__ void k_bench_dmma_chain(double* out, long long* cycles, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) { c[k][0] = 0.0; c[k][1] = 0.0; }
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) dmma(c[k][0], c[k][1], a, b);
+    }
+    const long long t1 = clock64();
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) sum += c[k][0] + c[k][1];
+    if (sum == 123.456) out[0] = sum;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+// which = 100 * warps + nacc
+double microbench_dmma_chain(int code, cudaStream_t s) {
+    const int warps = std::max(1, code / 100), nacc = code % 100;
+    double* out = nullptr;
+    long long* cyc = nullptr;
+    cudaMalloc(&out, 8);
+    cudaMalloc(&cyc, 8);
+    const int iters = 2000;
+    for (int rep = 0; rep < 2; ++rep) {
+        switch (nacc) {
+            case 1: k_bench_dmma_chain<1><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 2: k_bench_dmma_chain<2><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 3: k_bench_dmma_chain<3><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 4: k_bench_dmma_chain<4><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 6: k_bench_dmma_chain<6><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 8: k_bench_dmma_chain<8><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            case 12: k_bench_dmma_chain<12><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+            default: k_bench_dmma_chain<16><<<1, warps * 32, 0, s>>>(out, cyc, iters); break;
+        }
+    }
+    long long h = 0;
+    cudaStreamSynchronize(s);
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    cudaFree(cyc);
+    const int n = (nacc == 1 || nacc == 2 || nacc == 3 || nacc == 4 || nacc == 6 || nacc == 8 || nacc == 12) ? nacc : 16;
+    return (double)h / ((double)iters * n);
 }
 
 double microbench_dgemm(int n, cudaStream_t s) {
