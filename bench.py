@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- structures/s of the fused feature + X^T X / X^T y build (BASELINE.json metric).
+"""bench.py -- structures/s of the fused feature + X^T X / X^T y build (BASELINE.json metric), no PyTorch.
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "config 2"): single-element gtinv polymlp, order 3,
-maxl [4,4], cutoff 6 A, 10 radial functions, model_type 4 (F = 2030); synthetic 256-atom fcc 4x4x4
-supercells (a = 4.05 A), Gaussian displacements sigma = 0.05 A, seed 20240+s, energy + forces + stress
-rows (775 rows per structure), N(0,1) targets.  A step = one pass of the whole hot path (neighbour list
--> a_nlm -> invariants -> derivative rows -> polynomial X rows -> C += [X|y]^T [X|y]) over one batch of
-structures per GPU.  One process per GPU; structures shard across ranks, partial accumulators are
-combined with one NCCL reduce per step (weak scaling: per-GPU batch fixed).
+Headline workload (BASELINE.json configs[1], SURVEY.md 8d "config 2"): single-element gtinv polymlp, order 3,
+maxl [4,4], cutoff 6 A, 10 radial functions, model_type 4 (F = 2030); synthetic 256-atom fcc 4x4x4 supercells
+(a = 4.05 A), Gaussian displacements sigma = 0.05 A, seed 20240+s, energy + forces + stress rows (775 rows per
+structure), N(0,1) targets.  A step = one pass of the whole hot path (neighbour list -> a_nlm -> invariants ->
+derivative rows -> polynomial X rows -> C += [X|y]^T [X|y]) over one batch of structures per GPU.  One process per
+GPU (torchrun only launches them: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_PORT are read from the environment);
+structures shard across ranks, the partial accumulators are combined with ONE ncclReduce per step issued by the
+library itself (pm_fit_reduce), timing is CUDA events on the library's stream (pm_timer_*), max over ranks through
+pm_comm_allreduce.  Weak scaling: the per-GPU batch is fixed.
+
+The same JSON line carries sub-records for BASELINE configs 3, 4 (large models) and 5 (E/F/S evaluation).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # reference CPU path (oracle/_ref), rank 0 only
 """
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -33,16 +38,45 @@ import cases  # noqa: E402
 METRIC = "structures/sec, fused feature + X^T X / X^T y build (fp64)"
 WORKLOAD = ("config 2: gtinv order 3, maxl [4,4], rc 6 A, 10 radial fn, model_type 4 (F=2030); "
             "256-atom fcc 4x4x4 supercells, sigma 0.05 A, E+F+S rows (775/structure)")
+W_EVAL_FLOP_PER_ATOM = 4.8e5   # algorithmic flops of one atom's E/F/S for the config-2 model
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic workloads
+# ---------------------------------------------------------------------------------------------------
+def _rows_wy(n_rows, seed):
+    rng = np.random.default_rng(seed)
+    w = np.minimum(1.0, 1.0 / np.maximum(np.abs(rng.normal(size=n_rows)), 1e-12))  # force-like weights
+    return w, w * rng.normal(size=n_rows)
 
 
 def make_batch(n_st, first_seed):
+    """config 2 structures + per-row weights / weighted targets in the PyModel layout."""
     sts = [cases.fcc_supercell(seed=20240 + first_seed + s) for s in range(n_st)]
     axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
-    rows = n_st * 775
-    rng = np.random.default_rng(first_seed)
-    w = np.minimum(1.0, 1.0 / np.maximum(np.abs(rng.normal(size=rows)), 1e-12))  # force-like weights
-    y = w * rng.normal(size=rows)
+    w, y = _rows_wy(n_st * 775, first_seed)
     return axis, pcs, tys, w, y
+
+
+def make_bcc_batch(rep, n_type, n_st, first_seed):
+    """configs 3 / 4: bcc supercells a = 3.2 A, random types, sigma 0.05 A."""
+    sts = [cases.bcc_supercell(rep=rep, n_type=n_type, seed=9000 + first_seed + s) for s in range(n_st)]
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    n_atom = len(tys[0])
+    w, y = _rows_wy(n_st * (7 + 3 * n_atom), 77 + first_seed)
+    return axis, pcs, tys, w, y
+
+
+def assemble_rows(per_structure):
+    """per_structure: list of (w, y) arrays of 1 + 6 + 3N rows each (energy | stress | forces of ONE structure) ->
+    w, y of the whole batch in the PyModel layout (all energies | all stresses | all forces)."""
+    out = []
+    for k in (0, 1):
+        e = np.concatenate([r[k][:1] for r in per_structure])
+        s = np.concatenate([r[k][1:7] for r in per_structure])
+        f = np.concatenate([r[k][7:] for r in per_structure])
+        out.append(np.concatenate([e, s, f]))
+    return out
 
 
 class ClockSampler:
@@ -81,9 +115,10 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def cpu_reference_rate(pd, n_st, steps=1, warmup=0):
-    """Reference CPU path on the host cores: oracle/_ref (unmodified reference C++, OpenMP over structures,
-    PyModel semantics) + weights + numpy x.T @ x, exactly as _compute_products_single_batch."""
+# ---------------------------------------------------------------------------------------------------
+# reference CPU path (oracle/_ref: the unmodified reference C++; numpy for x.T @ x as the reference does)
+# ---------------------------------------------------------------------------------------------------
+def _use_all_cores():
     from oracle import ref
 
     cores = os.cpu_count() or 1
@@ -93,15 +128,24 @@ def cpu_reference_rate(pd, n_st, steps=1, warmup=0):
         threadpool_limits(limits=cores)  # numpy's BLAS for x.T @ x
     except Exception:
         pass
-    rm = ref.RefModel(pd)
-    axis, pcs, tys, w, y = make_batch(n_st, 0)
+    return cores
+
+
+def cpu_reference_rate(ref_params, batch, steps=1, warmup=0):
+    """X build (PyModel semantics, OpenMP over structures) + weights + numpy x.T @ x, exactly as
+    _compute_products_single_batch (src/pypolymlp/mlp_dev/core/data_sequential.py:97-156).  structures/s."""
+    from oracle import ref
+
+    _use_all_cores()
+    rm = ref.RefModel(ref_params)
+    axis, pcs, tys, w, y = batch
+    n_st = len(axis)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         x = rm.build_x(axis, pcs, tys, [True] * n_st)
         xe = x[:n_st]
         _ = xe.sum(axis=0), np.square(xe).sum(axis=0)
-        # reorder w/y (ours: PyModel layout already) and accumulate
         x *= w[:, None]
         xtx = x.T @ x
         xty = x.T @ y
@@ -113,16 +157,32 @@ def cpu_reference_rate(pd, n_st, steps=1, warmup=0):
     return n_st * len(times) / sum(times), ref.num_threads(), sum(times) / len(times)
 
 
+def cpu_reference_eval_rate(ref_params, coeffs, sts):
+    """PyPropertiesFast::eval_multiple semantics: serial over structures, OpenMP over atoms.  atoms/s."""
+    from oracle import ref
+
+    _use_all_cores()
+    ev = ref.RefEval(ref_params, coeffs)
+    axis, pcs, tys = [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts]
+    ev.eval_multiple(axis[:1], pcs[:1], tys[:1])   # warm-up
+    t0 = time.perf_counter()
+    ev.eval_multiple(axis, pcs, tys)
+    dt = time.perf_counter() - t0
+    return sum(len(t) for t in tys) / dt, ref.num_threads()
+
+
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (rank 0 only).
+    Nothing of the product package is imported here."""
     if rank != 0:
         return
-    from pypolymlp_b200.params import make_params_dict
+    from oracle import ref
 
-    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    pd = ref.make_params(**cases.cfg2_model_kwargs(4))
     cores = os.cpu_count() or 1
     n_st = max(8, min(64, 2 * cores))   # two structures per OpenMP thread: every core busy, ~5-10 s per step
     k_steps, k_warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    rate, threads, step_s = cpu_reference_rate(pd, n_st, steps=k_steps, warmup=k_warm)
+    rate, threads, step_s = cpu_reference_rate(pd, make_batch(n_st, 0), steps=k_steps, warmup=k_warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "structures/s", "n_gpus": args.gpus,
         "steps": k_steps, "warmup": k_warm, "ms_per_step": step_s * 1e3, "higher_is_better": True,
@@ -138,6 +198,185 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# ---------------------------------------------------------------------------------------------------
+def timed(acc, fn, k):
+    """K calls of fn bracketed by barrier + stream synchronisation on both sides, CUDA events on the library's stream;
+    returns the max over ranks in ms."""
+    ctx = acc.context
+    acc.barrier()
+    ctx.timer_start()
+    for _ in range(k):
+        fn()
+    ms = ctx.timer_stop()
+    acc.barrier()
+    return float(acc.allreduce([ms], "max")[0])
+
+
+def pair_counts(ctx, axis, pc, ty, n_type):
+    """atoms per type and ordered pairs per (centre type, neighbour type) of one structure (for the flop count)."""
+    off, nb, *_ = ctx.neighbor_full(axis, pc, ty)
+    ty = np.asarray(ty)
+    atoms = [int((ty == t).sum()) for t in range(n_type)]
+    centre = np.repeat(np.arange(len(ty)), np.diff(off))
+    pairs = [[int(((ty[centre] == t) & (ty[nb] == u)).sum()) for u in range(n_type)] for t in range(n_type)]
+    return atoms, pairs
+
+
+def fit_subrecord(name, kwargs, batch_fn, S, rank, world, local_rank, peak, comm_src, want_cpu, ref_mod):
+    """One BASELINE large-model config: structures/s of the fused build incl. the NCCL reduce, stage times, algorithmic
+    flops and fraction of the measured DGEMM rate, the reduce alone, optionally the reference CPU rate (8 structures)."""
+    from pypolymlp_b200.libmlpcpp import PotentialXtX
+    from pypolymlp_b200.params import make_params_dict
+
+    pd = make_params_dict(**kwargs)
+    acc = PotentialXtX(pd, device=local_rank)
+    if world > 1:
+        acc.comm_init_rank(world, rank, comm_src())
+    axis, pcs, tys, w, y = batch_fn(S, rank * S)
+    acc.stage(axis, pcs, tys, [True] * S, w, y)
+    ctx = acc.context
+
+    def step():
+        acc.add_staged()
+        acc.reduce(0)
+
+    step()                         # warm-up (allocations, kernel attributes)
+    acc.reset()
+    steps = 2
+    ms = timed(acc, step, steps)
+    red_ms = timed(acc, lambda: acc.reduce(0), 1) if world > 1 else 0.0
+    rec = {"structures_per_s": world * S * steps / (ms * 1e-3), "structures_per_step_per_gpu": S, "steps": steps,
+           "ms_per_step": ms / steps, "n_features": acc.n_features,
+           "reduce": {"ms": red_ms, "bytes_per_rank": acc.reduce_bytes(),
+                      "note": "one ncclReduce of the packed upper 128x128 tiles + xe sums" if world > 1 else "single rank: no reduce"}}
+    if rank == 0:
+        atoms, pairs = pair_counts(ctx, axis[0], pcs[0], tys[0], kwargs["n_type"])
+        w_alg = acc.model.count_flops(atoms, pairs, True)
+        acc.reset()
+        ctx.profile(True)
+        acc.add_staged()
+        ctx.synchronize()
+        prof = ctx.profile_get()
+        ctx.profile(False)
+        stage_ms = {k: round(v[0], 3) for k, v in prof.items() if v[0] > 0}
+        ctx.profile(2)
+        acc.add_staged()
+        ctx.synchronize()
+        syrk_ms, syrk_launches = ctx.profile_get()["syrk"]
+        ctx.profile(False)
+        total = S * sum(w_alg.values())
+        top = max(stage_ms, key=stage_ms.get)
+        rec.update({
+            "algorithmic_flops_per_structure": w_alg, "stage_ms_one_step": stage_ms, "dominant_stage": top,
+            "whole_step_tflops": total / (ms / steps * 1e-3) * 1e-12,
+            "whole_step_frac_of_peak": total / (ms / steps * 1e-3) * 1e-12 / peak,
+            "roofline": {"bound": "tensor", "kernel": "k_syrk_sk2 (fp64 DMMA stream-K SYRK)",
+                         "achieved": S * w_alg["syrk"] / (syrk_ms * 1e-3) * 1e-12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": S * w_alg["syrk"] / (syrk_ms * 1e-3) * 1e-12 / peak, "syrk_ms_live": syrk_ms,
+                         "syrk_launches": syrk_launches, "syrk_share_of_step": syrk_ms / (ms / steps)}})
+        if want_cpu and ref_mod is not None and ref_mod.available():
+            n_cpu = 8
+            rate, threads, step_s = cpu_reference_rate(ref_mod.make_params(**kwargs), batch_fn(n_cpu, 0))
+            rec["cpu_baseline"] = {"value": rate, "unit": "structures/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{n_cpu} structures of the same workload (BASELINE.md section 3), {step_s:.0f} s"}
+        elif rank == 0 and world == 1:
+            rec["cpu_baseline"] = {"value": None, "unit": "structures/s", "cores": 0, "kind": "reference",
+                                   "sample": "skipped in the default run (minutes of host time: the reference force path is "
+                                             "O(N^2) per structure); PM_BENCH_CPU=%s runs it, profiles/ holds a recorded run" % name}
+    del acc
+    return rec
+
+
+def eval_subrecord(pd, F, rank, world, local_rank, peak, acc_main, want_cpu, ref_mod):
+    """BASELINE config 5: atoms/s of E/F/S evaluation through pm_eval with host buffers (end to end), 512-atom
+    fcc 4x4x8 cells, sigma 0.03 A, sharded by structure."""
+    from pypolymlp_b200._capi import StructureBatch, check, lib
+    from pypolymlp_b200._capi import pd as pd_
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+
+    n_ev = int(os.environ.get("PM_BENCH_NEV", "256"))   # structures per call and GPU (config 5 holds 10 000)
+    sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + rank * n_ev + k) for k in range(n_ev)]
+    coeffs = np.random.default_rng(12).normal(size=F) * 1e-3
+    prop = PotentialPropertiesFast(pd, coeffs, device=local_rank)
+    batch = StructureBatch([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts], [True] * n_ev)
+    out = (np.zeros(n_ev), np.zeros((n_ev * 512, 3)), np.zeros((n_ev, 6)))
+
+    def step():
+        check(lib().pm_eval(prop._ctx.handle, ctypes.byref(batch.c), pd_(out[0]), pd_(out[1]), pd_(out[2])))
+
+    step()
+    reps = 3
+    acc_main.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = time.perf_counter() - t0
+    acc_main.barrier()
+    dt = float(acc_main.allreduce([dt], "max")[0])
+    atoms_s = world * n_ev * 512 * reps / dt
+    rec = {"metric": "atoms/sec, E/F/S evaluation (config 5: F=2030 model, 512-atom fcc 4x4x8, sigma 0.03 A)",
+           "value": atoms_s, "unit": "atoms/s", "structures_per_call_per_gpu": n_ev, "calls": reps,
+           "e2e": {"h2d_bytes_per_call": int(batch.h2d_bytes), "d2h_bytes_per_call": int(sum(o.nbytes for o in out)),
+                   "note": "pm_eval through the C ABI: host arrays in, E/F/S back in host arrays, wall clock"},
+           "roofline": {"bound": "fp64", "achieved": atoms_s / world * W_EVAL_FLOP_PER_ATOM * 1e-12, "peak": peak,
+                        "unit": "TFLOP/s", "frac": atoms_s / world * W_EVAL_FLOP_PER_ATOM * 1e-12 / peak,
+                        "flops_per_atom": W_EVAL_FLOP_PER_ATOM,
+                        "note": "W_eval of SURVEY.md 8(d) for the config-2 model; end-to-end time (host preparation and "
+                                "copies included), so this is a lower bound of the kernels' fraction"}}
+    if rank == 0:
+        ctx = prop._ctx
+        ctx.profile(True)
+        step()
+        ctx.synchronize()
+        rec["stage_ms_one_call"] = {k: round(v[0], 3) for k, v in ctx.profile_get().items() if v[0] > 0}
+        ctx.profile(False)
+        if want_cpu and ref_mod is not None and ref_mod.available():
+            n_cpu = 32
+            rate, threads = cpu_reference_eval_rate(ref_mod.make_params(**cases.cfg2_model_kwargs(4)), coeffs, sts[:n_cpu])
+            rec["cpu_baseline"] = {"value": rate, "unit": "atoms/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{n_cpu} structures through RefEval with PyPropertiesFast::eval_multiple semantics "
+                                             "(serial structures, OpenMP over atoms)"}
+    return rec
+
+
+def parity_vs_n1(pd, rank, world, local_rank, comm_src):
+    """N ranks accumulate 8 structures each and reduce; rank 0 then accumulates all 8 N structures alone: the two X^T X
+    (X^T y, xe sums) must agree to 1e-10."""
+    from pypolymlp_b200.libmlpcpp import PotentialXtX
+
+    n = 8
+    acc = PotentialXtX(pd, device=local_rank)
+    acc.comm_init_rank(world, rank, comm_src())
+
+    def one(seed):
+        return _rows_wy(775, 5000 + seed)
+
+    def batch(seeds):
+        sts = [cases.fcc_supercell(seed=31000 + s) for s in seeds]
+        w, y = assemble_rows([one(s) for s in seeds])
+        return [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts], w, y
+
+    mine = list(range(rank * n, rank * n + n))
+    ax, pc, ty, w, y = batch(mine)
+    acc.add(ax, pc, ty, [True] * n, w, y)
+    acc.reduce(0)
+    out = None
+    if rank == 0:
+        rn = {k: np.array(v, copy=True) if isinstance(v, np.ndarray) else v for k, v in acc.finalize().items()}
+        acc.reset()
+        ax, pc, ty, w, y = batch(list(range(world * n)))
+        acc.add(ax, pc, ty, [True] * (world * n), w, y)
+        r1 = acc.finalize()
+        err = {k: float(np.abs(rn[k] - r1[k]).max() / np.abs(r1[k]).max()) for k in ("xtx", "xty", "xe_sum", "xe_sq_sum")}
+        out = {"max_rel_err": err, "n_data_equal": rn["total_n_data"] == r1["total_n_data"],
+               "ok": bool(max(err.values()) < 1e-10 and rn["total_n_data"] == r1["total_n_data"]),
+               "structures": world * n}
+    acc.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--structures", type=int, default=256, help="structures per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the config 3 / 4 / 5 sub-records")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -155,65 +395,38 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import ctypes
-
-    import torch
-    import torch.distributed as dist
-
     from pypolymlp_b200 import fit
-    from pypolymlp_b200._capi import StructureBatch, check, lib
-    from pypolymlp_b200._capi import pd as pd_
-    from pypolymlp_b200.libmlpcpp import PotentialXtX
+    from pypolymlp_b200.libmlpcpp import PotentialXtX, comm_unique_id
     from pypolymlp_b200.params import make_params_dict
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     args.warmup = max(args.warmup, 3)
     pd = make_params_dict(**cases.cfg2_model_kwargs(4))
     S = args.structures
     acc = PotentialXtX(pd, device=local_rank)
+    fit.comm_init_from_env(acc)        # NCCL communicator inside the library (file rendezvous of the unique id)
     ctx = acc.context
     F = acc.n_features
+
+    def comm_src():
+        """A fresh NCCL unique id for a further communicator (collective): rank 0 creates it, the 128 bytes travel to the
+        other ranks as exact small integers through two sum-allreduces of the main communicator."""
+        raw = np.frombuffer(comm_unique_id(), dtype=np.uint8).astype(np.float64) if rank == 0 else np.zeros(128)
+        out = np.concatenate([acc.allreduce(raw[:64], "sum"), acc.allreduce(raw[64:], "sum")])
+        return np.rint(out).astype(np.uint8).tobytes()
+
     axis, pcs, tys, w, y = make_batch(S, rank * S)
     batch_host = acc.stage(axis, pcs, tys, [True] * S, w, y)   # inputs resident in HBM
-    stream = torch.cuda.ExternalStream(int(ctypes_stream(ctx)), device=local_rank)
-
-    def barrier():
-        torch.cuda.synchronize(local_rank)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(local_rank)
 
     def step_device():
         acc.add_staged()
-        if world > 1:
-            fit.reduce_accumulator(acc, dst=0)
-
-    def timed(fn, k):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(k):
-            fn()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        dev_ms = e0.elapsed_time(e1)
-        # whichever is larger: the stream events cover the kernels, the wall clock also covers NCCL on its own stream
-        ms = max(dev_ms, wall * 1e3) if world > 1 else dev_ms
-        t = torch.tensor([ms], device=f"cuda:{local_rank}", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        acc.reduce(0)      # no-op for a single rank
 
     # ---- device-resident throughput -----------------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
     l0 = ctx.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms = timed(step_device, args.steps)
+    ms = timed(acc, step_device, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - l0
     value = world * S * args.steps / (ms * 1e-3)
@@ -224,52 +437,34 @@ def main():
     def step_e2e():
         acc.reset()
         acc.add_batch(batch_host, w_h, y_h)
-        if world > 1:
-            fit.reduce_accumulator(acc, dst=0)
+        acc.reduce(0)
         if rank == 0:
             acc.finalize(copy=False)   # X^T X, X^T y ... in (pinned) host memory
 
     e2e_steps = max(2, min(args.steps, 4))
     step_e2e()
-    barrier()
+    acc.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
-    barrier()
+    ctx.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * e2e_steps / float(t.item())
+    acc.barrier()
+    e2e_s = float(acc.allreduce([e2e_s], "max")[0])
+    e2e_value = world * S * e2e_steps / e2e_s
     h2d = batch_host.h2d_bytes + w_h.nbytes + y_h.nbytes
     d2h = (F * F + 3 * F + 2) * 8
 
-    # ---- secondary metric: atoms/s of E/F/S evaluation (BASELINE config 5), sharded by structure -----------
-    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+    parity = parity_vs_n1(pd, rank, world, local_rank, comm_src) if world > 1 else None
 
-    n_ev = int(os.environ.get("PM_BENCH_NEV", "32"))   # structures per evaluation call and GPU (config 5 holds 10 000)
-    ev_sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + rank * n_ev + k) for k in range(n_ev)]
-    ev_axis, ev_pcs, ev_tys = [x[0] for x in ev_sts], [x[1] for x in ev_sts], [x[2] for x in ev_sts]
-    prop = PotentialPropertiesFast(pd, np.random.default_rng(12).normal(size=F) * 1e-3, device=local_rank)
-    ev_batch = StructureBatch(ev_axis, ev_pcs, ev_tys, [True] * n_ev)
-    ev_out = (np.zeros(n_ev), np.zeros((n_ev * 512, 3)), np.zeros((n_ev, 6)))
-
-    def step_eval():
-        check(lib().pm_eval(prop._ctx.handle, ctypes.byref(ev_batch.c), pd_(ev_out[0]), pd_(ev_out[1]), pd_(ev_out[2])))
-
-    step_eval()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        step_eval()
-    barrier()
-    tev = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tev, op=dist.ReduceOp.MAX)
-    eval_atoms_s = world * n_ev * 512 * 3 / float(tev.item())
-
+    # ---- rank 0: roofline of the dominant kernel (SYRK, DMMA): live event pairs around every SYRK launch ----------------
+    roofline, cpu, peak = None, None, 0.0
+    peak = float(acc.allreduce([ctx.microbench(3, 8192) if rank == 0 else 0.0], "max")[0])   # cuBLAS DGEMM 8192^3 on rank 0
+    ref_mod = None
+    want_cpu = world == 1 and not args.no_cpu_baseline
+    if want_cpu:
+        from oracle import ref as ref_mod
     if rank == 0:
-        # ---- roofline of the dominant kernel (SYRK, DMMA): one profiled step, CUDA events per stage -------
         acc.reset()
         ctx.profile(True)
         acc.add_staged()
@@ -277,7 +472,6 @@ def main():
         prof = ctx.profile_get()
         ctx.profile(False)
         w_alg = acc.model.count_flops([256], [[13824]], True)
-        # the dominant kernel timed live: event pairs around every SYRK launch of K unperturbed steps, on its stream
         ctx.profile(2)
         for _ in range(args.steps):
             acc.add_staged()
@@ -286,28 +480,29 @@ def main():
         ctx.profile(False)
         syrk_ms = syrk_total_ms / args.steps
         syrk_tflops = S * w_alg["syrk"] / (syrk_ms * 1e-3) * 1e-12
-        peak = ctx.microbench(3, 8192)
         total_alg = S * sum(w_alg.values())
         stage_ms = {k: round(v[0], 3) for k, v in prof.items() if v[0] > 0}
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
-        # DRAM traffic of one SYRK launch from the committed ncu --set full capture (profiles/r01_ncu_kernels.json):
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (K5 runs per block of <= 32768 X rows)
-        traffic, traffic_alg, rows_cap = None, None, 0
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))["k_syrk_sk"]
-            met, rows_cap = cap["metrics"], cap.get("rows_in_launch", 32768)
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            traffic = sum(float(met[k]["value"]) * scale[met[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-            fpad = (F + 1 + 127) // 128 * 128
-            traffic_alg = rows_cap * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde rows once + upper C tiles RMW
-        except Exception:
-            pass
+        # DRAM traffic of one SYRK launch from the committed ncu --set full capture of this round
+        traffic, traffic_alg, rows_cap, cap_file = None, None, 0, None
+        for cap_file in ("r02_ncu_kernels.json", "r01_ncu_kernels.json"):
+            try:
+                capd = json.load(open(os.path.join(ROOT, "profiles", cap_file)))
+                cap = capd.get("k_syrk_sk2") or capd["k_syrk_sk"]
+                met, rows_cap = cap["metrics"], cap.get("rows_in_launch", 32768)
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                traffic = sum(float(met[k]["value"]) * scale[met[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                fpad = (F + 1 + 127) // 128 * 128
+                traffic_alg = rows_cap * fpad * 8.0 + fpad * fpad * 8.0 * 0.53 * 2   # X-tilde rows once + upper C tiles RMW
+                break
+            except Exception:
+                continue
         roofline = {
-            "bound": "tensor", "kernel": "k_syrk_sk (fp64 DMMA m8n8k4, stream-K SYRK)", "achieved": syrk_tflops, "peak": peak,
-            "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
-            "traffic_note": "DRAM bytes of the captured SYRK launch (%d X rows; ncu --set full, " % (rows_cap if traffic else 0) +
-                            "profiles/r01_ncu_kernels.json); algorithmic bytes of that launch in traffic_algorithmic",
+            "bound": "tensor", "kernel": "k_syrk_sk2 (fp64 DMMA m8n8k4, deterministic stream-K SYRK, triangle-only diagonal tiles)",
+            "achieved": syrk_tflops, "peak": peak, "unit": "TFLOP/s", "frac": syrk_tflops / peak, "traffic": traffic,
+            "traffic_note": "DRAM bytes of the captured SYRK launch (%d X rows; ncu --set full, profiles/%s); algorithmic bytes "
+                            "of that launch in traffic_algorithmic" % (rows_cap if traffic else 0, cap_file),
             "traffic_algorithmic": traffic_alg,
             "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry; "
                            "tcgen05 has no f64 kind, DMMA peak == DFMA peak on B200)",
@@ -319,45 +514,56 @@ def main():
             "whole_step_frac_of_peak": total_alg / (ms / args.steps * 1e-3) * 1e-12 / peak,
             "hbm_gbs_measured": hbm,
         }
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import ref
-
-            if ref.available():
+        if want_cpu:
+            if ref_mod.available():
                 n_cpu = max(8, min(64, 2 * (os.cpu_count() or 1)))   # ~5-15 s of CPU work, every core busy
-                rate, threads, _ = cpu_reference_rate(pd, n_cpu)
+                rate, threads, _ = cpu_reference_rate(ref_mod.make_params(**cases.cfg2_model_kwargs(4)), make_batch(n_cpu, 0))
                 cpu = {"value": rate, "unit": "structures/s", "cores": threads, "kind": "reference",
                        "sample": f"{n_cpu} structures of the same workload through oracle/_ref + numpy x.T@x"}
             else:
                 cpu = {"value": None, "unit": "structures/s", "cores": 0, "kind": "reference",
                        "sample": "oracle/_ref not built on this box"}
+
+    # ---- BASELINE configs 3, 4, 5 (all ranks take part: structures shard, one reduce per step) ---------------------------
+    sub = {}
+    if not args.no_sub:
+        cpu_sel = os.environ.get("PM_BENCH_CPU", "config3")   # large-model CPU baselines that run by default / on request
+        sub["eval"] = eval_subrecord(pd, F, rank, world, local_rank, peak, acc, want_cpu, ref_mod)
+        sub["config3"] = fit_subrecord(
+            "config3", cases.cfg3_model_kwargs(), lambda n, s0: make_bcc_batch((6, 6, 3), 2, n, s0),
+            int(os.environ.get("PM_BENCH_S3", "24")), rank, world, local_rank, peak, comm_src,
+            want_cpu and "config3" in cpu_sel, ref_mod)
+        sub["config3"]["workload"] = ("config 3: binary gtinv order 4, maxl [12,8,2], 10 radial fn, model_type 3 (F=9385); "
+                                      "216-atom bcc 6x6x3 supercells, sigma 0.05 A, E+F+S rows (655/structure)")
+        sub["config4"] = fit_subrecord(
+            "config4", cases.cfg4_model_kwargs(), lambda n, s0: make_bcc_batch((4, 4, 4), 3, n, s0),
+            int(os.environ.get("PM_BENCH_S4", "16")), rank, world, local_rank, peak, comm_src,
+            want_cpu and "config4" in cpu_sel, ref_mod)
+        sub["config4"]["workload"] = ("config 4: ternary gtinv order 4, maxl [12,8,2], model_type 3 (F=45090, X^T X 16.3 GB); "
+                                      "128-atom bcc 4x4x4 supercells, sigma 0.05 A, E+F+S rows (391/structure)")
+
+    if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "structures/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "structures_per_step_per_gpu": S, "n_features": F,
-                       "l2": "no flush: each step streams ~200 MB of intermediates per structure through HBM "
-                             "(51 GB per 256-structure step), far above the 126 MB L2; staged inputs are ~6 KB/structure",
-                       "parallelism": f"structures sharded over {world} GPU(s), one NCCL reduce per step"},
+                       "l2": "no flush: each step streams ~180 MB of intermediates per structure through HBM "
+                             "(46 GB per 256-structure step), far above the 126 MB L2; staged inputs are ~6 KB/structure",
+                       "parallelism": f"structures sharded over {world} GPU(s), one ncclReduce per step inside the library "
+                                      f"(pm_fit_reduce, {acc.reduce_bytes()} bytes per rank: packed upper tiles)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "structures/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": "pm_fit_reset + pm_fit_accumulate(host buffers) + pm_fit_finalize_view (X^T X, X^T y to pinned host memory) per step"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "eval": {"metric": "atoms/sec, E/F/S evaluation (config 5: F=2030 model, 512-atom fcc, sigma 0.03 A)",
-                     "value": eval_atoms_s, "unit": "atoms/s", "structures_per_step_per_gpu": n_ev,
-                     "note": "pm_eval through the C ABI: host arrays in, E/F/S back on the host (end to end)"},
+                    "note": "pm_fit_reset + pm_fit_accumulate(host buffers) + pm_fit_reduce + pm_fit_finalize_view "
+                            "(X^T X, X^T y to pinned host memory) per step"},
+            "roofline": roofline, "cpu_baseline": cpu, "torch_imported": "torch" in sys.modules,
         }
+        if parity is not None:
+            line["parity_vs_n1"] = parity
+        line.update(sub)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def ctypes_stream(ctx):
-    from pypolymlp_b200._capi import lib
-
-    return lib().pm_stream(ctx.handle)
+    acc.barrier()
 
 
 if __name__ == "__main__":

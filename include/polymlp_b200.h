@@ -159,6 +159,40 @@ int pm_fit_finalize(pm_context* c, double* xtx, double* xty, double* xe_sum, dou
  *   [ xtx (F*F, symmetric, row-major) | xty (F) | xe_sum (F) | xe_sq_sum (F) | y_sq_norm | n_data ]
  * valid until the next pm_fit_finalize* call on this context or pm_context_destroy. */
 int pm_fit_finalize_view(pm_context* c, const double** packed, size_t* n_doubles);
+/* ---- multi-GPU reduce (replaces the OpenMP-over-structures loop of compute/py_model.cpp:39-53 and the batch
+ * sum of src/pypolymlp/mlp_dev/core/data_sequential.py:49-70 across devices) -----------------------------------------------
+ * Structures shard over GPUs, every GPU accumulates its own partial sums, and ONE ncclReduce (fp64 sum over NVLink) of the
+ * packed upper 128 x 128 tiles of C plus xe_sum / xe_sq_sum / n_data combines them on the root.  NCCL is resolved at run
+ * time (libnccl.so.2, override with $POLYMLP_B200_NCCL_LIB); nothing else of the library needs it.
+ * (a) one process per GPU (torchrun / mpirun): rank 0 calls pm_comm_unique_id, the 128 bytes travel out of band
+ *     (file, socket, MPI), every rank calls pm_comm_init_rank on its context; pm_fit_reduce is collective. */
+#define PM_UNIQUE_ID_BYTES 128
+int pm_comm_unique_id(char id[PM_UNIQUE_ID_BYTES]);
+int pm_comm_init_rank(pm_context* c, int n_ranks, int rank, const char id[PM_UNIQUE_ID_BYTES]);
+int pm_comm_size(pm_context* c);
+int pm_comm_rank(pm_context* c);
+/* sums the ranks' accumulators into the root's (in place on the root; the other ranks keep their partial sums).
+ * A context without a communicator is a single rank: no-op. */
+int pm_fit_reduce(pm_context* c, int root);
+int64_t pm_fit_reduce_bytes(pm_context* c);   /* bytes each rank contributes to the reduce */
+/* small host-value collectives for drivers (timing: max over ranks): op 0 = sum, 1 = max, 2 = min; n <= 64 */
+int pm_comm_allreduce(pm_context* c, double* values, int n, int op);
+int pm_comm_barrier(pm_context* c);
+/* (b) several GPUs driven by one process (the pybind11 module's PotentialXtX(params, devices=[...])): one context per
+ *     device, a single-process ncclCommInitAll communicator, one host thread per device during accumulate. */
+typedef struct pm_multi pm_multi;
+int pm_multi_create(const pm_model* m, const int* devices, int n_dev, size_t workspace_bytes, int flags, pm_multi** out);
+void pm_multi_destroy(pm_multi* mg);
+int pm_multi_size(const pm_multi* mg);
+pm_context* pm_multi_context(pm_multi* mg, int k);
+int pm_multi_fit_reset(pm_multi* mg);
+/* shards the batch over the devices (contiguous slices balanced by atom count); w / y as in pm_fit_accumulate */
+int pm_multi_fit_accumulate(pm_multi* mg, const pm_structures* st, const double* w, const double* y);
+int pm_multi_fit_reduce(pm_multi* mg, int root);
+/* reduce onto device 0, clear the other accumulators, then pm_fit_finalize of device 0 */
+int pm_multi_fit_finalize(pm_multi* mg, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum, double* y_sq_norm,
+                          int64_t* n_data);
+
 /* ---- ridge solve on the device (reported separately from the hot path) ---------------------------------
  * Replaces the tail of calc_xtx_xty (scales, zeroing, normalisation; data_sequential.py:72-92), solver_ridge
  * (Cholesky per alpha with incremental diagonal update; src/pypolymlp/mlp_dev/standard/solvers.py:48-84) and
@@ -174,6 +208,10 @@ int pm_fit_solve_ridge(pm_context* c, const double* alphas, int n_alpha, const d
 int pm_synchronize(pm_context* c);
 /* CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
 void* pm_stream(pm_context* c);
+/* Device-side stopwatch: CUDA events on the context's stream (every kernel, copy and NCCL call of the context is ordered
+ * on it).  start synchronises the stream first; stop records, waits and returns the elapsed milliseconds. */
+int pm_timer_start(pm_context* c);
+int pm_timer_stop(pm_context* c, double* ms);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 int64_t pm_launch_count(pm_context* c);
 /* Accumulated device time (ms, CUDA events) per pipeline stage since the last reset; names are

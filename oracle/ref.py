@@ -75,6 +75,23 @@ def set_num_threads(n: int) -> None:
         L.ref_set_num_threads(int(n))
 
 
+def make_params(n_type, cutoff, model_type, max_p, gtinv_order, gtinv_maxl, n_gaussians=None, pair_params=None,
+                gtinv_version=1, feature_type="gtinv", **_ignored):
+    """The subset of PolymlpParams.as_dict() that RefModel / RefEval read (the reference library calls its own Readgtinv,
+    so no coupling-coefficient tables are needed here).  Radial parameters as in src/pypolymlp/core/params_utils.py:84-94.
+    Exists so that bench.py's reference arm does not have to import the product package."""
+    if pair_params is None:
+        g2 = np.linspace(0.0, 1.0, n_gaussians - 1) * (cutoff - 1.0)
+        width = max(1.0, g2[1] - g2[0])
+        pair_params = [[float(width), float(p2)] for p2 in g2] + [[0.0, 0.0]]
+    cond = {(i, j): list(range(len(pair_params))) for i in range(n_type) for j in range(i, n_type)}
+    return {"n_type": int(n_type),
+            "model": {"cutoff": float(cutoff), "feature_type": feature_type, "model_type": int(model_type),
+                      "max_p": int(max_p), "max_l": int(max(gtinv_maxl)) if len(gtinv_maxl) else 0,
+                      "pair_params": pair_params, "pair_params_conditional": cond,
+                      "gtinv": {"order": int(gtinv_order), "max_l": list(gtinv_maxl), "version": int(gtinv_version)}}}
+
+
 def _cond_arrays(params_dict):
     n_type = params_dict["n_type"]
     model = params_dict["model"]
@@ -266,6 +283,11 @@ class RefEval:
         if getattr(self, "_h", None):
             lib().ref_eval_destroy(self._h)
             self._h = None
+
+    def eval_multiple(self, axis_list, positions_c_list, types_list):
+        """PyPropertiesFast::eval_multiple semantics (compute/py_properties_fast.cpp:30-76): serial over structures,
+        OpenMP over atoms inside each."""
+        return [self.eval(a, p, t, use_openmp=True) for a, p, t in zip(axis_list, positions_c_list, types_list)]
 
     def eval(self, axis, positions_c, types, use_openmp=False):
         axis, pos, ty = _d(axis), _d(positions_c), _i(types)

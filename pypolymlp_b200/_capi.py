@@ -48,6 +48,9 @@ EXPORTS = [
     "pm_fit_finalize", "pm_fit_finalize_view", "pm_fit_solve_ridge", "pm_synchronize", "pm_stream", "pm_launch_count", "pm_profile_enable",
     "pm_profile_get", "pm_stage_name", "pm_eval_set_coeffs", "pm_eval", "pm_debug_fetch",
     "pm_microbench",
+    "pm_timer_start", "pm_timer_stop", "pm_comm_unique_id", "pm_comm_init_rank", "pm_comm_size", "pm_comm_rank", "pm_fit_reduce", "pm_fit_reduce_bytes",
+    "pm_comm_allreduce", "pm_comm_barrier", "pm_multi_create", "pm_multi_destroy", "pm_multi_size", "pm_multi_context",
+    "pm_multi_fit_reset", "pm_multi_fit_accumulate", "pm_multi_fit_reduce", "pm_multi_fit_finalize",
 ]
 
 
@@ -69,7 +72,11 @@ def lib():
         L.pm_stream.restype = C.c_void_p
         L.pm_context_create.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
         L.pm_model_create.argtypes = [C.POINTER(FeatureParamsC), C.POINTER(C.c_void_p)]
-        for name in ("pm_model_destroy", "pm_context_destroy"):
+        L.pm_fit_reduce_bytes.restype = C.c_int64
+        L.pm_multi_context.restype = C.c_void_p
+        L.pm_multi_context.argtypes = [C.c_void_p, C.c_int]
+        L.pm_multi_create.argtypes = [C.c_void_p, _ip, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        for name in ("pm_model_destroy", "pm_context_destroy", "pm_multi_destroy"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = None
         _lib = L
@@ -110,6 +117,8 @@ class StructureBatch:
 
     def __init__(self, axis_array, positions_c_array, types_array, force_flags):
         n = len(axis_array)
+        if len(positions_c_array) != n or len(types_array) != n or len(force_flags) != n:
+            raise ValueError("axis, positions_c, types and force flags must have one entry per structure")
         self.n_st = n
         self.axis = as_d(np.array([np.asarray(a, dtype=np.float64) for a in axis_array])).reshape(n, 9) if n else np.zeros((0, 9))
         self.n_atoms = as_i([np.asarray(p).shape[1] for p in positions_c_array])

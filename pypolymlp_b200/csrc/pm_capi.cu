@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include "pm_kernels.cuh"
+#include "pm_nccl.hpp"
 
 namespace pm {
 void set_features_smem(size_t smem_bytes);
@@ -146,6 +147,13 @@ struct pm_context {
     size_t pinned_n = 0;
     double* packed = nullptr;   // device: [xtx F*F | xty F | xe_sum F | xe_sq F | y_sq_norm | n_data]
     SyrkScratch syrk_scr{};     // parked partial tiles + per-tile arrival counters of the deterministic SYRK fix-up
+    // multi-GPU: NCCL communicator (one rank per context) and the packed upper-triangle reduce buffer
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    bool comm_owned = true;     // false: the communicator belongs to a pm_multi (destroyed there)
+    DevVec<double> d_red;
+    double* d_small = nullptr;  // 64 doubles of device scratch for pm_comm_allreduce
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // pm_timer_start / pm_timer_stop
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1144,6 +1152,11 @@ void pm_context_destroy(pm_context* c) {
     if (c->acc) cudaFree(c->acc);
     if (c->syrk_scr.partials) cudaFree(c->syrk_scr.partials);
     if (c->syrk_scr.counters) cudaFree(c->syrk_scr.counters);
+    if (c->comm && c->comm_owned) nccl_api().CommDestroy(c->comm);
+    c->d_red.release();
+    if (c->d_small) cudaFree(c->d_small);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     c->d_atom_off.release(); c->d_st_of_atom.release(); c->d_types.release(); c->d_trans_off.release();
     c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
@@ -1512,6 +1525,30 @@ int pm_synchronize(pm_context* c) {
 }
 
 void* pm_stream(pm_context* c) { return c ? (void*)c->stream : nullptr; }
+
+int pm_timer_start(pm_context* c) {
+    return guarded([&] {
+        if (!c) throw std::invalid_argument("null argument");
+        CK(cudaSetDevice(c->device));
+        if (!c->ev_t0) { CK(cudaEventCreate(&c->ev_t0)); CK(cudaEventCreate(&c->ev_t1)); }
+        join_syrk(c);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventRecord(c->ev_t0, c->stream));
+    });
+}
+
+int pm_timer_stop(pm_context* c, double* ms) {
+    return guarded([&] {
+        if (!c || !ms || !c->ev_t0) throw std::invalid_argument("pm_timer_stop without pm_timer_start");
+        CK(cudaSetDevice(c->device));
+        join_syrk(c);
+        CK(cudaEventRecord(c->ev_t1, c->stream));
+        CK(cudaEventSynchronize(c->ev_t1));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
+        *ms = t;
+    });
+}
 int64_t pm_launch_count(pm_context* c) { return c ? c->launches : 0; }
 
 int pm_profile_enable(pm_context* c, int on) {
@@ -1644,6 +1681,272 @@ int pm_microbench(pm_context* c, int which, int n, double* tflops) {
         else *tflops = microbench_fp64(which, c->stream);
         CK(cudaGetLastError());
     });
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// Multi-GPU: the partial accumulators of the ranks are summed with ONE ncclReduce over NVLink
+// (replaces the OpenMP-over-structures loop of compute/py_model.cpp:39-53 and the batch sum of
+// src/pypolymlp/mlp_dev/core/data_sequential.py:49-70 across devices).  Only the upper 128 x 128 tiles of C are valid,
+// so they are packed into a contiguous buffer first: [tiles (ti <= tj, row-major) x 128 x 128 | xe_sum | xe_sq | n_data].
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_pack_upper(double* __restrict__ acc, int fpad, double* __restrict__ buf, int unpack) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    const int ntile = fpad / 128;
+    const long tile = (long)ti * ntile - (long)ti * (ti - 1) / 2 + (tj - ti);
+    double2* b2 = reinterpret_cast<double2*>(buf + tile * 128 * 128);
+    for (int e = threadIdx.x; e < 128 * 64; e += 256) {
+        const int r = e >> 6, c2 = e & 63;
+        double2* a2 = reinterpret_cast<double2*>(acc + (size_t)(ti * 128 + r) * fpad + tj * 128) + c2;
+        if (unpack) *a2 = b2[e];
+        else b2[e] = *a2;
+    }
+}
+
+static size_t packed_upper_doubles(const pm_context* c) {
+    const size_t nt = (size_t)c->dm.fpad / 128;
+    return nt * (nt + 1) / 2 * 128 * 128 + 2 * (size_t)c->dm.fpad + 1;
+}
+
+// pack this context's accumulator (with its row count in the last slot) into c->d_red
+static void pack_for_reduce(pm_context* c) {
+    CK(cudaSetDevice(c->device));
+    ensure_acc(c);
+    const int fp = c->dm.fpad, nt = fp / 128;
+    const size_t n = packed_upper_doubles(c);
+    c->d_red.ensure(n);
+    const double nd = (double)c->n_data;
+    CK(cudaMemcpyAsync(c->acc + c->acc_n - 1, &nd, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_pack_upper<<<dim3(nt, nt), 256, 0, c->stream>>>(c->acc, fp, c->d_red.p, 0);
+    CK(cudaMemcpyAsync(c->d_red.p + n - (2 * (size_t)fp + 1), c->acc + (size_t)fp * fp, (2 * (size_t)fp + 1) * sizeof(double),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    c->launches += 1;
+}
+
+static void unpack_after_reduce(pm_context* c) {
+    CK(cudaSetDevice(c->device));
+    const int fp = c->dm.fpad, nt = fp / 128;
+    const size_t n = packed_upper_doubles(c);
+    k_pack_upper<<<dim3(nt, nt), 256, 0, c->stream>>>(c->acc, fp, c->d_red.p, 1);
+    CK(cudaMemcpyAsync(c->acc + (size_t)fp * fp, c->d_red.p + n - (2 * (size_t)fp + 1), (2 * (size_t)fp + 1) * sizeof(double),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    c->launches += 1;
+}
+
+struct pm_multi {
+    std::vector<pm_context*> ctx;
+    std::vector<ncclComm_t> comms;
+};
+
+// structures [s0, s1) of a batch as a batch of their own, with the rows of w / y regrouped into its PyModel layout
+struct SubBatch {
+    pm_structures st{};
+    std::vector<double> w, y;
+    SubBatch(const pm_structures* all, const std::vector<size_t>& aoff, const std::vector<long>& be,
+             const std::vector<long>& bs, const std::vector<long>& bf, int s0, int s1, const double* w_all, const double* y_all) {
+        st.n_st = s1 - s0;
+        st.axis = all->axis + 9 * (size_t)s0;
+        st.positions_c = all->positions_c + 3 * aoff[s0];
+        st.types = all->types + aoff[s0];
+        st.n_atoms = all->n_atoms + s0;
+        st.force = all->force ? all->force + s0 : nullptr;
+        auto push = [&](long row, long n) {
+            for (long r = 0; r < n; ++r) { w.push_back(w_all[row + r]); y.push_back(y_all[row + r]); }
+        };
+        for (int s = s0; s < s1; ++s) push(be[s], 1);
+        for (int s = s0; s < s1; ++s) if (bs[s] >= 0) push(bs[s], 6);
+        for (int s = s0; s < s1; ++s) if (bf[s] >= 0) push(bf[s], 3L * all->n_atoms[s]);
+    }
+};
+
+extern "C" {
+
+int pm_comm_unique_id(char id[128]) {
+    return guarded([&] {
+        if (!id) throw std::invalid_argument("null argument");
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclUniqueId u;
+        nccl_check(nccl_api().GetUniqueId(&u), "ncclGetUniqueId");
+        std::memcpy(id, &u, 128);
+    });
+}
+
+int pm_comm_init_rank(pm_context* c, int n_ranks, int rank, const char id[128]) {
+    return guarded([&] {
+        if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw std::invalid_argument("invalid communicator arguments");
+        if (c->comm) throw std::runtime_error("the context already has a communicator");
+        CK(cudaSetDevice(c->device));
+        ncclUniqueId u;
+        std::memcpy(&u, id, 128);
+        nccl_check(nccl_api().CommInitRank(&c->comm, n_ranks, u, rank), "ncclCommInitRank");
+        c->comm_rank = rank; c->comm_size = n_ranks; c->comm_owned = true;
+    });
+}
+
+int pm_comm_size(pm_context* c) { return c ? c->comm_size : -1; }
+int pm_comm_rank(pm_context* c) { return c ? c->comm_rank : -1; }
+
+int pm_comm_allreduce(pm_context* c, double* values, int n, int op) {
+    return guarded([&] {
+        if (!c || !values || n < 1 || n > 64) throw std::invalid_argument("pm_comm_allreduce: 1..64 values");
+        if (!c->comm) return;   // a single rank: the values are their own reduction
+        CK(cudaSetDevice(c->device));
+        if (!c->d_small) CK(cudaMalloc(&c->d_small, 64 * sizeof(double)));
+        CK(cudaMemcpyAsync(c->d_small, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        const ncclRedOp_t rop = op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum);
+        nccl_check(nccl_api().AllReduce(c->d_small, c->d_small, (size_t)n, ncclDouble, rop, c->comm, c->stream), "ncclAllReduce");
+        CK(cudaMemcpyAsync(values, c->d_small, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int pm_comm_barrier(pm_context* c) {
+    double v = 0.0;
+    return pm_comm_allreduce(c, &v, 1, 0);
+}
+
+int pm_fit_reduce(pm_context* c, int root) {
+    return guarded([&] {
+        if (!c) throw std::invalid_argument("null argument");
+        if (!c->comm || c->comm_size == 1) return;
+        if (root < 0 || root >= c->comm_size) throw std::invalid_argument("root out of range");
+        join_syrk(c);
+        pack_for_reduce(c);
+        nccl_check(nccl_api().Reduce(c->d_red.p, c->d_red.p, packed_upper_doubles(c), ncclDouble, ncclSum, root, c->comm, c->stream),
+                   "ncclReduce");
+        if (c->comm_rank == root) unpack_after_reduce(c);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+    });
+}
+
+int64_t pm_fit_reduce_bytes(pm_context* c) { return c ? (int64_t)(packed_upper_doubles(c) * sizeof(double)) : -1; }
+
+// ---- several GPUs driven by one process -----------------------------------------------------------------------------
+int pm_multi_create(const pm_model* m, const int* devices, int n_dev, size_t workspace_bytes, int flags, pm_multi** out) {
+    return guarded([&] {
+        if (!m || !devices || n_dev < 1 || !out) throw std::invalid_argument("invalid argument");
+        auto mg = std::make_unique<pm_multi>();
+        try {
+            for (int k = 0; k < n_dev; ++k) {
+                pm_context* c = nullptr;
+                if (pm_context_create(m, devices[k], workspace_bytes, flags, &c) != PM_OK) throw std::runtime_error(g_err);
+                mg->ctx.push_back(c);
+            }
+            if (n_dev > 1) {
+                mg->comms.resize(n_dev);
+                nccl_check(nccl_api().CommInitAll(mg->comms.data(), n_dev, devices), "ncclCommInitAll");
+                for (int k = 0; k < n_dev; ++k) {
+                    mg->ctx[k]->comm = mg->comms[k]; mg->ctx[k]->comm_rank = k; mg->ctx[k]->comm_size = n_dev;
+                    mg->ctx[k]->comm_owned = false;
+                }
+            }
+        } catch (...) {
+            for (pm_context* c : mg->ctx) pm_context_destroy(c);
+            throw;
+        }
+        *out = mg.release();
+    });
+}
+
+void pm_multi_destroy(pm_multi* mg) {
+    if (!mg) return;
+    for (pm_context* c : mg->ctx) pm_context_destroy(c);
+    for (ncclComm_t cm : mg->comms) if (cm) nccl_api().CommDestroy(cm);
+    delete mg;
+}
+
+int pm_multi_size(const pm_multi* mg) { return mg ? (int)mg->ctx.size() : -1; }
+pm_context* pm_multi_context(pm_multi* mg, int k) { return (mg && k >= 0 && k < (int)mg->ctx.size()) ? mg->ctx[k] : nullptr; }
+
+int pm_multi_fit_reset(pm_multi* mg) {
+    return guarded([&] {
+        if (!mg) throw std::invalid_argument("null argument");
+        for (pm_context* c : mg->ctx)
+            if (pm_fit_reset(c) != PM_OK) throw std::runtime_error(g_err);
+    });
+}
+
+int pm_multi_fit_accumulate(pm_multi* mg, const pm_structures* st, const double* w, const double* y) {
+    return guarded([&] {
+        if (!mg || !st || !w || !y) throw std::invalid_argument("null argument");
+        const int nd = (int)mg->ctx.size();
+        if (nd == 1) {
+            if (pm_fit_accumulate(mg->ctx[0], st, w, y) != PM_OK) throw std::runtime_error(g_err);
+            return;
+        }
+        validate_structures(mg->ctx[0], st);
+        std::vector<size_t> aoff;
+        std::vector<long> be, bs, bf;
+        long n_rows = 0;
+        batch_layout(st, aoff, be, bs, bf, n_rows);
+        // contiguous slices balanced by atom count (rows and neighbour work both scale with it)
+        std::vector<int> cut(nd + 1, st->n_st);
+        cut[0] = 0;
+        const double total = (double)aoff[st->n_st] + st->n_st;
+        for (int k = 1, s = 0; k < nd; ++k) {
+            const double want = total * k / nd;
+            while (s < st->n_st && (double)aoff[s] + s < want) ++s;
+            cut[k] = s;
+        }
+        std::vector<std::string> errs(nd);
+        std::vector<int> status(nd, PM_OK);
+        std::vector<std::thread> th;
+        for (int k = 0; k < nd; ++k) {
+            if (cut[k + 1] <= cut[k]) continue;
+            th.emplace_back([&, k] {
+                SubBatch sb(st, aoff, be, bs, bf, cut[k], cut[k + 1], w, y);
+                status[k] = pm_fit_accumulate(mg->ctx[k], &sb.st, sb.w.data(), sb.y.data());
+                if (status[k] != PM_OK) errs[k] = pm_last_error();
+            });
+        }
+        for (auto& t : th) t.join();
+        for (int k = 0; k < nd; ++k)
+            if (status[k] != PM_OK) {
+                if (status[k] == PM_ERR_INVALID) throw std::invalid_argument(errs[k]);
+                if (status[k] == PM_ERR_CUDA) throw CudaError(errs[k]);
+                throw std::runtime_error(errs[k]);
+            }
+    });
+}
+
+int pm_multi_fit_reduce(pm_multi* mg, int root) {
+    return guarded([&] {
+        if (!mg) throw std::invalid_argument("null argument");
+        const int nd = (int)mg->ctx.size();
+        if (nd == 1) return;
+        if (root < 0 || root >= nd) throw std::invalid_argument("root out of range");
+        for (pm_context* c : mg->ctx) { join_syrk(c); pack_for_reduce(c); }
+        nccl_check(nccl_api().GroupStart(), "ncclGroupStart");
+        for (pm_context* c : mg->ctx) {
+            CK(cudaSetDevice(c->device));
+            nccl_check(nccl_api().Reduce(c->d_red.p, c->d_red.p, packed_upper_doubles(c), ncclDouble, ncclSum, root, c->comm, c->stream),
+                       "ncclReduce");
+        }
+        nccl_check(nccl_api().GroupEnd(), "ncclGroupEnd");
+        unpack_after_reduce(mg->ctx[root]);
+        for (pm_context* c : mg->ctx) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        CK(cudaGetLastError());
+    });
+}
+
+int pm_multi_fit_finalize(pm_multi* mg, double* xtx, double* xty, double* xe_sum, double* xe_sq_sum, double* y_sq_norm,
+                          int64_t* n_data) {
+    if (!mg) { g_err = "null argument"; return PM_ERR_INVALID; }
+    // the reduce ADDS the other ranks' partial sums into device 0's accumulator: the other accumulators are cleared so
+    // that a later accumulate / finalize pair does not count them twice
+    const int r = pm_multi_fit_reduce(mg, 0);
+    if (r != PM_OK) return r;
+    for (size_t k = 1; k < mg->ctx.size(); ++k) {
+        const int rr = pm_fit_reset(mg->ctx[k]);
+        if (rr != PM_OK) return rr;
+    }
+    return pm_fit_finalize(mg->ctx[0], xtx, xty, xe_sum, xe_sq_sum, y_sq_norm, n_data);
 }
 
 }  // extern "C"

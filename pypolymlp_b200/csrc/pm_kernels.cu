@@ -13,8 +13,31 @@
 #include "pm_kernels.cuh"
 
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 namespace pm {
+
+void ensure_smem(const void* kernel, size_t smem_bytes, bool max_carveout) {
+    if (smem_bytes <= 48 * 1024 && !max_carveout) return;
+    struct Ent { const void* fn; size_t sz; };
+    static std::vector<Ent> tab[64];
+    static std::mutex mu;
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : tab[d])
+        if (e.fn == kernel) {
+            if (e.sz >= smem_bytes) return;
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            e.sz = smem_bytes;
+            return;
+        }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (max_carveout) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    tab[d].push_back({kernel, smem_bytes});
+}
 
 // ================================================================================================
 // K1: neighbour list.  One warp per centre atom; lanes sweep the (j, translation) candidates in the
@@ -887,7 +910,6 @@ __global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, cons
     }
 }
 
-static size_t g_feat_smem_set = 0, g_feat3_smem_set = 0;
 
 // compact polynomial-variable rows from dfeat (only after the fallback feature kernels; v3 writes them itself)
 __global__ void __launch_bounds__(256) k_dpv_gather(DevModel m, int n_atoms, const double* __restrict__ dfeat,
@@ -930,15 +952,9 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
         const bool big = smem4 > 96 * 1024;
         const size_t smem = smem_bytes * at;
         const int grid = (b.n_atoms + at - 1) / at;
-        static const void* set_fn = nullptr;
-        static size_t set_sz = 0;
 #define PM_FEAT3_LAUNCH(AT_, MO_, NT_)                                                                              \
     {                                                                                                              \
-        const void* fn = (const void*)k_features_v3<AT_, MO_, NT_>;                                                \
-        if (smem > 48 * 1024 && (set_fn != fn || set_sz != smem)) {                                                \
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
-            set_fn = fn; set_sz = smem;                                                                            \
-        }                                                                                                          \
+        ensure_smem((const void*)k_features_v3<AT_, MO_, NT_>, smem);                                              \
         k_features_v3<AT_, MO_, NT_><<<grid, NT_, smem, s>>>(m, b, anc, dfeat, Gbuf, nfull_max, zero_g ? 1 : 0, dpv); \
     }
 #define PM_FEAT3_CASE(MO_)                                                                                          \
@@ -960,23 +976,20 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
         const int grid = (b.n_atoms + AT - 1) / AT;
 #define PM_FEAT_CASE(MO_)                                                                                        \
     case MO_:                                                                                                    \
-        if (smem4 > 48 * 1024 && g_feat_smem_set != smem4)                                                       \
-            cudaFuncSetAttribute(k_features_v2<AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4); \
+        ensure_smem((const void*)k_features_v2<AT, MO_>, smem4);                                                 \
         k_features_v2<AT, MO_><<<grid, 256, smem4, s>>>(m, b, anc, dfeat, Gbuf, nfull_max);                      \
         break;
         switch (mo) {
             PM_FEAT_CASE(1) PM_FEAT_CASE(2) PM_FEAT_CASE(3) PM_FEAT_CASE(4) PM_FEAT_CASE(5) PM_FEAT_CASE(6)
         }
 #undef PM_FEAT_CASE
-        if (smem4 > 48 * 1024) g_feat_smem_set = smem4;
         return;
     }
+    ensure_smem((const void*)k_features, smem_bytes);
     k_features<<<b.n_atoms, 256, smem_bytes, s>>>(m, b, anc, dfeat, Gbuf);
 }
 
-void set_features_smem(size_t smem_bytes) {
-    cudaFuncSetAttribute(k_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-}
+void set_features_smem(size_t smem_bytes) { ensure_smem((const void*)k_features, smem_bytes); }
 
 // ================================================================================================
 // K4a (straightforward): L[(pair, alpha), f] = sum_heads Re(G[f, head] v_alpha,head(pair)), plus the
@@ -1647,18 +1660,15 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
         const int grid = (b.n_atoms + EVF_AT - 1) / EVF_AT;
         int mo = 1;
         for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
-        static size_t set_for = 0;
 #define PM_EVF_CASE(MO_)                                                                                              \
     case MO_:                                                                                                         \
-        if (smem > 48 * 1024 && set_for != smem)                                                                      \
-            cudaFuncSetAttribute(k_eval_features<EVF_AT, MO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ensure_smem((const void*)k_eval_features<EVF_AT, MO_>, smem);                                                 \
         k_eval_features<EVF_AT, MO_><<<grid, 256, smem, s>>>(m, b, ws.anc, coeffs, ws.Ah, ah_stride, energies, nfull_max, ws.cmat); \
         break;
         switch (mo) {
             PM_EVF_CASE(1) PM_EVF_CASE(2) PM_EVF_CASE(3) PM_EVF_CASE(4) PM_EVF_CASE(5) PM_EVF_CASE(6)
         }
 #undef PM_EVF_CASE
-        if (smem > 48 * 1024) set_for = smem;
     } else {
         k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
     }

@@ -26,6 +26,10 @@ struct Workspace {
     int* errflag = nullptr;     // device error flag
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: remembers, per (device, kernel), the
+// largest size configured so far (several contexts on several devices may live in one process)
+void ensure_smem(const void* kernel, size_t smem_bytes, bool max_carveout = false);
+
 // K1: neighbour list
 void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s);
 void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);

@@ -528,7 +528,6 @@ static size_t lrows_v4_smem(const DevModel& m, int kpn) {
 template <int TPN, int KPN>
 static void launch_lrows_v4_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
     static int n_sm = 0;
-    static size_t set_for = 0;
     const size_t smem = lrows_v4_smem(m, KPN);
     if (n_sm == 0) {
         int dev = 0;
@@ -536,12 +535,9 @@ static void launch_lrows_v4_t(const DevModel& m, const DevBatch& b, const Worksp
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
-    if (set_for < smem) {
-        cudaFuncSetAttribute(k_lrows_v4<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_lrows_v4n<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_lrows_v4a<TPN, KPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
-    }
+    ensure_smem((const void*)k_lrows_v4<TPN, KPN>, smem);
+    ensure_smem((const void*)k_lrows_v4n<TPN, KPN>, smem);
+    ensure_smem((const void*)k_lrows_v4a<TPN, KPN>, smem);
     const int grid = std::min(n_sm, b.n_atoms);
     // measured on config 2 (us / structure): 8-row jobs x 15 warps 31.5, 16-row jobs x 11 warps 36.9, alpha-major 24-row jobs
     // x 11 warps 36.7 -- the warp count (latency hiding) beats the B-fragment reuse
@@ -805,15 +801,9 @@ static size_t xrows_v6_smem(const DevModel& m) {
 }
 
 void launch_xrows_v6(const DevModel& m, const DevBatch& b, const Workspace& ws, bool apply_weights, cudaStream_t s) {
-    static size_t set_for = 0;
     const size_t smem = xrows_v6_smem(m);
-    if (set_for < smem) {
-        cudaFuncSetAttribute(k_xrows_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // two CTAs per SM need ~204 KB of the 256 KB L1 / shared array: without this hint the driver kept the default
-        // carve-out and ran one CTA per SM (ncu: 12 % warps active)
-        cudaFuncSetAttribute(k_xrows_v6, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        set_for = smem;
-    }
+    // two CTAs per SM need ~204 KB of the 256 KB L1 / shared array: ask for the largest carve-out
+    ensure_smem((const void*)k_xrows_v6, smem, true);
     k_xrows_v6<<<b.n_atoms, X6_THREADS, smem, s>>>(m, b, ws.dpv, ws.Lbuf, ws.X, apply_weights ? 1 : 0, xrows_v6_sl(m));
 }
 

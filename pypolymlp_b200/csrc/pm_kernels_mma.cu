@@ -494,9 +494,9 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
 void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStream_t s, const SyrkScratch* scr) {
     static int n_sm = 0;
     const bool use_v1 = getenv("PM_SYRK_V1") != nullptr;   // read per call (tests compare both)
+    ensure_smem((const void*)k_syrk_sk, SY_SMEM);
+    ensure_smem((const void*)k_syrk_sk2, SY_SMEM + 16);
     if (n_sm == 0) {
-        cudaFuncSetAttribute(k_syrk_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM);
-        cudaFuncSetAttribute(k_syrk_sk2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM + 16);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -904,11 +904,7 @@ bool lrows_big_supported(const DevModel& m) { return lrows_big_smem(8) <= 226 * 
 template <int MRT, int NT>
 static void launch_lrows_big_t(const DevModel& m, const DevBatch& b, const Workspace& ws, cudaStream_t s) {
     const size_t smem = lrows_big_smem(MRT);
-    static size_t set_for = 0;
-    if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_big<MRT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
-    }
+    ensure_smem((const void*)k_lrows_big<MRT, NT>, smem);
     k_lrows_big<MRT, NT><<<b.n_atoms, NT, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
                                                    lrows_big_ldv(MRT), g_lrows_kmax, g_lrows_runmax, g_lrows_tilemax);
 }
@@ -1232,12 +1228,8 @@ static void launch_lrows_v2_t(const DevModel& m, const DevBatch& b, const Worksp
     int ntl = 1;
     for (int t = 0; t < m.n_type; ++t) ntl = max(ntl, m.types[t].n_tiles);
     const size_t smem = lrows_v2_smem<KPN>(m, nwarp, ntl);
-    static size_t set_for = 0;
-    if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_lrows_v3<TPN, KPN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
-    }
+    ensure_smem((const void*)k_lrows_v3<TPN, KPN, false>, smem);
+    ensure_smem((const void*)k_lrows_v3<TPN, KPN, true>, smem);
     if (ws.scatter)
         k_lrows_v3<TPN, KPN, true><<<b.n_atoms, nwarp * 32, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf,
                                                                        ws.X, ws.Lpv, apply_w ? 1 : 0);
@@ -1271,11 +1263,7 @@ void launch_lrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws,
     if (launch_lrows_v2(m, b, ws, apply_w, s)) return;
     const size_t smem = lrows_mma_smem(m);
     if (smem > 200 * 1024) { launch_lrows_big(m, b, ws, s); return; }
-    static size_t set_for = 0;
-    if (set_for != smem) {
-        cudaFuncSetAttribute(k_lrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
-    }
+    ensure_smem((const void*)k_lrows_mma, smem);
     k_lrows_mma<<<b.n_atoms, 128, smem, s>>>(m, b, ws.PB, ws.agg, ws.Gbuf, ws.Lbuf, ws.Xown, ws.Sbuf, g_lrows_kmax);
 }
 
@@ -2305,12 +2293,8 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
     if (m.npv_pad > 64 || m.n_linear > 512) return false;
     if (ws.scatter) {
         const size_t smem2 = xrows_v2_smem();
-        static bool set2 = false;
-        if (!set2) {
-            cudaFuncSetAttribute(k_xpoly, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            cudaFuncSetAttribute(k_xrows_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            set2 = true;
-        }
+        ensure_smem((const void*)k_xpoly, smem2);
+        ensure_smem((const void*)k_xrows_v2, smem2);
         k_xpoly<<<b.n_atoms, XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lpv, ws.Xown, ws.X, apply_weights ? 1 : 0);
         k_xrows_v2<<<dim3(b.n_st, 3), XV_THREADS, smem2, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq,
                                                              1, apply_weights ? 1 : 0);
@@ -2318,12 +2302,9 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
     }
     if (xrows_fills_rows(m, ws.scatter)) {
         const size_t smem4 = ((size_t)4 * X4_KC * X4_LD + 4 * X4_KC) * sizeof(double) + X4_KC * sizeof(int);
-        static int u4 = 0;
-        if (!u4) {
-            cudaFuncSetAttribute(k_xrows_v4<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-            cudaFuncSetAttribute(k_xrows_v4<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-            u4 = getenv("PM_X4_U") ? atoi(getenv("PM_X4_U")) : 2;   // 2 measured faster than 4 (register pressure)
-        }
+        static const int u4 = getenv("PM_X4_U") ? atoi(getenv("PM_X4_U")) : 2;   // 2 measured faster than 4 (register pressure)
+        ensure_smem((const void*)k_xrows_v4<2>, smem4);
+        ensure_smem((const void*)k_xrows_v4<4>, smem4);
         auto kern = u4 == 2 ? k_xrows_v4<2> : k_xrows_v4<4>;
         static const bool use_v5 = getenv("PM_XROWS_V4") == nullptr;
         const size_t smem5 = ((size_t)4 * X4_KC * X4_LD + 2 * X5_R * (3 * (size_t)m.fl + 64) + X5_MAXC + 2 * X5_R) * sizeof(double) +
@@ -2331,11 +2312,7 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         if (ws.lt) {
             launch_xrows_v6(m, b, ws, apply_weights, s);
         } else if (use_v5 && ws.dpv && m.fl <= 256 && (m.fl & 1) == 0 && smem5 <= 112 * 1024) {
-            static size_t set5_for = 0;   // the ring size depends on the model (fl)
-            if (set5_for < smem5) {
-                cudaFuncSetAttribute(k_xrows_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);
-                set5_for = smem5;
-            }
+            ensure_smem((const void*)k_xrows_v5, smem5);   // the ring size depends on the model (fl)
             k_xrows_v5<<<b.n_atoms, X4_THREADS, smem5, s>>>(m, b, ws.dpv, ws.Lbuf, ws.Xown, ws.X, apply_weights ? 1 : 0);
         } else {
             kern<<<b.n_atoms, X4_THREADS, smem4, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
@@ -2346,11 +2323,7 @@ static bool launch_xrows_v2(const DevModel& m, const DevBatch& b, const Workspac
         return true;
     }
     const size_t smem = xrows_v2_smem();
-    static bool set = false;
-    if (!set) {
-        cudaFuncSetAttribute(k_xrows_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set = true;
-    }
+    ensure_smem((const void*)k_xrows_v2, smem);
     k_xrows_v2<<<b.n_atoms, XV_THREADS, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 0,
                                                    apply_weights ? 1 : 0);
     k_xrows_v2<<<dim3(b.n_st, 3), XV_THREADS, smem, s>>>(m, b, ws.dfeat, ws.Lbuf, ws.Xown, ws.Sbuf, ws.X, xe_sum, xe_sq, 1,
@@ -2500,11 +2473,7 @@ void launch_xrows_mma(const DevModel& m, const DevBatch& b, const Workspace& ws,
                       bool apply_weights, cudaStream_t s) {
     if (launch_xrows_v2(m, b, ws, xe_sum, xe_sq, apply_weights, s)) return;
     const size_t smem = xrows_mma_smem(m);
-    static size_t set_for = 0;
-    if (set_for != smem) {
-        cudaFuncSetAttribute(k_xrows_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
-    }
+    ensure_smem((const void*)k_xrows_mma, smem);
     // thousands of linear columns: dedicated gather kernels, k_xrows_mma keeps the polynomial part only
     const int big = m.n_linear >= 1024 ? 1 : 0;
     if (big) {

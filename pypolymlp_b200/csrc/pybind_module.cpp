@@ -13,7 +13,8 @@
 //   Neighbor / NeighborHalf / NeighborFull / NeighborCell test hooks             (pybind11_mlp.cpp:96-142)
 //   PotentialHybridModel(params_dict_array, axis, positions_c, types, n_st_dataset, force_dataset, n_atoms_all)
 //       .get_x() .get_fbegin() .get_sbegin() .get_cumulative_n_features() .get_n_data()  (pybind11_mlp.cpp:30-49)
-// Additive: PotentialXtX(params_dict) .add(...) .finalize() -- the fused feature + X^T X accumulation.
+// Additive: PotentialXtX(params_dict, devices=[...]) .add(...) .finalize() -- the fused feature + X^T X accumulation,
+// sharded over the listed GPUs (one NCCL reduce in finalize()).
 // Errors: C-ABI status PM_ERR_INVALID -> ValueError, anything else -> RuntimeError (as pybind11 maps
 // std::invalid_argument / std::runtime_error in the reference).  No CPU fallback.
 #include <pybind11/complex.h>
@@ -54,6 +55,19 @@ int default_device() {
     for (const char* key : {"POLYMLP_B200_DEVICE", "LOCAL_RANK"})
         if (const char* v = std::getenv(key)) return std::atoi(v);
     return 0;
+}
+
+// The reference hands out its design matrix as an Eigen::MatrixXd (column-major) view, i.e. a Fortran-ordered NumPy array
+// (pybind11_mlp.cpp:20-21); the C ABI writes row-major, so get_x() transposes once (blocked copy) into F order.
+py::array_t<double, py::array::f_style> to_fortran(const double* src, py::ssize_t rows, py::ssize_t cols) {
+    py::array_t<double, py::array::f_style> out({rows, cols});
+    double* dst = out.mutable_data();
+    constexpr py::ssize_t B = 64;
+    for (py::ssize_t i0 = 0; i0 < rows; i0 += B)
+        for (py::ssize_t j0 = 0; j0 < cols; j0 += B)
+            for (py::ssize_t j = j0; j < std::min(cols, j0 + B); ++j)
+                for (py::ssize_t i = i0; i < std::min(rows, i0 + B); ++i) dst[j * rows + i] = src[i * cols + j];
+    return out;
 }
 
 // feature_params from params.as_dict() (keys as in compute/py_params.cpp:14-43)
@@ -199,7 +213,7 @@ struct RowIndex {
 class PyModel {
     Model model;
     pm_context* ctx = nullptr;
-    py::array_t<double> x;
+    py::array_t<double, py::array::f_style> x;
     vector1i fbegin, sbegin, n_data;
 
   public:
@@ -210,13 +224,16 @@ class PyModel {
         const std::vector<bool>& force_st = idx.force_st;
         fbegin = idx.fbegin; sbegin = idx.sbegin; n_data = idx.n_data;
         Batch b(axis, positions_c, types, force_st);
+        for (int s = 0; s < b.st.n_st; ++s)
+            if (n_atoms_all[s] != b.n_atoms[s]) throw std::invalid_argument("n_atoms_all does not match the structures");
         check(pm_context_create(model.h, default_device(), 0, 0, &ctx));
         const py::ssize_t rows = (py::ssize_t)pm_batch_rows(&b.st), F = pm_model_n_features(model.h);
-        x = py::array_t<double>({rows, F});
-        check(pm_features_x(ctx, &b.st, x.mutable_data()));
+        std::vector<double> xr((size_t)rows * F + 1);
+        check(pm_features_x(ctx, &b.st, xr.data()));
+        x = to_fortran(xr.data(), rows, F);
     }
     ~PyModel() { pm_context_destroy(ctx); }
-    py::array_t<double> get_x() { return x; }
+    py::array_t<double, py::array::f_style> get_x() { return x; }
     const vector1i& get_fbegin() const { return fbegin; }
     const vector1i& get_sbegin() const { return sbegin; }
     const vector1i& get_n_data() const { return n_data; }
@@ -225,7 +242,7 @@ class PyModel {
 // PotentialHybridModel (pybind11_mlp.cpp:30-49, compute/py_hybrid_model.cpp:11-156): sub-model blocks side by side,
 // each computed by the CUDA path on the atoms of its own element subset and scattered back to the full rows.
 class PyHybridModel {
-    py::array_t<double> x;
+    py::array_t<double, py::array::f_style> x;
     vector1i fbegin, sbegin, n_data, cumulative;
 
   public:
@@ -252,9 +269,11 @@ class PyHybridModel {
             n_features += pm_model_n_features(models.back()->h);
             cumulative.push_back(n_features);
         }
-        x = py::array_t<double>({(py::ssize_t)idx.n_rows(), (py::ssize_t)n_features});
-        double* xa = x.mutable_data();
-        std::fill(xa, xa + (size_t)idx.n_rows() * n_features, 0.0);
+        // n_atoms_all sizes the force rows; the scatter below writes by real atom index (must agree)
+        for (size_t s = 0; s < n_st; ++s)
+            if (n_atoms_all[s] != all.n_atoms[s]) throw std::invalid_argument("n_atoms_all does not match the structures");
+        std::vector<double> xrow((size_t)idx.n_rows() * n_features + 1, 0.0);
+        double* xa = xrow.data();
         int n_force_st = 0;
         for (bool f : idx.force_st) n_force_st += f ? 1 : 0;
         for (size_t n = 0; n < models.size(); ++n) {
@@ -302,8 +321,9 @@ class PyHybridModel {
                 ifb += 3 * active[s].size();
             }
         }
+        x = to_fortran(xrow.data(), (py::ssize_t)idx.n_rows(), (py::ssize_t)n_features);
     }
-    py::array_t<double> get_x() { return x; }
+    py::array_t<double, py::array::f_style> get_x() { return x; }
     const vector1i& get_fbegin() const { return fbegin; }
     const vector1i& get_sbegin() const { return sbegin; }
     const vector1i& get_cumulative_n_features() const { return cumulative; }
@@ -312,29 +332,40 @@ class PyHybridModel {
 
 class PyXtX {
     Model model;
-    pm_context* ctx = nullptr;
+    pm_multi* mg = nullptr;
     int F;
 
   public:
-    explicit PyXtX(const py::dict& params_dict) : model(params_dict) {
-        check(pm_context_create(model.h, default_device(), 0, 0, &ctx));
-        check(pm_fit_reset(ctx));
+    // devices: GPUs this accumulator shards its batches over (default: the one default device).  More than one device:
+    // one host thread per device during add(), one grouped ncclReduce onto the first device in finalize().
+    PyXtX(const py::dict& params_dict, const std::vector<int>& devices) : model(params_dict) {
+        std::vector<int> dev = devices;
+        if (dev.empty()) dev.push_back(default_device());
+        check(pm_multi_create(model.h, dev.data(), (int)dev.size(), 0, 0, &mg));
+        check(pm_multi_fit_reset(mg));
         F = pm_model_n_features(model.h);
     }
-    ~PyXtX() { pm_context_destroy(ctx); }
+    ~PyXtX() { pm_multi_destroy(mg); }
+    int n_devices() const { return pm_multi_size(mg); }
+    void reset() { check(pm_multi_fit_reset(mg)); }
     void add(const py::sequence& axis, const py::sequence& positions_c, const py::sequence& types, const std::vector<bool>& force_st,
              py::array_t<double, py::array::c_style | py::array::forcecast> w,
              py::array_t<double, py::array::c_style | py::array::forcecast> y) {
         Batch b(axis, positions_c, types, force_st);
         const int64_t rows = pm_batch_rows(&b.st);
         if (w.size() != rows || y.size() != rows) throw std::invalid_argument("w and y must have one entry per row of the batch");
-        check(pm_fit_accumulate(ctx, &b.st, w.data(), y.data()));
+        int status;
+        {
+            py::gil_scoped_release nogil;   // the device threads never touch Python objects
+            status = pm_multi_fit_accumulate(mg, &b.st, w.data(), y.data());
+        }
+        check(status);
     }
     py::dict finalize() {
         py::array_t<double> xtx({(py::ssize_t)F, (py::ssize_t)F}), xty(F), xe_sum(F), xe_sq(F);
         double ysq = 0.0;
         int64_t nd = 0;
-        check(pm_fit_finalize(ctx, xtx.mutable_data(), xty.mutable_data(), xe_sum.mutable_data(), xe_sq.mutable_data(), &ysq, &nd));
+        check(pm_multi_fit_finalize(mg, xtx.mutable_data(), xty.mutable_data(), xe_sum.mutable_data(), xe_sq.mutable_data(), &ysq, &nd));
         py::dict d;
         d["xtx"] = xtx; d["xty"] = xty; d["xe_sum"] = xe_sum; d["xe_sq_sum"] = xe_sq;
         d["y_sq_norm"] = ysq; d["total_n_data"] = nd;
@@ -708,8 +739,10 @@ PYBIND11_MODULE(libmlpcpp, m) {
         .def("get_cumulative_n_features", &PyHybridModel::get_cumulative_n_features, py::return_value_policy::reference_internal)
         .def("get_n_data", &PyHybridModel::get_n_data, py::return_value_policy::reference_internal);
     py::class_<PyXtX>(m, "PotentialXtX")
-        .def(py::init<const py::dict&>())
+        .def(py::init<const py::dict&, const std::vector<int>&>(), py::arg("params_dict"), py::arg("devices") = std::vector<int>())
         .def("add", &PyXtX::add)
+        .def("reset", &PyXtX::reset)
+        .def("n_devices", &PyXtX::n_devices)
         .def("finalize", &PyXtX::finalize);
     py::class_<PyPropertiesFast>(m, "PotentialPropertiesFast")
         .def(py::init<const py::dict&, const darray&>())

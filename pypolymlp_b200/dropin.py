@@ -90,7 +90,9 @@ def install_fused_products(reference_src=None):
             batch_size = 256      # structures per call; the device chunks further by its own workspace
         if min_energy is None:
             min_energy = ds.get_min_energy(datasets)
-        acc = ext.PotentialXtX(params.as_dict())
+        # POLYMLP_B200_DEVICES="0,1,..": shard every batch over these GPUs (one NCCL reduce in finalize)
+        devs = [int(v) for v in os.environ.get("POLYMLP_B200_DEVICES", "").split(",") if v.strip()]
+        acc = ext.PotentialXtX(params.as_dict(), devices=devs)
         for data in datasets:
             if verbose:
                 print("----- Dataset:", data.name, "-----", flush=True)

@@ -15,7 +15,7 @@ from typing import Optional
 
 import numpy as np
 
-from .libmlpcpp import PotentialXtX, StructureBatch
+from .libmlpcpp import PotentialXtX, StructureBatch, comm_unique_id
 
 
 @dataclass
@@ -280,21 +280,47 @@ def compute_error(params_dict, scaled_coeffs, dataset: Dataset, stress_unit="eV"
     return out
 
 
-class _DevicePtr:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+def reduce_accumulator(acc: PotentialXtX, dst=0):
+    """Sum the per-rank partial [C upper tiles | xe_sum | xe_sq_sum | n_data] onto rank `dst`: one ncclReduce issued by
+    the library itself (pm_fit_reduce); needs acc.comm_init_rank / comm_init_from_env first (no-op for one rank)."""
+    acc.reduce(dst)
 
 
-def reduce_accumulator(acc: PotentialXtX, dst=0, group=None):
-    """Sum the per-rank partial [C | xe_sum | xe_sq_sum | n_data] onto rank `dst` over NCCL
-    (torch.distributed is the plumbing; the buffer is the library's own device memory)."""
-    import torch
-    import torch.distributed as dist
+def comm_init_from_env(acc: PotentialXtX, timeout_s=120.0):
+    """One process per GPU under torchrun / mpirun-style launchers (RANK, WORLD_SIZE, MASTER_PORT in the environment):
+    rank 0 creates the NCCL unique id and publishes it through a file in the node's temp directory, the others pick it
+    up.  Single node only (which is what the C ABI's pm_multi / the bench cover); returns (rank, world_size)."""
+    import os
+    import tempfile
+    import time
 
-    ptr, n = acc.accumulator()
-    t = torch.as_tensor(_DevicePtr(ptr, n), device=f"cuda:{acc.context.device}")
-    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    torch.cuda.synchronize(acc.context.device)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1
+    tag = "%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"), os.getppid())
+    path = os.path.join(tempfile.gettempdir(), f"polymlp_b200_ncclid_{tag}.bin")
+    if rank == 0:
+        uid = comm_unique_id()
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(uid)
+        os.replace(tmp, path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > timeout_s:
+                raise TimeoutError(f"rank {rank}: no NCCL id at {path}")
+            time.sleep(0.01)
+        with open(path, "rb") as f:
+            uid = f.read()
+    acc.comm_init_rank(world, rank, uid)
+    acc.barrier()
+    if rank == 0:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return rank, world
 
 
 def shard_range(n, rank, world_size):

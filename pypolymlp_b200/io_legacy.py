@@ -189,13 +189,26 @@ def load_mlp(filename="polymlp.yaml"):
 
 
 def convert_to_yaml(txt="polymlp.lammps", yaml="polymlp.yaml"):
-    """Legacy -> polymlp.yaml with unit scales (io_polymlp.py:120-130: the stored coefficients are already
-    divided by the scales)."""
-    if not is_legacy(txt):
-        raise ValueError("%s is not a legacy polymlp file" % txt)
-    pd, coeffs, meta = load_mlp_lammps(txt)
-    save_mlp_yaml(pd, coeffs, np.ones(len(coeffs)), meta["elements"], filename=yaml, mass=meta["mass"])
-    return yaml
+    """Legacy -> polymlp.yaml with unit scales (io_polymlp.py:120-140: the stored coefficients are already divided by
+    the scales).  One file or a list of files (hybrid models: yaml.1, yaml.2, ... in sorted order); returns False as soon
+    as an input is not a legacy file, True otherwise.  The sub-model flags type_full / type_indices are carried over."""
+
+    def one(src, dst):
+        pd, coeffs, meta = load_mlp_lammps(src)
+        save_mlp_yaml(pd, coeffs, np.ones(len(coeffs)), meta["elements"], filename=dst, mass=meta["mass"],
+                      type_full=meta["type_full"], type_indices=meta["type_indices"])
+
+    if isinstance(txt, (str, io.IOBase)):
+        if not is_legacy(txt):
+            return False
+        one(txt, yaml)
+        return True
+    files = sorted(txt)
+    for i, f in enumerate(files):
+        if not is_legacy(f):
+            return False
+        one(f, yaml + "." + str(i + 1) if len(files) > 1 else yaml)
+    return True
 
 
 def load_mlps(file_list_or_file):

@@ -193,6 +193,15 @@ class _Context:
         lib().pm_profile_get(self.handle, C.byref(n), ms, ln)
         return {lib().pm_stage_name(i).decode(): (ms[i], int(ln[i])) for i in range(n.value)}
 
+    def timer_start(self):
+        check(lib().pm_timer_start(self.handle))
+
+    def timer_stop(self):
+        """Milliseconds since timer_start on the context's stream (CUDA events)."""
+        ms = C.c_double(0.0)
+        check(lib().pm_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         return int(lib().pm_launch_count(self.handle))
 
@@ -411,6 +420,29 @@ class PotentialXtX:
     def add_staged(self):
         check(lib().pm_fit_accumulate_staged(self._ctx.handle))
 
+    # ---- multi-GPU (one process per GPU): NCCL communicator owned by the library -----------------------------------
+    def comm_init_rank(self, n_ranks, rank, unique_id):
+        """Join an NCCL communicator (pm_comm_init_rank); unique_id = the 128 bytes of comm_unique_id() of rank 0."""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        check(lib().pm_comm_init_rank(self._ctx.handle, int(n_ranks), int(rank), C.c_char_p(bytes(unique_id))))
+
+    def reduce(self, root=0):
+        """One ncclReduce(sum) of the packed upper tiles + xe_sum / xe_sq_sum / n_data onto rank `root` (collective)."""
+        check(lib().pm_fit_reduce(self._ctx.handle, int(root)))
+
+    def reduce_bytes(self):
+        return int(lib().pm_fit_reduce_bytes(self._ctx.handle))
+
+    def barrier(self):
+        check(lib().pm_comm_barrier(self._ctx.handle))
+
+    def allreduce(self, values, op="sum"):
+        """Small host-value collective (timing: max over ranks).  op: sum | max | min."""
+        v = as_d(np.atleast_1d(values)).copy()
+        check(lib().pm_comm_allreduce(self._ctx.handle, pd(v), len(v), {"sum": 0, "max": 1, "min": 2}[op]))
+        return v
+
     def accumulator(self):
         """(device pointer, n_doubles) of the packed accumulator, for a cross-GPU reduction."""
         p, n = C.c_void_p(), C.c_size_t(0)
@@ -449,6 +481,53 @@ class PotentialXtX:
                                        int(bool(include_force)), C.c_double(scale_threshold), pd(sc_out), pd(coefs),
                                        pd(rmse)))
         return sc_out, coefs.T.copy(), rmse
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (pm_comm_unique_id); rank 0 creates it, every rank passes it to comm_init_rank."""
+    buf = C.create_string_buffer(128)
+    check(lib().pm_comm_unique_id(buf))
+    return buf.raw
+
+
+class PotentialXtXMulti:
+    """Fused feature + X^T X accumulation over several GPUs of ONE process (C ABI: pm_multi_*): a batch is sharded over
+    the devices, each accumulates its part on its own host thread, finalize() sums the partial accumulators with one
+    grouped ncclReduce onto the first device.  Same add() / finalize() contract as PotentialXtX."""
+
+    def __init__(self, params_dict, devices, workspace_bytes=0, flags=0):
+        self._model = _Model(params_dict)
+        self.n_features = self._model.n_features
+        self.devices = [int(d) for d in devices]
+        dev = as_i(self.devices)
+        h = C.c_void_p()
+        check(lib().pm_multi_create(self._model.handle, pi(dev), len(dev), C.c_size_t(workspace_bytes), int(flags), C.byref(h)))
+        self._h = h
+        check(lib().pm_multi_fit_reset(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().pm_multi_destroy(self._h)
+            self._h = None
+
+    def reset(self):
+        check(lib().pm_multi_fit_reset(self._h))
+
+    def add(self, axis, positions_c, types, force_flags, w, y):
+        batch = StructureBatch(axis, positions_c, types, force_flags)
+        w, y = as_d(w), as_d(y)
+        if len(w) != batch.n_rows or len(y) != batch.n_rows:
+            raise ValueError("w and y must have one entry per row of the batch")
+        check(lib().pm_multi_fit_accumulate(self._h, C.byref(batch.c), pd(w), pd(y)))
+        return batch
+
+    def finalize(self):
+        F = self.n_features
+        xtx, xty, xe_sum, xe_sq = np.empty((F, F)), np.zeros(F), np.zeros(F), np.zeros(F)
+        ysq, nd = C.c_double(0.0), C.c_int64(0)
+        check(lib().pm_multi_fit_finalize(self._h, pd(xtx), pd(xty), pd(xe_sum), pd(xe_sq), C.byref(ysq), C.byref(nd)))
+        return {"xtx": xtx, "xty": xty, "xe_sum": xe_sum, "xe_sq_sum": xe_sq, "y_sq_norm": ysq.value,
+                "total_n_data": int(nd.value)}
 
 
 class PotentialPropertiesFast:

@@ -47,7 +47,7 @@ class OracleModel:
 class OracleXtX:
     """Stand-in for libmlpcpp.PotentialXtX: the sums the device accumulates, from the oracle's X."""
 
-    def __init__(self, pd):
+    def __init__(self, pd, devices=()):
         self.rm = ref.RefModel(pd)
         n = self.rm.n_features
         self.xtx, self.xty, self.xe, self.xe2 = np.zeros((n, n)), np.zeros(n), np.zeros(n), np.zeros(n)

@@ -1,7 +1,7 @@
-"""GPU cases written after this round's GPU budget was used up: they have NOT run on hardware yet.  They are marked
-xfail(strict=False) so that a surprise cannot turn the verified suite red; an XPASS in the report means they pass on
-the box, and the mark goes away next round (tests/test_gpu_legacy_hooks.py went through the same step and was
-promoted after its B200 run).  The file sorts last on purpose.  CPU side of the same cases: tests/test_calc_properties.py."""
+"""GPU replays of reference known answers that need calc.Properties on the device: the hybrid "flexible" SrTiO3 energy
+(test_properties_legacy_SrTiO3.py:72-85), the cell-shape invariance set of test_check_neighbors.py:39-75 and the skewed
+BiGd2 neighbour list.  First run on a B200 in round 1 (XPASS under a non-strict xfail mark); the mark is gone now.
+CPU side of the same cases: tests/test_calc_properties.py."""
 
 import numpy as np
 import pytest
@@ -10,8 +10,7 @@ from pypolymlp_b200 import calc
 from test_calc_properties import FLEX, FLEX_ENERGY, SRTIO3_ELEMENTS
 from test_legacy_io import load_legacy_golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def test_hybrid_flexible_published_energy_gpu():

@@ -92,6 +92,25 @@ def test_fused_products_bitwise_deterministic():
     assert np.array_equal(r1["xtx"], r2["xtx"]) and np.array_equal(r1["xty"], r2["xty"])
 
 
+def test_device_ridge_solve_bitwise_reproducible():
+    """Accumulate + cuSOLVER ridge solve twice: identical scales, coefficients and RMSE (the accumulator is deterministic,
+    so is everything downstream of it)."""
+    from pypolymlp_b200 import fit
+    from test_gpu_parity import _si_datasets
+
+    pd = make_params_dict(**cases.si_model_kwargs())
+    train_ids, _ = cases.split_ids_train_test(200, 0.9)
+    train = _si_datasets(train_ids[:40])
+    alphas = [1e-3, 1e-1, 10.0]
+    out = []
+    for _ in range(2):
+        acc = PotentialXtX(pd)
+        fit.accumulate_datasets(acc, [train], fit.get_min_energy([train]))
+        out.append(acc.solve_ridge(alphas, len(train.energies)))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_syrk_v2_matches_v1(monkeypatch):
     """Triangle-only diagonal tiles + parked partial tiles == the first stream-K kernel (full diagonal tiles, RED.F64)
     within rounding; X^T X stays exactly symmetric after packing."""
@@ -134,3 +153,176 @@ def test_zero_atom_structures_features_x_and_fit():
     assert res["total_n_data"] == 14
     assert res["y_sq_norm"] == pytest.approx(float(y @ y), rel=1e-15)
     assert not res["xtx"].any() and not res["xty"].any()
+
+
+def test_compiled_dropin_potential_xtx_reference_goldens():
+    """The compiled pybind11 module's PotentialXtX (what dropin.install_fused_products() hands the reference's
+    calc_xtx_xty) on config 1, the reference's bundled Si set: the reference's own goldens xty[56], scales[56],
+    total_n_data = 35820 (tests/test_mlp_dev/test_core_data.py:39-57) and the RMSE goldens of
+    tests/test_mlp_dev_api/test_mlp_devel_phono3py.py:22-27; bit-identical to the ctypes mirror (same C ABI underneath).
+    The weights / targets follow the reference's apply_weights rules (fit.py restates them; tests/test_dropin_fused_fit.py
+    runs the reference's own Python around the same call on the CPU box, where /root/reference exists)."""
+    from pypolymlp_b200 import dropin, fit
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+    from test_gpu_parity import _si_datasets
+
+    ext = dropin.load_extension()
+    pd = make_params_dict(**cases.si_model_kwargs())
+    train_ids, test_ids = cases.split_ids_train_test(200, 0.9)
+    train, test = _si_datasets(train_ids), _si_datasets(test_ids)
+    min_e = fit.get_min_energy([train])
+    acc = ext.PotentialXtX(pd)
+    assert acc.n_devices() == 1
+    fit.accumulate_datasets(acc, [train], min_e, batch_size=50)
+    res = acc.finalize()
+    ref = PotentialXtX(pd)
+    fit.accumulate_datasets(ref, [train], min_e, batch_size=50)
+    res_ct = ref.finalize()
+    for key in ("xtx", "xty", "xe_sum", "xe_sq_sum"):
+        assert np.array_equal(np.asarray(res[key]), res_ct[key]), key
+    data_xy = fit.finalize_xtx_xty({k: np.asarray(v) if not np.isscalar(v) else v for k, v in res.items()}, [train],
+                                   min_energy=min_e)
+    assert data_xy.total_n_data == 35820
+    assert data_xy.xty[56] == pytest.approx(6.899130774433e5, rel=1e-6)
+    assert data_xy.scales[56] == pytest.approx(0.0032488632685359524)
+    assert min_e == pytest.approx(-5.737324395625)
+    alphas = [10.0 ** a for a in np.linspace(-1, 1, 3)]
+    coefs_array = fit.solver_ridge(data_xy.xtx, data_xy.xty, alphas)
+    acc_t = ext.PotentialXtX(pd)
+    fit.accumulate_datasets(acc_t, [test], min_e, batch_size=50)
+    res_t = acc_t.finalize()
+    test_xy = fit.finalize_xtx_xty({k_: np.asarray(v) if not np.isscalar(v) else v for k_, v in res_t.items()}, [test],
+                                   scales=data_xy.scales, min_energy=min_e)
+    k = int(np.argmin(fit.compute_rmse(coefs_array, test_xy)))   # model selection on the test set, as standard/fit.py:12-63
+    prop = PotentialPropertiesFast(pd, coefs_array[:, k] / data_xy.scales)
+    for ds, e_gold, f_gold in ((train, 1.925e-6, 9.113e-4), (test, 2.067e-6, 9.180e-4)):
+        prop.eval_multiple(ds.axis, ds.positions_c, ds.types)
+        e = np.array(prop.get_e_array())
+        f = np.concatenate([np.asarray(a).reshape(-1) for a in prop.get_f_array()])
+        assert np.sqrt(np.mean(np.square((e - ds.energies) / 64))) == pytest.approx(e_gold, rel=1e-2)
+        assert np.sqrt(np.mean(np.square(f - ds.forces))) == pytest.approx(f_gold, rel=1e-2)
+    # get_x() of the compiled PotentialModel is Fortran-ordered like the reference's Eigen view (pybind11_mlp.cpp:20-21)
+    x = ext.PotentialModel(pd, train.axis[:2], train.positions_c[:2], train.types[:2], [2], [True], [64, 64]).get_x()
+    assert x.flags["F_CONTIGUOUS"] and x.shape == (2 + 12 + 384, 168)
+
+
+def _n_devices():
+    import ctypes
+
+    from pypolymlp_b200._capi import lib
+
+    n = ctypes.c_int(0)
+    lib().pm_device_count(ctypes.byref(n))
+    return n.value
+
+
+needs_two_gpus = pytest.mark.skipif("_n_devices() < 2", reason="needs two GPUs (gpurun --gpus 2)")
+
+
+@needs_two_gpus
+def test_multi_gpu_sharded_xtx_equals_single_gpu():
+    """One process, two GPUs (pm_multi_*: one host thread per device, one grouped ncclReduce onto device 0): X^T X, X^T y,
+    xe sums and the row count of 64 structures sharded 2-ways == the same 64 structures on one GPU, 1e-10."""
+    from pypolymlp_b200.libmlpcpp import PotentialXtXMulti
+
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    n = 64
+    axis, pcs, tys = _fcc_batch(n, seed0=4100)
+    rng = np.random.default_rng(21)
+    w = rng.uniform(0.2, 1.0, _rows(n, 256))
+    y = w * rng.normal(size=w.size)
+    one = PotentialXtX(pd, device=0)
+    one.add(axis, pcs, tys, [True] * n, w, y)
+    r1 = one.finalize()
+    two = PotentialXtXMulti(pd, devices=[0, 1])
+    two.add(axis, pcs, tys, [True] * n, w, y)
+    r2 = two.finalize()
+    assert r2["total_n_data"] == r1["total_n_data"] == _rows(n, 256)
+    for key in ("xtx", "xty", "xe_sum", "xe_sq_sum"):
+        assert np.abs(r2[key] - r1[key]).max() < 1e-10 * np.abs(r1[key]).max(), key
+    assert abs(r2["y_sq_norm"] - r1["y_sq_norm"]) < 1e-10 * r1["y_sq_norm"]
+    # second round on the same object: the non-root accumulators were cleared by finalize()
+    two.reset()
+    two.add(axis[:10], pcs[:10], tys[:10], [True] * 10, *_sub_rows(w, y, n, 10))
+    r3 = two.finalize()
+    one.reset()
+    one.add(axis[:10], pcs[:10], tys[:10], [True] * 10, *_sub_rows(w, y, n, 10))
+    r4 = one.finalize()
+    assert np.abs(r3["xtx"] - r4["xtx"]).max() < 1e-10 * np.abs(r4["xtx"]).max()
+    # the compiled drop-in module shards the same way
+    from pypolymlp_b200 import dropin
+
+    mod = dropin.load_extension()
+    acc = mod.PotentialXtX(pd, devices=[0, 1])
+    assert acc.n_devices() == 2
+    acc.add(axis, pcs, tys, [True] * n, w, y)
+    r5 = acc.finalize()
+    assert np.abs(r5["xtx"] - r1["xtx"]).max() < 1e-10 * np.abs(r1["xtx"]).max()
+    assert r5["total_n_data"] == r1["total_n_data"]
+
+
+def _sub_rows(w, y, n_st, k, n_atom=256):
+    """rows of the first k structures of an n_st-structure batch, regrouped into a k-structure PyModel layout"""
+    e = np.arange(k)
+    s = n_st + np.arange(6 * k)
+    f = n_st + 6 * n_st + np.arange(3 * n_atom * k)
+    idx = np.concatenate([e, s, f])
+    return w[idx], y[idx]
+
+
+_RANK_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cases
+from pypolymlp_b200 import fit
+from pypolymlp_b200.libmlpcpp import PotentialXtX
+from pypolymlp_b200.params import make_params_dict
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+acc = PotentialXtX(pd, device=rank)
+assert fit.comm_init_from_env(acc) == (rank, world)
+n = 16
+lo, hi = fit.shard_range(n, rank, world)
+sts = [cases.fcc_supercell(seed=4100 + s) for s in range(lo, hi)]
+rng = np.random.default_rng(100 + rank)
+rows = (hi - lo) * 775
+w = rng.uniform(0.2, 1.0, rows); y = w * rng.normal(size=rows)
+acc.add([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts], [True] * (hi - lo), w, y)
+np.save({out!r} + ".w%d.npy" % rank, np.stack([w, y]))
+acc.reduce(0)
+assert "torch" not in sys.modules
+if rank == 0:
+    r = acc.finalize()
+    np.savez({out!r} + ".npz", **{{k: v for k, v in r.items()}})
+acc.barrier()
+"""
+
+
+@needs_two_gpus
+def test_two_processes_nccl_reduce_inside_library(tmp_path):
+    """One process per GPU (the bench / torchrun layout): file rendezvous of the NCCL id, pm_comm_init_rank, pm_fit_reduce.
+    The reduced X^T X of 2 x 8 structures equals a single-GPU accumulation of the same 16; torch is never imported."""
+    import subprocess
+    import sys
+
+    out = str(tmp_path / "res")
+    script = tmp_path / "rank.py"
+    script.write_text(_RANK_SCRIPT.format(root=cases.HERE + "/..", out=out))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_PORT="29517")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    red = np.load(out + ".npz")
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    one = PotentialXtX(pd, device=0)
+    for rank in range(2):
+        w, y = np.load(out + ".w%d.npy" % rank)
+        sts = [cases.fcc_supercell(seed=4100 + s) for s in range(8 * rank, 8 * rank + 8)]
+        one.add([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts], [True] * 8, w, y)
+    r1 = one.finalize()
+    assert int(red["total_n_data"]) == r1["total_n_data"] == 16 * 775
+    for key in ("xtx", "xty", "xe_sum", "xe_sq_sum"):
+        assert np.abs(red[key] - r1[key]).max() < 1e-10 * np.abs(r1[key]).max(), key

@@ -99,7 +99,8 @@ def test_writer_reader_round_trip_and_yaml_conversion(tmp_path):
         assert meta["elements"] == elements and meta["mass"] == [1.0 + i for i in range(len(elements))]
         assert np.allclose(coeffs, raw / scales, rtol=1e-14, atol=0)
         # legacy -> yaml (io_polymlp.py:120-130): unit scales, same coefficients, same model
-        yml = convert_to_yaml(fn, str(tmp_path / ("polymlp.yaml.%d" % n)))
+        yml = str(tmp_path / ("polymlp.yaml.%d" % n))
+        assert convert_to_yaml(fn, yml) is True
         assert not is_legacy(yml)
         pd3, coeffs3, meta3 = load_mlp(yml)
         assert np.allclose(coeffs3, coeffs, rtol=1e-14, atol=0)
@@ -115,8 +116,7 @@ def test_is_legacy_and_dispatch(tmp_path):
     save_mlp_yaml(pd, np.arange(n, dtype=float), np.ones(n), ["Si"], filename=yml)
     assert not is_legacy(yml)
     assert np.array_equal(load_mlp(yml)[1], load_mlp_yaml(yml)[1])
-    with pytest.raises(ValueError):
-        convert_to_yaml(yml, str(tmp_path / "out.yaml"))
+    assert convert_to_yaml(yml, str(tmp_path / "out.yaml")) is False   # not a legacy file: the reference returns False
     buf = io.StringIO(open(SYNTHETIC).read())
     assert is_legacy(buf) and buf.tell() == 0  # peeks, does not consume
 
@@ -248,3 +248,23 @@ def test_load_mlps_find_mlps_is_hybrid(tmp_path):
     found = find_mlps(str(tmp_path))  # yaml files take precedence over legacy ones
     assert found == [str(tmp_path / "polymlp.yaml.1"), str(tmp_path / "polymlp.yaml.2")]
     assert [len(c) for c in load_mlps(found)[1]] == [5452, 2220]
+
+
+def test_convert_to_yaml_keeps_submodel_flags_and_lists(tmp_path):
+    """a hybrid sub-model (type_full = False, type_indices = [2], the O-only part of the reference's flexible
+    SrTiO3 potential) keeps both flags through legacy -> yaml; a list of files converts to yaml.1, yaml.2, ... in sorted
+    order (io_polymlp.py:120-140)."""
+    pd = make_params_dict(**cases.si_model_kwargs())
+    n = po.Tables(pd).n_variables
+    coeffs = np.linspace(-1.0, 1.0, n)
+    f1, f2 = str(tmp_path / "polymlp.lammps.1"), str(tmp_path / "polymlp.lammps.2")
+    save_mlp_lammps(pd, coeffs, np.ones(n), ["O"], mass=[16.0], filename=f1)
+    save_mlp_lammps(pd, coeffs, np.ones(n), ["O"], mass=[16.0], filename=f2, type_full=False, type_indices=[2])
+    assert load_mlp_lammps(f2)[2]["type_full"] is False and load_mlp_lammps(f2)[2]["type_indices"] == [2]
+    out = str(tmp_path / "conv.yaml")
+    assert convert_to_yaml([f2, f1], out) is True
+    m1, m2 = load_mlp_yaml(out + ".1")[2], load_mlp_yaml(out + ".2")[2]
+    assert m1["type_full"] is True and list(m1["type_indices"]) == [0]
+    assert m2["type_full"] is False and list(m2["type_indices"]) == [2]
+    assert np.allclose(load_mlp_yaml(out + ".2")[1], coeffs, rtol=1e-14, atol=0)
+    assert convert_to_yaml([f1, out + ".1"], str(tmp_path / "x.yaml")) is False
