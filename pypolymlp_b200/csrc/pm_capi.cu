@@ -92,6 +92,11 @@ struct HostChunk {
     int n_st = 0, n_atoms = 0, n_rows = 0, max_trans = 0, max_atoms = 0;
     std::vector<int> atom_off, st_of_atom, types, trans_off, force, erow, srow, frow;
     std::vector<double> x, y, z, trans, w, yv;
+    // device cell list (K1): per-structure parameters, see DevBatch
+    std::vector<int> cl_int, cl_tmap;
+    std::vector<double> cl_ainv;
+    int n_bins = 0, cl_nmax = 1, cl_tmax = 1;
+    bool use_cl = false;
     std::vector<double> we;   // fit: true weights of the energy rows (w[erow] is 1 on the device, see k_xe_reduce)
     std::vector<long> brow_e, brow_s, brow_f;  // rows in the caller's batch layout
 };
@@ -113,10 +118,11 @@ struct pm_context {
     int64_t n_data = 0;
     // chunk device buffers
     DevVec<int> d_atom_off, d_st_of_atom, d_types, d_trans_off, d_force, d_erow, d_srow, d_frow, d_counts, d_seg_off,
-        d_nbr, d_centre, d_rev, d_err;
+        d_nbr, d_centre, d_rev, d_err, d_cl_int, d_cl_tmap, d_bin_start, d_bin_atoms, d_atom_bin, d_atom_img, d_bin_count, d_cl_hkey;
     DevVec<ulonglong2> d_masks;
     DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_cmat, d_e,
         d_f, d_s, d_we;
+    DevVec<double> d_cl_ainv, d_cl_hd;
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
     DevBatch last_batch{};
@@ -572,24 +578,101 @@ static void prepare_chunk(const pm_context* c, const pm_structures* st, const st
     h.n_st = s1 - s0;
     h.atom_off.push_back(0);
     h.trans_off.push_back(0);
+    // lattice translations / cell reduction of every structure: independent, a few host threads for large chunks (the
+    // E/F/S path spends as long here as the GPU needs for the chunk otherwise)
+    const int nst = s1 - s0;
+    std::vector<CellTranslations> cts(nst);
+    std::vector<std::vector<double>> poss(nst);
+    {
+        auto work = [&](int k0, int k1) {
+            for (int k = k0; k < k1; ++k) {
+                const int s = s0 + k, na = st->n_atoms[s];
+                poss[k].assign(st->positions_c + 3 * aoff[s], st->positions_c + 3 * aoff[s] + 3 * (size_t)na);
+                find_translations(st->axis + 9 * (size_t)s, poss[k].data(), na, c->dm.cutoff, cts[k]);
+            }
+        };
+        const int nthr = nst >= 16 ? (int)std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nthr <= 1) {
+            work(0, nst);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; ++t) th.emplace_back(work, (int)((long)nst * t / nthr), (int)((long)nst * (t + 1) / nthr));
+            for (auto& t : th) t.join();
+        }
+    }
+    {
+        const size_t natom = aoff[s1] - aoff[s0];
+        h.x.reserve(natom); h.y.reserve(natom); h.z.reserve(natom); h.types.reserve(natom); h.st_of_atom.reserve(natom);
+    }
     for (int s = s0; s < s1; ++s) {
         const int na = st->n_atoms[s];
-        std::vector<double> pos(st->positions_c + 3 * aoff[s], st->positions_c + 3 * aoff[s] + 3 * (size_t)na);
-        CellTranslations ct;
-        find_translations(st->axis + 9 * (size_t)s, pos.data(), na, c->dm.cutoff, ct);
-        for (int a = 0; a < na; ++a) {
-            h.x.push_back(pos[a]); h.y.push_back(pos[na + a]); h.z.push_back(pos[2 * (size_t)na + a]);
-            h.types.push_back(st->types[aoff[s] + a]);
-            h.st_of_atom.push_back(s - s0);
-        }
+        const std::vector<double>& pos = poss[s - s0];
+        const CellTranslations& ct = cts[s - s0];
+        h.x.insert(h.x.end(), pos.begin(), pos.begin() + na);
+        h.y.insert(h.y.end(), pos.begin() + na, pos.begin() + 2 * (size_t)na);
+        h.z.insert(h.z.end(), pos.begin() + 2 * (size_t)na, pos.end());
+        h.types.insert(h.types.end(), st->types + aoff[s], st->types + aoff[s] + na);
+        h.st_of_atom.insert(h.st_of_atom.end(), na, s - s0);
         h.trans.insert(h.trans.end(), ct.trans.begin(), ct.trans.end());
         h.trans_off.push_back((int)(h.trans.size() / 3));
+        {   // cell-list parameters of the structure: inverse axis, bins of >= r_c / 2 per lattice direction, search range
+            const double* A = ct.axis;
+            const double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+                               A[2] * (A[3] * A[7] - A[4] * A[6]);
+            double inv[9] = {0};
+            bool ok = std::fabs(det) > 1e-300 && na > 0;
+            if (ok) {
+                inv[0] = (A[4] * A[8] - A[5] * A[7]) / det; inv[1] = (A[2] * A[7] - A[1] * A[8]) / det; inv[2] = (A[1] * A[5] - A[2] * A[4]) / det;
+                inv[3] = (A[5] * A[6] - A[3] * A[8]) / det; inv[4] = (A[0] * A[8] - A[2] * A[6]) / det; inv[5] = (A[2] * A[3] - A[0] * A[5]) / det;
+                inv[6] = (A[3] * A[7] - A[4] * A[6]) / det; inv[7] = (A[1] * A[6] - A[0] * A[7]) / det; inv[8] = (A[0] * A[4] - A[1] * A[3]) / det;
+            }
+            const double rc = c->dm.cutoff;
+            int nb[3] = {1, 1, 1}, R[3] = {1, 1, 1};
+            double hgt[3] = {1, 1, 1};
+            for (int d = 0; d < 3 && ok; ++d) {
+                const double nrm = std::sqrt(inv[3 * d] * inv[3 * d] + inv[3 * d + 1] * inv[3 * d + 1] + inv[3 * d + 2] * inv[3 * d + 2]);
+                hgt[d] = 1.0 / nrm;   // spacing of the lattice planes along direction d
+                nb[d] = std::max(1, std::min(1024, (int)std::floor(hgt[d] / (0.5 * rc * (1.0 + 1e-6)))));
+            }
+            while (ok && (long)nb[0] * nb[1] * nb[2] > 8L * na + 64) {   // sparse cells: do not build more bins than atoms
+                const int dmax = nb[0] >= nb[1] && nb[0] >= nb[2] ? 0 : (nb[1] >= nb[2] ? 1 : 2);
+                nb[dmax] = std::max(1, nb[dmax] / 2);
+            }
+            for (int d = 0; d < 3 && ok; ++d) R[d] = (int)std::ceil(rc / (hgt[d] / nb[d]) * (1.0 + 1e-6));
+            const int vals[CL_NI] = {nb[0], nb[1], nb[2], R[0], R[1], R[2], ct.mx[0], ct.mx[1], ct.mx[2], (int)h.cl_tmap.size(),
+                                     h.n_bins, ok ? 1 : 0};
+            h.cl_int.insert(h.cl_int.end(), vals, vals + CL_NI);
+            h.cl_ainv.insert(h.cl_ainv.end(), inv, inv + 9);
+            h.cl_tmap.insert(h.cl_tmap.end(), ct.tmap.begin(), ct.tmap.end());
+            h.n_bins += nb[0] * nb[1] * nb[2];
+        }
         h.max_trans = std::max(h.max_trans, (int)(ct.trans.size() / 3));
         h.atom_off.push_back(h.atom_off.back() + na);
         h.max_atoms = std::max(h.max_atoms, na);
         h.force.push_back(st->force ? (st->force[s] != 0) : 0);
     }
     h.n_atoms = h.atom_off.back();
+    {   // cell list or masked sweep: estimated distance tests of either, and the sort key must fit 31 bits
+        double cost_cl = 0.0, cost_sweep = 0.0;
+        bool ok = getenv("PM_NO_CELL_LIST") == nullptr;
+        for (int k = 0; k < h.n_st; ++k) {
+            const int* ci = &h.cl_int[(size_t)CL_NI * k];
+            const double na = h.atom_off[k + 1] - h.atom_off[k];
+            const double nt_ = h.trans_off[k + 1] - h.trans_off[k];
+            const double bins = (double)ci[0] * ci[1] * ci[2];
+            cost_cl += na * (2.0 * ci[3] + 1) * (2.0 * ci[4] + 1) * (2.0 * ci[5] + 1) * (na / bins + 2.0);
+            cost_sweep += na * na * nt_;
+            ok = ok && (ci[11] != 0 || na == 0);
+        }
+        h.cl_nmax = std::max(1, h.max_atoms);
+        h.cl_tmax = std::max(1, h.max_trans);
+        const double keys = (double)c->dm.n_type * h.cl_nmax * h.cl_tmax;
+        // a cell-list candidate (table lookups, scattered loads, two passes) costs ~20 sweep tests (regular, one pass with
+        // stored hit masks): measured break-even between config 2 (256 atoms x 33 translations: sweep 5.0 vs 5.6 us) and
+        // config 5 (512 atoms x 57: cell list 2.7 vs 3.9 ms per 131072 atoms)
+        h.use_cl = ok && keys < 2.0e9 && 20.0 * cost_cl < cost_sweep;
+        if (const char* e = getenv("PM_CELL_LIST")) h.use_cl = ok && keys < 2.0e9 && atoi(e) != 0;
+    }
     // chunk-local PyModel layout
     int ns_force = 0;
     for (int f : h.force) ns_force += f;
@@ -727,6 +810,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         h2d(c->d_srow, h.srow, s); h2d(c->d_frow, h.frow, s);
         h2d(c->d_x, h.x, s); h2d(c->d_y, h.y, s); h2d(c->d_z, h.z, s); h2d(c->d_trans, h.trans, s);
         h2d(c->d_w, h.w, s); h2d(c->d_yv, h.yv, s); h2d(c->d_we, h.we, s);
+        h2d(c->d_cl_int, h.cl_int, s); h2d(c->d_cl_ainv, h.cl_ainv, s); h2d(c->d_cl_tmap, h.cl_tmap, s);
     }
     DevBatch b{};
     b.n_st = h.n_st; b.n_atoms = h.n_atoms; b.n_pairs = 0; b.n_rows = h.n_rows; b.max_trans = h.max_trans;
@@ -753,9 +837,9 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     const size_t nseg = (size_t)h.n_atoms * nt;
     c->d_counts.ensure(nseg + 1);
     c->d_seg_off.ensure(nseg + 1);
-    c->d_err.ensure(1);
+    c->d_err.ensure(2);
     CK(cudaMemsetAsync(c->d_counts.p + nseg, 0, sizeof(int), s));
-    CK(cudaMemsetAsync(c->d_err.p, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(c->d_err.p, 0, 2 * sizeof(int), s));
     // the count pass keeps its per-(i, j) hit masks (<= 128 translations) so that the fill pass does not repeat the
     // distance sweep; skipped when the table would be large (very ragged or very big cells)
     b.mask_stride = 0; b.masks = nullptr;
@@ -767,10 +851,27 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
             b.masks = c->d_masks.p;
         }
     }
-    launch_neighbor_count(d, b, c->d_counts.p, s);
+    b.use_cl = h.use_cl ? 1 : 0;
+    b.cl_nmax = h.cl_nmax; b.cl_tmax = h.cl_tmax;
+    int* d_maxc = c->d_err.p + 1;   // second int of the error buffer: largest neighbour count of an atom (cell-list fill capacity)
+    if (b.use_cl) {
+        c->d_bin_start.ensure((size_t)h.n_bins + 2); c->d_bin_count.ensure((size_t)h.n_bins + 2);
+        c->d_bin_atoms.ensure(h.n_atoms); c->d_atom_bin.ensure(h.n_atoms); c->d_atom_img.ensure(3 * (size_t)h.n_atoms);
+        b.cl_int = c->d_cl_int.p; b.cl_ainv = c->d_cl_ainv.p; b.cl_tmap = c->d_cl_tmap.p;
+        b.cl_bin_start = c->d_bin_start.p; b.cl_bin_atoms = c->d_bin_atoms.p; b.cl_atom_bin = c->d_atom_bin.p;
+        b.cl_atom_img = c->d_atom_img.p;
+        c->d_cl_hkey.ensure((size_t)h.n_atoms * CL_CAP); c->d_cl_hd.ensure((size_t)h.n_atoms * CL_CAP * 3);
+        b.cl_hkey = c->d_cl_hkey.p; b.cl_hd = c->d_cl_hd.p;
+        b.mask_stride = 0; b.masks = nullptr;
+        launch_cl_bins(d, b, h.n_bins, c->d_bin_count.p, s);
+        launch_neighbor_cl_count(d, b, c->d_counts.p, d_maxc, s);
+    } else {
+        launch_neighbor_count(d, b, c->d_counts.p, s);
+    }
     launch_scan_exclusive(c->d_counts.p, c->d_seg_off.p, (int)(nseg + 1), s);
-    int n_pairs = 0;
+    int n_pairs = 0, max_count = 0;
     CK(cudaMemcpyAsync(&n_pairs, c->d_seg_off.p + nseg, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (b.use_cl) CK(cudaMemcpyAsync(&max_count, d_maxc, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     b.n_pairs = n_pairs;
     b.seg_off = c->d_seg_off.p;
@@ -778,9 +879,10 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     c->d_nbr.ensure(np1); c->d_centre.ensure(np1); c->d_rev.ensure(np1);
     c->d_PB.ensure(pb_doubles(np1, d.pbstride));
     b.nbr = c->d_nbr.p; b.centre = c->d_centre.p; b.rev = c->d_rev.p;
-    launch_neighbor_fill(d, b, c->d_PB.p, s);
+    if (b.use_cl && max_count <= CL_CAP) launch_neighbor_cl_fill(d, b, c->d_PB.p, s);
+    else launch_neighbor_fill(d, b, c->d_PB.p, s);   // (an atom with > CL_CAP neighbours: the sweep's fill orders any count)
     launch_neighbor_rev(d, b, c->d_PB.p, c->d_err.p, s);
-    tm.mark(ST_NEIGH, 5);
+    tm.mark(ST_NEIGH, b.use_cl ? 8 : 5);
     c->last_batch = b;
     c->last_pairs = n_pairs;
     if (mode == MODE_NEIGH) return;
@@ -790,12 +892,16 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     if (mode == MODE_EVAL) any_force = true;
 
     // ---- K2 ------------------------------------------------------------------------------------
-    launch_pair_basis(d, b, c->d_PB.p, s);
-    tm.mark(ST_BASIS, 1);
     c->d_anc.ensure((size_t)h.n_atoms * d.hmax);
     c->d_agg.ensure(any_force ? (size_t)h.n_atoms * d.hmax * 9 : 1);
-    launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s);
-    tm.mark(ST_ANLM, 1);
+    if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s)) {
+        tm.mark(ST_ANLM, 1);   // fused pair basis + a_nlm kernel: its time is booked under "anlm"
+    } else {
+        launch_pair_basis(d, b, c->d_PB.p, s);
+        tm.mark(ST_BASIS, 1);
+        launch_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s);
+        tm.mark(ST_ANLM, 1);
+    }
 
     // ---- K3 ------------------------------------------------------------------------------------
     c->d_dfeat.ensure((size_t)h.n_atoms * d.fl);
@@ -1161,6 +1267,8 @@ void pm_context_destroy(pm_context* c) {
     c->d_force.release(); c->d_erow.release(); c->d_srow.release(); c->d_frow.release(); c->d_counts.release();
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release(); c->d_we.release();
+    c->d_cl_int.release(); c->d_cl_tmap.release(); c->d_bin_start.release(); c->d_bin_atoms.release(); c->d_atom_bin.release();
+    c->d_atom_img.release(); c->d_bin_count.release(); c->d_cl_ainv.release(); c->d_cl_hkey.release(); c->d_cl_hd.release();
     c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_masks.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
     c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_cmat.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
@@ -1233,18 +1341,34 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
     const int F = d.n_variables;
     StageTimer tm(c);
     // The host prepares chunk k+1 (translations, row maps) while the GPU still works on chunk k.
+    const bool dbg = getenv("PM_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    const auto t_start = now();
     const auto chunks = plan_chunks(c, st);
+    if (dbg) fprintf(stderr, "[pm] layout + plan (%zu chunks): %.3f ms\n", chunks.size(), ms_since(t_start));
     HostChunk h_next;
     auto prepare = [&](size_t k, HostChunk& out) {
         prepare_chunk(c, st, aoff, be, bs, bf, chunks[k].first, chunks[k].second, w, y, out);
         if (mode == MODE_EVAL)
             for (auto& f : out.force) f = 1;
     };
-    if (!chunks.empty()) prepare(0, h_next);
+    {
+        const auto t0 = now();
+        if (!chunks.empty()) prepare(0, h_next);
+        if (dbg) fprintf(stderr, "[pm] prepare chunk 0: %.3f ms\n", ms_since(t0));
+    }
     for (size_t ck = 0; ck < chunks.size(); ++ck) {
         const int s0 = chunks[ck].first;
         HostChunk h = std::move(h_next);
+        const auto t_run = now();
         run_chunk(c, h, mode, true, tm);
+        if (dbg) fprintf(stderr, "[pm] chunk %zu (%d structures): run_chunk host %.3f ms\n", ck, h.n_st, ms_since(t_run));
+        // the next chunk is prepared while the device works on this one -- BEFORE the result copies below, which block the
+        // host until the chunk's kernels are done (device -> pageable host memory)
+        const auto t_prep = now();
+        if (ck + 1 < chunks.size()) prepare(ck + 1, h_next);
+        const double prep_ms = ms_since(t_prep);
         if (mode == MODE_X && h.n_atoms == 0) {
             for (int k = 0; k < h.n_st; ++k) {   // no atoms: zero rows, as the reference returns them
                 std::fill_n(x_out + (size_t)h.brow_e[k] * F, (size_t)F, 0.0);
@@ -1276,9 +1400,10 @@ static void process_batch(pm_context* c, const pm_structures* st, const double* 
         } else if (mode == MODE_EVAL) {
             for (int k = 0; k < h.n_st; ++k) { e_out[s0 + k] = 0.0; for (int r = 0; r < 6; ++r) s_out[6 * (size_t)(s0 + k) + r] = 0.0; }
         }
-        if (ck + 1 < chunks.size()) prepare(ck + 1, h_next);
+        const auto t_wait = now();
         if (h.n_atoms > 0) check_device_error(c);
         else CK(cudaStreamSynchronize(c->stream));
+        if (dbg) fprintf(stderr, "[pm] chunk %zu: prepare next %.3f ms, wait for the device %.3f ms\n", ck, prep_ms, ms_since(t_wait));
     }
     join_syrk(c);   // later work on the main stream (reset, finalize, the caller's events) is ordered after K5
 }
@@ -1330,11 +1455,14 @@ int pm_fit_stage(pm_context* c, const pm_structures* st, const double* w, const 
             put(h.x.data(), h.x.size() * 8); put(h.y.data(), h.y.size() * 8); put(h.z.data(), h.z.size() * 8);
             put(h.trans.data(), h.trans.size() * 8); put(h.w.data(), h.w.size() * 8); put(h.yv.data(), h.yv.size() * 8);
             put(h.we.data(), h.we.size() * 8);
+            put(h.cl_int.data(), h.cl_int.size() * 4); put(h.cl_ainv.data(), h.cl_ainv.size() * 8);
+            put(h.cl_tmap.data(), h.cl_tmap.size() * 4);
             c->staged_dev.push_back(dev);
             // keep only the metadata on the host
             HostChunk meta;
             meta.n_st = h.n_st; meta.n_atoms = h.n_atoms; meta.n_rows = h.n_rows; meta.force = h.force;
             meta.max_trans = h.max_trans; meta.max_atoms = h.max_atoms;
+            meta.n_bins = h.n_bins; meta.cl_nmax = h.cl_nmax; meta.cl_tmax = h.cl_tmax; meta.use_cl = h.use_cl;
             c->staged.push_back(std::move(meta));
         }
     });
@@ -1354,12 +1482,13 @@ int pm_fit_accumulate_staged(pm_context* c) {
             auto save = [&](auto& vec) { saved.push_back({vec.p, vec.cap}); };
             save(c->d_atom_off); save(c->d_st_of_atom); save(c->d_types); save(c->d_trans_off); save(c->d_force);
             save(c->d_erow); save(c->d_srow); save(c->d_frow); save(c->d_x); save(c->d_y); save(c->d_z); save(c->d_trans);
-            save(c->d_w); save(c->d_yv); save(c->d_we);
+            save(c->d_w); save(c->d_yv); save(c->d_we); save(c->d_cl_int); save(c->d_cl_ainv); save(c->d_cl_tmap);
             swap_in(c->d_atom_off, dev[0]); swap_in(c->d_st_of_atom, dev[1]); swap_in(c->d_types, dev[2]);
             swap_in(c->d_trans_off, dev[3]); swap_in(c->d_force, dev[4]); swap_in(c->d_erow, dev[5]);
             swap_in(c->d_srow, dev[6]); swap_in(c->d_frow, dev[7]); swap_in(c->d_x, dev[8]); swap_in(c->d_y, dev[9]);
             swap_in(c->d_z, dev[10]); swap_in(c->d_trans, dev[11]); swap_in(c->d_w, dev[12]); swap_in(c->d_yv, dev[13]);
-            swap_in(c->d_we, dev[14]);
+            swap_in(c->d_we, dev[14]); swap_in(c->d_cl_int, dev[15]); swap_in(c->d_cl_ainv, dev[16]);
+            swap_in(c->d_cl_tmap, dev[17]);
             std::exception_ptr ex;
             try {
                 run_chunk(c, c->staged[k], MODE_FIT, false, tm);
@@ -1369,6 +1498,7 @@ int pm_fit_accumulate_staged(pm_context* c) {
             restore(c->d_atom_off); restore(c->d_st_of_atom); restore(c->d_types); restore(c->d_trans_off);
             restore(c->d_force); restore(c->d_erow); restore(c->d_srow); restore(c->d_frow); restore(c->d_x);
             restore(c->d_y); restore(c->d_z); restore(c->d_trans); restore(c->d_w); restore(c->d_yv); restore(c->d_we);
+            restore(c->d_cl_int); restore(c->d_cl_ainv); restore(c->d_cl_tmap);
             if (ex) std::rethrow_exception(ex);
         }
         join_syrk(c);

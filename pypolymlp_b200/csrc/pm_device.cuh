@@ -98,6 +98,8 @@ struct DevModel {
 // pair-basis record items (doubles): dx dy dz 1/r | fn[n_fn] | fn'[n_fn] | Y (re,im)[nh] | Yx | Yy | Yz
 // Storage is blocked: 32 consecutive pairs form a block [item][32], so a warp that writes item k of 32
 // pairs touches 256 contiguous bytes, and the records of consecutive pairs are contiguous per item.
+constexpr int CL_NI = 12;      // ints per structure in DevBatch::cl_int
+constexpr int CL_CAP = 160;    // neighbours of one atom the cell-list fill pass can order (else: masked-sweep fill)
 constexpr int PB_BLK = 32;
 struct PBRec {
     const double* base;
@@ -142,6 +144,19 @@ struct DevBatch {
     const int* frow;        // [n_st] first force row or -1
     const double* w;        // [n_rows]
     const double* yv;       // [n_rows] weighted targets
+    // device cell list (K1, when it prunes): per structure CL_NI ints {nb[3], R[3], mx[3], tmap offset, first bin} and the
+    // inverse axis; per atom its bin and lattice image; bins as CSR over the chunk
+    int use_cl;             // 1: cell-list kernels, 0: masked sweep over (atom, translation)
+    int cl_nmax, cl_tmax;   // key = (type * cl_nmax + local atom) * cl_tmax + translation
+    const int* cl_int;      // [n_st][CL_NI]
+    const double* cl_ainv;  // [n_st][9]
+    const int* cl_tmap;     // translation index of an integer triple or -1
+    int* cl_bin_start;      // [n_bins + 1]
+    int* cl_bin_atoms;      // [n_atoms]
+    int* cl_atom_bin;       // [n_atoms] chunk-global bin
+    int* cl_atom_img;       // [n_atoms][3] floor of the fractional coordinates
+    int* cl_hkey;           // [n_atoms][CL_CAP] hits of the count pass (sort key), reused by the fill pass
+    double* cl_hd;          // [n_atoms][CL_CAP][3] their displacements
     int* seg_off;           // [n_atoms * n_type + 1] pair offsets by (atom, neighbour type)
     int* nbr;               // [n_pairs] neighbour atom (chunk-global index)
     int* centre;            // [n_pairs]

@@ -12,6 +12,7 @@
 // variants of K4a/K4b/K5 live in pm_kernels_mma.cu and are validated against these.
 #include "pm_kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <mutex>
 #include <vector>
@@ -228,6 +229,163 @@ void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cuda
     k_neighbor<true><<<blocks, threads, 0, s>>>(m, b, nullptr, PB, m.cutoff * m.cutoff, tol * tol);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 with a cell list.  The masked sweep above tests every (centre, atom, translation) triple: 2.2 M tests for 13 824
+// neighbours per 256-atom config-2 structure, 15.7 M for a 512-atom config-5 cell.  Here the atoms are binned in
+// fractional space (bin width >= r_c / 2 along every lattice direction), a centre looks at the +-R bins around its own
+// (R = 2 except for very small cells) and every candidate IMAGE is one (atom, integer lattice triple): ~200 candidates
+// per centre.  The decision and the stored displacement use the reference's arithmetic on the reference's own
+// translation vector (triple -> index through the host's lookup table), so the list is bit-identical; the hits are
+// ranked by (neighbour type, j, translation index) to restore the reference order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cl_bin(DevBatch b, int* __restrict__ bin_count) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= b.n_atoms) return;
+    const int s = b.st_of_atom[a];
+    const int* ci = b.cl_int + CL_NI * s;
+    const double* ai = b.cl_ainv + 9 * s;
+    const double x = b.x[a], y = b.y[a], z = b.z[a];
+    int bin = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double f = ai[3 * d] * x + ai[3 * d + 1] * y + ai[3 * d + 2] * z;
+        const double fl_ = floor(f);
+        const int nb = ci[d];
+        const int bd = min(nb - 1, max(0, (int)((f - fl_) * nb)));
+        b.cl_atom_img[3 * a + d] = (int)fl_;
+        bin = bin * nb + bd;
+    }
+    bin += ci[10];
+    b.cl_atom_bin[a] = bin;
+    atomicAdd(bin_count + bin, 1);
+}
+
+__global__ void __launch_bounds__(256) k_cl_fill(DevBatch b, int* __restrict__ cursor) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= b.n_atoms) return;
+    const int bin = b.cl_atom_bin[a];
+    b.cl_bin_atoms[b.cl_bin_start[bin] + atomicAdd(cursor + bin, 1)] = a;
+}
+
+__device__ __forceinline__ int cl_floordiv(int a, int n) { return a >= 0 ? a / n : -((-a + n - 1) / n); }
+
+// Count pass: the search.  Every hit is also parked in the per-atom scratch (key, displacement) so that the fill pass only
+// has to rank the hits (no second search).
+__global__ void __launch_bounds__(256) k_neighbor_cl_count(DevModel m, DevBatch b, int* __restrict__ counts,
+                                                            int* __restrict__ max_count, double cutoff_sq, double tol_sq) {
+    __shared__ int s_nh[8];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wib;
+    if (i >= b.n_atoms) return;
+    const int s = b.st_of_atom[i];
+    const int a0 = b.atom_off[s];
+    const int t0 = b.trans_off[s];
+    const int* ci = b.cl_int + CL_NI * s;
+    const int nb0 = ci[0], nb1 = ci[1], nb2 = ci[2];
+    const int R0 = ci[3], R1 = ci[4], R2 = ci[5];
+    const int mx0 = ci[6], mx1 = ci[7], mx2 = ci[8];
+    const int* tmap = b.cl_tmap + ci[9];
+    const int bin0 = ci[10];
+    const int nt = m.n_type;
+    const double xi = b.x[i], yi = b.y[i], zi = b.z[i];
+    const int ni0 = b.cl_atom_img[3 * i], ni1 = b.cl_atom_img[3 * i + 1], ni2 = b.cl_atom_img[3 * i + 2];
+    int bi = b.cl_atom_bin[i] - bin0;
+    const int b2 = bi % nb2; bi /= nb2;
+    const int b1 = bi % nb1;
+    const int b0 = bi / nb1;
+    if (lane == 0) s_nh[wib] = 0;
+    __syncwarp();
+    int* hkey = b.cl_hkey + (size_t)i * CL_CAP;
+    double* hd = b.cl_hd + (size_t)i * CL_CAP * 3;
+    int cnt[MAXT] = {0, 0, 0, 0};
+    const int s1 = 2 * R1 + 1, s2 = 2 * R2 + 1;
+    const int nsearch = (2 * R0 + 1) * s1 * s2;
+    for (int bidx = lane; bidx < nsearch; bidx += 32) {   // lanes walk the searched bins
+        const int d2 = bidx % s2 - R2, d1 = (bidx / s2) % s1 - R1, d0 = bidx / (s1 * s2) - R0;
+        const int u0 = ni0 * nb0 + b0 + d0, u1 = ni1 * nb1 + b1 + d1, u2 = ni2 * nb2 + b2 + d2;   // unwrapped bin
+        const int q0 = cl_floordiv(u0, nb0), q1 = cl_floordiv(u1, nb1), q2 = cl_floordiv(u2, nb2);
+        const int bin = ((u0 - q0 * nb0) * nb1 + (u1 - q1 * nb1)) * nb2 + (u2 - q2 * nb2) + bin0;
+        for (int k = b.cl_bin_start[bin]; k < b.cl_bin_start[bin + 1]; ++k) {
+            const int j = b.cl_bin_atoms[k];
+            // the image of j in this bin is j shifted by the lattice triple L = q - floor(frac_j)
+            const int L0 = q0 - b.cl_atom_img[3 * j], L1 = q1 - b.cl_atom_img[3 * j + 1], L2 = q2 - b.cl_atom_img[3 * j + 2];
+            if (abs(L0) > mx0 || abs(L1) > mx1 || abs(L2) > mx2) continue;   // not in the reference's translation list
+            const int t = tmap[((L0 + mx0) * (2 * mx1 + 1) + (L1 + mx1)) * (2 * mx2 + 1) + (L2 + mx2)];
+            if (t < 0) continue;
+            const double* tr = b.trans + 3 * (size_t)(t0 + t);
+            const double dx = __dadd_rn(__dsub_rn(b.x[j], xi), tr[0]);
+            const double dy = __dadd_rn(__dsub_rn(b.y[j], yi), tr[1]);
+            const double dz = __dadd_rn(__dsub_rn(b.z[j], zi), tr[2]);
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (!(r2 < cutoff_sq && r2 > tol_sq)) continue;
+            const int u = nt == 1 ? 0 : b.types[j];
+#pragma unroll
+            for (int v = 0; v < MAXT; ++v) cnt[v] += (u == v) ? 1 : 0;
+            const int pos = atomicAdd(&s_nh[wib], 1);
+            if (pos < CL_CAP) {
+                hkey[pos] = (u * b.cl_nmax + (j - a0)) * b.cl_tmax + t;
+                hd[3 * pos] = dx; hd[3 * pos + 1] = dy; hd[3 * pos + 2] = dz;
+            }
+        }
+    }
+    int tot = 0;
+#pragma unroll
+    for (int v = 0; v < MAXT; ++v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt[v] += __shfl_xor_sync(0xffffffffu, cnt[v], d);
+        if (v < nt) { if (lane == 0) counts[i * nt + v] = cnt[v]; tot += cnt[v]; }
+    }
+    if (lane == 0) atomicMax(max_count, tot);
+}
+
+// Fill pass: rank the parked hits of each atom by (neighbour type, j, translation) and write them in that order.
+__global__ void __launch_bounds__(256) k_neighbor_cl_fill(DevModel m, DevBatch b, double* __restrict__ PB) {
+    __shared__ int s_key[8][CL_CAP];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wib;
+    if (i >= b.n_atoms) return;
+    const int nt = m.n_type;
+    const int a0 = b.atom_off[b.st_of_atom[i]];
+    const int nh = min(CL_CAP, b.seg_off[i * nt + nt] - b.seg_off[i * nt]);
+    const int* hkey = b.cl_hkey + (size_t)i * CL_CAP;
+    const double* hd = b.cl_hd + (size_t)i * CL_CAP * 3;
+    for (int hh = lane; hh < nh; hh += 32) s_key[wib][hh] = hkey[hh];
+    __syncwarp();
+    const int per_type = b.cl_nmax * b.cl_tmax;
+    for (int hh = lane; hh < nh; hh += 32) {
+        const int key = s_key[wib][hh];
+        const int u = key / per_type;
+        int rank = 0;
+        for (int o = 0; o < nh; ++o) {
+            const int ko = s_key[wib][o];
+            rank += (ko < key && ko / per_type == u) ? 1 : 0;
+        }
+        const int pos = b.seg_off[i * nt + u] + rank;
+        b.nbr[pos] = a0 + (key - u * per_type) / b.cl_tmax;
+        b.centre[pos] = i;
+        const PBRecW rec = pb_rec_w(PB, pos, m.pbstride);
+        rec[0] = hd[3 * hh]; rec[1] = hd[3 * hh + 1]; rec[2] = hd[3 * hh + 2];
+    }
+}
+
+void launch_cl_bins(const DevModel& m, const DevBatch& b, int n_bins, int* bin_count, cudaStream_t s) {
+    // bin_count: [n_bins + 1] scratch (counts, then fill cursors); b.cl_bin_start receives the exclusive scan
+    cudaMemsetAsync(bin_count, 0, (size_t)(n_bins + 1) * sizeof(int), s);
+    k_cl_bin<<<(b.n_atoms + 255) / 256, 256, 0, s>>>(b, bin_count);
+    launch_scan_exclusive(bin_count, b.cl_bin_start, n_bins + 1, s);
+    cudaMemsetAsync(bin_count, 0, (size_t)(n_bins + 1) * sizeof(int), s);
+    k_cl_fill<<<(b.n_atoms + 255) / 256, 256, 0, s>>>(b, bin_count);
+}
+
+void launch_neighbor_cl_count(const DevModel& m, const DevBatch& b, int* counts, int* max_count, cudaStream_t s) {
+    const double tol = 1e-10;
+    k_neighbor_cl_count<<<(b.n_atoms + 7) / 8, 256, 0, s>>>(m, b, counts, max_count, m.cutoff * m.cutoff, tol * tol);
+}
+
+void launch_neighbor_cl_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
+    k_neighbor_cl_fill<<<(b.n_atoms + 7) / 8, 256, 0, s>>>(m, b, PB);
+}
+
 // reverse pair: (i -> j, D) <-> (j -> i, -D); exact because negation is exact in every step above.
 __global__ void __launch_bounds__(256) k_neighbor_rev(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                        int* __restrict__ errflag) {
@@ -295,17 +453,13 @@ void init_pair_basis_tables() {
     done[dev] = true;
 }
 
-template <int LT>
-__global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= b.n_pairs) return;
-    const PBRecW rec = pb_rec_w(PB, p, m.pbstride);
-    const double dx = rec[0], dy = rec[1], dz = rec[2];
+// One pair-basis record: every item is handed to put(item, value) (k_pair_basis stores it in the blocked global layout,
+// the fused k_pair_anlm also keeps it in its shared-memory tile).
+template <int LT, class Put>
+__device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, double dy, double dz, int tp, Put put) {
     const double r = sqrt(dx * dx + dy * dy + dz * dz);
     const double rinv = 1.0 / r;
-    rec[3] = rinv;
-    const int ti = b.types[b.centre[p]], tj = b.types[b.nbr[p]];
-    const int tp = m.type_pairs[ti * m.n_type + tj];
+    put(3, rinv);
 
     // radial
     const double pi = 3.1415926535897932384626433832795;
@@ -330,8 +484,8 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             fnd = bfd * fc + bf * fcd;
             if (fn < 1e-20) { fn = 0.0; fnd = 0.0; }  // reference skip rule (local.cpp:164)
         }
-        rec[4 + n] = fn;
-        rec[4 + m.n_fn + n] = fnd;
+        put(4 + n, fn);
+        put(4 + m.n_fn + n, fnd);
     }
 
     // angular
@@ -372,20 +526,17 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             }
         }
     }
-    const PBRecW Y = rec + pb_y(m, 0);
-    const PBRecW Yx = rec + pb_y(m, 1);
-    const PBRecW Yy = rec + pb_y(m, 2);
-    const PBRecW Yz = rec + pb_y(m, 3);
+    const int oY = pb_y(m, 0), oYx = pb_y(m, 1), oYy = pb_y(m, 2), oYz = pb_y(m, 3);
     const double hs2 = 0.70710678118654752440;
 #pragma unroll
     for (int l = 0; l <= L; ++l) {
         const int idx = LM2I(l, 0) + l;
-        Y[2 * idx] = pl[LM2I(l, 0)] * hs2; Y[2 * idx + 1] = 0.0;
+        put(oY + 2 * idx, pl[LM2I(l, 0)] * hs2); put(oY + 2 * idx + 1, 0.0);
         double common = 0.0;
         if (l >= 1) common = ql[LM2I(l, 1)] * st * rinv * c_sq0[l];
-        Yx[2 * idx] = common * ct * cp; Yx[2 * idx + 1] = 0.0;
-        Yy[2 * idx] = common * ct * sp; Yy[2 * idx + 1] = 0.0;
-        Yz[2 * idx] = -common * st; Yz[2 * idx + 1] = 0.0;
+        put(oYx + 2 * idx, common * ct * cp); put(oYx + 2 * idx + 1, 0.0);
+        put(oYy + 2 * idx, common * ct * sp); put(oYy + 2 * idx + 1, 0.0);
+        put(oYz + 2 * idx, -common * st); put(oYz + 2 * idx + 1, 0.0);
     }
     double c1 = 1.0, c2 = cp, s1 = 0.0, s2 = -sp;
     const double tc = 2.0 * c2;
@@ -399,7 +550,7 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
         for (int l = mp; l <= L; ++l) {
             const int idx = LM2I(l, -mp) + l;
             const double tmp = sign * pl[LM2I(l, mp)] * hs2;
-            Y[2 * idx] = tmp * cs; Y[2 * idx + 1] = -tmp * sn;
+            put(oY + 2 * idx, tmp * cs); put(oY + 2 * idx + 1, -tmp * sn);
             // common = e^{i m phi} / sqrt(2) / r
             const double cr = cs * hs2 * rinv, ci = sn * hs2 * rinv;
             double dth = mp * ct * ql[LM2I(l, mp)];
@@ -410,13 +561,24 @@ __global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, doub
             const double ay = dth * ct * sp, by = dph * cp;
             const double az = -dth * st;
             // (cr + i ci)(a + i b) = (cr a - ci b) + i (cr b + ci a); result = sign * conj(.)
-            Yx[2 * idx] = sign * (cr * ax - ci * bx); Yx[2 * idx + 1] = -sign * (cr * bx + ci * ax);
-            Yy[2 * idx] = sign * (cr * ay - ci * by); Yy[2 * idx + 1] = -sign * (cr * by + ci * ay);
-            Yz[2 * idx] = sign * (cr * az); Yz[2 * idx + 1] = -sign * (ci * az);
+            put(oYx + 2 * idx, sign * (cr * ax - ci * bx)); put(oYx + 2 * idx + 1, -sign * (cr * bx + ci * ax));
+            put(oYy + 2 * idx, sign * (cr * ay - ci * by)); put(oYy + 2 * idx + 1, -sign * (cr * by + ci * ay));
+            put(oYz + 2 * idx, sign * (cr * az)); put(oYz + 2 * idx + 1, -sign * (ci * az));
         }
         sign = -sign;
     }
 #undef LM2I
+}
+
+template <int LT>
+__global__ void __launch_bounds__(128) k_pair_basis(DevModel m, DevBatch b, double* __restrict__ PB) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n_pairs) return;
+    const PBRecW rec = pb_rec_w(PB, p, m.pbstride);
+    const double dx = rec[0], dy = rec[1], dz = rec[2];
+    const int ti = b.types[b.centre[p]], tj = b.types[b.nbr[p]];
+    const int tp = m.type_pairs[ti * m.n_type + tj];
+    pair_basis_items<LT>(m, dx, dy, dz, tp, [&](int item, double v) { rec[item] = v; });
 }
 
 void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s) {
@@ -579,6 +741,127 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
 #pragma unroll
         for (int k = 0; k < 9; ++k) gp[k] = make_double2(gr[k], gi[k]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a + K2b fused (models whose pair record fits a 64-pair shared-memory tile: max_l <= ~6): one CTA per atom.
+// Phase 1: thread = pair, the whole basis record is computed in registers and written BOTH to the global pair-basis
+// buffer (K4a / the eval pair pass read it) and to the CTA's shared-memory tile [item][pair]; phase 2: thread = head,
+// thread-private sums over the tile as in k_anlm_v2.  Compared with the two separate kernels this removes the 16 MB /
+// structure re-read of the records and the ~7800 eight-byte cp.async staging copies per atom that paced k_anlm_v2.
+// ------------------------------------------------------------------------------------------------
+constexpr int PA_PT = 64;          // pairs per tile
+constexpr int PA_LD = PA_PT + 1;   // odd row stride: the head threads read different items of one pair
+
+template <int LT>
+__global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __restrict__ PB,
+                                                    double2* __restrict__ anc, double2* __restrict__ agg) {
+    extern __shared__ __align__(16) double sm_pa[];   // [pbstride][PA_LD]
+    const int i = blockIdx.x;
+    const int t = b.types[i];
+    const DevType& T = m.types[t];
+    const bool force = b.force[b.st_of_atom[i]] != 0 && b.need_agg != 0;
+    const int nt = m.n_type;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int pa = b.seg_off[i * nt], pe = b.seg_off[i * nt + nt];
+    const int oy = pb_y(m, 0), oyx = pb_y(m, 1), oyy = pb_y(m, 2), oyz = pb_y(m, 3);
+    const int h = tid;
+    const bool active = h < T.n_head;
+    int nid = 0, key = 0, ps0 = 0, ps1 = 0;
+    if (active) {
+        const int u = T.head_seg[h];
+        nid = T.head_nid[h];
+        key = T.head_key[h];
+        ps0 = b.seg_off[i * nt + u];
+        ps1 = b.seg_off[i * nt + u + 1];
+    }
+    // Tile by tile (one tile covers <= 64 neighbours, i.e. nearly every atom): the sums are tile-local so that no
+    // accumulator is live across the register-hungry record computation; later tiles add to the stored sums (same
+    // thread, fixed order: deterministic).  An atom without neighbours still stores its zeros.
+    for (int pf = pa; pf < pe || pf == pa; pf += PA_PT) {
+        if (pf > pa) __syncthreads();   // the previous tile has been consumed
+        for (int pp = tid; pp < min(PA_PT, pe - pf); pp += nthr) {
+            const int p = pf + pp;
+            const PBRecW rec = pb_rec_w(PB, p, m.pbstride);
+            const double dx = rec[0], dy = rec[1], dz = rec[2];
+            const int tp = m.type_pairs[t * nt + b.types[b.nbr[p]]];
+            double* col = sm_pa + pp;
+            col[0] = dx; col[PA_LD] = dy; col[2 * PA_LD] = dz;
+            pair_basis_items<LT>(m, dx, dy, dz, tp, [&](int item, double v) {
+                rec[item] = v;
+                col[item * PA_LD] = v;
+            });
+        }
+        __syncthreads();
+        if (!active) continue;
+        double ar = 0.0, ai = 0.0, gr[9], gi[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { gr[k] = 0.0; gi[k] = 0.0; }
+        const int q0 = max(pf, ps0), q1 = min(min(pf + PA_PT, pe), ps1);
+        for (int p = q0; p < q1; ++p) {
+            const double* rb = sm_pa + (p - pf);
+#define REC(item) rb[(item) * PA_LD]
+            const double fn = REC(4 + nid);
+            if (fn == 0.0) continue;   // (a branch-free, unrolled body measured slower: 14.4 vs 13.2 us / structure)
+            const double2 y = make_double2(REC(oy + 2 * key), REC(oy + 2 * key + 1));
+            ar += fn * y.x; ai += fn * y.y;
+            if (force) {
+                const double dx = REC(0), dy = REC(1), dz = REC(2);
+                const double d1 = REC(4 + m.n_fn + nid) * REC(3);
+                const double d1r = d1 * y.x, d1i = d1 * y.y;
+                const double2 yx = make_double2(REC(oyx + 2 * key), REC(oyx + 2 * key + 1));
+                const double2 yy = make_double2(REC(oyy + 2 * key), REC(oyy + 2 * key + 1));
+                const double2 yz = make_double2(REC(oyz + 2 * key), REC(oyz + 2 * key + 1));
+                const double vxr = d1r * dx + fn * yx.x, vxi = d1i * dx + fn * yx.y;
+                const double vyr = d1r * dy + fn * yy.x, vyi = d1i * dy + fn * yy.y;
+                const double vzr = d1r * dz + fn * yz.x, vzi = d1i * dz + fn * yz.y;
+                gr[0] += vxr; gi[0] += vxi; gr[1] += vyr; gi[1] += vyi; gr[2] += vzr; gi[2] += vzi;
+                gr[3] -= vxr * dx; gi[3] -= vxi * dx;
+                gr[4] -= vyr * dy; gi[4] -= vyi * dy;
+                gr[5] -= vzr * dz; gi[5] -= vzi * dz;
+                gr[6] -= vxr * dy; gi[6] -= vxi * dy;
+                gr[7] -= vyr * dz; gi[7] -= vyi * dz;
+                gr[8] -= vzr * dx; gi[8] -= vzi * dx;
+            }
+#undef REC
+        }
+        double2* ap = anc + (size_t)i * m.hmax + h;
+        double2* gp = agg + ((size_t)i * m.hmax + h) * 9;
+        if (pf == pa) {
+            *ap = make_double2(ar, ai);
+            if (force) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gp[k] = make_double2(gr[k], gi[k]);
+            }
+        } else {
+            const double2 o = *ap;
+            *ap = make_double2(o.x + ar, o.y + ai);
+            if (force) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { const double2 g0 = gp[k]; gp[k] = make_double2(g0.x + gr[k], g0.y + gi[k]); }
+            }
+        }
+    }
+}
+
+// true if the fused kernel served the model (then neither launch_pair_basis nor launch_anlm must be called)
+bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s) {
+    if (b.n_atoms == 0) return true;
+    const bool off = getenv("PM_K2_SPLIT") != nullptr;   // A/B switch: the two separate kernels
+    const int threads = std::max(64, (m.hmax + 31) / 32 * 32);
+    const size_t smem = (size_t)m.pbstride * PA_LD * sizeof(double);
+    if (off || threads > 256 || smem > 100 * 1024 || m.maxl > 6) return false;
+    init_pair_basis_tables();
+#define PM_PA_CASE(L_)                                                                 \
+    case L_:                                                                           \
+        ensure_smem((const void*)k_pair_anlm<L_>, smem);                               \
+        k_pair_anlm<L_><<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);          \
+        break;
+    switch (m.maxl) {
+        PM_PA_CASE(0) PM_PA_CASE(1) PM_PA_CASE(2) PM_PA_CASE(3) PM_PA_CASE(4) PM_PA_CASE(5) PM_PA_CASE(6)
+    }
+#undef PM_PA_CASE
+    return true;
 }
 
 void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s,
@@ -1296,11 +1579,23 @@ __global__ void __launch_bounds__(128) k_eval_pairs(DevModel m, DevBatch b, cons
 // Cartesian components are accumulated together.  Virial sums are reduced over the warp before the atomics.
 constexpr int EV_MAXFN = 16;
 
+constexpr int EP_NC = 6;   // centre atoms whose head adjoints a CTA of k_eval_pairs_v2 keeps in shared memory
+
+// The head adjoints Ah of the centres this CTA's 128 consecutive pairs belong to (2-4 centres at ~54 neighbours each) are
+// staged in shared memory first: ncu showed 72 % long-scoreboard stalls on the 300 dependent-latency global loads of
+// Ah per thread; a pair whose centre lies beyond the staged window reads global memory as before.
 __global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                         const double* __restrict__ Ah, int ah_stride,
-                                                        double* __restrict__ forces, double* __restrict__ stresses) {
+                                                        double* __restrict__ forces, double* __restrict__ stresses, int nc_max) {
+    extern __shared__ __align__(16) double s_ah[];   // [nc_max][ah_stride]
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = p < b.n_pairs;
+    const int c_first = b.centre[min(blockIdx.x * blockDim.x, b.n_pairs - 1)];
+    const int c_last = b.centre[min(blockIdx.x * blockDim.x + (int)blockDim.x - 1, b.n_pairs - 1)];
+    const int n_stage = min(nc_max, c_last - c_first + 1);
+    for (int e = threadIdx.x; e < n_stage * ah_stride; e += blockDim.x)
+        s_ah[e] = Ah[(size_t)c_first * ah_stride + e];
+    __syncthreads();
     double g[3] = {0.0, 0.0, 0.0};
     double dl[3] = {0.0, 0.0, 0.0};
     int i = 0, j = 0, s = -1;
@@ -1311,7 +1606,7 @@ __global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, c
         const DevType& T = m.types[b.types[i]];
         const int u = b.types[j];
         const int segstride = ah_stride / m.n_type;
-        const double* ah = Ah + (size_t)i * ah_stride + u * segstride;
+        const double* ah = (i - c_first < n_stage ? s_ah + (size_t)(i - c_first) * ah_stride : Ah + (size_t)i * ah_stride) + u * segstride;
         const PBRec rec = pb_rec(PB, p, m.pbstride);
         const double rinv = rec[3];
         dl[0] = rec[0]; dl[1] = rec[1]; dl[2] = rec[2];
@@ -1674,7 +1969,14 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
     }
     if (b.n_pairs > 0) {
         if (m.n_fn <= EV_MAXFN)
-            k_eval_pairs_v2<<<(b.n_pairs + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
+            // (a half-pair variant -- each unordered pair once with Ah_i + (-1)^l Ah_j, the reference's trick -- measured
+            // slower, 11.2 vs 8.7 ms per 131072 atoms: the idle lanes of a warp still pull the same 32-byte sectors of the
+            // blocked pair records, and the second adjoint is an extra L2 gather)
+        {
+            const int nc = (int)std::min<size_t>(EP_NC, (48 * 1024) / ((size_t)ah_stride * sizeof(double)));   // 0: adjoints from global
+            k_eval_pairs_v2<<<(b.n_pairs + 127) / 128, 128, (size_t)nc * ah_stride * sizeof(double), s>>>(m, b, ws.PB, ws.Ah, ah_stride,
+                                                                                                    forces, stresses, nc);
+        }
         else
             k_eval_pairs<<<(b.n_pairs * 3 + 127) / 128, 128, 0, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses);
     }

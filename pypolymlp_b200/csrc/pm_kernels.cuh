@@ -34,10 +34,17 @@ void ensure_smem(const void* kernel, size_t smem_bytes, bool max_carveout = fals
 void launch_neighbor_count(const DevModel& m, const DevBatch& b, int* counts, cudaStream_t s);
 void launch_neighbor_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
 void launch_neighbor_rev(const DevModel& m, const DevBatch& b, const double* PB, int* errflag, cudaStream_t s);
+// K1 with a device cell list: bins of >= r_c / 2 in fractional space, +-2 bins searched, every candidate image decided by
+// the same exact arithmetic as the sweep, hits ordered by (neighbour type, j, translation) -> the identical list
+void launch_cl_bins(const DevModel& m, const DevBatch& b, int n_bins, int* bin_count, cudaStream_t s);
+void launch_neighbor_cl_count(const DevModel& m, const DevBatch& b, int* counts, int* max_count, cudaStream_t s);
+void launch_neighbor_cl_fill(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
 // K2: pair basis + order parameters
 void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStream_t s);
 void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s,
                  bool small_footprint = false);
+// K2a + K2b fused for small angular expansions; false -> call launch_pair_basis + launch_anlm instead
+bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s, bool zero_g = true,

@@ -658,13 +658,18 @@ void find_translations(const double* axis9, double* pos, int n_atom, double cuto
         for (int j = -1; j < 2; ++j)
             for (int k = -1; k < 2; ++k) max_len = std::max(max_len, c.dist(i, j, k));
     out.trans.clear();
+    out.tmap.clear();
+    for (int d = 0; d < 3; ++d) out.mx[d] = mx[d];
     for (int i = -mx[0]; i <= mx[0]; ++i)
         for (int j = -mx[1]; j <= mx[1]; ++j)
             for (int k = -mx[2]; k <= mx[2]; ++k) {
                 double v[3];
                 c.cart(i, j, k, v);
                 if (std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) < max_len + cutoff) {
+                    out.tmap.push_back((int)(out.trans.size() / 3));
                     out.trans.push_back(v[0]); out.trans.push_back(v[1]); out.trans.push_back(v[2]);
+                } else {
+                    out.tmap.push_back(-1);
                 }
             }
     for (int i = 0; i < 3; ++i)

@@ -139,6 +139,8 @@ struct CellTranslations {
     double axis[9];                  // row-major 3x3, columns are a, b, c (possibly refined)
     bool refined = false;
     std::vector<double> trans;       // [n_trans][3]
+    int mx[3] = {0, 0, 0};           // the list enumerates integer triples (i, j, k), |i| <= mx[0] ..., in loop order
+    std::vector<int> tmap;           // [(2 mx0 + 1)(2 mx1 + 1)(2 mx2 + 1)] index into trans of a triple, or -1 (filtered out)
 };
 // positions_c (3 x n_atom, row-major) is rewritten in place when the cell is refined.
 void find_translations(const double* axis9, double* positions_c, int n_atom, double cutoff, CellTranslations& out);

@@ -102,6 +102,16 @@ def bcc_supercell(rep=(3, 3, 2), a=3.2, n_type=2, sigma=0.05, seed=5):
     return axis, pc, types
 
 
+def cfg4_small_cell():
+    """16-atom ternary bcc cell for the config-4 model goldens (all three centre types, all six type pairs)."""
+    return bcc_supercell(rep=(2, 2, 2), a=3.2, n_type=3, seed=8)
+
+
+def projection_matrix(n_features, n_proj=16, seed=4):
+    """Seeded Gaussian matrix for the projected-row goldens of models whose rows are too wide to store in full."""
+    return np.random.default_rng(seed).normal(size=(n_features, n_proj))
+
+
 def load_si_dataset():
     """The reference's bundled Si-64 phono3py training set (tests/files/phonopy_training_dataset.yaml.xz),
     stored as arrays by tests/golden/make_golden.py."""

@@ -206,6 +206,68 @@ def test_compiled_dropin_potential_xtx_reference_goldens():
     assert x.flags["F_CONTIGUOUS"] and x.shape == (2 + 12 + 384, 168)
 
 
+G2 = np.load(os.path.join(cases.GOLDEN, "ref_vectors_r02.npz"))
+
+
+@pytest.mark.parametrize("mrt", ["", "8", "9", "12", "16"])
+def test_x_config4_ternary_order4_vs_reference(mrt, monkeypatch):
+    """BASELINE config 4 model (ternary, F = 45090, three neighbour-type segments per centre, six type pairs) through the
+    large-model kernels -- every k_lrows_big row-tile variant -- against the reference (oracle/_ref) goldens: the
+    energy row column by column, every stress / force row through 16 seeded projections of the column-scaled row."""
+    if mrt:
+        monkeypatch.setenv("PM_LROWS_MRT", mrt)
+    pd = make_params_dict(**cases.cfg4_model_kwargs())
+    ax, pc, ty = cases.cfg4_small_cell()
+    assert np.array_equal(ty, G2["cfg4_types"])
+    x = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [16]).get_x()
+    assert x.shape == (1 + 6 + 48, 45090)
+    assert cases.x_rel_err(x[0], G2["cfg4_xe"]) < 1e-10
+    proj = (x / G2["cfg4_colscale"]) @ cases.projection_matrix(45090)
+    # entries of the scaled rows are <= 1 and agree to ~1e-13; a 1e-9 error in any single column moves a projection by ~1e-9
+    assert np.abs(proj - G2["cfg4_proj"]).max() < 2e-10
+    assert np.abs(x.sum(axis=1) - G2["cfg4_rowsum"]).max() < 1e-10 * np.abs(G2["cfg4_rowsum"]).max()
+
+
+def test_eval_config4_model_vs_reference():
+    pd = make_params_dict(**cases.cfg4_model_kwargs())
+    ax, pc, ty = cases.cfg4_small_cell()
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+
+    coeffs = np.random.default_rng(14).normal(size=45090) * 1e-3
+    prop = PotentialPropertiesFast(pd, coeffs)
+    prop.eval(ax, pc, ty, True)
+    assert abs(prop.get_e() - G2["cfg4_e"][0]) < 1e-10 * abs(G2["cfg4_e"][0])
+    assert np.abs(np.asarray(prop.get_f()) - G2["cfg4_f"]).max() < 1e-10 * np.abs(G2["cfg4_f"]).max()
+    assert np.abs(np.asarray(prop.get_s()) - G2["cfg4_s"]).max() < 1e-10 * np.abs(G2["cfg4_s"]).max()
+
+
+def test_eval_config5_shape_vs_reference():
+    """BASELINE config 5 shape: the F = 2030 model on an elongated fcc 4x4x8 cell (512 atoms, sigma 0.03 A; a different
+    translation set from the cubic cells) -- neighbour list checksums and E / F / S against RefEval, alone and inside a
+    batch (eval_multiple) with other cells around it."""
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast, _Context, _Model
+
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    ax, pc, ty = cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777)
+    off, nb, dx, dy, dz = _Context(_Model(pd)).neighbor_full(ax, pc, ty)
+    assert off[-1] == G2["cfg5_nbr_count"][0]
+    assert float(nb.sum()) == G2["cfg5_nbr_checksum"][0]
+    assert np.square(dx).sum() + np.square(dy).sum() + np.square(dz).sum() == pytest.approx(G2["cfg5_nbr_checksum"][1], rel=1e-14)
+    coeffs = np.random.default_rng(12).normal(size=2030) * 1e-3
+    prop = PotentialPropertiesFast(pd, coeffs)
+    prop.eval(ax, pc, ty, True)
+    for e, f, s_ in ((prop.get_e(), prop.get_f(), prop.get_s()),):
+        assert abs(e - G2["cfg5_e"][0]) < 1e-10 * abs(G2["cfg5_e"][0])
+        assert np.abs(np.asarray(f) - G2["cfg5_f"]).max() < 1e-10 * np.abs(G2["cfg5_f"]).max()
+        assert np.abs(np.asarray(s_) - G2["cfg5_s"]).max() < 1e-10 * np.abs(G2["cfg5_s"]).max()
+    other = cases.fcc_supercell(rep=(4, 4, 4), seed=5)
+    prop.eval_multiple([other[0], ax, other[0]], [other[1], pc, other[1]], [other[2], ty, other[2]])
+    assert abs(prop.get_e_array()[1] - G2["cfg5_e"][0]) < 1e-10 * abs(G2["cfg5_e"][0])
+    assert np.abs(np.asarray(prop.get_f_array()[1]) - G2["cfg5_f"]).max() < 1e-10 * np.abs(G2["cfg5_f"]).max()
+    assert np.abs(np.asarray(prop.get_s_array()[1]) - G2["cfg5_s"]).max() < 1e-10 * np.abs(G2["cfg5_s"]).max()
+    assert prop.get_e_array()[0] == pytest.approx(prop.get_e_array()[2], rel=1e-13)   # atomics: order varies
+
+
 def _n_devices():
     import ctypes
 
