@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(NT) k_features_v3(DevModel m, DevBatch b, cons
                                                       int nfull_max, int zero_g, double* __restrict__ dpv) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
     constexpr int NW = (MO + 1) / 2;
-    constexpr int UN = NT > 256 ? 4 : 2;   // table slots in flight per lane (the 512-thread CTAs run alone on their SM)
+    constexpr int UN = NT > 256 ? 4 : 2;   // table slots in flight per lane (4 for the small-model CTAs too: measured no gain)
     const int i0 = blockIdx.x * AT;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;

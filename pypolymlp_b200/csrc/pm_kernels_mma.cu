@@ -365,15 +365,9 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
         const int tile = (int)(cur / nkb);
         const int kb0 = (int)(cur - (long)tile * nkb);
         const int kb1 = (int)min((long)nkb, (long)kb0 + (cur_end - cur));
-        bool diag = tile < ntile;
+        const bool diag = tile < ntile;
         int ti = tile, tj = tile;
-        if (full_diag == 3) {   // A/B switch: the row-major tile order of k_syrk_sk (needs cost_diag == 16)
-            int rem = tile;
-            ti = 0;
-            while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
-            tj = ti + rem;
-            diag = ti == tj;
-        } else if (!diag) {
+        if (!diag) {
             int rem = tile - ntile;
             ti = 0;
             while (rem >= ntile - 1 - ti) { rem -= ntile - 1 - ti; ++ti; }
@@ -381,7 +375,7 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
         }
         // warp tile (64 x 32) inside the 128 x 128 tile; diagonal tiles: (0,3) (0,2) (0,1) (0,0) | (1,0) (1,1) (1,2) (1,3),
         // i.e. 32 | 32 | 26 + 10 | 10 + 26 blocks on the four SM sub-partitions (warps w and w + 4 share one)
-        const bool tri = diag && full_diag != 1 && full_diag != 3;   // full_diag = 1: A/B switch, diagonal tiles computed in full
+        const bool tri = diag && !full_diag;   // full_diag = 1: A/B switch, diagonal tiles computed in full
         const int wm = warp >> 2;
         const int wn = tri ? (warp < 4 ? 3 - warp : warp - 4) : (warp & 3);
         const int off = tri ? 4 * wn - 8 * wm : 12;   // block (a, b) of the warp tile is on or above the diagonal iff b >= a - off
@@ -416,19 +410,7 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
         cp_async_wait<0>();
         const bool whole = kb0 == 0 && kb1 == nkb;
         bool reduce = whole;
-        if (!whole && full_diag == 2) {   // A/B switch: the old RED.F64 fix-up (non-deterministic)
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const int row = ti * SY_BM + wm * 64 + a * 8 + g;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    if (b < a - off) continue;
-                    double* dst = C + (size_t)row * fpad + tj * SY_BM + wn * 32 + b * 8 + 2 * q;
-                    atomicAdd(dst, acc[a][b][0]);
-                    atomicAdd(dst + 1, acc[a][b][1]);
-                }
-            }
-        } else if (!whole) {
+        if (!whole) {
             // park the partial tile: thread-major fragment order, coalesced
             double* ws = part + ((size_t)blockIdx.x * 2 + (kb0 == 0 ? 1 : 0)) * SY_TILE_D + tid;
 #pragma unroll
@@ -514,8 +496,9 @@ void launch_syrk_mma(const double* X, int n_rows, int fpad, double* C, cudaStrea
         const int grid = (int)std::min<long>(n_sm, units);
         if (v2) {
             const char* ec = getenv("PM_SYRK_DIAGCOST");
-            const int full_diag = getenv("PM_SYRK_ROWMAJOR") ? 3 : (getenv("PM_SYRK_FULLDIAG") ? 1 : (getenv("PM_SYRK_ATOMIC") ? 2 : 0));
-            const int cost = ec ? std::max(1, std::min(16, atoi(ec))) : ((full_diag == 1 || full_diag == 3) ? 16 : 10);   // 10/16 measured best (9/16 = DMMA count alone)
+            const int full_diag = getenv("PM_SYRK_FULLDIAG") ? 1 : 0;
+            // cost of a diagonal k-block: 9/16 by DMMA count; 10/16 measured best (sweep 7..13: 127 112 102.8 95.3 96.0 96.8 97.4 us/structure)
+            const int cost = ec ? std::max(1, std::min(16, atoi(ec))) : (full_diag ? 16 : 10);
             // every CTA must own at least one k-block (the fix-up counts the contributors of a tile by CTA index):
             // cost per CTA >= the cost of a full k-block
             const long ctot = (long)cost * ntile * nkb + SY_COST_FULL * (units - (long)ntile * nkb);

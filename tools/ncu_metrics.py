@@ -18,7 +18,10 @@ out = {}
 for arg in sys.argv[2:]:
     name, rest = arg.split("=", 1)
     path, _, note = rest.partition(":")
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):   # a `--page raw --csv` dump made on the GPU box
+        txt = open(path).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     ix = {h: i for i, h in enumerate(hdr)}
