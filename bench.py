@@ -28,6 +28,11 @@ import time
 
 import numpy as np
 
+# the CPU-baseline legs run OpenMP / BLAS thread pools in this process: idle pool threads must sleep, not spin, or they
+# compete with the host side of the GPU legs that follow (measured: 6.4 vs 8.7 M atoms/s on the eval sub-record)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+os.environ.setdefault("GOMP_SPINCOUNT", "0")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
@@ -321,7 +326,7 @@ def eval_subrecord(pd, F, rank, world, local_rank, peak, acc_main, want_cpu, ref
            "e2e": {"h2d_bytes_per_call": int(batch.h2d_bytes), "d2h_bytes_per_call": int(sum(o.nbytes for o in out)),
                    "note": "pm_eval through the C ABI: host arrays in, E/F/S back in host arrays, wall clock"},
            "roofline": {"bound": "fp64", "achieved": atoms_s / world * W_EVAL_FLOP_PER_ATOM * 1e-12, "peak": peak,
-                        "unit": "TFLOP/s", "frac": atoms_s / world * W_EVAL_FLOP_PER_ATOM * 1e-12 / peak,
+                        "unit": "TFLOP/s", "frac": (atoms_s / world * W_EVAL_FLOP_PER_ATOM * 1e-12 / peak) if peak else None,
                         "flops_per_atom": W_EVAL_FLOP_PER_ATOM,
                         "note": "W_eval of SURVEY.md 8(d) for the config-2 model; end-to-end time (host preparation and "
                                 "copies included), so this is a lower bound of the kernels' fraction"}}
@@ -457,6 +462,12 @@ def main():
 
     parity = parity_vs_n1(pd, rank, world, local_rank, comm_src) if world > 1 else None
 
+    # BASELINE config 5 is measured here, before any CPU-baseline leg: the OpenMP / BLAS pools those legs leave behind in
+    # this process slow the host side of pm_eval (8.7 -> 6.4 M atoms/s measured)
+    sub = {}
+    if not args.no_sub:
+        sub["eval"] = eval_subrecord(pd, F, rank, world, local_rank, 0.0, acc, False, None)
+
     # ---- rank 0: roofline of the dominant kernel (SYRK, DMMA): live event pairs around every SYRK launch ----------------
     roofline, cpu, peak = None, None, 0.0
     peak = float(acc.allreduce([ctx.microbench(3, 8192) if rank == 0 else 0.0], "max")[0])   # cuBLAS DGEMM 8192^3 on rank 0
@@ -525,10 +536,18 @@ def main():
                        "sample": "oracle/_ref not built on this box"}
 
     # ---- BASELINE configs 3, 4, 5 (all ranks take part: structures shard, one reduce per step) ---------------------------
-    sub = {}
     if not args.no_sub:
         cpu_sel = os.environ.get("PM_BENCH_CPU", "config3")   # large-model CPU baselines that run by default / on request
-        sub["eval"] = eval_subrecord(pd, F, rank, world, local_rank, peak, acc, want_cpu, ref_mod)
+        ev = sub["eval"]
+        ev["roofline"].update({"peak": peak, "frac": ev["roofline"]["achieved"] / peak})
+        if rank == 0 and want_cpu and ref_mod.available():
+            n_cpu = 32
+            sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + k) for k in range(n_cpu)]
+            rate, threads = cpu_reference_eval_rate(ref_mod.make_params(**cases.cfg2_model_kwargs(4)),
+                                                    np.random.default_rng(12).normal(size=F) * 1e-3, sts)
+            ev["cpu_baseline"] = {"value": rate, "unit": "atoms/s", "cores": threads, "kind": "reference",
+                                  "sample": f"{n_cpu} structures through RefEval with PyPropertiesFast::eval_multiple semantics "
+                                            "(serial structures, OpenMP over atoms)"}
         sub["config3"] = fit_subrecord(
             "config3", cases.cfg3_model_kwargs(), lambda n, s0: make_bcc_batch((6, 6, 3), 2, n, s0),
             int(os.environ.get("PM_BENCH_S3", "24")), rank, world, local_rank, peak, comm_src,
