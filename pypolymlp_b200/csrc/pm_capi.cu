@@ -881,8 +881,10 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     b.nbr = c->d_nbr.p; b.centre = c->d_centre.p; b.rev = c->d_rev.p;
     if (b.use_cl && max_count <= CL_CAP) launch_neighbor_cl_fill(d, b, c->d_PB.p, s);
     else launch_neighbor_fill(d, b, c->d_PB.p, s);   // (an atom with > CL_CAP neighbours: the sweep's fill orders any count)
-    launch_neighbor_rev(d, b, c->d_PB.p, c->d_err.p, s);
-    tm.mark(ST_NEIGH, b.use_cl ? 8 : 5);
+    // reverse-pair index: K4a's target-major rows need it; it is also the symmetry check of the list (error flag).  The
+    // eval kernels use neither (forces are scattered to both atoms of a pair).
+    if (mode != MODE_EVAL) launch_neighbor_rev(d, b, c->d_PB.p, c->d_err.p, s);
+    tm.mark(ST_NEIGH, (b.use_cl ? 8 : 5) - (mode == MODE_EVAL ? 1 : 0));
     c->last_batch = b;
     c->last_pairs = n_pairs;
     if (mode == MODE_NEIGH) return;
@@ -894,7 +896,10 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     // ---- K2 ------------------------------------------------------------------------------------
     c->d_anc.ensure((size_t)h.n_atoms * d.hmax);
     c->d_agg.ensure(any_force ? (size_t)h.n_atoms * d.hmax * 9 : 1);
-    if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s)) {
+    // eval through the fused front end: the pair pass recomputes the basis records, K2 does not store them
+    const bool eval_fused = mode == MODE_EVAL && !c->simple_s && eval_fused_supported(d, c->feat_smem);
+    const bool pairs_rc = eval_fused && eval_pairs_rc_supported(d);
+    if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s, !pairs_rc)) {
         tm.mark(ST_ANLM, 1);   // fused pair basis + a_nlm kernel: its time is booked under "anlm"
     } else {
         launch_pair_basis(d, b, c->d_PB.p, s);
@@ -905,7 +910,6 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
 
     // ---- K3 ------------------------------------------------------------------------------------
     c->d_dfeat.ensure((size_t)h.n_atoms * d.fl);
-    const bool eval_fused = mode == MODE_EVAL && !c->simple_s && eval_fused_supported(d, c->feat_smem);
     c->d_G.ensure(any_force && !eval_fused ? (size_t)h.n_atoms * d.gstride : 1);
     // single-type models: every atom slot of G has the same zero pattern, so the buffer is cleared once per
     // allocation and the kernel only writes the non-zero entries afterwards
@@ -945,6 +949,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         CK(cudaMemsetAsync(c->d_f.p, 0, ((size_t)h.n_atoms * 3 + 1) * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_s.p, 0, (size_t)h.n_st * 6 * sizeof(double), s));
         ws.cmat = c->has_cmat ? c->d_cmat.p : nullptr;
+        ws.pairs_rc = pairs_rc;
         launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s, eval_fused ? c->feat_smem : 0);
         tm.mark(ST_EVAL, 5);
         return;

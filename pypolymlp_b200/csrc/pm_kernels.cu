@@ -11,6 +11,7 @@
 // This file holds the straightforward kernels (one thread per output); the tensor-core (DMMA)
 // variants of K4a/K4b/K5 live in pm_kernels_mma.cu and are validated against these.
 #include "pm_kernels.cuh"
+#include "pm_mma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -453,17 +454,10 @@ void init_pair_basis_tables() {
     done[dev] = true;
 }
 
-// One pair-basis record: every item is handed to put(item, value) (k_pair_basis stores it in the blocked global layout,
-// the fused k_pair_anlm also keeps it in its shared-memory tile).
-template <int LT, class Put>
-__device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, double dy, double dz, int tp, Put put) {
-    const double r = sqrt(dx * dx + dy * dy + dz * dz);
-    const double rinv = 1.0 / r;
-    put(3, rinv);
-
-    // radial
+// Radial part of a pair: cosine cutoff x Gaussians and d/dr, handed to rad(n, f_n, f_n') for n < m.n_fn.
+__device__ __forceinline__ void radial_cutoff(const DevModel& m, double r, double& fc, double& fcd) {
     const double pi = 3.1415926535897932384626433832795;
-    double fc = 0.0, fcd = 0.0;
+    fc = 0.0; fcd = 0.0;
     if (r < m.cutoff) {
         const double v1 = pi / m.cutoff, v2 = v1 * r;
         double sv, cv;
@@ -471,24 +465,40 @@ __device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, d
         fc = 0.5 * (cv + 1.0);
         fcd = -0.5 * v1 * sv;
     }
+}
+
+__device__ __forceinline__ void radial_one(const double* __restrict__ prm, int nfn, int n, double r, double fc, double fcd,
+                                           double& fn, double& fnd) {
+    fn = 0.0; fnd = 0.0;
+    if (n < nfn) {
+        const double beta = prm[2 * n], mu = prm[2 * n + 1];
+        const double d = r - mu;
+        const double bf = exp(-beta * d * d);
+        const double bfd = -2.0 * beta * d * bf;
+        fn = bf * fc;
+        fnd = bfd * fc + bf * fcd;
+        if (fn < 1e-20) { fn = 0.0; fnd = 0.0; }  // reference skip rule (local.cpp:164)
+    }
+}
+
+template <class Rad>
+__device__ __forceinline__ void pair_radial(const DevModel& m, double r, int tp, Rad rad) {
+    double fc, fcd;
+    radial_cutoff(m, r, fc, fcd);
     const int nfn = m.tp_nfn[tp];
     const double* prm = m.tp_params + (size_t)tp * m.n_fn * 2;
     for (int n = 0; n < m.n_fn; ++n) {
-        double fn = 0.0, fnd = 0.0;
-        if (n < nfn) {
-            const double beta = prm[2 * n], mu = prm[2 * n + 1];
-            const double d = r - mu;
-            const double bf = exp(-beta * d * d);
-            const double bfd = -2.0 * beta * d * bf;
-            fn = bf * fc;
-            fnd = bfd * fc + bf * fcd;
-            if (fn < 1e-20) { fn = 0.0; fnd = 0.0; }  // reference skip rule (local.cpp:164)
-        }
-        put(4 + n, fn);
-        put(4 + m.n_fn + n, fnd);
+        double fn, fnd;
+        radial_one(prm, nfn, n, r, fc, fcd, fn, fnd);
+        rad(n, fn, fnd);
     }
+}
 
-    // angular
+// Angular part of a pair: complex Y_lm (m <= 0) and its Cartesian gradient, handed key by key to
+// ang(key, Re Y, Im Y, Re dY/dx, Im dY/dx, Re dY/dy, Im dY/dy, Re dY/dz, Im dY/dz); key = l (l + 1) / 2 + l - |m| is the
+// index of (l, m) in the record.  Order of the calls: m = 0 for every l, then |m| = 1, 2, ... for l >= |m|.
+template <int LT, class Ang>
+__device__ __forceinline__ void pair_angular(const DevModel& m, double dx, double dy, double dz, double r, double rinv, Ang ang) {
     const int L = LT >= 0 ? LT : m.maxl;
     constexpr int NHT = LT >= 0 ? (LT + 1) * (LT + 2) / 2 : MAX_NH;
     // a true division, as the reference does (polymlp_functions_interface.cpp:124 cos_theta = z / r): dz * rinv can be
@@ -526,17 +536,13 @@ __device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, d
             }
         }
     }
-    const int oY = pb_y(m, 0), oYx = pb_y(m, 1), oYy = pb_y(m, 2), oYz = pb_y(m, 3);
     const double hs2 = 0.70710678118654752440;
 #pragma unroll
     for (int l = 0; l <= L; ++l) {
         const int idx = LM2I(l, 0) + l;
-        put(oY + 2 * idx, pl[LM2I(l, 0)] * hs2); put(oY + 2 * idx + 1, 0.0);
         double common = 0.0;
         if (l >= 1) common = ql[LM2I(l, 1)] * st * rinv * c_sq0[l];
-        put(oYx + 2 * idx, common * ct * cp); put(oYx + 2 * idx + 1, 0.0);
-        put(oYy + 2 * idx, common * ct * sp); put(oYy + 2 * idx + 1, 0.0);
-        put(oYz + 2 * idx, -common * st); put(oYz + 2 * idx + 1, 0.0);
+        ang(idx, pl[LM2I(l, 0)] * hs2, 0.0, common * ct * cp, 0.0, common * ct * sp, 0.0, -common * st, 0.0);
     }
     double c1 = 1.0, c2 = cp, s1 = 0.0, s2 = -sp;
     const double tc = 2.0 * c2;
@@ -550,7 +556,6 @@ __device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, d
         for (int l = mp; l <= L; ++l) {
             const int idx = LM2I(l, -mp) + l;
             const double tmp = sign * pl[LM2I(l, mp)] * hs2;
-            put(oY + 2 * idx, tmp * cs); put(oY + 2 * idx + 1, -tmp * sn);
             // common = e^{i m phi} / sqrt(2) / r
             const double cr = cs * hs2 * rinv, ci = sn * hs2 * rinv;
             double dth = mp * ct * ql[LM2I(l, mp)];
@@ -561,13 +566,33 @@ __device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, d
             const double ay = dth * ct * sp, by = dph * cp;
             const double az = -dth * st;
             // (cr + i ci)(a + i b) = (cr a - ci b) + i (cr b + ci a); result = sign * conj(.)
-            put(oYx + 2 * idx, sign * (cr * ax - ci * bx)); put(oYx + 2 * idx + 1, -sign * (cr * bx + ci * ax));
-            put(oYy + 2 * idx, sign * (cr * ay - ci * by)); put(oYy + 2 * idx + 1, -sign * (cr * by + ci * ay));
-            put(oYz + 2 * idx, sign * (cr * az)); put(oYz + 2 * idx + 1, -sign * (ci * az));
+            ang(idx, tmp * cs, -tmp * sn, sign * (cr * ax - ci * bx), -sign * (cr * bx + ci * ax),
+                sign * (cr * ay - ci * by), -sign * (cr * by + ci * ay), sign * (cr * az), -sign * (ci * az));
         }
         sign = -sign;
     }
 #undef LM2I
+}
+
+// One pair-basis record: every item is handed to put(item, value) (k_pair_basis stores it in the blocked global layout,
+// the fused k_pair_anlm also keeps it in its shared-memory tile).
+template <int LT, class Put>
+__device__ __forceinline__ void pair_basis_items(const DevModel& m, double dx, double dy, double dz, int tp, Put put) {
+    const double r = sqrt(dx * dx + dy * dy + dz * dz);
+    const double rinv = 1.0 / r;
+    put(3, rinv);
+    pair_radial(m, r, tp, [&](int n, double fn, double fnd) {
+        put(4 + n, fn);
+        put(4 + m.n_fn + n, fnd);
+    });
+    const int oY = pb_y(m, 0), oYx = pb_y(m, 1), oYy = pb_y(m, 2), oYz = pb_y(m, 3);
+    pair_angular<LT>(m, dx, dy, dz, r, rinv, [&](int idx, double yr, double yi, double xr, double xi, double wr, double wi,
+                                                  double zr, double zi) {
+        put(oY + 2 * idx, yr); put(oY + 2 * idx + 1, yi);
+        put(oYx + 2 * idx, xr); put(oYx + 2 * idx + 1, xi);
+        put(oYy + 2 * idx, wr); put(oYy + 2 * idx + 1, wi);
+        put(oYz + 2 * idx, zr); put(oYz + 2 * idx + 1, zi);
+    });
 }
 
 template <int LT>
@@ -753,7 +778,7 @@ __global__ void __launch_bounds__(256) k_anlm_v2(DevModel m, DevBatch b, const d
 constexpr int PA_PT = 64;          // pairs per tile
 constexpr int PA_LD = PA_PT + 1;   // odd row stride: the head threads read different items of one pair
 
-template <int LT>
+template <int LT, bool STORE>
 __global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __restrict__ PB,
                                                     double2* __restrict__ anc, double2* __restrict__ agg) {
     extern __shared__ __align__(16) double sm_pa[];   // [pbstride][PA_LD]
@@ -788,7 +813,7 @@ __global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __re
             double* col = sm_pa + pp;
             col[0] = dx; col[PA_LD] = dy; col[2 * PA_LD] = dz;
             pair_basis_items<LT>(m, dx, dy, dz, tp, [&](int item, double v) {
-                rec[item] = v;
+                if (STORE) rec[item] = v;   // (the eval pair pass recomputes the record from D: no 1.2 KB / pair store)
                 col[item * PA_LD] = v;
             });
         }
@@ -845,7 +870,8 @@ __global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __re
 }
 
 // true if the fused kernel served the model (then neither launch_pair_basis nor launch_anlm must be called)
-bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s) {
+bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s,
+                      bool store_records) {
     if (b.n_atoms == 0) return true;
     const bool off = getenv("PM_K2_SPLIT") != nullptr;   // A/B switch: the two separate kernels
     const int threads = std::max(64, (m.hmax + 31) / 32 * 32);
@@ -854,8 +880,13 @@ bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2*
     init_pair_basis_tables();
 #define PM_PA_CASE(L_)                                                                 \
     case L_:                                                                           \
-        ensure_smem((const void*)k_pair_anlm<L_>, smem);                               \
-        k_pair_anlm<L_><<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);          \
+        if (store_records) {                                                           \
+            ensure_smem((const void*)k_pair_anlm<L_, true>, smem);                     \
+            k_pair_anlm<L_, true><<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg);  \
+        } else {                                                                       \
+            ensure_smem((const void*)k_pair_anlm<L_, false>, smem);                    \
+            k_pair_anlm<L_, false><<<b.n_atoms, threads, smem, s>>>(m, b, PB, anc, agg); \
+        }                                                                              \
         break;
     switch (m.maxl) {
         PM_PA_CASE(0) PM_PA_CASE(1) PM_PA_CASE(2) PM_PA_CASE(3) PM_PA_CASE(4) PM_PA_CASE(5) PM_PA_CASE(6)
@@ -1672,6 +1703,142 @@ __global__ void __launch_bounds__(128) k_eval_pairs_v2(DevModel m, DevBatch b, c
 }
 
 
+// Pair pass that RECOMPUTES the basis record of its pair from the displacement (3 doubles) instead of reading the 1.2 KB
+// record k_pair_anlm would have stored: per chunk of 41 x 512 atoms that removes a 1.4 GB write and a 1.4 GB read.  Same
+// contraction as k_eval_pairs_v2, key by key as pair_angular produces them.  The head adjoints of the CTA's centres arrive
+// by one TMA bulk copy that overlaps the radial part; when every centre of the CTA is staged (the normal case) they are
+// read with ld.shared at compile-time offsets, otherwise from global memory.  NF = radial functions per segment, padded
+// (absent ones carry f = f' = 0 and point at group 0).  Used when the fused K2 kernel ran without storing
+// (single decision in pm_capi.cu: eval_pairs_rc_supported).
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int LT, int NF>
+__global__ void __launch_bounds__(128, 3) k_eval_pairs_rc(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                           const double* __restrict__ Ah, int ah_stride,
+                                                           double* __restrict__ forces, double* __restrict__ stresses, int nc_max) {
+    extern __shared__ __align__(16) double s_ah[];   // [nc_max][ah_stride] | mbarrier
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = p < b.n_pairs;
+    const int c_first = b.centre[min(blockIdx.x * blockDim.x, b.n_pairs - 1)];
+    const int c_last = b.centre[min(blockIdx.x * blockDim.x + (int)blockDim.x - 1, b.n_pairs - 1)];
+    const bool staged = c_last - c_first + 1 <= nc_max;   // CTA-uniform
+    const unsigned bar = smem_u32(s_ah + (size_t)nc_max * ah_stride);
+    if (staged && threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)((c_last - c_first + 1) * ah_stride * sizeof(double));
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(s_ah), Ah + (size_t)c_first * ah_stride, bytes, bar);
+    }
+    __syncthreads();   // the barrier is initialised before anyone polls it
+    double g[3] = {0.0, 0.0, 0.0};
+    double dl[3] = {0.0, 0.0, 0.0};
+    int i = 0, j = 0, s = -1;
+    if (act) {
+        i = b.centre[p];
+        j = b.nbr[p];
+        s = b.st_of_atom[i];
+        const int ti = b.types[i], u = b.types[j];
+        const DevType& T = m.types[ti];
+        const int segstride = ah_stride / m.n_type;
+        const PBRec rec = pb_rec(PB, p, m.pbstride);
+        dl[0] = rec[0]; dl[1] = rec[1]; dl[2] = rec[2];
+        const double r = sqrt(dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2]);
+        const double rinv = 1.0 / r;
+        const int* snid = T.seg_nid[u];
+        const int* snoff = T.seg_n_off[u];
+        // f_n and f_n' / r of the radial functions of this (centre type, neighbour type) segment, in segment order, and the
+        // element offset of each radial group in the adjoint row
+        double fr[NF], fd[NF];
+        int qo[NF];
+        {
+            double fc, fcd;
+            radial_cutoff(m, r, fc, fcd);
+            const int tp = m.type_pairs[ti * m.n_type + u];
+            const int nfn = m.tp_nfn[tp];
+            const double* prm = m.tp_params + (size_t)tp * m.n_fn * 2;
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                fr[n] = 0.0; fd[n] = 0.0; qo[n] = 0;
+                if (n < m.n_fn) {
+                    const int nid = snid[n];
+                    const int q0 = snoff[n];
+                    if (nid >= 0 && snoff[n + 1] > q0) {
+                        double fnd;
+                        radial_one(prm, nfn, nid, r, fc, fcd, fr[n], fnd);
+                        fd[n] = fnd * rinv;
+                        qo[n] = 2 * q0;
+                    }
+                }
+            }
+        }
+        auto contract = [&](auto load) {
+            pair_angular<LT>(m, dl[0], dl[1], dl[2], r, rinv, [&](int key, double yr, double yi, double xr, double xi,
+                                                                  double wr, double wi, double zr, double zi) {
+                double s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const double2 a = load(n, key);   // every radial group lists all lm keys in order
+                    s1r += fd[n] * a.x; s1i += fd[n] * a.y;
+                    s2r += fr[n] * a.x; s2i += fr[n] * a.y;
+                }
+                // g_alpha += Re-part contraction: (f' Y D_alpha / r + f dY_alpha) . Ah
+                const double t1 = yr * s1r + yi * s1i;
+                g[0] += t1 * dl[0] + xr * s2r + xi * s2i;
+                g[1] += t1 * dl[1] + wr * s2r + wi * s2i;
+                g[2] += t1 * dl[2] + zr * s2r + zi * s2i;
+            });
+        };
+        if (staged) {
+            const unsigned base = smem_u32(s_ah) + (unsigned)(((i - c_first) * ah_stride + u * segstride) * sizeof(double));
+            unsigned qa[NF];
+#pragma unroll
+            for (int n = 0; n < NF; ++n) qa[n] = base + qo[n] * (unsigned)sizeof(double);
+            mbar_wait(bar, 0);
+            contract([&](int n, int key) { return lds_f64x2(qa[n] + 16u * key); });
+        } else {
+            const double* ah = Ah + (size_t)i * ah_stride + u * segstride;
+            contract([&](int n, int key) { return *reinterpret_cast<const double2*>(ah + qo[n] + 2 * key); });
+        }
+#pragma unroll
+        for (int al = 0; al < 3; ++al) {
+            atomicAdd(forces + (size_t)i * 3 + al, g[al]);
+            atomicAdd(forces + (size_t)j * 3 + al, -g[al]);
+        }
+    }
+    // virial: xx yy zz xy yz zx = -g_alpha * D_beta, reduced over the warp when all lanes share the structure
+    double sv[6] = {-g[0] * dl[0], -g[1] * dl[1], -g[2] * dl[2], -g[0] * dl[1], -g[1] * dl[2], -g[2] * dl[0]};
+    const int s0 = __shfl_sync(0xffffffffu, s, 0);
+    const bool uniform = __all_sync(0xffffffffu, s == s0 || s < 0);
+    if (uniform) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], d);
+        }
+        const int sl = __reduce_max_sync(0xffffffffu, s);
+        if ((threadIdx.x & 31) == 0 && sl >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(stresses + (size_t)sl * 6 + k, sv[k]);
+        }
+    } else if (act) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(stresses + (size_t)s * 6 + k, sv[k]);
+    }
+}
+
+static int eval_ah_stride(const DevModel& m);
+bool eval_pairs_rc_supported(const DevModel& m) {
+    // (ah_stride even: the adjoints are read as double2; it is n_type * 2 * maxseg by construction)
+    return getenv("PM_EVAL_STORED_PB") == nullptr && m.maxl <= 6 && m.n_fn <= EV_MAXFN &&
+           (size_t)eval_ah_stride(m) * sizeof(double) + 16 <= 160 * 1024;
+}
+
+
 // Fused eval front end (single launch instead of K3 + k_eval_atom, no G buffer): for AT atoms per CTA
 //   (1) linear invariants d_f from the sliced term tables (as k_features_v3),
 //   (2) E_i and w_f = dE_i/dd_f from the polynomial terms (shared-memory atomics),
@@ -1967,7 +2134,24 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
     } else {
         k_eval_atom<<<b.n_atoms, 256, 0, s>>>(m, b, ws.dfeat, ws.Gbuf, coeffs, ws.Xown, ws.Ah, ah_stride, energies);
     }
-    if (b.n_pairs > 0) {
+    if (b.n_pairs > 0 && ws.pairs_rc) {
+        const int nc = (int)std::max<size_t>(1, std::min<size_t>(EP_NC, (48 * 1024 - 16) / ((size_t)ah_stride * sizeof(double))));
+        const size_t smem = (size_t)nc * ah_stride * sizeof(double) + 16;
+        const int grid = (b.n_pairs + 127) / 128;
+        init_pair_basis_tables();
+#define PM_RC_CASE(L_, NF_)                                                                                           \
+    {                                                                                                                 \
+        ensure_smem((const void*)k_eval_pairs_rc<L_, NF_>, smem);                                                     \
+        k_eval_pairs_rc<L_, NF_><<<grid, 128, smem, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses, nc);         \
+    }
+#define PM_RC_L(L_)                                                                                                   \
+    case L_:                                                                                                          \
+        if (m.n_fn <= 8) PM_RC_CASE(L_, 8) else if (m.n_fn <= 12) PM_RC_CASE(L_, 12) else PM_RC_CASE(L_, 16)          \
+        break;
+        switch (m.maxl) { PM_RC_L(0) PM_RC_L(1) PM_RC_L(2) PM_RC_L(3) PM_RC_L(4) PM_RC_L(5) PM_RC_L(6) }
+#undef PM_RC_L
+#undef PM_RC_CASE
+    } else if (b.n_pairs > 0) {
         if (m.n_fn <= EV_MAXFN)
             // (a half-pair variant -- each unordered pair once with Ah_i + (-1)^l Ah_j, the reference's trick -- measured
             // slower, 11.2 vs 8.7 ms per 131072 atoms: the idle lanes of a warp still pull the same 32-byte sectors of the

@@ -22,6 +22,7 @@ struct Workspace {
     double* Sbuf = nullptr;     // [n_atoms][6][fl]
     double* X = nullptr;        // [n_rows][fpad]
     double* Ah = nullptr;       // [n_atoms][ah_stride] head adjoints (eval)
+    bool pairs_rc = false;      // eval: PB holds only the displacements, the pair pass recomputes the records (k_eval_pairs_rc)
     const double* cmat = nullptr;  // [n_type][64][64] order-2 coefficient matrix over the polynomial variables (eval, max_p = 2) or null
     int* errflag = nullptr;     // device error flag
 };
@@ -44,7 +45,11 @@ void launch_pair_basis(const DevModel& m, const DevBatch& b, double* PB, cudaStr
 void launch_anlm(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, double2* agg, cudaStream_t s,
                  bool small_footprint = false);
 // K2a + K2b fused for small angular expansions; false -> call launch_pair_basis + launch_anlm instead
-bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s);
+bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s,
+                      bool store_records = true);
+// eval: the pair pass recomputes the basis records from the displacements (k_eval_pairs_rc), so the fused K2 kernel need
+// not store them
+bool eval_pairs_rc_supported(const DevModel& m);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s, bool zero_g = true,
