@@ -160,6 +160,12 @@ struct pm_context {
     DevVec<double> d_red;
     double* d_small = nullptr;  // 64 doubles of device scratch for pm_comm_allreduce
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // pm_timer_start / pm_timer_stop
+    // pm_eval on a large batch runs two lanes: this context and a sibling context on the same device (own stream and
+    // chunk buffers) work on the two halves of the batch from two host threads, so that the copies, the host-side chunk
+    // preparation and the K1 round trip of one lane overlap the kernels of the other
+    pm_context* sibling = nullptr;
+    size_t ws_arg = 0;          // workspace_bytes as given to pm_context_create
+    uint64_t coeff_version = 0; // bumped by pm_eval_set_coeffs (the sibling copies the coefficients when it is behind)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1229,7 +1235,7 @@ int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int
         if (device < 0 || device >= ndev) throw std::invalid_argument("device index out of range");
         CK(cudaSetDevice(device));
         auto c = std::make_unique<pm_context>();
-        c->model = m; c->device = device; c->flags = flags;
+        c->model = m; c->device = device; c->flags = flags; c->ws_arg = workspace_bytes;
         c->ws_cap = workspace_bytes ? workspace_bytes : (size_t)12 << 30;   // measured sweet spot on B200 (bigger chunks: less SYRK fix-up; smaller: more host/device overlap)
         if (!workspace_bytes && getenv("PM_WORKSPACE_GB")) c->ws_cap = (size_t)atol(getenv("PM_WORKSPACE_GB")) << 30;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1253,6 +1259,7 @@ int pm_context_create(const pm_model* m, int device, size_t workspace_bytes, int
 
 void pm_context_destroy(pm_context* c) {
     if (!c) return;
+    if (c->sibling) { pm_context_destroy(c->sibling); c->sibling = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -1756,6 +1763,7 @@ int pm_eval_set_coeffs(pm_context* c, const double* coeffs, int n) {
         c->d_coeffs.ensure(n);
         CK(cudaMemcpy(c->d_coeffs.p, coeffs, n * sizeof(double), cudaMemcpyHostToDevice));
         c->has_coeffs = true;
+        ++c->coeff_version;
         // dense order-2 coefficient matrix over the polynomial variables for the fused eval kernel (max_p = 2, <= 64
         // variables, one column per unordered pair): C'[a][b] = C'[b][a] = c_col, diagonal doubled (d E / d d_a)
         const HostModel& hm = c->model->hm;
@@ -1778,11 +1786,72 @@ int pm_eval_set_coeffs(pm_context* c, const double* coeffs, int n) {
     });
 }
 
+// second eval lane: a sibling context on the same device with the same coefficients
+static pm_context* eval_sibling(pm_context* c) {
+    if (!c->sibling) {
+        pm_context* sib = nullptr;
+        if (pm_context_create(c->model, c->device, c->ws_arg, c->flags, &sib) != PM_OK) throw std::runtime_error(pm_last_error());
+        sib->simple_l = c->simple_l; sib->simple_x = c->simple_x; sib->simple_s = c->simple_s; sib->scatter = c->scatter;
+        c->sibling = sib;
+    }
+    pm_context* sib = c->sibling;
+    if (sib->coeff_version != c->coeff_version) {
+        CK(cudaSetDevice(c->device));
+        sib->d_coeffs.ensure(c->dm.n_variables);
+        CK(cudaMemcpy(sib->d_coeffs.p, c->d_coeffs.p, (size_t)c->dm.n_variables * sizeof(double), cudaMemcpyDeviceToDevice));
+        if (c->has_cmat) {
+            const size_t n = (size_t)c->dm.n_type * 4096;
+            sib->d_cmat.ensure(n);
+            CK(cudaMemcpy(sib->d_cmat.p, c->d_cmat.p, n * sizeof(double), cudaMemcpyDeviceToDevice));
+        }
+        sib->has_cmat = c->has_cmat; sib->has_coeffs = true;
+        sib->coeff_version = c->coeff_version;
+    }
+    return sib;
+}
+
 int pm_eval(pm_context* c, const pm_structures* st, double* energies, double* forces, double* stresses) {
     return guarded([&] {
         if (!c || !st || !energies || !forces || !stresses) throw std::invalid_argument("null argument");
         if (!c->has_coeffs) throw std::runtime_error("coefficients are not set");
-        process_batch(c, st, nullptr, nullptr, MODE_EVAL, nullptr, energies, forces, stresses);
+        // two lanes for batches that span several chunks' worth of work (PM_EVAL_LANES=1: one lane)
+        const int lanes = getenv("PM_EVAL_LANES") ? atoi(getenv("PM_EVAL_LANES")) : 2;
+        size_t total = 0;
+        if (st->n_atoms)
+            for (int s = 0; s < st->n_st; ++s) total += (size_t)std::max(st->n_atoms[s], 0);
+        if (lanes < 2 || st->n_st < 2 || total < 16384 || c->profile) {
+            process_batch(c, st, nullptr, nullptr, MODE_EVAL, nullptr, energies, forces, stresses);
+            return;
+        }
+        validate_structures(c, st);
+        pm_context* sib = eval_sibling(c);
+        int k = 1;
+        size_t a0 = (size_t)st->n_atoms[0];
+        while (k < st->n_st - 1 && 2 * a0 < total) a0 += (size_t)st->n_atoms[k++];
+        pm_structures sa = *st, sb = *st;
+        sa.n_st = k;
+        sb.n_st = st->n_st - k;
+        sb.axis = st->axis + 9 * (size_t)k;
+        sb.positions_c = st->positions_c + 3 * a0;
+        sb.types = st->types + a0;
+        sb.n_atoms = st->n_atoms + k;
+        sb.force = st->force ? st->force + k : nullptr;
+        std::exception_ptr err_b;
+        std::thread lane_b([&] {
+            try {
+                process_batch(sib, &sb, nullptr, nullptr, MODE_EVAL, nullptr, energies + k, forces + 3 * a0, stresses + 6 * (size_t)k);
+            } catch (...) { err_b = std::current_exception(); }
+        });
+        std::exception_ptr err_a;
+        try {
+            process_batch(c, &sa, nullptr, nullptr, MODE_EVAL, nullptr, energies, forces, stresses);
+        } catch (...) { err_a = std::current_exception(); }
+        lane_b.join();
+        c->launches += sib->launches;
+        for (int q = 0; q < ST_COUNT; ++q) { c->stage_launches[q] += sib->stage_launches[q]; sib->stage_launches[q] = 0; }
+        sib->launches = 0;
+        if (err_a) std::rethrow_exception(err_a);
+        if (err_b) std::rethrow_exception(err_b);
     });
 }
 

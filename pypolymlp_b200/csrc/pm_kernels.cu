@@ -428,6 +428,8 @@ __constant__ double c_sqd[CT_L * CT_L];        // sqrt((l - m)(l + m + 1))
 
 void init_pair_basis_tables() {
     static bool done[64] = {false};
+    static std::mutex mu;   // (several host threads may start their first chunk at the same time: pm_multi, the eval lanes)
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
