@@ -123,6 +123,7 @@ struct pm_context {
     DevVec<double> d_x, d_y, d_z, d_trans, d_w, d_yv, d_PB, d_dfeat, d_dpv, d_G, d_L, d_Lpv, d_Xown, d_S, d_X, d_Ah, d_coeffs, d_cmat, d_e,
         d_f, d_s, d_we;
     DevVec<double> d_cl_ainv, d_cl_hd;
+    DevVec<double> d_clin;      // [n_type][fl] coefficient of the linear column of each padded feature (eval, with d_cmat)
     DevVec<double2> d_anc, d_agg;
     DevVec<unsigned char> d_scan_tmp;
     DevBatch last_batch{};
@@ -375,6 +376,67 @@ static void build_device_model(pm_context* c) {
             cb[k].pad = 0;
         }
         D.contribs = upload(c, cb);
+        {   // plain tables of the lane = atom eval kernel: packed terms, entries grouped by head
+            const int mo = std::max(T.max_order, 1);
+            bool ok = mo <= 4 && T.n_full < 32768;
+            std::vector<LaItem> lt(T.term_coeff.size());
+            std::vector<int> forder(T.n_feat, 1);
+            for (int f = 0; f < T.n_feat && ok; ++f)
+                for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti) {
+                    const int o = T.term_order[ti];
+                    if (ti > T.term_off[f] && o != forder[f]) ok = false;
+                    forder[f] = o;
+                    unsigned id[4] = {0, 0, 0, 0};
+                    for (int q = 0; q < o && q < 4; ++q) id[q] = (unsigned)T.term_ids[(size_t)ti * mo + q];
+                    lt[ti].coeff = T.term_coeff[ti]; lt[ti].w0 = id[0] | id[1] << 16; lt[ti].w1 = id[2] | id[3] << 16;
+                }
+            // head-major flat item lists: every contribution carries its entry's padded feature id, its id count and a
+            // "last contribution of the entry" flag, so that a warp streams one contiguous list per head
+            const int ne = (int)T.ent_pos_re.size();
+            if (c->dm.fl > 4096) ok = false;
+            std::vector<LaItem> hitems;
+            std::vector<int> hoff{0}, hpos;
+            if (ok) {
+                std::map<int, std::vector<int>> by_head;   // head position key -> entries
+                for (int e = 0; e < ne; ++e) {
+                    const int pos = T.ent_pos_re[e];
+                    const auto& blk = T.blocks[pos / 32];
+                    by_head[(blk.seg << 20) | (4 * blk.kchunk + pos % 4)].push_back(e);
+                }
+                std::vector<std::pair<long, int>> cost;   // (-work, key): most expensive head first
+                for (const auto& kv : by_head) {
+                    long n = 0;
+                    for (int e : kv.second)
+                        for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) n += std::max(T.contribs[q].n_ids, 1) + 1;
+                    cost.push_back({-n, kv.first});
+                }
+                std::sort(cost.begin(), cost.end());
+                for (const auto& ck : cost) {
+                    for (int e : by_head[ck.second]) {
+                        const int pos = T.ent_pos_re[e];
+                        const auto& blk = T.blocks[pos / 32];
+                        const unsigned fpad_id = (unsigned)(blk.tile * 8 + (pos % 32) / 4);
+                        for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) {
+                            const auto& cbq = T.contribs[q];
+                            if (cbq.n_ids > 3) { ok = false; break; }
+                            unsigned id[3] = {0, 0, 0};
+                            for (int z = 0; z < cbq.n_ids; ++z) id[z] = (unsigned)cbq.ids[z];
+                            LaItem it;
+                            it.coeff = cbq.coeff;
+                            it.w0 = id[0] | id[1] << 16 | (cbq.conj ? 0x80000000u : 0u);
+                            it.w1 = id[2] | fpad_id << 15 | (unsigned)cbq.n_ids << 27 | (q + 1 == T.ent_off[e + 1] ? 1u << 30 : 0u);
+                            hitems.push_back(it);
+                        }
+                    }
+                    hoff.push_back((int)hitems.size());
+                    hpos.push_back(ck.second);
+                }
+            }
+            D.la_ok = ok ? 1 : 0;
+            D.n_la_heads = ok ? (int)hpos.size() : 0;
+            D.la_terms = upload(c, lt); D.la_forder = upload(c, forder); D.la_hitems = upload(c, hitems);
+            D.la_hoff = upload(c, hoff); D.la_hpos = upload(c, hpos);
+        }
         {   // sliced tables (k_features_v3)
             const int mo = std::max(T.max_order, 1);
             const int nw = (mo + 1) / 2;
@@ -905,7 +967,9 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     // eval through the fused front end: the pair pass recomputes the basis records, K2 does not store them
     const bool eval_fused = mode == MODE_EVAL && !c->simple_s && eval_fused_supported(d, c->feat_smem);
     const bool pairs_rc = eval_fused && eval_pairs_rc_supported(d);
-    if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s, !pairs_rc)) {
+    if (pairs_rc && launch_anlm_eval(d, b, c->d_PB.p, c->d_anc.p, s)) {
+        tm.mark(ST_ANLM, 1);
+    } else if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s, !pairs_rc)) {
         tm.mark(ST_ANLM, 1);   // fused pair basis + a_nlm kernel: its time is booked under "anlm"
     } else {
         launch_pair_basis(d, b, c->d_PB.p, s);
@@ -955,6 +1019,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         CK(cudaMemsetAsync(c->d_f.p, 0, ((size_t)h.n_atoms * 3 + 1) * sizeof(double), s));
         CK(cudaMemsetAsync(c->d_s.p, 0, (size_t)h.n_st * 6 * sizeof(double), s));
         ws.cmat = c->has_cmat ? c->d_cmat.p : nullptr;
+        ws.clin = c->has_cmat ? c->d_clin.p : nullptr;
         ws.pairs_rc = pairs_rc;
         launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s, eval_fused ? c->feat_smem : 0);
         tm.mark(ST_EVAL, 5);
@@ -1280,7 +1345,7 @@ void pm_context_destroy(pm_context* c) {
     c->d_seg_off.release(); c->d_nbr.release(); c->d_centre.release(); c->d_rev.release(); c->d_err.release();
     c->d_x.release(); c->d_y.release(); c->d_z.release(); c->d_trans.release(); c->d_w.release(); c->d_yv.release(); c->d_we.release();
     c->d_cl_int.release(); c->d_cl_tmap.release(); c->d_bin_start.release(); c->d_bin_atoms.release(); c->d_atom_bin.release();
-    c->d_atom_img.release(); c->d_bin_count.release(); c->d_cl_ainv.release(); c->d_cl_hkey.release(); c->d_cl_hd.release();
+    c->d_atom_img.release(); c->d_bin_count.release(); c->d_cl_ainv.release(); c->d_cl_hkey.release(); c->d_cl_hd.release(); c->d_clin.release();
     c->d_PB.release(); c->d_dfeat.release(); c->d_dpv.release(); c->d_masks.release(); c->d_G.release(); c->d_L.release(); c->d_Xown.release(); c->d_S.release();
     c->d_X.release(); c->d_Lpv.release(); c->d_Ah.release(); c->d_coeffs.release(); c->d_cmat.release(); c->d_e.release(); c->d_f.release(); c->d_s.release();
     c->d_anc.release(); c->d_agg.release(); c->d_scan_tmp.release();
@@ -1781,6 +1846,12 @@ int pm_eval_set_coeffs(pm_context* c, const double* coeffs, int n) {
             }
             c->d_cmat.ensure(cm.size());
             CK(cudaMemcpy(c->d_cmat.p, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
+            std::vector<double> cl((size_t)nt * c->dm.fl, 0.0);
+            for (int t = 0; t < nt; ++t)
+                for (int col = 0; col < c->dm.n_linear; ++col)
+                    if (hm.colterm[t][col].order == 1) cl[(size_t)t * c->dm.fl + hm.colterm[t][col].fp[0]] = coeffs[col];
+            c->d_clin.ensure(cl.size());
+            CK(cudaMemcpy(c->d_clin.p, cl.data(), cl.size() * sizeof(double), cudaMemcpyHostToDevice));
             c->has_cmat = true;
         }
     });
@@ -1803,6 +1874,9 @@ static pm_context* eval_sibling(pm_context* c) {
             const size_t n = (size_t)c->dm.n_type * 4096;
             sib->d_cmat.ensure(n);
             CK(cudaMemcpy(sib->d_cmat.p, c->d_cmat.p, n * sizeof(double), cudaMemcpyDeviceToDevice));
+            const size_t nl = (size_t)c->dm.n_type * c->dm.fl;
+            sib->d_clin.ensure(nl);
+            CK(cudaMemcpy(sib->d_clin.p, c->d_clin.p, nl * sizeof(double), cudaMemcpyDeviceToDevice));
         }
         sib->has_cmat = c->has_cmat; sib->has_coeffs = true;
         sib->coeff_version = c->coeff_version;

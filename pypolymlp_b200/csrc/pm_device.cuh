@@ -18,6 +18,12 @@ struct DevContribution {
     int pad;
 };
 
+// lane = atom eval kernel (k_eval_features_la): one 16-byte item per gtinv term / per contribution, read warp-uniformly
+struct __align__(16) LaItem {
+    double coeff;
+    unsigned w0, w1;   // terms: full ids, 16 bits each (w0 = id0 | id1 << 16, w1 = id2 | id3 << 16); contributions: see la_hitems
+};
+
 struct DevPolyTerm {
     int order;  // 0 = column absent for this centre type
     int fp0, fp1, fp2;
@@ -59,6 +65,14 @@ struct DevType {
     const int2* esl_out;          // [n_esl][32] (pos_re, pos_im) in the atom's G buffer, or (-1, -1)
     const int2* esl_fh;           // [n_esl][32] (padded feature id, segment << 20 | real position inside the segment's
                                   //  head list) of the entry, or (-1, -1): the eval path folds G into the head adjoint
+    // plain (warp-uniform) tables of k_eval_features_la; la_ok = 0: not built (product order > 4, mixed orders, ids >= 32768)
+    int la_ok, n_la_heads;
+    const LaItem* la_terms;       // [n_terms] in the order of term_off
+    const int* la_forder;         // [n_feat] product order of the feature's terms
+    const LaItem* la_hitems;      // contributions grouped by head, then by entry: w1 = id2 | padded feature id << 15 |
+                                  // ids of the contribution << 27 | last contribution of its entry << 30
+    const int* la_hoff;           // [n_la_heads + 1] item range of each head (most expensive head first)
+    const int* la_hpos;           // [n_la_heads] segment << 20 | real position inside the segment's head list
     const double* sl_coeff;       // [n_slots]
     const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;

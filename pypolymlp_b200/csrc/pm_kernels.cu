@@ -871,6 +871,105 @@ __global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2 for evaluation (the pair pass recomputes the records, nothing is stored and no derivative item is needed here): one CTA
+// per AE_AT consecutive atoms.  Phase 1: thread = pair of any of these atoms, f_n and Y_lm only (the compiler drops the
+// gradient arithmetic of pair_angular) into a shared-memory tile [item][pair]; phase 2: thread = (atom, head), private sum
+// over the atom's pairs of the head's neighbour-type segment, in pair order (deterministic).  Against k_pair_anlm (one atom
+// per CTA, a third of the threads busy in phase 1, 1.2 KB stored per pair) this took the eval K2 stage from 0.45 to ... ms
+// per 21 000 atoms.
+// ------------------------------------------------------------------------------------------------
+constexpr int AE_AT = 4;      // atoms per CTA
+constexpr int AE_PT = 256;    // pairs per tile
+constexpr int AE_LD = AE_PT + 1;
+constexpr int AE_NI = 4;      // (atom, head) items per thread: AE_AT * hmax <= AE_NI * 256
+
+template <int LT>
+__global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, const double* __restrict__ PB,
+                                                    double2* __restrict__ anc) {
+    extern __shared__ __align__(16) double sm_ae[];   // [n_fn + 2 nh][AE_LD]
+    const int i0 = blockIdx.x * AE_AT;
+    const int na = min(AE_AT, b.n_atoms - i0);
+    const int nt = m.n_type;
+    const int tid = threadIdx.x;
+    const int pa = b.seg_off[i0 * nt], pe = b.seg_off[(i0 + na) * nt];
+    const int oy = m.n_fn;   // tile rows: f_n (n_fn), then Re / Im Y per key
+    // the (atom, head) items of this thread
+    int it_nid[AE_NI], it_key[AE_NI], it_p0[AE_NI], it_p1[AE_NI];
+    double ar[AE_NI], ai[AE_NI];
+#pragma unroll
+    for (int k = 0; k < AE_NI; ++k) {
+        const int w = tid + k * 256;
+        const int a = w / m.hmax, h = w - a * m.hmax;
+        it_p0[k] = 0; it_p1[k] = 0; it_nid[k] = 0; it_key[k] = 0; ar[k] = 0.0; ai[k] = 0.0;
+        if (a < na) {
+            const int i = i0 + a;
+            const DevType& T = m.types[b.types[i]];
+            if (h < T.n_head) {
+                const int u = T.head_seg[h];
+                it_nid[k] = T.head_nid[h];
+                it_key[k] = T.head_key[h];
+                it_p0[k] = b.seg_off[i * nt + u];
+                it_p1[k] = b.seg_off[i * nt + u + 1];
+            }
+        }
+    }
+    for (int pf = pa; pf < pe; pf += AE_PT) {
+        if (pf > pa) __syncthreads();   // the previous tile has been consumed
+        const int np = min(AE_PT, pe - pf);
+        for (int pp = tid; pp < np; pp += 256) {
+            const int p = pf + pp;
+            const PBRec rec = pb_rec(PB, p, m.pbstride);
+            const double dx = rec[0], dy = rec[1], dz = rec[2];
+            const int tp = m.type_pairs[b.types[b.centre[p]] * nt + b.types[b.nbr[p]]];
+            double* col = sm_ae + pp;
+            const double r = sqrt(dx * dx + dy * dy + dz * dz);
+            const double rinv = 1.0 / r;
+            pair_radial(m, r, tp, [&](int n, double fn, double) { col[n * AE_LD] = fn; });
+            pair_angular<LT>(m, dx, dy, dz, r, rinv, [&](int key, double yr, double yi, double, double, double, double,
+                                                         double, double) {
+                col[(oy + 2 * key) * AE_LD] = yr;
+                col[(oy + 2 * key + 1) * AE_LD] = yi;
+            });
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < AE_NI; ++k) {
+            const int q0 = max(pf, it_p0[k]), q1 = min(pf + np, it_p1[k]);
+            const double* rf = sm_ae + it_nid[k] * AE_LD - pf;
+            const double* ry = sm_ae + (oy + 2 * it_key[k]) * AE_LD - pf;
+            for (int p = q0; p < q1; ++p) {
+                const double fn = rf[p];
+                if (fn == 0.0) continue;
+                ar[k] += fn * ry[p];
+                ai[k] += fn * ry[p + AE_LD];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < AE_NI; ++k) {
+        const int w = tid + k * 256;
+        const int a = w / m.hmax, h = w - a * m.hmax;
+        if (a < na && h < m.types[b.types[i0 + a]].n_head) anc[(size_t)(i0 + a) * m.hmax + h] = make_double2(ar[k], ai[k]);
+    }
+}
+
+bool launch_anlm_eval(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, cudaStream_t s) {
+    if (b.n_atoms == 0) return true;
+    const size_t smem = (size_t)(m.n_fn + 2 * m.nh) * AE_LD * sizeof(double);
+    if (getenv("PM_EVAL_K2_FIT") != nullptr || m.maxl > 6 || AE_AT * m.hmax > AE_NI * 256 || smem > 200 * 1024) return false;
+    init_pair_basis_tables();
+    const int grid = (b.n_atoms + AE_AT - 1) / AE_AT;
+#define PM_AE_CASE(L_)                                                  \
+    case L_:                                                            \
+        ensure_smem((const void*)k_anlm_eval<L_>, smem);                \
+        k_anlm_eval<L_><<<grid, 256, smem, s>>>(m, b, PB, anc);         \
+        break;
+    switch (m.maxl) { PM_AE_CASE(0) PM_AE_CASE(1) PM_AE_CASE(2) PM_AE_CASE(3) PM_AE_CASE(4) PM_AE_CASE(5) PM_AE_CASE(6) }
+#undef PM_AE_CASE
+    return true;
+}
+
 // true if the fused kernel served the model (then neither launch_pair_basis nor launch_anlm must be called)
 bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2* anc, double2* agg, cudaStream_t s,
                       bool store_records) {
@@ -2095,6 +2194,184 @@ __global__ void __launch_bounds__(256) k_eval_features(DevModel m, DevBatch b, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused eval front end, lane = atom: one CTA takes 32 consecutive atoms, lane a of EVERY warp works on atom a, and a warp
+// walks one gtinv term list (stage 1: one feature; stage 3: all entries of one head) whose items it reads warp-uniformly.
+// The a_nlm arrays live in shared memory as [full id][atom], so every gather is one conflict-free 512-byte row (4 wavefronts
+// for 32 useful 16-byte values; the slice kernel above averages ~11 wavefronts for the same 32 values at random addresses,
+// and it re-streams the tables for every 4 atoms instead of every 32).  No shared-memory atomics: a head's adjoint is
+// summed in registers by the one warp that owns the head.  Needs the max_p = 2 coefficient matrix path (cmat / clin),
+// product order <= 4 and (16 n_full + 8 fl + 512) * 32 bytes of shared memory; large batches only (grid = atoms / 32).
+// ------------------------------------------------------------------------------------------------
+constexpr int LA_AT = 32;
+constexpr int LA_NT = 1024;
+constexpr int LA_PF = 4;      // table items a warp keeps in flight
+
+template <int MO>
+__global__ void __launch_bounds__(LA_NT) k_eval_features_la(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                             double* __restrict__ Ah, int ah_stride,
+                                                             double* __restrict__ energies, int nfull_max,
+                                                             const double* __restrict__ cmat, const double* __restrict__ clin) {
+    extern __shared__ double2 la_af[];   // [nfull_max][32] | sdw [fl][32] | sdpv [64][32] | s_e [32] | s_next [2 MAXT]
+    double* sdw = reinterpret_cast<double*>(la_af + (size_t)nfull_max * LA_AT);
+    double* sdpv = sdw + (size_t)m.fl * LA_AT;
+    double* s_e = sdpv + 64 * LA_AT;
+    int* s_next = reinterpret_cast<int*>(s_e + LA_AT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = LA_NT / 32;
+    const int i = blockIdx.x * LA_AT + lane;
+    const bool valid = i < b.n_atoms;
+    const int ty = valid ? b.types[i] : -1;
+    const int segstride = ah_stride / m.n_type;
+    for (int k = warp; k < nfull_max; k += NW) {
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) {
+            const DevType& T = m.types[ty];
+            if (k < T.n_full) {
+                v = anc[(size_t)i * m.hmax + T.full_head[k]];
+                if (T.full_conj[k]) {
+                    const double cc = T.full_cc[k];
+                    v = make_double2(cc * v.x, -cc * v.y);
+                }
+            }
+        }
+        la_af[k * LA_AT + lane] = v;
+    }
+    for (int k = tid; k < m.fl * LA_AT; k += LA_NT) sdw[k] = 0.0;
+    if (tid < LA_AT) s_e[tid] = 0.0;
+    if (tid < 2 * MAXT) s_next[tid] = 0;
+    __syncthreads();
+    // (1) linear invariants: a warp takes the next feature, lane = atom
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        if (!__any_sync(0xffffffffu, ty == tt)) continue;   // (the same answer in every warp: lanes map to the same atoms)
+        const DevType& T = m.types[tt];
+        const LaItem* __restrict__ terms = T.la_terms;
+        for (;;) {
+            int f = 0;
+            if (lane == 0) f = atomicAdd(&s_next[tt], 1);
+            f = __shfl_sync(0xffffffffu, f, 0);
+            if (f >= T.n_feat) break;
+            const int o = T.la_forder[f];
+            const int t0 = T.term_off[f], t1 = T.term_off[f + 1];
+            double sum = 0.0;
+            LaItem buf[LA_PF];
+#pragma unroll
+            for (int k = 0; k < LA_PF; ++k) buf[k] = terms[max(min(t0 + k, t1 - 1), 0)];
+            for (int tb = t0; tb < t1; tb += LA_PF) {   // (a feature without terms: t1 == t0, the clamped loads above read a neighbour's item and nothing is used)
+                LaItem cur[LA_PF];
+#pragma unroll
+                for (int k = 0; k < LA_PF; ++k) { cur[k] = buf[k]; buf[k] = terms[min(tb + LA_PF + k, t1 - 1)]; }
+#pragma unroll
+                for (int k = 0; k < LA_PF; ++k) {
+                    if (tb + k < t1) {
+                        const LaItem it = cur[k];
+                        double2 pr = la_af[(it.w0 & 0xffffu) * LA_AT + lane];
+                        if (MO > 1 && o > 1) pr = cmul(pr, la_af[(it.w0 >> 16) * LA_AT + lane]);
+                        if (MO > 2 && o > 2) pr = cmul(pr, la_af[(it.w1 & 0xffffu) * LA_AT + lane]);
+                        if (MO > 3 && o > 3) pr = cmul(pr, la_af[(it.w1 >> 16) * LA_AT + lane]);
+                        sum += it.coeff * pr.x;
+                    }
+                }
+            }
+            if (ty == tt) sdw[T.feat_pad[f] * LA_AT + lane] = sum;
+        }
+    }
+    __syncthreads();
+    // (2) polynomial (max_p = 2 over <= 64 polynomial variables): E and w = dE/dd, w replaces d in sdw
+    for (int k = tid; k < 64 * LA_AT; k += LA_NT) {
+        const int pv = k >> 5;
+        double v = 0.0;
+        if (valid && pv < m.npv_pad) {
+            const int fp = m.pv_fp[(size_t)ty * m.npv_pad + pv];
+            if (fp >= 0) v = sdw[fp * LA_AT + lane];
+        }
+        sdpv[k] = v;
+    }
+    __syncthreads();
+    double e = 0.0;
+    if (valid)
+        for (int k = tid; k < m.fl * LA_AT; k += LA_NT) {
+            const double cl = clin[(size_t)ty * m.fl + (k >> 5)];
+            e += cl * sdw[k];
+            sdw[k] = cl;
+        }
+    __syncthreads();
+    if (valid)
+        for (int pv = warp; pv < m.npv_pad; pv += NW) {
+            const int fp = m.pv_fp[(size_t)ty * m.npv_pad + pv];
+            if (fp < 0) continue;
+            const double* __restrict__ cm = cmat + (size_t)ty * 4096 + pv;   // column pv = row pv (symmetric)
+            double w2 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < 64; ++q) w2 += cm[q * 64] * sdpv[q * LA_AT + lane];
+            sdw[fp * LA_AT + lane] += w2;
+            e += 0.5 * sdpv[pv * LA_AT + lane] * w2;
+        }
+    atomicAdd(&s_e[lane], e);
+    __syncthreads();
+    if (warp == 0 && valid) atomicAdd(energies + b.st_of_atom[i], s_e[lane]);
+    // (3) head adjoints: a warp takes the next head and sums all its (feature, contribution) entries
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        if (!__any_sync(0xffffffffu, ty == tt)) continue;
+        const DevType& T = m.types[tt];
+        const LaItem* __restrict__ items = T.la_hitems;
+        for (;;) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(&s_next[MAXT + tt], 1);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (j >= T.n_la_heads) break;
+            const int q0 = T.la_hoff[j], q1 = T.la_hoff[j + 1];
+            const int hp = T.la_hpos[j];
+            double accr = 0.0, acci = 0.0, gr = 0.0, gi = 0.0;
+            // the item list is streamed LA_PF items ahead of its use (warp-uniform 16-byte loads, L2 latency)
+            LaItem buf[LA_PF];
+#pragma unroll
+            for (int k = 0; k < LA_PF; ++k) buf[k] = items[max(min(q0 + k, q1 - 1), 0)];
+            for (int qb = q0; qb < q1; qb += LA_PF) {
+                LaItem cur[LA_PF];
+#pragma unroll
+                for (int k = 0; k < LA_PF; ++k) { cur[k] = buf[k]; buf[k] = items[min(qb + LA_PF + k, q1 - 1)]; }
+#pragma unroll
+                for (int k = 0; k < LA_PF; ++k) {
+                    if (qb + k < q1) {
+                        const LaItem it = cur[k];
+                        const int cn = (it.w1 >> 27) & 7;
+                        double2 pr = make_double2(1.0, 0.0);
+                        if (MO > 1 && cn > 0) pr = la_af[(it.w0 & 0xffffu) * LA_AT + lane];
+                        if (MO > 2 && cn > 1) pr = cmul(pr, la_af[((it.w0 >> 16) & 0x7fffu) * LA_AT + lane]);
+                        if (MO > 3 && cn > 2) pr = cmul(pr, la_af[(it.w1 & 0x7fffu) * LA_AT + lane]);
+                        gr += it.coeff * pr.x;
+                        gi += ((it.w0 >> 31) ? -it.coeff : it.coeff) * pr.y;
+                        if (it.w1 & (1u << 30)) {   // last contribution of its (feature, head) entry
+                            const double w = sdw[((it.w1 >> 15) & 0xfffu) * LA_AT + lane];
+                            accr += w * gr;
+                            acci -= w * gi;
+                            gr = 0.0; gi = 0.0;
+                        }
+                    }
+                }
+            }
+            if (ty == tt) {
+                double* ah = Ah + (size_t)i * ah_stride + (hp >> 20) * segstride + (hp & 0xfffff);
+                ah[0] = accr;
+                ah[1] = acci;
+            }
+        }
+    }
+}
+
+static size_t eval_la_smem(const DevModel& m, size_t feat_smem) {
+    return (size_t)LA_AT * (feat_smem + (size_t)m.fl * sizeof(double) + 64 * sizeof(double) + sizeof(double)) + 2 * MAXT * sizeof(int);
+}
+static bool eval_la_supported(const DevModel& m, const DevBatch& b, const Workspace& ws, size_t feat_smem) {
+    if (getenv("PM_EVAL_LA") && atoi(getenv("PM_EVAL_LA")) == 0) return false;
+    const int min_atoms = getenv("PM_EVAL_LA_MIN") ? atoi(getenv("PM_EVAL_LA_MIN")) : 148 * LA_AT * 2;
+    if (!ws.cmat || !ws.clin || m.npv_pad > 64 || b.n_atoms < min_atoms) return false;
+    for (int t = 0; t < m.n_type; ++t)
+        if (!m.types[t].la_ok || m.types[t].max_order > 4) return false;
+    return eval_la_smem(m, feat_smem) <= 227 * 1024;
+}
+
 constexpr int EVF_AT = 4;
 static int eval_ah_stride(const DevModel& m) {
     int maxseg = 0;
@@ -2118,7 +2395,21 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
                          double* energies, double* forces, double* stresses, cudaStream_t s, size_t feat_smem) {
     if (b.n_atoms == 0) return;
     const int ah_stride = eval_ah_stride(m);
-    if (feat_smem > 0) {
+    if (feat_smem > 0 && eval_la_supported(m, b, ws, feat_smem)) {
+        const size_t smem = eval_la_smem(m, feat_smem);
+        const int nfull_max = (int)(feat_smem / sizeof(double2));
+        const int grid = (b.n_atoms + LA_AT - 1) / LA_AT;
+        int mo = 1;
+        for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
+        cudaMemsetAsync(ws.Ah, 0, (size_t)b.n_atoms * ah_stride * sizeof(double), s);   // positions no head entry writes
+#define PM_LA_CASE(MO_)                                                                                               \
+    case MO_:                                                                                                         \
+        ensure_smem((const void*)k_eval_features_la<MO_>, smem);                                                      \
+        k_eval_features_la<MO_><<<grid, LA_NT, smem, s>>>(m, b, ws.anc, ws.Ah, ah_stride, energies, nfull_max, ws.cmat, ws.clin); \
+        break;
+        switch (mo) { PM_LA_CASE(1) PM_LA_CASE(2) PM_LA_CASE(3) PM_LA_CASE(4) }
+#undef PM_LA_CASE
+    } else if (feat_smem > 0) {
         const size_t smem = eval_fused_smem(m, feat_smem);
         const int nfull_max = (int)(feat_smem / sizeof(double2));
         const int grid = (b.n_atoms + EVF_AT - 1) / EVF_AT;
