@@ -396,38 +396,38 @@ static void build_device_model(pm_context* c) {
             if (c->dm.fl > 4096) ok = false;
             std::vector<LaItem> hitems;
             std::vector<int> hoff{0}, hpos;
+            std::map<int, std::vector<LaItem>> head_items;   // head position key -> its contributions, entry by entry
             if (ok) {
-                std::map<int, std::vector<int>> by_head;   // head position key -> entries
-                for (int e = 0; e < ne; ++e) {
+                for (int e = 0; e < ne && ok; ++e) {
                     const int pos = T.ent_pos_re[e];
                     const auto& blk = T.blocks[pos / 32];
-                    by_head[(blk.seg << 20) | (4 * blk.kchunk + pos % 4)].push_back(e);
+                    const unsigned fpad_id = (unsigned)(blk.tile * 8 + (pos % 32) / 4);
+                    auto& dst = head_items[(blk.seg << 20) | (4 * blk.kchunk + pos % 4)];
+                    for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) {
+                        const auto& cbq = T.contribs[q];
+                        if (cbq.n_ids > 3) { ok = false; break; }
+                        unsigned id[3] = {0, 0, 0};
+                        for (int z = 0; z < cbq.n_ids; ++z) id[z] = (unsigned)cbq.ids[z];
+                        LaItem it;
+                        it.coeff = cbq.coeff;
+                        it.w0 = id[0] | id[1] << 16 | (cbq.conj ? 0x80000000u : 0u);
+                        it.w1 = id[2] | fpad_id << 15 | (unsigned)cbq.n_ids << 27 | (q + 1 == T.ent_off[e + 1] ? 1u << 30 : 0u);
+                        dst.push_back(it);
+                    }
                 }
+            }
+            auto item_cost = [](const std::vector<LaItem>& v) {
+                long n = 0;
+                for (const auto& it : v) n += std::max<int>((it.w1 >> 27) & 7, 1) + 1;
+                return n;
+            };
+            if (ok) {
                 std::vector<std::pair<long, int>> cost;   // (-work, key): most expensive head first
-                for (const auto& kv : by_head) {
-                    long n = 0;
-                    for (int e : kv.second)
-                        for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) n += std::max(T.contribs[q].n_ids, 1) + 1;
-                    cost.push_back({-n, kv.first});
-                }
+                for (const auto& kv : head_items) cost.push_back({-item_cost(kv.second), kv.first});
                 std::sort(cost.begin(), cost.end());
                 for (const auto& ck : cost) {
-                    for (int e : by_head[ck.second]) {
-                        const int pos = T.ent_pos_re[e];
-                        const auto& blk = T.blocks[pos / 32];
-                        const unsigned fpad_id = (unsigned)(blk.tile * 8 + (pos % 32) / 4);
-                        for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) {
-                            const auto& cbq = T.contribs[q];
-                            if (cbq.n_ids > 3) { ok = false; break; }
-                            unsigned id[3] = {0, 0, 0};
-                            for (int z = 0; z < cbq.n_ids; ++z) id[z] = (unsigned)cbq.ids[z];
-                            LaItem it;
-                            it.coeff = cbq.coeff;
-                            it.w0 = id[0] | id[1] << 16 | (cbq.conj ? 0x80000000u : 0u);
-                            it.w1 = id[2] | fpad_id << 15 | (unsigned)cbq.n_ids << 27 | (q + 1 == T.ent_off[e + 1] ? 1u << 30 : 0u);
-                            hitems.push_back(it);
-                        }
-                    }
+                    const auto& v = head_items[ck.second];
+                    hitems.insert(hitems.end(), v.begin(), v.end());
                     hoff.push_back((int)hitems.size());
                     hpos.push_back(ck.second);
                 }
@@ -436,6 +436,133 @@ static void build_device_model(pm_context* c) {
             D.n_la_heads = ok ? (int)hpos.size() : 0;
             D.la_terms = upload(c, lt); D.la_forder = upload(c, forder); D.la_hitems = upload(c, hitems);
             D.la_hoff = upload(c, hoff); D.la_hpos = upload(c, hpos);
+
+            // ---- radial replication: the term lists of radial index n are those of n = 0 with every full id shifted by
+            // n * S, the padded feature id by n * Fs and the head position by n * Ps (the usual gtinv model: every
+            // product shares one radial index).  Verified item by item; k_eval_features_lb then decodes each item once
+            // for a block of radial indices.
+            int nr = 0, S = 0, Fs = 0, Ps = 0;
+            std::vector<LaItem> bterms, bhitems;
+            std::vector<int> bfoff{0}, bforder, bfpad;
+            std::vector<int4> bwork, bfwork;
+            if (ok && T.n_feat > 0 && getenv("PM_EVAL_NO_RADIAL_BATCH") == nullptr) {
+                bool reg = true;
+                std::vector<std::vector<int>> fn_(hm.fp.n_fn);
+                for (int f = 0; f < T.n_feat; ++f) fn_[T.tile_n[T.feat_pad[f] / 8]].push_back(f);
+                nr = 0;
+                while (nr < hm.fp.n_fn && !fn_[nr].empty()) ++nr;
+                for (int n = nr; n < hm.fp.n_fn; ++n) if (!fn_[n].empty()) reg = false;
+                const size_t G = fn_[0].size();
+                for (int n = 0; n < nr; ++n) if (fn_[n].size() != G) reg = false;
+                if (nr < 2 || G == 0) reg = false;
+                auto idk = [&](int ti, int k) { return T.term_ids[(size_t)ti * mo + k]; };
+                if (reg) {
+                    Fs = T.feat_pad[fn_[1][0]] - T.feat_pad[fn_[0][0]];
+                    const int ta = T.term_off[fn_[0][0]], tb = T.term_off[fn_[1][0]];
+                    if (T.term_off[fn_[0][0] + 1] == ta || T.term_off[fn_[1][0] + 1] == tb) reg = false;
+                    else S = idk(tb, 0) - idk(ta, 0);
+                    if (S <= 0 || Fs <= 0) reg = false;
+                }
+                for (int n = 1; n < nr && reg; ++n)
+                    for (size_t g = 0; g < G && reg; ++g) {
+                        const int f0 = fn_[0][g], f1 = fn_[n][g];
+                        const int t0 = T.term_off[f0], t1 = T.term_off[f1], cnt = T.term_off[f0 + 1] - t0;
+                        if (T.feat_pad[f1] - T.feat_pad[f0] != n * Fs || T.term_off[f1 + 1] - t1 != cnt) { reg = false; break; }
+                        for (int k = 0; k < cnt && reg; ++k) {
+                            if (T.term_coeff[t0 + k] != T.term_coeff[t1 + k] || T.term_order[t0 + k] != T.term_order[t1 + k]) reg = false;
+                            for (int z = 0; z < T.term_order[t0 + k] && reg; ++z)
+                                if (idk(t1 + k, z) - idk(t0 + k, z) != n * S) reg = false;
+                        }
+                    }
+                // heads of radial index 0 and their images
+                auto head_n = [&](int key) {
+                    const int u = key >> 20, hp = (key & 0xfffff) / 2;
+                    for (int n = 0; n < hm.fp.n_fn; ++n)
+                        if (hp >= T.seg_n_off[u][n] && hp < T.seg_n_off[u][n + 1]) return n;
+                    return -1;
+                };
+                std::vector<int> keys0;
+                if (reg) {
+                    for (const auto& kv : head_items) {
+                        const int n = head_n(kv.first);
+                        if (n < 0 || n >= nr) { reg = false; break; }
+                        if (n == 0) keys0.push_back(kv.first);
+                    }
+                    if (keys0.empty()) reg = false;
+                }
+                if (reg) {
+                    const int u0 = keys0[0] >> 20;
+                    Ps = 2 * (T.seg_n_off[u0][1] - T.seg_n_off[u0][0]);
+                    if (Ps <= 0 || head_items.size() != keys0.size() * (size_t)nr) reg = false;
+                }
+                for (size_t k = 0; k < keys0.size() && reg; ++k)
+                    for (int n = 1; n < nr && reg; ++n) {
+                        const auto itn = head_items.find(keys0[k] + n * Ps);
+                        const auto& v0 = head_items[keys0[k]];
+                        if (itn == head_items.end() || itn->second.size() != v0.size()) { reg = false; break; }
+                        for (size_t q = 0; q < v0.size() && reg; ++q) {
+                            const LaItem &a0 = v0[q], &a1 = itn->second[q];
+                            const int cn = (a0.w1 >> 27) & 7;
+                            if (a0.coeff != a1.coeff || (a0.w0 >> 31) != (a1.w0 >> 31) || (a0.w1 >> 27) != (a1.w1 >> 27)) reg = false;
+                            if ((int)((a1.w1 >> 15) & 0xfffu) - (int)((a0.w1 >> 15) & 0xfffu) != n * Fs) reg = false;
+                            const int d0 = (int)(a1.w0 & 0xffffu) - (int)(a0.w0 & 0xffffu);
+                            const int d1 = (int)((a1.w0 >> 16) & 0x7fffu) - (int)((a0.w0 >> 16) & 0x7fffu);
+                            const int d2 = (int)(a1.w1 & 0x7fffu) - (int)(a0.w1 & 0x7fffu);
+                            if ((cn > 0 && d0 != n * S) || (cn > 1 && d1 != n * S) || (cn > 2 && d2 != n * S)) reg = false;
+                        }
+                    }
+                if (reg) {
+                    // features of radial index 0, most terms first
+                    std::vector<int> gs(G);
+                    for (size_t g = 0; g < G; ++g) gs[g] = (int)g;
+                    std::stable_sort(gs.begin(), gs.end(), [&](int x, int y) {
+                        return T.term_off[fn_[0][x] + 1] - T.term_off[fn_[0][x]] > T.term_off[fn_[0][y] + 1] - T.term_off[fn_[0][y]];
+                    });
+                    const int tchunk = getenv("PM_LB_TCHUNK") ? atoi(getenv("PM_LB_TCHUNK")) : 16;
+                    for (int g : gs) {
+                        const int f0 = fn_[0][g];
+                        const int tb0 = (int)bterms.size();
+                        for (int ti = T.term_off[f0]; ti < T.term_off[f0 + 1]; ++ti) bterms.push_back(lt[ti]);
+                        bfoff.push_back((int)bterms.size());
+                        bforder.push_back(forder[f0]);
+                        bfpad.push_back(T.feat_pad[f0]);
+                        // stage-1 work items: chunks of <= tchunk terms of one feature (partial sums are added in shared memory)
+                        for (int q = tb0; q < (int)bterms.size(); q += tchunk)
+                            bfwork.push_back(make_int4(q, std::min(q + tchunk, (int)bterms.size()), (int)bforder.size() - 1, 0));
+                    }
+                    std::stable_sort(bfwork.begin(), bfwork.end(), [](const int4& x, const int4& y) { return x.y - x.x > y.y - y.x; });
+                    // head work list: chunks of >= hchunk items that end on entry boundaries, most expensive head first
+                    const int hchunk = getenv("PM_LB_HCHUNK") ? atoi(getenv("PM_LB_HCHUNK")) : 24;
+                    std::vector<std::pair<long, int>> cost;
+                    for (int key : keys0) cost.push_back({-item_cost(head_items[key]), key});
+                    std::sort(cost.begin(), cost.end());
+                    for (const auto& ck : cost) {
+                        const auto& v = head_items[ck.second];
+                        int q0 = (int)bhitems.size(), cnt = 0;
+                        for (size_t q = 0; q < v.size(); ++q) {
+                            bhitems.push_back(v[q]);
+                            ++cnt;
+                            const bool last = (v[q].w1 >> 30) & 1u;
+                            if ((last && cnt >= hchunk) || q + 1 == v.size()) {
+                                bwork.push_back(make_int4(q0, (int)bhitems.size(), ck.second, 0));
+                                q0 = (int)bhitems.size();
+                                cnt = 0;
+                            }
+                        }
+                    }
+                    std::stable_sort(bwork.begin(), bwork.end(), [](const int4& x, const int4& y) { return x.y - x.x > y.y - y.x; });
+                } else {
+                    nr = 0;
+                }
+            }
+            D.lb_nr = nr; D.lb_S = S; D.lb_Fs = Fs; D.lb_Ps = Ps;
+            D.lb_G = (int)bforder.size(); D.lb_nwork = (int)bwork.size();
+            D.lb_terms = upload(c, bterms); D.lb_foff = upload(c, bfoff); D.lb_forder = upload(c, bforder);
+            D.lb_fpad = upload(c, bfpad); D.lb_hitems = upload(c, bhitems); D.lb_work = upload(c, bwork);
+            D.lb_fwork = upload(c, bfwork); D.lb_nfwork = (int)bfwork.size();
+            if (getenv("PM_DEBUG_TABLES"))
+                fprintf(stderr, "[pm] type %d: la_ok %d, radial batch nr %d S %d Fs %d Ps %d, %zu features (%zu terms, %zu chunks), %zu head items in %zu chunks\n", t, D.la_ok,
+                        nr, S, Fs, Ps, bforder.size(), bterms.size(), bfwork.size(), bhitems.size(), bwork.size());
         }
         {   // sliced tables (k_features_v3)
             const int mo = std::max(T.max_order, 1);

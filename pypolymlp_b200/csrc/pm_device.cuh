@@ -73,6 +73,16 @@ struct DevType {
                                   // ids of the contribution << 27 | last contribution of its entry << 30
     const int* la_hoff;           // [n_la_heads + 1] item range of each head (most expensive head first)
     const int* la_hpos;           // [n_la_heads] segment << 20 | real position inside the segment's head list
+    // radial-batched tables of k_eval_features_lb (lb_nr = 0: the model is not a radial replication)
+    int lb_nr, lb_S, lb_Fs, lb_Ps;   // replicas; strides of the full id, the padded feature id and the head position per radial index
+    int lb_G, lb_nwork, lb_nfwork;
+    const LaItem* lb_terms;       // terms of the radial-0 features, most terms first
+    const int* lb_foff;           // [lb_G + 1]
+    const int* lb_forder;         // [lb_G]
+    const int* lb_fpad;           // [lb_G] padded feature id of the radial-0 feature
+    const LaItem* lb_hitems;      // contributions of the radial-0 heads (format of la_hitems)
+    const int4* lb_fwork;         // [lb_nfwork] (first term, end, feature index g, 0): chunks of one feature's terms
+    const int4* lb_work;          // [lb_nwork] (first item, end, head position key, 0): chunks ending on entry boundaries
     const double* sl_coeff;       // [n_slots]
     const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;

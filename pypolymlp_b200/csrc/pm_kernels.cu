@@ -2360,6 +2360,233 @@ __global__ void __launch_bounds__(LA_NT) k_eval_features_la(DevModel m, DevBatch
     }
 }
 
+// Radial-batched variant of the lane = atom kernel for models that are a radial replication (DevType::lb_nr > 0): the term
+// lists of radial index n are those of radial index 0 with shifted ids, so a warp decodes each table item ONCE and applies
+// it to NB radial indices (NB independent gather / multiply / accumulate chains): ~2.5x fewer instructions per useful
+// gather than k_eval_features_la.  Work items: stage 1 (radial-0 feature, block of NB radial indices); stage 3 (chunk of a
+// radial-0 head's contribution list, block of NB radial indices) -- the chunks of one head add into Ah with RED.F64.
+constexpr int LB_NT = 768;   // 24 warps at <= 80 registers
+
+template <int NB>
+__global__ void __launch_bounds__(LB_NT) k_eval_features_lb(DevModel m, DevBatch b, const double2* __restrict__ anc,
+                                                             double* __restrict__ Ah, int ah_stride,
+                                                             double* __restrict__ energies, int nfull_max,
+                                                             const double* __restrict__ cmat, const double* __restrict__ clin) {
+    extern __shared__ double2 la_af[];   // [nfull_max][32] | sdw [fl][32] | sdpv [64][32] | s_e [32] | s_next [2 MAXT]
+    double* sdw = reinterpret_cast<double*>(la_af + (size_t)nfull_max * LA_AT);
+    double* sdpv = sdw + (size_t)m.fl * LA_AT;
+    double* s_e = sdpv + 64 * LA_AT;
+    int* s_next = reinterpret_cast<int*>(s_e + LA_AT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = LB_NT / 32;
+    const int i = blockIdx.x * LA_AT + lane;
+    const bool valid = i < b.n_atoms;
+    const int ty = valid ? b.types[i] : -1;
+    const int segstride = ah_stride / m.n_type;
+#pragma unroll 4
+    for (int k = warp; k < nfull_max; k += NW) {
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) {
+            const DevType& T = m.types[ty];
+            if (k < T.n_full) {
+                v = anc[(size_t)i * m.hmax + T.full_head[k]];
+                if (T.full_conj[k]) {
+                    const double cc = T.full_cc[k];
+                    v = make_double2(cc * v.x, -cc * v.y);
+                }
+            }
+        }
+        la_af[k * LA_AT + lane] = v;
+    }
+    for (int k = tid; k < m.fl * LA_AT; k += LB_NT) sdw[k] = 0.0;
+    if (tid < LA_AT) s_e[tid] = 0.0;
+    if (tid < 2 * MAXT) s_next[tid] = 0;
+    __syncthreads();
+    // shared-memory byte addresses: a_nlm row of full id k for this lane = af_l + k * 512; radial stride S * 512
+    const unsigned af_l = smem_u32(la_af) + (unsigned)lane * 16u;
+    const unsigned sdw_l = smem_u32(sdw) + (unsigned)lane * 8u;
+    // (1) linear invariants.  (NB divides the number of radial indices: no tail; the product order is uniform per feature,
+    // so the branch on it sits outside the radial loop and the loop bodies are branch-free.)
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        if (!__any_sync(0xffffffffu, ty == tt)) continue;
+        const DevType& T = m.types[tt];
+        const LaItem* __restrict__ terms = T.lb_terms;
+        const int4* __restrict__ fwork = T.lb_fwork;
+        const int nblk = T.lb_nr / NB, nwork = T.lb_nfwork * nblk;
+        const unsigned Sb = (unsigned)T.lb_S * 512u, Fb = (unsigned)T.lb_Fs * 256u;
+        for (;;) {
+            int wk = 0;
+            if (lane == 0) wk = atomicAdd(&s_next[tt], 1);
+            wk = __shfl_sync(0xffffffffu, wk, 0);
+            if (wk >= nwork) break;
+            const int cidx = wk / nblk, n0 = (wk - cidx * nblk) * NB;
+            const int4 wi = fwork[cidx];   // first term, end, feature index
+            const int o = T.lb_forder[wi.z];
+            const unsigned afn = af_l + (unsigned)n0 * Sb;
+            double sum[NB];
+#pragma unroll
+            for (int n = 0; n < NB; ++n) sum[n] = 0.0;
+            LaItem nxt = terms[wi.x], nx2 = terms[min(wi.x + 1, wi.y - 1)];
+            for (int ti = wi.x; ti < wi.y; ++ti) {
+                const LaItem it = nxt;
+                nxt = nx2;
+                nx2 = terms[min(ti + 2, wi.y - 1)];
+                const unsigned a0 = afn + (it.w0 & 0xffffu) * 512u, a1 = afn + (it.w0 >> 16) * 512u;
+                const unsigned a2 = afn + (it.w1 & 0xffffu) * 512u, a3 = afn + (it.w1 >> 16) * 512u;
+                if (o == 2) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = lds_f64x2(a0 + n * Sb), q = lds_f64x2(a1 + n * Sb);
+                        sum[n] += it.coeff * (p.x * q.x - p.y * q.y);
+                    }
+                } else if (o == 3) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = cmul(lds_f64x2(a0 + n * Sb), lds_f64x2(a1 + n * Sb)), q = lds_f64x2(a2 + n * Sb);
+                        sum[n] += it.coeff * (p.x * q.x - p.y * q.y);
+                    }
+                } else if (o == 1) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) sum[n] += it.coeff * lds_f64x2(a0 + n * Sb).x;
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = cmul(lds_f64x2(a0 + n * Sb), lds_f64x2(a1 + n * Sb));
+                        const double2 q = cmul(lds_f64x2(a2 + n * Sb), lds_f64x2(a3 + n * Sb));
+                        sum[n] += it.coeff * (p.x * q.x - p.y * q.y);
+                    }
+                }
+            }
+            if (ty == tt) {
+                double* dst = sdw + (size_t)(T.lb_fpad[wi.z] + n0 * T.lb_Fs) * LA_AT + lane;
+#pragma unroll
+                for (int n = 0; n < NB; ++n) atomicAdd(dst + (size_t)n * T.lb_Fs * LA_AT, sum[n]);   // (chunks of one feature)
+            }
+        }
+    }
+    __syncthreads();
+    // (2) polynomial (max_p = 2 over <= 64 polynomial variables): E and w = dE/dd, w replaces d in sdw
+    for (int k = tid; k < 64 * LA_AT; k += LB_NT) {
+        const int pv = k >> 5;
+        double v = 0.0;
+        if (valid && pv < m.npv_pad) {
+            const int fp = m.pv_fp[(size_t)ty * m.npv_pad + pv];
+            if (fp >= 0) v = sdw[fp * LA_AT + lane];
+        }
+        sdpv[k] = v;
+    }
+    __syncthreads();
+    double e = 0.0;
+    if (valid)
+        for (int k = tid; k < m.fl * LA_AT; k += LB_NT) {
+            const double cl = clin[(size_t)ty * m.fl + (k >> 5)];
+            e += cl * sdw[k];
+            sdw[k] = cl;
+        }
+    __syncthreads();
+    if (valid) {
+        // four polynomial variables per warp pass: four independent sums share each d_q (and the coefficient loads are
+        // warp-uniform 32-byte rows)
+        const double* __restrict__ cmt = cmat + (size_t)ty * 4096;
+        for (int pv0 = warp * 4; pv0 < m.npv_pad; pv0 += NW * 4) {
+            double w2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+            for (int q = 0; q < 64; ++q) {
+                const double dq = sdpv[q * LA_AT + lane];
+                const double4 cq = *reinterpret_cast<const double4*>(cmt + q * 64 + pv0);   // row q = column q (symmetric)
+                w2[0] += cq.x * dq; w2[1] += cq.y * dq; w2[2] += cq.z * dq; w2[3] += cq.w * dq;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int pv = pv0 + r;
+                const int fp = pv < m.npv_pad ? m.pv_fp[(size_t)ty * m.npv_pad + pv] : -1;
+                if (fp < 0) continue;
+                sdw[fp * LA_AT + lane] += w2[r];
+                e += 0.5 * sdpv[pv * LA_AT + lane] * w2[r];
+            }
+        }
+    }
+    atomicAdd(&s_e[lane], e);
+    __syncthreads();
+    if (warp == 0 && valid) atomicAdd(energies + b.st_of_atom[i], s_e[lane]);
+    // (3) head adjoints: the branch on the number of factors of a contribution is warp-uniform and outside the radial loop
+    for (int tt = 0; tt < m.n_type; ++tt) {
+        if (!__any_sync(0xffffffffu, ty == tt)) continue;
+        const DevType& T = m.types[tt];
+        const LaItem* __restrict__ items = T.lb_hitems;
+        const int4* __restrict__ work = T.lb_work;
+        const int nblk = T.lb_nr / NB, nwork = T.lb_nwork * nblk;
+        const unsigned Sb = (unsigned)T.lb_S * 512u, Fb = (unsigned)T.lb_Fs * 256u;
+        const int Ps = T.lb_Ps;
+        for (;;) {
+            int wk = 0;
+            if (lane == 0) wk = atomicAdd(&s_next[MAXT + tt], 1);
+            wk = __shfl_sync(0xffffffffu, wk, 0);
+            if (wk >= nwork) break;
+            const int c = wk / nblk, n0 = (wk - c * nblk) * NB;
+            const int4 wi = work[c];   // first item, end, head position key
+            const unsigned afn = af_l + (unsigned)n0 * Sb, swn = sdw_l + (unsigned)n0 * Fb;
+            double accr[NB], acci[NB], gr[NB], gi[NB];
+#pragma unroll
+            for (int n = 0; n < NB; ++n) { accr[n] = 0.0; acci[n] = 0.0; gr[n] = 0.0; gi[n] = 0.0; }
+            LaItem nxt = items[wi.x], nx2 = items[min(wi.x + 1, wi.y - 1)];
+            for (int q = wi.x; q < wi.y; ++q) {
+                const LaItem it = nxt;
+                nxt = nx2;
+                nx2 = items[min(q + 2, wi.y - 1)];
+                const int cn = (it.w1 >> 27) & 7;
+                const unsigned a0 = afn + (it.w0 & 0xffffu) * 512u, a1 = afn + ((it.w0 >> 16) & 0x7fffu) * 512u;
+                const unsigned a2 = afn + (it.w1 & 0x7fffu) * 512u;
+                const double cfi = (it.w0 >> 31) ? -it.coeff : it.coeff;
+                if (cn == 2) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = lds_f64x2(a0 + n * Sb), r = lds_f64x2(a1 + n * Sb);
+                        gr[n] += it.coeff * (p.x * r.x - p.y * r.y);
+                        gi[n] += cfi * (p.x * r.y + p.y * r.x);
+                    }
+                } else if (cn == 1) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = lds_f64x2(a0 + n * Sb);
+                        gr[n] += it.coeff * p.x;
+                        gi[n] += cfi * p.y;
+                    }
+                } else if (cn == 0) {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) gr[n] += it.coeff;
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        const double2 p = cmul(cmul(lds_f64x2(a0 + n * Sb), lds_f64x2(a1 + n * Sb)), lds_f64x2(a2 + n * Sb));
+                        gr[n] += it.coeff * p.x;
+                        gi[n] += cfi * p.y;
+                    }
+                }
+                if (it.w1 & (1u << 30)) {   // last contribution of its (feature, head) entry
+                    const unsigned fo = swn + ((it.w1 >> 15) & 0xfffu) * 256u;
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        double w;
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"(fo + n * Fb));
+                        accr[n] += w * gr[n];
+                        acci[n] -= w * gi[n];
+                        gr[n] = 0.0; gi[n] = 0.0;
+                    }
+                }
+            }
+            if (ty == tt) {
+                double* ah = Ah + (size_t)i * ah_stride + (wi.z >> 20) * segstride + (wi.z & 0xfffff) + (size_t)n0 * Ps;
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    atomicAdd(ah + n * Ps, accr[n]);
+                    atomicAdd(ah + n * Ps + 1, acci[n]);
+                }
+            }
+        }
+    }
+}
+
 static size_t eval_la_smem(const DevModel& m, size_t feat_smem) {
     return (size_t)LA_AT * (feat_smem + (size_t)m.fl * sizeof(double) + 64 * sizeof(double) + sizeof(double)) + 2 * MAXT * sizeof(int);
 }
@@ -2402,6 +2629,20 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
         int mo = 1;
         for (int t = 0; t < m.n_type; ++t) mo = max(mo, m.types[t].max_order);
         cudaMemsetAsync(ws.Ah, 0, (size_t)b.n_atoms * ah_stride * sizeof(double), s);   // positions no head entry writes
+        bool radial = getenv("PM_EVAL_LB") == nullptr || atoi(getenv("PM_EVAL_LB")) != 0;
+        int nr = m.types[0].lb_nr;
+        for (int t = 0; t < m.n_type; ++t) radial = radial && m.types[t].lb_nr > 0 && m.types[t].lb_nr == nr;
+        radial = radial && (nr % 2 == 0 || nr % 3 == 0 || nr % 5 == 0);   // NB must divide the number of radial indices
+        if (radial) {
+#define PM_LB_CASE(NB_)                                                                                               \
+    {                                                                                                                 \
+        ensure_smem((const void*)k_eval_features_lb<NB_>, smem);                                                      \
+        k_eval_features_lb<NB_><<<grid, LB_NT, smem, s>>>(m, b, ws.anc, ws.Ah, ah_stride, energies, nfull_max, ws.cmat, ws.clin); \
+    }
+            if (nr % 5 == 0) PM_LB_CASE(5) else if (nr % 4 == 0) PM_LB_CASE(4) else if (nr % 6 == 0) PM_LB_CASE(6)
+            else if (nr % 3 == 0) PM_LB_CASE(3) else PM_LB_CASE(2)
+#undef PM_LB_CASE
+        } else
 #define PM_LA_CASE(MO_)                                                                                               \
     case MO_:                                                                                                         \
         ensure_smem((const void*)k_eval_features_la<MO_>, smem);                                                      \
