@@ -27,6 +27,23 @@ def test_published_legacy_answers_gpu(key):
         check_legacy_eval(key, prop.get_e_array()[k], prop.get_f_array()[k], prop.get_s_array()[k], axis)
 
 
+@pytest.mark.parametrize("key", sorted(LEGACY_EVAL))
+def test_published_legacy_answers_lane_atom_kernels_gpu(key, monkeypatch):
+    """Same published answers with the large-batch eval kernels forced on (multi-type models: lanes of one warp carry atoms
+    of different types; models the lane = atom kernels do not serve fall back by themselves)."""
+    monkeypatch.setenv("PM_EVAL_LA_MIN", "1")
+    name, st = LEGACY_EVAL[key][:2]
+    L = load_legacy_golden()
+    prop = PotentialPropertiesFast(params_from_golden(name), L[key + "_coeffs"])
+    axis, pos, types = L[st + "_axis"], L[st + "_pos"], L[st + "_types"]
+    prop.eval_multiple([axis] * 5, [pos] * 5, [types] * 5)
+    for k in range(5):
+        check_legacy_eval(key, prop.get_e_array()[k], prop.get_f_array()[k], prop.get_s_array()[k], axis)
+    monkeypatch.setenv("PM_EVAL_LB", "0")
+    prop.eval_multiple([axis] * 2, [pos] * 2, [types] * 2)
+    check_legacy_eval(key, prop.get_e_array()[1], prop.get_f_array()[1], prop.get_s_array()[1], axis)
+
+
 def test_legacy_mgo_pair_published_answers_gpu():
     from test_oracle_golden import check_mgo_eval
 

@@ -268,6 +268,47 @@ def test_eval_config5_shape_vs_reference():
     assert prop.get_e_array()[0] == pytest.approx(prop.get_e_array()[2], rel=1e-13)   # atomics: order varies
 
 
+_EVAL_VARIANTS = {
+    "default": {},
+    "generic_lane_atom": {"PM_EVAL_LB": "0"},
+    "slice_kernel": {"PM_EVAL_LA": "0"},
+    "stored_pair_records": {"PM_EVAL_STORED_PB": "1"},
+    "fit_k2_kernel": {"PM_EVAL_K2_FIT": "1"},
+    "one_lane": {"PM_EVAL_LANES": "1"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(_EVAL_VARIANTS))
+def test_eval_large_batch_kernel_variants(variant, monkeypatch):
+    """The large-batch eval path -- two lanes (sibling context + host thread), a_nlm-only K2 kernel, lane = atom feature /
+    adjoint kernels (radial-batched and generic), pair pass that recomputes the basis records -- and each of its A/B
+    switches against (a) the reference golden of the config-5 cell and (b) the one-structure-at-a-time path, which uses
+    the first-generation eval kernels (small batches never reach the lane = atom kernels)."""
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    coeffs = np.random.default_rng(12).normal(size=2030) * 1e-3
+    sts = [cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777 + k) for k in range(34)]   # 17 408 atoms: two lanes
+    sts.append(cases.fcc_supercell(rep=(2, 2, 2), sigma=0.02, seed=3))                        # ragged tail
+    prop = PotentialPropertiesFast(pd, coeffs)
+    singles = []
+    for k in (0, 16, 17, 33, 34):    # both sides of the lane split
+        prop.eval(*sts[k], True)
+        singles.append((k, prop.get_e(), np.array(prop.get_f()), np.array(prop.get_s())))
+    monkeypatch.setenv("PM_EVAL_LA_MIN", "1")
+    for name, val in _EVAL_VARIANTS[variant].items():
+        monkeypatch.setenv(name, val)
+    prop.eval_multiple([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts])
+    e, f, s_ = prop.get_e_array(), prop.get_f_array(), prop.get_s_array()
+    assert abs(e[0] - G2["cfg5_e"][0]) < 1e-10 * abs(G2["cfg5_e"][0])
+    assert np.abs(np.asarray(f[0]) - G2["cfg5_f"]).max() < 1e-10 * np.abs(G2["cfg5_f"]).max()
+    assert np.abs(np.asarray(s_[0]) - G2["cfg5_s"]).max() < 1e-10 * np.abs(G2["cfg5_s"]).max()
+    for k, e1, f1, s1 in singles:
+        assert e[k] == pytest.approx(e1, rel=1e-12)
+        assert np.abs(np.asarray(f[k]) - f1).max() < 1e-11 * np.abs(f1).max()
+        assert np.abs(np.asarray(s_[k]) - s1).max() < 1e-11 * np.abs(s1).max()
+
+
 def _n_devices():
     import ctypes
 
