@@ -1094,9 +1094,11 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
     // eval through the fused front end: the pair pass recomputes the basis records, K2 does not store them
     const bool eval_fused = mode == MODE_EVAL && !c->simple_s && eval_fused_supported(d, c->feat_smem);
     const bool pairs_rc = eval_fused && eval_pairs_rc_supported(d);
-    if (pairs_rc && launch_anlm_eval(d, b, c->d_PB.p, c->d_anc.p, s)) {
+    bool pairs_rads = getenv("PM_EVAL_RC_RADS") != nullptr;   // A/B: the pair pass reads f_n, f_n' from the records
+    if (pairs_rc && launch_anlm_eval(d, b, c->d_PB.p, c->d_anc.p, s, pairs_rads)) {
         tm.mark(ST_ANLM, 1);
     } else if (!c->simple_s && launch_pair_anlm(d, b, c->d_PB.p, c->d_anc.p, c->d_agg.p, s, !pairs_rc)) {
+        if (pairs_rc) pairs_rads = false;   // (ran without storing anything)
         tm.mark(ST_ANLM, 1);   // fused pair basis + a_nlm kernel: its time is booked under "anlm"
     } else {
         launch_pair_basis(d, b, c->d_PB.p, s);
@@ -1148,6 +1150,7 @@ static void run_chunk(pm_context* c, const HostChunk& h, int mode, bool upload_i
         ws.cmat = c->has_cmat ? c->d_cmat.p : nullptr;
         ws.clin = c->has_cmat ? c->d_clin.p : nullptr;
         ws.pairs_rc = pairs_rc;
+        ws.pairs_rads = pairs_rads;
         launch_eval_adjoint(d, b, ws, c->d_coeffs.p, c->d_e.p, c->d_f.p, c->d_s.p, s, eval_fused ? c->feat_smem : 0);
         tm.mark(ST_EVAL, 5);
         return;

@@ -881,36 +881,65 @@ __global__ void __maxnreg__(80) k_pair_anlm(DevModel m, DevBatch b, double* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int AE_AT = 4;      // atoms per CTA
 constexpr int AE_PT = 256;    // pairs per tile
-constexpr int AE_LD = AE_PT + 1;
 constexpr int AE_NI = 4;      // (atom, head) items per thread: AE_AT * hmax <= AE_NI * 256
 
-template <int LT>
-__global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, const double* __restrict__ PB,
-                                                    double2* __restrict__ anc) {
+// RECT (DevModel::front2: one atom type, every radial group lists all m <= 0 heads in Y_lm key order): phase 2 is the small
+// matrix product A[n][y] = sum_p F[n][p] Y[y][p] (n: radial index, y: Re / Im of a Y_lm key, p: the atom's pairs) on the
+// FP64 tensor cores, two warps per atom (each takes half of the y tiles): 14 k-steps of 8 DMMA per atom instead of 150 heads
+// x 54 pairs x (3 LDS + 2 DFMA).  The tile row stride is 4 (mod 16) so that the fragment loads are conflict-free.
+template <int LT, bool RECT>
+__global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, double* __restrict__ PBw,
+                                                    double2* __restrict__ anc, int store_radial) {
+    constexpr int AE_LD = RECT ? AE_PT + 4 : AE_PT + 1;
+    constexpr int NH = LT >= 0 ? (LT + 1) * (LT + 2) / 2 : MAX_NH;
+    constexpr int NTW = ((2 * NH + 7) / 8 + 1) / 2;   // 8-column tiles of y per warp (RECT)
+    const double* PB = PBw;
     extern __shared__ __align__(16) double sm_ae[];   // [n_fn + 2 nh][AE_LD]
     const int i0 = blockIdx.x * AE_AT;
     const int na = min(AE_AT, b.n_atoms - i0);
     const int nt = m.n_type;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pa = b.seg_off[i0 * nt], pe = b.seg_off[(i0 + na) * nt];
     const int oy = m.n_fn;   // tile rows: f_n (n_fn), then Re / Im Y per key
-    // the (atom, head) items of this thread
+    // generic path: the (atom, head) items of this thread
     int it_nid[AE_NI], it_key[AE_NI], it_p0[AE_NI], it_p1[AE_NI];
     double ar[AE_NI], ai[AE_NI];
+    // RECT path: fragment rows of this lane and the accumulator tiles [n tile][y tile]
+    int arow[2] = {-1, -1}, brow[NTW], ahead[2] = {-1, -1};
+    double acc[2][NTW][2];
+    if (RECT) {
+        const DevType& T = m.types[0];
 #pragma unroll
-    for (int k = 0; k < AE_NI; ++k) {
-        const int w = tid + k * 256;
-        const int a = w / m.hmax, h = w - a * m.hmax;
-        it_p0[k] = 0; it_p1[k] = 0; it_nid[k] = 0; it_key[k] = 0; ar[k] = 0.0; ai[k] = 0.0;
-        if (a < na) {
-            const int i = i0 + a;
-            const DevType& T = m.types[b.types[i]];
-            if (h < T.n_head) {
-                const int u = T.head_seg[h];
-                it_nid[k] = T.head_nid[h];
-                it_key[k] = T.head_key[h];
-                it_p0[k] = b.seg_off[i * nt + u];
-                it_p1[k] = b.seg_off[i * nt + u + 1];
+        for (int mt = 0; mt < 2; ++mt) {
+            const int n = mt * 8 + (lane >> 2);
+            if (n < m.n_fn && T.seg_n_off[0][n + 1] > T.seg_n_off[0][n]) {
+                ahead[mt] = T.seg_n_off[0][n];                       // position of (n, key 0) in the segment's head list
+                arow[mt] = T.head_nid[T.seg_heads[0][ahead[mt]]];    // tile row of f_n
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NTW; ++q) {
+            const int y = (((warp & 1) * NTW + q) * 8) + (lane >> 2);
+            brow[q] = y < 2 * m.nh ? oy + y : -1;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { acc[mt][q][0] = 0.0; acc[mt][q][1] = 0.0; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < AE_NI; ++k) {
+            const int w = tid + k * 256;
+            const int a = w / m.hmax, h = w - a * m.hmax;
+            it_p0[k] = 0; it_p1[k] = 0; it_nid[k] = 0; it_key[k] = 0; ar[k] = 0.0; ai[k] = 0.0;
+            if (a < na) {
+                const int i = i0 + a;
+                const DevType& T = m.types[b.types[i]];
+                if (h < T.n_head) {
+                    const int u = T.head_seg[h];
+                    it_nid[k] = T.head_nid[h];
+                    it_key[k] = T.head_key[h];
+                    it_p0[k] = b.seg_off[i * nt + u];
+                    it_p1[k] = b.seg_off[i * nt + u + 1];
+                }
             }
         }
     }
@@ -925,7 +954,15 @@ __global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, const
             double* col = sm_ae + pp;
             const double r = sqrt(dx * dx + dy * dy + dz * dz);
             const double rinv = 1.0 / r;
-            pair_radial(m, r, tp, [&](int n, double fn, double) { col[n * AE_LD] = fn; });
+            // f_n goes to the tile.  store_radial (A/B switch PM_EVAL_RC_RADS): 1 / r, f_n and f_n' also go to the pair
+            // record and the pair pass reads these 21 doubles instead of evaluating the Gaussians a second time --
+            // measured slower than recomputing them (4.40 vs 4.26 ms per 131 072 atoms), so it is off by default
+            const PBRecW recw = pb_rec_w(PBw, p, m.pbstride);
+            if (store_radial) recw[3] = rinv;
+            pair_radial(m, r, tp, [&](int n, double fn, double fnd) {
+                col[n * AE_LD] = fn;
+                if (store_radial) { recw[4 + n] = fn; recw[4 + m.n_fn + n] = fnd; }
+            });
             pair_angular<LT>(m, dx, dy, dz, r, rinv, [&](int key, double yr, double yi, double, double, double, double,
                                                          double, double) {
                 col[(oy + 2 * key) * AE_LD] = yr;
@@ -933,18 +970,59 @@ __global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, const
             });
         }
         __syncthreads();
+        if (RECT) {
+            const int a = warp >> 1;
+            if (a < na) {
+                const int q0 = max(pf, b.seg_off[i0 + a]), q1 = min(pf + np, b.seg_off[i0 + a + 1]);
+                for (int k0 = q0; k0 < q1; k0 += 4) {
+                    const int p = k0 + (lane & 3);
+                    const bool pv = p < q1;
+                    const double* colp = sm_ae + (p - pf);
+                    double av[2];
 #pragma unroll
-        for (int k = 0; k < AE_NI; ++k) {
-            const int q0 = max(pf, it_p0[k]), q1 = min(pf + np, it_p1[k]);
-            const double* rf = sm_ae + it_nid[k] * AE_LD - pf;
-            const double* ry = sm_ae + (oy + 2 * it_key[k]) * AE_LD - pf;
-            for (int p = q0; p < q1; ++p) {
-                const double fn = rf[p];
-                if (fn == 0.0) continue;
-                ar[k] += fn * ry[p];
-                ai[k] += fn * ry[p + AE_LD];
+                    for (int mt = 0; mt < 2; ++mt) av[mt] = (pv && arow[mt] >= 0) ? colp[arow[mt] * AE_LD] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < NTW; ++q) {
+                        const double bv = (pv && brow[q] >= 0) ? colp[brow[q] * AE_LD] : 0.0;
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) dmma(acc[mt][q][0], acc[mt][q][1], av[mt], bv);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < AE_NI; ++k) {
+                const int q0 = max(pf, it_p0[k]), q1 = min(pf + np, it_p1[k]);
+                const double* rf = sm_ae + it_nid[k] * AE_LD - pf;
+                const double* ry = sm_ae + (oy + 2 * it_key[k]) * AE_LD - pf;
+                for (int p = q0; p < q1; ++p) {
+                    const double fn = rf[p];
+                    if (fn == 0.0) continue;
+                    ar[k] += fn * ry[p];
+                    ai[k] += fn * ry[p + AE_LD];
+                }
             }
         }
+    }
+    if (RECT) {
+        // accumulator (row, columns 2 c, 2 c + 1) = (Re, Im) of head (n = tile row, key = 4 * y tile + c)
+        const int a = warp >> 1;
+        if (a < na) {
+            const DevType& T = m.types[0];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (ahead[mt] < 0) continue;
+#pragma unroll
+                for (int q = 0; q < NTW; ++q) {
+                    const int key = ((warp & 1) * NTW + q) * 4 + (lane & 3);
+                    if (key < m.nh) {
+                        const int h = T.seg_heads[0][ahead[mt] + key];
+                        anc[(size_t)(i0 + a) * m.hmax + h] = make_double2(acc[mt][q][0], acc[mt][q][1]);
+                    }
+                }
+            }
+        }
+        return;
     }
 #pragma unroll
     for (int k = 0; k < AE_NI; ++k) {
@@ -954,16 +1032,22 @@ __global__ void __launch_bounds__(256) k_anlm_eval(DevModel m, DevBatch b, const
     }
 }
 
-bool launch_anlm_eval(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, cudaStream_t s) {
+bool launch_anlm_eval(const DevModel& m, const DevBatch& b, double* PB, double2* anc, cudaStream_t s, bool store_radial) {
     if (b.n_atoms == 0) return true;
-    const size_t smem = (size_t)(m.n_fn + 2 * m.nh) * AE_LD * sizeof(double);
+    const bool rect = m.front2 && m.n_fn <= 16 && getenv("PM_EVAL_K2_NO_DMMA") == nullptr;
+    const size_t smem = (size_t)(m.n_fn + 2 * m.nh) * (AE_PT + (rect ? 4 : 1)) * sizeof(double);
     if (getenv("PM_EVAL_K2_FIT") != nullptr || m.maxl > 6 || AE_AT * m.hmax > AE_NI * 256 || smem > 200 * 1024) return false;
     init_pair_basis_tables();
     const int grid = (b.n_atoms + AE_AT - 1) / AE_AT;
-#define PM_AE_CASE(L_)                                                  \
-    case L_:                                                            \
-        ensure_smem((const void*)k_anlm_eval<L_>, smem);                \
-        k_anlm_eval<L_><<<grid, 256, smem, s>>>(m, b, PB, anc);         \
+#define PM_AE_CASE(L_)                                                          \
+    case L_:                                                                    \
+        if (rect) {                                                             \
+            ensure_smem((const void*)k_anlm_eval<L_, true>, smem);              \
+            k_anlm_eval<L_, true><<<grid, 256, smem, s>>>(m, b, PB, anc, store_radial ? 1 : 0);  \
+        } else {                                                                \
+            ensure_smem((const void*)k_anlm_eval<L_, false>, smem);             \
+            k_anlm_eval<L_, false><<<grid, 256, smem, s>>>(m, b, PB, anc, store_radial ? 1 : 0); \
+        }                                                                       \
         break;
     switch (m.maxl) { PM_AE_CASE(0) PM_AE_CASE(1) PM_AE_CASE(2) PM_AE_CASE(3) PM_AE_CASE(4) PM_AE_CASE(5) PM_AE_CASE(6) }
 #undef PM_AE_CASE
@@ -1817,7 +1901,7 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     return v;
 }
 
-template <int LT, int NF>
+template <int LT, int NF, bool RADS>
 __global__ void __launch_bounds__(128, 3) k_eval_pairs_rc(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                            const double* __restrict__ Ah, int ah_stride,
                                                            double* __restrict__ forces, double* __restrict__ stresses, int nc_max) {
@@ -1853,12 +1937,13 @@ __global__ void __launch_bounds__(128, 3) k_eval_pairs_rc(DevModel m, DevBatch b
         const int* snid = T.seg_nid[u];
         const int* snoff = T.seg_n_off[u];
         // f_n and f_n' / r of the radial functions of this (centre type, neighbour type) segment, in segment order, and the
-        // element offset of each radial group in the adjoint row
+        // element offset of each radial group in the adjoint row.  RADS: K2 left f_n, f_n' in the pair record (k_anlm_eval);
+        // else they are evaluated here.
         double fr[NF], fd[NF];
         int qo[NF];
         {
-            double fc, fcd;
-            radial_cutoff(m, r, fc, fcd);
+            double fc = 0.0, fcd = 0.0;
+            if (!RADS) radial_cutoff(m, r, fc, fcd);
             const int tp = m.type_pairs[ti * m.n_type + u];
             const int nfn = m.tp_nfn[tp];
             const double* prm = m.tp_params + (size_t)tp * m.n_fn * 2;
@@ -1869,9 +1954,14 @@ __global__ void __launch_bounds__(128, 3) k_eval_pairs_rc(DevModel m, DevBatch b
                     const int nid = snid[n];
                     const int q0 = snoff[n];
                     if (nid >= 0 && snoff[n + 1] > q0) {
-                        double fnd;
-                        radial_one(prm, nfn, nid, r, fc, fcd, fr[n], fnd);
-                        fd[n] = fnd * rinv;
+                        if (RADS) {
+                            fr[n] = rec[4 + nid];
+                            fd[n] = rec[4 + m.n_fn + nid] * rinv;
+                        } else {
+                            double fnd;
+                            radial_one(prm, nfn, nid, r, fc, fcd, fr[n], fnd);
+                            fd[n] = fnd * rinv;
+                        }
                         qo[n] = 2 * q0;
                     }
                 }
@@ -2675,8 +2765,13 @@ void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& 
         init_pair_basis_tables();
 #define PM_RC_CASE(L_, NF_)                                                                                           \
     {                                                                                                                 \
-        ensure_smem((const void*)k_eval_pairs_rc<L_, NF_>, smem);                                                     \
-        k_eval_pairs_rc<L_, NF_><<<grid, 128, smem, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses, nc);         \
+        if (ws.pairs_rads) {                                                                                          \
+            ensure_smem((const void*)k_eval_pairs_rc<L_, NF_, true>, smem);                                           \
+            k_eval_pairs_rc<L_, NF_, true><<<grid, 128, smem, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses, nc);  \
+        } else {                                                                                                      \
+            ensure_smem((const void*)k_eval_pairs_rc<L_, NF_, false>, smem);                                          \
+            k_eval_pairs_rc<L_, NF_, false><<<grid, 128, smem, s>>>(m, b, ws.PB, ws.Ah, ah_stride, forces, stresses, nc); \
+        }                                                                                                             \
     }
 #define PM_RC_L(L_)                                                                                                   \
     case L_:                                                                                                          \

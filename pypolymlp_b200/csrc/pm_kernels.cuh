@@ -23,6 +23,7 @@ struct Workspace {
     double* X = nullptr;        // [n_rows][fpad]
     double* Ah = nullptr;       // [n_atoms][ah_stride] head adjoints (eval)
     bool pairs_rc = false;      // eval: PB holds only the displacements, the pair pass recomputes the records (k_eval_pairs_rc)
+    bool pairs_rads = false;    // ... and 1 / r, f_n, f_n' (left there by k_anlm_eval or the storing K2 kernels): only the angular part is recomputed
     const double* cmat = nullptr;  // [n_type][64][64] order-2 coefficient matrix over the polynomial variables (eval, max_p = 2) or null
     const double* clin = nullptr;  // [n_type][fl] linear-column coefficient of each padded feature (eval, with cmat) or null
     int* errflag = nullptr;     // device error flag
@@ -53,7 +54,7 @@ bool launch_pair_anlm(const DevModel& m, const DevBatch& b, double* PB, double2*
 bool eval_pairs_rc_supported(const DevModel& m);
 // K2 of the eval path when the pair pass recomputes: a_nlm only, several atoms per CTA, nothing stored per pair; false if
 // the model is not served (then launch_pair_anlm / launch_anlm)
-bool launch_anlm_eval(const DevModel& m, const DevBatch& b, const double* PB, double2* anc, cudaStream_t s);
+bool launch_anlm_eval(const DevModel& m, const DevBatch& b, double* PB, double2* anc, cudaStream_t s, bool store_radial);
 // K3: invariants and G = d feature / d head
 void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
                      size_t smem_bytes, cudaStream_t s, bool zero_g = true,

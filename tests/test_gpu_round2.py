@@ -275,6 +275,8 @@ _EVAL_VARIANTS = {
     "stored_pair_records": {"PM_EVAL_STORED_PB": "1"},
     "fit_k2_kernel": {"PM_EVAL_K2_FIT": "1"},
     "one_lane": {"PM_EVAL_LANES": "1"},
+    "k2_without_dmma": {"PM_EVAL_K2_NO_DMMA": "1"},
+    "radial_items_from_records": {"PM_EVAL_RC_RADS": "1"},
 }
 
 
