@@ -1902,7 +1902,7 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
 }
 
 template <int LT, int NF, bool RADS>
-__global__ void __launch_bounds__(128, 3) k_eval_pairs_rc(DevModel m, DevBatch b, const double* __restrict__ PB,
+__global__ void __launch_bounds__(128, 4) k_eval_pairs_rc(DevModel m, DevBatch b, const double* __restrict__ PB,
                                                            const double* __restrict__ Ah, int ah_stride,
                                                            double* __restrict__ forces, double* __restrict__ stresses, int nc_max) {
     extern __shared__ __align__(16) double s_ah[];   // [nc_max][ah_stride] | mbarrier

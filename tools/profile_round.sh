@@ -14,7 +14,7 @@ for k in k_syrk_sk2 k_lrows_v4n k_xrows_v6 k_pair_anlm k_features_v3; do
   ncu -i gpurun_out/prof_${k}_$R.ncu-rep --page raw --csv > gpurun_out/prof_${k}_$R.raw.csv 2>/dev/null
   rm -f gpurun_out/prof_${k}_$R.ncu-rep      # gpurun merges at most 64 MiB back: keep the two CSV pages only
 done
-for k in k_eval_features k_eval_pairs_v2 k_neighbor_cl_count; do
+for k in k_eval_features_lb k_eval_pairs_rc k_anlm_eval k_neighbor_cl_count; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_${k}_$R \
       python tools/eval_probe2.py 64 > gpurun_out/ncu_${k}_$R.log 2>&1
   echo "$k rc=$?"
@@ -22,4 +22,8 @@ for k in k_eval_features k_eval_pairs_v2 k_neighbor_cl_count; do
   ncu -i gpurun_out/prof_${k}_$R.ncu-rep --page raw --csv > gpurun_out/prof_${k}_$R.raw.csv 2>/dev/null
   rm -f gpurun_out/prof_${k}_$R.ncu-rep
 done
+# eval: stage profile (one lane, host sync after every stage) and launch list
+python tools/eval_probe2.py 256 > gpurun_out/eval_stages_$R.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 150 --csv \
+   --log-file gpurun_out/eval_launches_$R.csv python tools/eval_probe2.py 128 > gpurun_out/eval_ncu_$R.log 2>&1
 ls -la gpurun_out/*_$R* | awk '{print $5, $9}'

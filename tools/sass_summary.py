@@ -11,8 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pypolymlp_b200", "lib", "libpolymlp_b200.so")
 OPS = ["DMMA", "UBLKCP", "SYNCS", "LDGSTS", "REDG", "ATOMG", "ATOMS", "LDS", "LDG", "STG", "DFMA", "DMUL", "DADD", "BAR"]
-HOT = ["k_syrk_sk2", "k_syrk_sk(", "k_lrows_v4n<3, 8>", "k_lrows_v4<3, 8>", "k_lrows_v4a<3, 8>", "k_xrows_v6", "k_pair_anlm<4>",
+HOT = ["k_syrk_sk2", "k_syrk_sk(", "k_lrows_v4n<3, 8>", "k_lrows_v4<3, 8>", "k_lrows_v4a<3, 8>", "k_xrows_v6", "k_pair_anlm<4, true>",
        "k_features_v3<4, 3, 256>", "k_lrows_big<12, 512>", "k_lrows_big<8, 256>", "k_xrows_v5", "k_lrows_v3<3, 8, false>",
+       "k_anlm_eval<4, true>", "k_eval_features_lb<5>", "k_eval_features_la<3>", "k_eval_pairs_rc<4, 12, false>",
        "k_eval_features<4, 3>", "k_eval_pairs_v2", "k_neighbor_cl_count", "k_neighbor_cl_fill", "k_neighbor_mask<false>",
        "k_pack_upper", "k_xe_reduce"]
 
@@ -34,7 +35,7 @@ def main():
             continue
         if cur is None:
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)((?:\.[A-Z0-9_]+)*)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)((?:\.[A-Z0-9_]+)*)", line)
         if m:
             counts[cur][m.group(1)] += 1
             if m.group(1) in ("REDG", "ATOMG", "RED", "ATOM") and ".F64" in m.group(2):
