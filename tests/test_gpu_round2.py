@@ -311,6 +311,42 @@ def test_eval_large_batch_kernel_variants(variant, monkeypatch):
         assert np.abs(np.asarray(s_[k]) - s1).max() < 1e-11 * np.abs(s1).max()
 
 
+def test_eval_lanes_ragged_batches_and_errors():
+    """Lane splitting of pm_eval: batches with fewer structures than lanes, one dominant structure, an empty structure in the
+    middle of a large batch, and an invalid structure in a later lane (the error surfaces, the context stays usable)."""
+    from pypolymlp_b200.libmlpcpp import PotentialPropertiesFast
+
+    pd = make_params_dict(**cases.cfg2_model_kwargs(4))
+    prop = PotentialPropertiesFast(pd, np.random.default_rng(12).normal(size=2030) * 1e-3)
+    big = cases.fcc_supercell(rep=(4, 4, 8), sigma=0.03, seed=777)
+    small = cases.fcc_supercell(rep=(2, 2, 2), sigma=0.02, seed=3)
+    prop.eval(*big, True)
+    e_big, f_big = prop.get_e(), np.array(prop.get_f())
+    prop.eval(*small, True)
+    e_small, f_small = prop.get_e(), np.array(prop.get_f())
+    empty = (small[0], np.zeros((3, 0)), np.zeros(0, dtype=np.int32))
+    for sts in ([big] * 40 + [empty] + [small] * 3 + [big] * 2,          # 21 504 atoms, empty structure inside
+                [big] * 33 + [small],                                     # 2 lanes' worth, ragged tail
+                [small] * 2 + [big] * 36):
+        prop.eval_multiple([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts])
+        e, f = prop.get_e_array(), prop.get_f_array()
+        for k, st in enumerate(sts):
+            if st is big:
+                assert e[k] == pytest.approx(e_big, rel=1e-12)
+                assert np.abs(np.asarray(f[k]) - f_big).max() < 1e-11 * np.abs(f_big).max()
+            elif st is small:
+                assert e[k] == pytest.approx(e_small, rel=1e-12)
+                assert np.abs(np.asarray(f[k]) - f_small).max() < 1e-11 * np.abs(f_small).max()
+            else:
+                assert e[k] == 0.0 and np.asarray(f[k]).size == 0
+    bad = (big[0], big[1], np.full(512, 7, dtype=np.int32))   # atom type outside the model
+    sts = [big] * 39 + [bad]
+    with pytest.raises((ValueError, RuntimeError)):
+        prop.eval_multiple([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts])
+    prop.eval(*small, True)
+    assert prop.get_e() == pytest.approx(e_small, rel=1e-12)
+
+
 def _n_devices():
     import ctypes
 
