@@ -564,7 +564,16 @@ static void build_device_model(pm_context* c) {
                 fprintf(stderr, "[pm] type %d: la_ok %d, radial batch nr %d S %d Fs %d Ps %d, %zu features (%zu terms, %zu chunks), %zu head items in %zu chunks\n", t, D.la_ok,
                         nr, S, Fs, Ps, bforder.size(), bterms.size(), bfwork.size(), bhitems.size(), bwork.size());
         }
-        {   // sliced tables (k_features_v3)
+        // sliced tables (k_features_v3): `feats` / `ents` select the features and G entries that are sliced
+        struct Sliced {
+            std::vector<double> scoef;
+            std::vector<unsigned> flat;
+            std::vector<int4> fmeta, emeta;
+            std::vector<int> fout;
+            std::vector<int2> eout, efh;
+            bool ids_fit = true;
+        };
+        auto build_slices = [&](const std::vector<int>& feats, const std::vector<int>& ents, Sliced& out) {
             const int mo = std::max(T.max_order, 1);
             const int nw = (mo + 1) / 2;
             std::vector<double> scoef;
@@ -579,9 +588,9 @@ static void build_device_model(pm_context* c) {
             bool ids_fit = T.n_full < 32768;
             // features: rows of 8, 4 k-lanes
             {
-                std::vector<int> order_of(T.n_feat, 1), idx(T.n_feat);
-                for (int f = 0; f < T.n_feat; ++f) {
-                    idx[f] = f;
+                const int n_feat_sel = (int)feats.size();
+                std::vector<int> order_of(T.n_feat, 1), idx(feats);
+                for (int f : feats) {
                     int o = 1;
                     for (int ti = T.term_off[f]; ti < T.term_off[f + 1]; ++ti) o = std::max(o, T.term_order[ti]);
                     order_of[f] = o;
@@ -592,9 +601,9 @@ static void build_device_model(pm_context* c) {
                     if (na != nb) return na > nb;
                     return a < b2;
                 });
-                for (int p0 = 0; p0 < T.n_feat;) {
+                for (int p0 = 0; p0 < n_feat_sel;) {
                     int p1 = p0;
-                    while (p1 < T.n_feat && p1 - p0 < 8 && order_of[idx[p1]] == order_of[idx[p0]]) ++p1;
+                    while (p1 < n_feat_sel && p1 - p0 < 8 && order_of[idx[p1]] == order_of[idx[p0]]) ++p1;
                     int mx = 0;
                     for (int p = p0; p < p1; ++p) mx = std::max(mx, T.term_off[idx[p] + 1] - T.term_off[idx[p]]);
                     const int iters = (mx + 3) / 4;
@@ -619,9 +628,8 @@ static void build_device_model(pm_context* c) {
             }
             // G entries: 32 per slice
             {
-                std::vector<int> idx(T.ent_pos_re.size()), cn_of(idx.size(), 0);
-                for (size_t e = 0; e < idx.size(); ++e) {
-                    idx[e] = (int)e;
+                std::vector<int> idx(ents), cn_of(T.ent_pos_re.size(), 0);
+                for (int e : ents) {
                     int cn = 0;
                     for (int q = T.ent_off[e]; q < T.ent_off[e + 1]; ++q) {
                         if (q > T.ent_off[e] && T.contribs[q].n_ids != cn) ids_fit = false;
@@ -688,15 +696,24 @@ static void build_device_model(pm_context* c) {
                 }
                 emeta.swap(em2); eout.swap(eo2); efh.swap(ef2);
             }
-            D.n_fsl = ids_fit ? (int)fmeta.size() : 0;
-            D.n_esl = ids_fit ? (int)emeta.size() : 0;
-            D.sl_words = nw;
-            D.n_slots = (long)scoef.size();
-            std::vector<unsigned> flat;
-            for (auto& w : sw) flat.insert(flat.end(), w.begin(), w.end());
-            D.fsl_meta = upload(c, fmeta); D.fsl_out = upload(c, fout);
-            D.esl_meta = upload(c, emeta); D.esl_out = upload(c, eout); D.esl_fh = upload(c, efh);
-            D.sl_coeff = upload(c, scoef); D.sl_ids = upload(c, flat);
+            out.ids_fit = ids_fit;
+            out.scoef.swap(scoef);
+            for (auto& w : sw) out.flat.insert(out.flat.end(), w.begin(), w.end());
+            out.fmeta.swap(fmeta); out.emeta.swap(emeta); out.fout.swap(fout); out.eout.swap(eout); out.efh.swap(efh);
+        };
+        {
+            std::vector<int> feats(T.n_feat), ents(T.ent_pos_re.size());
+            for (int f = 0; f < T.n_feat; ++f) feats[f] = f;
+            for (size_t e = 0; e < ents.size(); ++e) ents[e] = (int)e;
+            Sliced sl;
+            build_slices(feats, ents, sl);
+            D.n_fsl = sl.ids_fit ? (int)sl.fmeta.size() : 0;
+            D.n_esl = sl.ids_fit ? (int)sl.emeta.size() : 0;
+            D.sl_words = (std::max(T.max_order, 1) + 1) / 2;
+            D.n_slots = (long)sl.scoef.size();
+            D.fsl_meta = upload(c, sl.fmeta); D.fsl_out = upload(c, sl.fout);
+            D.esl_meta = upload(c, sl.emeta); D.esl_out = upload(c, sl.eout); D.esl_fh = upload(c, sl.efh);
+            D.sl_coeff = upload(c, sl.scoef); D.sl_ids = upload(c, sl.flat);
             if (getenv("PM_DEBUG_TABLES"))
                 fprintf(stderr, "[pm] type %d: %d feature slices, %d entry slices, %ld slots (terms %zu, contribs %zu)\n",
                         t, D.n_fsl, D.n_esl, D.n_slots, T.term_coeff.size(), T.contribs.size());
