@@ -741,11 +741,18 @@ k_xrows_v6(DevModel m, DevBatch b, const double* __restrict__ dpv, const double*
             }
         }
         // the warp that finishes a slot last refills it (no producer warp: 8 warps x 112 registers let two CTAs share an SM)
+        // (release: this warp's reads of the slot are ordered before its count; acquire + proxy fence: the refill, an
+        // async-proxy write, is ordered after every warp's count)
         __syncwarp();
         int last = 0;
         if (lane == 0) {
+            __threadfence_block();
             last = atomicAdd(s_cnt + slot, 1) == X6_MMA_WARPS - 1;
-            if (last) s_cnt[slot] = 0;
+            if (last) {
+                s_cnt[slot] = 0;
+                __threadfence_block();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && st + X6_STAGES < nst) issue_stage(st + X6_STAGES);
