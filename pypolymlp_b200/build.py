@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpolymlp_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["pm_tables.cpp", "pm_kernels.cu", "pm_kernels_mma.cu", "pm_kernels_front.cu", "pm_solver.cu", "pm_capi.cu"]
+SOURCES = ["pm_tables.cpp", "pm_kernels.cu", "pm_kernels_mma.cu", "pm_kernels_front.cu", "pm_kernels_feat.cu", "pm_solver.cu", "pm_capi.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off",

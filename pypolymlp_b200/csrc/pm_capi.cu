@@ -718,6 +718,104 @@ static void build_device_model(pm_context* c) {
                 fprintf(stderr, "[pm] type %d: %d feature slices, %d entry slices, %ld slots (terms %zu, contribs %zu)\n",
                         t, D.n_fsl, D.n_esl, D.n_slots, T.term_coeff.size(), T.contribs.size());
         }
+        {   // ---- radial replication for the sliced K3 tables of LARGE models (k_features_v4r) ------------------------
+            // The term lists and G entries of radial index n are those of radial index 0 with every full id shifted by
+            // n * S, the padded feature id by n * Fs, the head position by n * Ps(segment) and the G position by n * Gs.
+            // Verified entry by entry; then only the radial-0 features / entries are sliced (tables 1 / n_radial of the
+            // size: the big K3 kernel is bound by streaming its ~15 MB of tables per type from L2 for every CTA).
+            int nr = 0, S = 0, Fs = 0, Gs = 0;
+            std::vector<int> r0_feats, r0_ents, gs_u;
+            const int mo = std::max(T.max_order, 1);
+            const int n_fn = hm.fp.n_fn;
+            const int ne = (int)T.ent_pos_re.size();
+            bool reg = T.n_feat > 0 && mo <= 4 && getenv("PM_FEAT_NO_RADIAL") == nullptr;
+            int why = 0;   // first failed check (PM_DEBUG_TABLES)
+#define PM_RFAIL(code) { if (reg) why = code; reg = false; }
+            std::vector<std::vector<int>> fn_(n_fn);
+            if (reg) {
+                for (int f = 0; f < T.n_feat; ++f) fn_[T.tile_n[T.feat_pad[f] / 8]].push_back(f);
+                while (nr < n_fn && !fn_[nr].empty()) ++nr;
+                for (int n = nr; n < n_fn; ++n) if (!fn_[n].empty()) PM_RFAIL(1)
+                for (int n = 1; n < nr; ++n) if (fn_[n].size() != fn_[0].size()) PM_RFAIL(2)
+                if (nr < 2) PM_RFAIL(3)
+            }
+            auto idk = [&](int ti, int k) { return T.term_ids[(size_t)ti * mo + k]; };
+            if (reg) {
+                Fs = T.feat_pad[fn_[1][0]] - T.feat_pad[fn_[0][0]];
+                const int ta = T.term_off[fn_[0][0]], tb = T.term_off[fn_[1][0]];
+                if (T.term_off[fn_[0][0] + 1] == ta || T.term_off[fn_[1][0] + 1] == tb) PM_RFAIL(4)
+                else S = idk(tb, 0) - idk(ta, 0);
+                if (S <= 0 || Fs <= 0) PM_RFAIL(5)
+            }
+            for (int n = 1; n < nr && reg; ++n)
+                for (size_t g = 0; g < fn_[0].size() && reg; ++g) {
+                    const int f0 = fn_[0][g], f1 = fn_[n][g];
+                    const int t0 = T.term_off[f0], t1 = T.term_off[f1], cnt = T.term_off[f0 + 1] - t0;
+                    if (T.feat_pad[f1] - T.feat_pad[f0] != n * Fs || T.term_off[f1 + 1] - t1 != cnt) { PM_RFAIL(6) break; }
+                    for (int k = 0; k < cnt && reg; ++k) {
+                        if (T.term_coeff[t0 + k] != T.term_coeff[t1 + k] || T.term_order[t0 + k] != T.term_order[t1 + k]) PM_RFAIL(7)
+                        for (int z = 0; z < T.term_order[t0 + k] && reg; ++z)
+                            if (idk(t1 + k, z) - idk(t0 + k, z) != n * S) PM_RFAIL(8)
+                    }
+                }
+            if (reg) {
+                auto ent_key = [&](int e) {   // (padded feature id, segment, head position inside the segment)
+                    const int pos = T.ent_pos_re[e];
+                    const auto& blk = T.blocks[pos / 32];
+                    return std::array<int, 3>{blk.tile * 8 + (pos % 32) / 4, blk.seg, 2 * blk.kchunk + (pos % 4) / 2};
+                };
+                std::map<std::array<int, 3>, int> ent_of;
+                for (int e = 0; e < ne; ++e) ent_of[ent_key(e)] = e;
+                gs_u.assign(d.n_type, 0);
+                for (int e = 0; e < ne && reg; ++e) {
+                    const auto k0 = ent_key(e);
+                    if (T.tile_n[k0[0] / 8] != 0) continue;
+                    r0_ents.push_back(e);
+                    const int u = k0[1];
+                    const int ps = T.seg_n_off[u][1] - T.seg_n_off[u][0];   // heads per radial group of this segment
+                    for (int n = 1; n < nr && reg; ++n) {
+                        if (T.seg_n_off[u][n + 1] - T.seg_n_off[u][n] != ps) { PM_RFAIL(9) break; }
+                        const auto it = ent_of.find({k0[0] + n * Fs, u, k0[2] + n * ps});
+                        if (it == ent_of.end()) { PM_RFAIL(10) break; }
+                        const int e1 = it->second;
+                        // blocks are sorted by (segment, tile, k-chunk): the G stride per radial index is per segment
+                        const int d = T.ent_pos_re[e1] - T.ent_pos_re[e];
+                        if (gs_u[u] == 0 && n == 1) gs_u[u] = d;
+                        if (d != n * gs_u[u] || T.ent_pos_im[e1] - T.ent_pos_im[e] != n * gs_u[u]) PM_RFAIL(11)
+                        const int c0 = T.ent_off[e], c1 = T.ent_off[e1], cnt = T.ent_off[e + 1] - c0;
+                        if (T.ent_off[e1 + 1] - c1 != cnt) { PM_RFAIL(12) break; }
+                        for (int q = 0; q < cnt && reg; ++q) {
+                            const auto &a0 = T.contribs[c0 + q], &a1 = T.contribs[c1 + q];
+                            if (a0.coeff != a1.coeff || a0.conj != a1.conj || a0.n_ids != a1.n_ids || a0.n_ids > 3) PM_RFAIL(13)
+                            for (int z = 0; z < a0.n_ids && reg; ++z)
+                                if (a1.ids[z] - a0.ids[z] != n * S) PM_RFAIL(14)
+                        }
+                    }
+                }
+                for (int e : r0_ents) if (gs_u[T.blocks[T.ent_pos_re[e] / 32].seg] <= 0) PM_RFAIL(16)
+                if (!gs_u.empty()) Gs = gs_u[0];
+                if ((size_t)r0_ents.size() * nr != (size_t)ne) PM_RFAIL(15)
+            }
+            Sliced sl;
+            if (reg) build_slices(fn_[0], r0_ents, sl);
+            const bool okr = reg && sl.ids_fit && !sl.fmeta.empty();
+            D.r_nr = okr ? nr : 0; D.r_S = S; D.r_Fs = Fs; D.r_Gs = Gs;
+            D.r_n_fsl = okr ? (int)sl.fmeta.size() : 0;
+            D.r_n_esl = okr ? (int)sl.emeta.size() : 0;
+            D.r_n_slots = (long)sl.scoef.size();
+            D.r_fsl_meta = upload(c, sl.fmeta); D.r_fsl_out = upload(c, sl.fout);
+            std::vector<int4> eout4(sl.eout.size());   // (pos_re, pos_im, G stride per radial index of the entry's segment, 0)
+            for (size_t k = 0; k < eout4.size(); ++k) {
+                const int2 pz = sl.eout[k];
+                eout4[k] = make_int4(pz.x, pz.y, pz.x >= 0 && okr ? gs_u[T.blocks[pz.x / 32].seg] : 0, 0);
+            }
+            D.r_esl_meta = upload(c, sl.emeta); D.r_esl_out = upload(c, eout4);
+            D.r_sl_coeff = upload(c, sl.scoef); D.r_sl_ids = upload(c, sl.flat);
+            if (getenv("PM_DEBUG_TABLES"))
+                fprintf(stderr, "[pm] type %d: radial-0 slices: nr %d S %d Fs %d Gs %d, %d feature slices, %d entry slices, %ld slots (failed check %d, slices fit %d)\n",
+                        t, D.r_nr, S, Fs, Gs, D.r_n_fsl, D.r_n_esl, D.r_n_slots, why, (int)sl.ids_fit);
+#undef PM_RFAIL
+        }
         std::vector<int> bk(T.blocks.size());
         for (size_t k = 0; k < bk.size(); ++k) bk[k] = T.blocks[k].kchunk;
         D.blk_kchunk = upload(c, bk);

@@ -83,6 +83,17 @@ struct DevType {
     const LaItem* lb_hitems;      // contributions of the radial-0 heads (format of la_hitems)
     const int4* lb_fwork;         // [lb_nfwork] (first term, end, feature index g, 0): chunks of one feature's terms
     const int4* lb_work;          // [lb_nwork] (first item, end, head position key, 0): chunks ending on entry boundaries
+    // radial-0 slices of k_features_v4r, large models (r_nr = 0: not a radial replication): the sliced tables restricted to the
+    // features / entries of radial index 0; radial index n adds n * r_S to every full id, n * r_Fs to the padded feature id
+    // and n * (stride of its segment) to the G positions
+    int r_nr, r_S, r_Fs, r_Gs, r_n_fsl, r_n_esl;
+    long r_n_slots;
+    const int4* r_fsl_meta;
+    const int* r_fsl_out;
+    const int4* r_esl_meta;
+    const int4* r_esl_out;        // (pos_re, pos_im, G stride per radial index of the entry's segment, 0)
+    const double* r_sl_coeff;
+    const unsigned* r_sl_ids;
     const double* sl_coeff;       // [n_slots]
     const unsigned* sl_ids;       // [sl_words][n_slots]; bit 31 of word 0 = conjugate flag (entries)
     const int* blk_kchunk;

@@ -1429,9 +1429,13 @@ void launch_features(const DevModel& m, const DevBatch& b, const double2* anc, d
             if (armed && dpv) k_dpv_gather<<<(int)(((long)b.n_atoms * 64 + 255) / 256), 256, 0, s>>>(m, b.n_atoms, dfeat, dpv);
         }
     } dpv_fallback{m, b, dfeat, dpv, s};
-    // (a radial-batched variant of k_features_v3 -- slices of the radial-0 features only, every decoded slot applied to a
-    // block of 1 / 2 / 5 radial indices, as k_eval_features_lb does -- measured slower on config 2: 11.3 - 14.3 vs 10.7 us per
-    // structure; the 128 radial-0 entries pack badly into 32-row slices and there are too few work items per CTA)
+    // large radial-replication models: the radial-batched kernel (pm_kernels_feat.cu).  (On config 2 it measured slower,
+    // 11.3 - 14.3 vs 10.7 us per structure: the 128 radial-0 entries pack badly into 32-row slices and there are too few
+    // work items per CTA -- it declines small models.)
+    if (launch_features_radial(m, b, anc, dfeat, Gbuf, smem_bytes, s, zero_g, dpv)) {
+        dpv_fallback.armed = false;
+        return;
+    }
     // smem_bytes = bytes of one atom's full a_nlm array
     const int nfull_max = (int)(smem_bytes / sizeof(double2));
     constexpr int AT = 4;

@@ -90,6 +90,10 @@ int syrk_launches(int n_rows, int fpad, bool simple);
 void launch_eval_adjoint(const DevModel& m, const DevBatch& b, const Workspace& ws, const double* coeffs,
                          double* energies, double* forces, double* stresses, cudaStream_t s, size_t feat_smem = 0);
 bool eval_fused_supported(const DevModel& m, size_t feat_smem);
+// K3 for large radial-replication models (DevType::r_nr > 0): each decoded table slot serves a block of radial indices;
+// false if the model is not served (then launch_features runs k_features_v3 & co.)
+bool launch_features_radial(const DevModel& m, const DevBatch& b, const double2* anc, double* dfeat, double* Gbuf,
+                            size_t smem_bytes, cudaStream_t s, bool zero_g, double* dpv);
 // micro-benchmarks (TFLOP/s)
 double microbench_fp64(int which, cudaStream_t s);
 

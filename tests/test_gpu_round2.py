@@ -228,6 +228,20 @@ def test_x_config4_ternary_order4_vs_reference(mrt, monkeypatch):
     assert np.abs(x.sum(axis=1) - G2["cfg4_rowsum"]).max() < 1e-10 * np.abs(G2["cfg4_rowsum"]).max()
 
 
+@pytest.mark.parametrize("env", [{"PM_FEAT_V3": "1"}, {"PM_FEAT_NB": "2"}, {"PM_FEAT_NB": "1"}, {"PM_FEAT_NO_RADIAL": "1"}])
+def test_x_config4_radial_batched_k3_variants(env, monkeypatch):
+    """Large-model K3: the radial-batched kernel (k_features_v4r, default for big a_nlm arrays; the test above pins it to the
+    reference goldens) against the slice kernel k_features_v3 and against its own other radial block sizes."""
+    pd = make_params_dict(**cases.cfg4_model_kwargs())
+    ax, pc, ty = cases.cfg4_small_cell()
+    x0 = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [16]).get_x()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    x1 = PotentialModel(pd, [ax], [pc], [ty], [1], [True], [16]).get_x()   # (a new model / context: tables are built per context)
+    scale = np.abs(x0).max(axis=0) + 1e-300
+    assert np.abs((x1 - x0) / scale).max() < 1e-12
+
+
 def test_eval_config4_model_vs_reference():
     pd = make_params_dict(**cases.cfg4_model_kwargs())
     ax, pc, ty = cases.cfg4_small_cell()
