@@ -13,7 +13,7 @@ LIB = os.path.join(ROOT, "pypolymlp_b200", "lib", "libpolymlp_b200.so")
 OPS = ["DMMA", "UBLKCP", "SYNCS", "LDGSTS", "REDG", "ATOMG", "ATOMS", "LDS", "LDG", "STG", "DFMA", "DMUL", "DADD", "BAR"]
 HOT = ["k_syrk_sk2", "k_syrk_sk(", "k_lrows_v4n<3, 8>", "k_lrows_v4<3, 8>", "k_lrows_v4a<3, 8>", "k_xrows_v6", "k_pair_anlm<4, true>",
        "k_features_v3<4, 3, 256>", "k_lrows_big<12, 512>", "k_lrows_big<8, 256>", "k_xrows_v5", "k_lrows_v3<3, 8, false>",
-       "k_anlm_eval<4, true>", "k_eval_features_lb<5>", "k_eval_features_la<3>", "k_eval_pairs_rc<4, 12, false>",
+       "k_features_v4r<1, 512, 5>", "k_anlm_eval<4, true>", "k_eval_features_lb<5>", "k_eval_features_la<3>", "k_eval_pairs_rc<4, 12, false>",
        "k_eval_features<4, 3>", "k_eval_pairs_v2", "k_neighbor_cl_count", "k_neighbor_cl_fill", "k_neighbor_mask<false>",
        "k_pack_upper", "k_xe_reduce"]
 
@@ -41,7 +41,7 @@ def main():
             if m.group(1) in ("REDG", "ATOMG", "RED", "ATOM") and ".F64" in m.group(2):
                 fp_atom[cur] += 1
     names = demangle(list(counts))
-    short = {k: re.sub(r"\(.*", "(", v).replace("void ", "") for k, v in names.items()}
+    short = {k: re.sub(r"\(.*", "(", v.replace("(anonymous namespace)::", "")).replace("void ", "") for k, v in names.items()}
     print(f"# Round {tag[1:].lstrip('0')} — SASS summary of `pypolymlp_b200/lib/libpolymlp_b200.so` (`cuobjdump -sass`, static instruction "
           "counts; `python tools/sass_summary.py`)\n")
     print("tcgen05 / UMMA has no f64 kind: the fp64 tensor path on sm_100a is `mma.sync.m8n8k4.f64` = `DMMA.8x8x4`.  `UBLKCP` = 1-D TMA "
