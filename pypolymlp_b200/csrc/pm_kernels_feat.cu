@@ -24,7 +24,7 @@ __device__ __forceinline__ double2 cmulf(double2 a, double2 b) {
 }
 
 template <int AT, int NT, int NB>
-__global__ void __launch_bounds__(NT) k_features_v4r(DevModel m, DevBatch b, const double2* __restrict__ anc,
+__global__ void __launch_bounds__(NT, 2) k_features_v4r(DevModel m, DevBatch b, const double2* __restrict__ anc,
                                                       double* __restrict__ dfeat, double* __restrict__ Gbuf,
                                                       int nfull_max, int zero_g, double* __restrict__ dpv) {
     extern __shared__ double2 afull[];   // [AT][nfull_max]
@@ -232,9 +232,9 @@ bool launch_features_radial(const DevModel& m, const DevBatch& b, const double2*
     int nb = nr % 5 == 0 ? 5 : (nr % 4 == 0 ? 4 : (nr % 3 == 0 ? 3 : (nr % 2 == 0 ? 2 : 1)));
     if (getenv("PM_FEAT_NB")) { const int want = atoi(getenv("PM_FEAT_NB")); if (want >= 1 && want <= 5 && nr % want == 0) nb = want; }
     const int nfull_max = (int)(smem_bytes / sizeof(double2));
-    // atoms per CTA: 2 when two CTAs of 2 atoms fit an SM, else 1 (two CTAs per SM when they fit)
-    const size_t half = 113 * 1024;
-    int at = 2 * smem_bytes <= half ? 2 : 1;
+    // one atom per CTA, two 512-thread CTAs per SM at 64 registers (measured on configs 3 / 4: 12.0 / 16.6 ms against 13.1 /
+    // 20.4 ms with two atoms per CTA and 14.7 / 19.4 ms with one 107-register CTA per SM)
+    int at = 1;
     if (getenv("PM_FEAT_AT")) { const int want = atoi(getenv("PM_FEAT_AT")); if (want == 1 || want == 2) at = want; }
     if ((size_t)at * smem_bytes > 226 * 1024) at = 1;
     if (smem_bytes > 226 * 1024) return false;
