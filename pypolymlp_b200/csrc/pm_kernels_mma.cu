@@ -898,10 +898,13 @@ static void launch_lrows_big(const DevModel& m, const DevBatch& b, const Workspa
     const double rows = 3.0 * b.n_pairs / std::max(1, b.n_atoms * m.n_type) + 9.0;
     const int force_mrt = getenv("PM_LROWS_MRT") ? atoi(getenv("PM_LROWS_MRT")) : 0;
     const bool two9 = 2 * (lrows_big_smem(9) + 1024) <= 228 * 1024;
+    // (re-measured in round 2, ms per step: config 3, ~99 rows: 34.9 / 36.1 / 33.1 / 30.9 for 8 / 9 / 12 / 16 row tiles;
+    // config 4, ~67 rows on average but ragged: 36.8 / 44.1 / 29.5 / 33.6 -- an average near 64 means that half of the
+    // segments split into two chunks of a 64-row CTA)
+    (void)two9;
     int mrt = 8;
-    if (rows > 64.0 && rows <= 72.0 && two9) mrt = 9;
-    else if (rows > 84.0 && lrows_big_smem(16) <= 226 * 1024) mrt = 16;     // segments around 96 rows: 12 tiles would split half of them
-    else if (rows > 72.0 && lrows_big_smem(12) <= 226 * 1024) mrt = 12;
+    if (rows > 84.0 && lrows_big_smem(16) <= 226 * 1024) mrt = 16;     // segments around 96 rows: 12 tiles would split half of them
+    else if (rows > 56.0 && lrows_big_smem(12) <= 226 * 1024) mrt = 12;
     if ((force_mrt == 8 || force_mrt == 9 || force_mrt == 12 || force_mrt == 16) && lrows_big_smem(force_mrt) <= 226 * 1024)
         mrt = force_mrt;
     if (mrt == 16) launch_lrows_big_t<16, 512>(m, b, ws, s);
