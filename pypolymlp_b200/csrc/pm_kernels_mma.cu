@@ -295,38 +295,49 @@ __device__ __forceinline__ void sy_load_stage(const SyLoader& L, int fpad, int s
 // b >= a - OFF (OFF >= 7: all 32; 4: 26; 0: 10; < -3: none) -- compile-time, so skipped DMMAs are not issued at all
 // (a predicated-off DMMA still occupies the tensor pipe: measured).
 template <int OFF>
-__device__ __forceinline__ void sy_mainloop(double (&acc)[8][4][2], const double* __restrict__ smem, const SyLoader& L,
+__device__ __forceinline__ void sy_kblock(double (&acc)[8][4][2], const double* __restrict__ smem, const SyLoader& L,
+                                          int fpad, int kt, int nk, int r_end, bool diag, int wm, int wn, int g, int q) {
+    const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
+    const double* sB = diag ? sA : sA + SY_BK * SY_LD;
+    const double* pa = sA + q * SY_LD + wm * 64 + g;
+    const double* pb = sB + q * SY_LD + wn * 32 + g;
+#pragma unroll
+    for (int ks = 0; ks < SY_BK / 4; ++ks) {
+        if (ks == SY_ISSUE_AT) {
+            // the copies of k-block kt + 2 are issued behind the first DMMAs of this k-block (the slot they overwrite
+            // was released by the barrier of this k-block), so the tensor pipe is fed right after the barrier
+            const int nx = kt + SY_STAGES - 1;
+            if (nx < nk) sy_load_stage(L, fpad, nx % SY_STAGES, nx, r_end, diag);
+            cp_async_commit();
+        }
+        if (OFF > -4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (a - OFF <= 3) af[a] = pa[ks * 4 * SY_LD + a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b >= a - OFF) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+}
+
+// The k loop with its block barrier is common code: `off` differs between the warps of a diagonal tile, and a barrier
+// reached from per-warp instantiations of the whole loop is, formally, a barrier in divergent code (compute-sanitizer
+// synccheck reports it).  The warp-uniform choice of the k-block body sits inside the iteration.
+__device__ __forceinline__ void sy_mainloop(int off, double (&acc)[8][4][2], const double* __restrict__ smem, const SyLoader& L,
                                             int fpad, int nk, int r_end, bool diag, int wm, int wn, int g, int q) {
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<SY_STAGES - 2>();
         __syncthreads();
-        const double* sA = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DOUBLES;
-        const double* sB = diag ? sA : sA + SY_BK * SY_LD;
-        const double* pa = sA + q * SY_LD + wm * 64 + g;
-        const double* pb = sB + q * SY_LD + wn * 32 + g;
-#pragma unroll
-        for (int ks = 0; ks < SY_BK / 4; ++ks) {
-            if (ks == SY_ISSUE_AT) {
-                // the copies of k-block kt + 2 are issued behind the first DMMAs of this k-block (the slot they overwrite
-                // was released by the barrier above), so the tensor pipe is fed right after the barrier
-                const int nx = kt + SY_STAGES - 1;
-                if (nx < nk) sy_load_stage(L, fpad, nx % SY_STAGES, nx, r_end, diag);
-                cp_async_commit();
-            }
-            if (OFF > -4) {
-                double af[8], bf[4];
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    if (a - OFF <= 3) af[a] = pa[ks * 4 * SY_LD + a * 8];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) bf[b] = pb[ks * 4 * SY_LD + b * 8];
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (b >= a - OFF) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-            }
-        }
+        if (off >= 7) sy_kblock<12>(acc, smem, L, fpad, kt, nk, r_end, diag, wm, wn, g, q);
+        else if (off == 4) sy_kblock<4>(acc, smem, L, fpad, kt, nk, r_end, diag, wm, wn, g, q);
+        else if (off == 0) sy_kblock<0>(acc, smem, L, fpad, kt, nk, r_end, diag, wm, wn, g, q);
+        else sy_kblock<-8>(acc, smem, L, fpad, kt, nk, r_end, diag, wm, wn, g, q);
     }
 }
 
@@ -403,10 +414,7 @@ __global__ void __maxnreg__(192) k_syrk_sk2(const double* __restrict__ X, int n_
             if (s < nk) sy_load_stage(L, fpad, s, s, r_end, diag);
             cp_async_commit();
         }
-        if (off >= 7) sy_mainloop<12>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
-        else if (off == 4) sy_mainloop<4>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
-        else if (off == 0) sy_mainloop<0>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
-        else sy_mainloop<-8>(acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
+        sy_mainloop(off, acc, smem, L, fpad, nk, r_end, diag, wm, wn, g, q);
         cp_async_wait<0>();
         const bool whole = kb0 == 0 && kb1 == nkb;
         bool reduce = whole;
