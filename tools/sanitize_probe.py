@@ -29,3 +29,11 @@ acc = PotentialXtX(pd)
 acc.add([s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts], [True] * len(sts), w, y)
 r = acc.finalize()
 print("fit", float(np.trace(r["xtx"])))
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    # the large-model kernels (k_lrows_big, k_features_v4r, the head passes of k_anlm_v2, k_xrows_v2 ...) on the 16-atom ternary cell
+    from pypolymlp_b200.libmlpcpp import PotentialModel
+
+    pd4 = make_params_dict(**cases.cfg4_model_kwargs())
+    ax, pc, ty = cases.cfg4_small_cell()
+    x = PotentialModel(pd4, [ax], [pc], [ty], [1], [True], [16]).get_x()
+    print("big X", x.shape, float(np.abs(x).sum()))
