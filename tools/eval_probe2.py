@@ -35,6 +35,9 @@ dt = (time.perf_counter() - t0) / 3
 print("eval %d x 512 atoms: %.2f ms/call = %.2f M atoms/s" % (n_ev, dt * 1e3, n_ev * 512 / dt * 1e-6))
 ctx = prop._ctx
 ctx.profile(True)
+step()             # (one lane, other chunk sizes than the timed calls: this call grows the chunk buffers)
+ctx.synchronize()
+ctx.profile(True)  # resets the stage sums
 step()
 ctx.synchronize()
 for k, (ms, ln) in ctx.profile_get().items():
